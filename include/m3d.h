@@ -1,0 +1,342 @@
+/*
+ * m3d.h -- C ABI of libm3dgpu: the B200 (sm_100a) implementation of model3d's
+ * ray-tracing hot path.
+ *
+ * This is the drop-in boundary.  The reference (github.com/unixpickle/model3d, Go)
+ * has no FFI; its seam is a set of Go interfaces.  Every entry point below names
+ * the reference interface it replaces (file:line relative to the reference tree).
+ * A Go maintainer binds these with cgo (see INTEGRATION.md and go/gpu3d/).
+ *
+ * Conventions
+ *   - every function returns an int32 status (M3D_OK == 0); m3d_last_error() gives
+ *     a thread-local, NUL-terminated message owned by the library;
+ *   - host buffers are borrowed for the duration of the call only;
+ *   - handles are opaque, immutable after build, freed with *_destroy;
+ *   - bulk arrays (vertices, rays, hits, pixels) are float32 / int32;
+ *     scalar parameters (camera, materials, lights) are float64 like the Go fields;
+ *   - "triangle id" == index of the triangle in the caller's array
+ *     (the reference identifies triangles by pointer, model3d/collisions.go:39-46);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with M3D_ERR_CUDA.
+ */
+#ifndef M3D_H_
+#define M3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3D_ABI_VERSION 1
+
+typedef enum {
+  M3D_OK = 0,
+  M3D_ERR_INVALID_ARG = 1,
+  M3D_ERR_UNSUPPORTED = 2, /* object / material / feature outside the GPU path */
+  M3D_ERR_CUDA = 3,
+  M3D_ERR_NCCL = 4,
+  M3D_ERR_OOM = 5
+} m3d_status;
+
+typedef struct m3d_ctx m3d_ctx;     /* one CUDA device + stream pool            */
+typedef struct m3d_mesh m3d_mesh;   /* triangle mesh + wide BVH, device resident */
+typedef struct m3d_scene m3d_scene; /* objects + materials, device resident      */
+typedef struct m3d_scene_builder m3d_scene_builder;
+
+/* ---- library / context ------------------------------------------------- */
+
+int32_t m3d_abi_version(void);
+const char *m3d_last_error(void);
+
+/* device < 0 -> current CUDA device. */
+int32_t m3d_ctx_create(int32_t device, m3d_ctx **out);
+void m3d_ctx_destroy(m3d_ctx *ctx);
+int32_t m3d_ctx_device(const m3d_ctx *ctx);
+int32_t m3d_ctx_synchronize(m3d_ctx *ctx);
+
+/* ---- statistics ---------------------------------------------------------- */
+
+/* Filled by trace / render calls when a non-NULL pointer is passed.
+ * nodes_visited / tris_tested are only counted when M3D_TRACE_COUNTERS is set
+ * (a separate kernel instantiation; never set in timed runs). */
+typedef struct {
+  int64_t rays;          /* rays traced (all kinds)                      */
+  int64_t hits;          /* rays that hit something                      */
+  int64_t nodes_visited; /* wide-BVH nodes fetched                       */
+  int64_t tris_tested;   /* ray/triangle tests executed                  */
+  double kernel_ms;      /* device time of the compute kernels           */
+  double h2d_ms, d2h_ms; /* host<->device copy time (host-buffer calls)  */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t launches;      /* kernels of this library launched by the call */
+} m3d_stats;
+
+/* ---- mesh collider ----------------------------------------------------------
+ * Replaces model3d.MeshToCollider / GroupTriangles / GroupedTrianglesToCollider
+ * (model3d/collisions.go:138-179, model3d/bvh.go:118-156) and
+ * MeshToInterpNormalCollider (collisions.go:147-162) when vnormals != NULL.
+ */
+#define M3D_MESH_BUILD_HOST_SAH 0u   /* host binned-SAH build, collapsed to 8-wide */
+#define M3D_MESH_BUILD_DEVICE_LBVH 1u /* device Morton/radix/Karras build         */
+
+typedef struct {
+  int64_t num_triangles;
+  int64_t num_nodes;     /* 8-wide compressed nodes                   */
+  int64_t node_bytes;    /* bytes of one node record (80)             */
+  int64_t tri_bytes;     /* bytes of one triangle record (48)         */
+  int64_t device_bytes;  /* total HBM footprint                       */
+  int32_t max_depth;
+  double build_ms;
+  double sah_cost;
+} m3d_mesh_info;
+
+/* tris: n*9 floats (v0 v1 v2 per triangle, caller order == triangle id).
+ * vnormals: NULL or n*9 floats (per-corner normals, smooth shading). */
+int32_t m3d_mesh_create(m3d_ctx *ctx, const float *tris, int64_t n,
+                        const float *vnormals, uint32_t build_flags,
+                        m3d_mesh **out);
+void m3d_mesh_destroy(m3d_mesh *mesh);
+int32_t m3d_mesh_get_info(const m3d_mesh *mesh, m3d_mesh_info *info);
+/* Collider.Min()/Max()  (model3d/collisions.go:255-261) */
+int32_t m3d_mesh_bounds(const m3d_mesh *mesh, double min_out[3], double max_out[3]);
+
+#define M3D_TRACE_COUNTERS 1u   /* count nodes/triangles (slower; not for timing) */
+#define M3D_TRACE_NO_REFINE 2u  /* skip the float64 final-hit refinement          */
+
+/* Batched Collider.FirstRayCollision (model3d/collisions.go:275-290 +
+ * model3d/primitives.go:181-249).  Host buffers.
+ *   org, dir : n*3 floats; dir is NOT normalised, t is in units of |dir|
+ *   t        : n floats   (RayCollision.Scale; undefined on miss)
+ *   prim     : n int32    (triangle id; -1 == miss)
+ *   normal   : n*3 floats or NULL (RayCollision.Normal: flat, never flipped,
+ *              or interpolated when the mesh has vnormals)
+ *   bary     : n*3 floats or NULL (TriangleCollision.Barycentric)
+ */
+int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org,
+                                      const float *dir, int64_t n, float *t,
+                                      int32_t *prim, float *normal, float *bary,
+                                      uint32_t flags, m3d_stats *stats);
+
+/* Same query on device-resident SoA buffers (what the renderers use internally
+ * and what bench.py times with inputs already in HBM).
+ *   d_org_tmin : n float4  (ox, oy, oz, tmin)
+ *   d_dir_tmax : n float4  (dx, dy, dz, tmax)
+ *   d_hit0     : n float4  (t, bary1, bary2, bits(prim))   prim == -1 on miss
+ *   d_hit1     : n float4  (nx, ny, nz, bits(object))
+ * stream: a cudaStream_t cast to void* (NULL == the context's stream). */
+int32_t m3d_mesh_first_ray_collisions_device(m3d_mesh *mesh, const void *d_org_tmin,
+                                             const void *d_dir_tmax, int64_t n,
+                                             void *d_hit0, void *d_hit1,
+                                             uint32_t flags, void *stream,
+                                             m3d_stats *stats);
+
+/* ---- scene -------------------------------------------------------------------
+ * Replaces render3d.Object trees built from JoinedObject / ColliderObject /
+ * Translate / MatrixMultiply (render3d/object.go:12-153, transform.go:6-85) over
+ * model3d.Sphere / Rect / Cylinder / mesh colliders (model3d/shapes.go:35-93,
+ * 177-247, 601-705) and render3d materials (render3d/material.go:119-479,554-631).
+ * Anything else is M3D_ERR_UNSUPPORTED at build time.
+ */
+typedef enum {
+  M3D_MAT_LAMBERT = 0, /* material.go:119-167 */
+  M3D_MAT_PHONG = 1,   /* material.go:172-269 */
+  M3D_MAT_REFRACT = 2, /* material.go:343-479 */
+  M3D_MAT_JOINED = 3   /* material.go:554-631 */
+} m3d_material_kind;
+
+#define M3D_MAT_NO_FLUX_CORRECTION 1u /* PhongMaterial.NoFluxCorrection */
+#define M3D_MAT_CHECKER 2u   /* showcase FloorObject: diffuse = checker(p.x,p.y) ? c0 : c1 */
+#define M3D_MAT_Z_GRADIENT 4u /* showcase VaseObject: diffuse = lerp over z/max_z */
+#define M3D_MAX_SUBMATERIALS 4
+
+typedef struct {
+  int32_t kind;
+  uint32_t flags;
+  double diffuse[3];
+  double specular[3];
+  double emission[3];
+  double ambient[3];
+  double refract[3];
+  double alpha;               /* Phong exponent */
+  double index_of_refraction; /* RefractMaterial.IndexOfRefraction */
+  /* procedural variants: second colour + scalar (checker alt colour, gradient max_z) */
+  double diffuse2[3];
+  double proc_param;
+  /* JoinedMaterial */
+  int32_t num_sub;
+  int32_t sub[M3D_MAX_SUBMATERIALS];
+  double sub_prob[M3D_MAX_SUBMATERIALS];
+} m3d_material_desc;
+
+#define M3D_OBJ_FLIP_NORMAL 1u /* showcase DomeObject: reported normal negated */
+
+/* Optional rigid/affine wrapper: x_world = matrix * x_object + offset
+ * (render3d.Translate / MatrixMultiply, transform.go:6-85).  Row-major like
+ * the wrapper passes it; NULL == identity. */
+typedef struct {
+  double matrix[9];
+  double offset[3];
+} m3d_transform;
+
+int32_t m3d_scene_builder_create(m3d_ctx *ctx, m3d_scene_builder **out);
+void m3d_scene_builder_destroy(m3d_scene_builder *b);
+/* each add_* returns the new index in *index_out (may be NULL) */
+int32_t m3d_scene_add_material(m3d_scene_builder *b, const m3d_material_desc *mat,
+                               int32_t *index_out);
+int32_t m3d_scene_add_mesh(m3d_scene_builder *b, const float *tris, int64_t n,
+                           const float *vnormals, int32_t material, uint32_t flags,
+                           const m3d_transform *xf, int32_t *index_out);
+int32_t m3d_scene_add_sphere(m3d_scene_builder *b, const double center[3], double radius,
+                             int32_t material, uint32_t flags, const m3d_transform *xf,
+                             int32_t *index_out);
+int32_t m3d_scene_add_rect(m3d_scene_builder *b, const double min[3], const double max[3],
+                           int32_t material, uint32_t flags, const m3d_transform *xf,
+                           int32_t *index_out);
+int32_t m3d_scene_add_cylinder(m3d_scene_builder *b, const double p1[3], const double p2[3],
+                               double radius, int32_t material, uint32_t flags,
+                               const m3d_transform *xf, int32_t *index_out);
+int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **out);
+void m3d_scene_destroy(m3d_scene *scene);
+int32_t m3d_scene_bounds(const m3d_scene *scene, double min_out[3], double max_out[3]);
+
+/* Batched Object.Cast (render3d/object.go:141-153): like
+ * m3d_mesh_first_ray_collisions plus obj (object index, -1 miss); prim is the
+ * triangle id inside that object's mesh (or 0 for analytic shapes). */
+int32_t m3d_scene_cast(m3d_scene *scene, const float *org, const float *dir, int64_t n,
+                       float *t, int32_t *obj, int32_t *prim, float *normal,
+                       uint32_t flags, m3d_stats *stats);
+
+/* ---- renderers ------------------------------------------------------------- */
+
+/* render3d.Camera (render3d/camera.go:19-41) */
+typedef struct {
+  double origin[3];
+  double screen_x[3];
+  double screen_y[3];
+  double field_of_view;
+} m3d_camera;
+
+/* render3d.PointLight (render3d/light.go:57-66) */
+typedef struct {
+  double origin[3];
+  double color[3];
+  int32_t quad_dropoff;
+  int32_t _pad;
+} m3d_point_light;
+
+/* Work partition for multi-GPU: this call renders rows [row_begin,row_end) of the
+ * frame and samples [sample_begin, sample_begin+sample_count) of every pixel. */
+typedef struct {
+  int32_t row_begin, row_end; /* 0,0 == whole frame */
+  int64_t sample_begin;       /* first Philox sample index of this shard */
+} m3d_partition;
+
+/* (*RayCaster).Render (render3d/raycast.go:15-39).
+ * rgb: W*H*3 floats, linear RGB, row-major idx = x + y*W (render3d/image.go:33-47);
+ * pixels whose ray misses are left untouched, exactly like the reference. */
+int32_t m3d_render_raycast(m3d_scene *scene, const m3d_camera *cam,
+                           const m3d_point_light *lights, int32_t num_lights,
+                           int32_t width, int32_t height, const m3d_partition *part,
+                           float *rgb, m3d_stats *stats);
+/* Device-buffer variant: d_rgb is a device pointer to W*H*3 floats. */
+int32_t m3d_render_raycast_device(m3d_scene *scene, const m3d_camera *cam,
+                                  const m3d_point_light *lights, int32_t num_lights,
+                                  int32_t width, int32_t height, const m3d_partition *part,
+                                  void *d_rgb, void *stream, m3d_stats *stats);
+
+typedef enum {
+  M3D_FOCUS_PHONG = 0, /* render3d.PhongFocusPoint  (focus_point.go:30-71)  */
+  M3D_FOCUS_SPHERE = 1 /* render3d.SphereFocusPoint (focus_point.go:73-153) */
+} m3d_focus_kind;
+
+#define M3D_MAX_FOCUS_POINTS 4
+/* MaterialFilter closures cannot cross the ABI: the wrapper pre-evaluates the
+ * filter once per material and passes the result as a bit mask
+ * (bit i set == focus applies to material i; all-ones when the filter is nil). */
+typedef struct {
+  int32_t kind;
+  int32_t _pad;
+  double target[3]; /* Target / Center */
+  double alpha;     /* PhongFocusPoint.Alpha */
+  double radius;    /* SphereFocusPoint.Radius */
+  uint64_t material_mask;
+  double prob;      /* FocusPointProbs[i] */
+} m3d_focus_point;
+
+/* RecursiveRayTracer fields (render3d/raytrace.go:14-95). */
+typedef struct {
+  int32_t max_depth;
+  int32_t num_samples;
+  int32_t min_samples;           /* adaptive stop (ray_renderer.go:128-148) */
+  int32_t num_focus_points;
+  double max_stddev;
+  double oversaturated_stddevs;
+  double cutoff;
+  double antialias;
+  double epsilon;                /* 0 -> DefaultEpsilon (raytrace.go:10) */
+  m3d_focus_point focus[M3D_MAX_FOCUS_POINTS];
+  uint64_t seed;                 /* Philox key */
+} m3d_path_params;
+
+/* (*RecursiveRayTracer).Render (render3d/raytrace.go:98-100, ray_renderer.go:25-56).
+ * Outputs are per-pixel SUMS over the samples of this partition so that shards
+ * add up: rgb_sum (W*H*3), rgb_sumsq (W*H*3 or NULL).  The caller divides by the
+ * total sample count (ray_renderer.go:150) after reducing across GPUs. */
+int32_t m3d_render_path(m3d_scene *scene, const m3d_camera *cam,
+                        const m3d_point_light *lights, int32_t num_lights,
+                        const m3d_path_params *params, int32_t width, int32_t height,
+                        const m3d_partition *part, int32_t sample_count,
+                        float *rgb_sum, float *rgb_sumsq, m3d_stats *stats);
+int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam,
+                               const m3d_point_light *lights, int32_t num_lights,
+                               const m3d_path_params *params, int32_t width, int32_t height,
+                               const m3d_partition *part, int32_t sample_count,
+                               void *d_rgb_sum, void *d_rgb_sumsq, void *stream,
+                               m3d_stats *stats);
+
+/* Area lights for BidirPathTracer.Light (render3d/light.go:104-314): the objects
+ * of the scene that are also sampled as emitters (mesh or sphere objects). */
+typedef struct {
+  int32_t object;      /* scene object index */
+  int32_t _pad;
+  double emission[3];
+} m3d_area_light;
+
+/* BidirPathTracer fields (render3d/bidir.go:14-63). */
+typedef struct {
+  int32_t max_depth;
+  int32_t max_light_depth;
+  int32_t min_depth;
+  int32_t num_samples;
+  double roulette_delta;
+  double power_heuristic;
+  double cutoff;
+  double antialias;
+  double epsilon;
+  uint64_t seed;
+} m3d_bidir_params;
+
+/* (*BidirPathTracer).Render (render3d/bidir.go:66-68,101-159). Sums, as above. */
+int32_t m3d_render_bidir(m3d_scene *scene, const m3d_camera *cam,
+                         const m3d_area_light *lights, int32_t num_lights,
+                         const m3d_bidir_params *params, int32_t width, int32_t height,
+                         const m3d_partition *part, int32_t sample_count,
+                         float *rgb_sum, float *rgb_sumsq, m3d_stats *stats);
+int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam,
+                                const m3d_area_light *lights, int32_t num_lights,
+                                const m3d_bidir_params *params, int32_t width, int32_t height,
+                                const m3d_partition *part, int32_t sample_count,
+                                void *d_rgb_sum, void *d_rgb_sumsq, void *stream,
+                                m3d_stats *stats);
+
+/* colorSum/numSamples + optional 8-bit sRGB (ray_renderer.go:150, image.go:125-145,
+ * light.go:41-47).  d_sum: W*H*3 floats; writes mean into d_mean (may alias d_sum)
+ * and, if d_srgb8 != NULL, W*H*3 bytes. */
+int32_t m3d_finalize_image_device(m3d_ctx *ctx, const void *d_sum, int64_t num_pixels,
+                                  double inv_samples, void *d_mean, void *d_srgb8,
+                                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3D_H_ */

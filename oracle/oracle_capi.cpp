@@ -1,0 +1,367 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see vec.hpp header).
+// C entry points (ctypes) over the float64 restatement.  Built by oracle/Makefile
+// into oracle/liboracle.so.  Never linked into or called by libm3dgpu.
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+#include "collide.hpp"
+#include "meshgen.hpp"
+#include "render.hpp"
+#include "scene.hpp"
+
+using namespace orc;
+
+namespace {
+template <class F>
+void parallel_for(int64_t n, int nthreads, F f) {
+  if (nthreads <= 1 || n < 2) {
+    f(0, n, 0);
+    return;
+  }
+  std::vector<std::thread> th;
+  // dynamic chunks: ray cost is very uneven
+  std::atomic<int64_t> next{0};
+  const int64_t chunk = 4096;
+  for (int t = 0; t < nthreads; t++)
+    th.emplace_back([&, t] {
+      for (;;) {
+        int64_t b = next.fetch_add(chunk);
+        if (b >= n) break;
+        f(b, std::min(n, b + chunk), t);
+      }
+    });
+  for (auto &x : th) x.join();
+}
+
+void tris_from_f32(const float *v, int64_t n, const float *vn, std::vector<Triangle> &out) {
+  out.resize(n);
+  for (int64_t i = 0; i < n; i++)
+    for (int k = 0; k < 3; k++) {
+      out[i].p[k] = V3(v[i * 9 + k * 3], v[i * 9 + k * 3 + 1], v[i * 9 + k * 3 + 2]);
+      if (vn) out[i].vn[k] = V3(vn[i * 9 + k * 3], vn[i * 9 + k * 3 + 1], vn[i * 9 + k * 3 + 2]);
+    }
+}
+void tris_to_f64(const std::vector<Triangle> &m, double *out) {
+  for (size_t i = 0; i < m.size(); i++)
+    for (int k = 0; k < 3; k++) {
+      out[i * 9 + k * 3 + 0] = m[i].p[k].x;
+      out[i * 9 + k * 3 + 1] = m[i].p[k].y;
+      out[i * 9 + k * 3 + 2] = m[i].p[k].z;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// ---- mesh generators (float64 out, n*9) --------------------------------------------
+int64_t orc_mesh_icosphere_count(int n) { return 20LL * n * n; }
+void orc_mesh_icosphere(double cx, double cy, double cz, double radius, int n, double *out) {
+  tris_to_f64(mesh_icosphere(V3(cx, cy, cz), radius, n), out);
+}
+void orc_mesh_rect(const double mn[3], const double mx[3], double *out /*12*9*/) {
+  tris_to_f64(mesh_rect(v3(mn), v3(mx)), out);
+}
+int64_t orc_mesh_polar_count(int stops) { return 2LL * stops * (stops - 1); }
+void orc_mesh_polar(double ra, double rb, int stops, double *out) {
+  tris_to_f64(mesh_polar(ra, rb, stops), out);
+}
+
+// ---- mesh collider --------------------------------------------------------------------
+void *orc_collider_create(const float *tris, int64_t n, const float *vnormals) {
+  auto *m = new MeshCollider();
+  tris_from_f32(tris, n, vnormals, m->tris);
+  m->interp = vnormals != nullptr;
+  m->build(false);
+  return m;
+}
+void *orc_collider_create_f64(const double *tris, int64_t n) {
+  auto *m = new MeshCollider();
+  m->tris.resize(n);
+  for (int64_t i = 0; i < n; i++)
+    for (int k = 0; k < 3; k++) m->tris[i].p[k] = V3(tris[i * 9 + k * 3], tris[i * 9 + k * 3 + 1], tris[i * 9 + k * 3 + 2]);
+  m->build(false);
+  return m;
+}
+void orc_collider_destroy(void *h) { delete (MeshCollider *)h; }
+int64_t orc_collider_num_nodes(void *h) { return (int64_t)((MeshCollider *)h)->nodes.size(); }
+void orc_collider_bounds(void *h, double mn[3], double mx[3]) {
+  auto *m = (MeshCollider *)h;
+  V3 a = m->mn(), b = m->mx();
+  for (int i = 0; i < 3; i++) {
+    mn[i] = a[i];
+    mx[i] = b[i];
+  }
+}
+void orc_collider_order(void *h, int32_t *out) {
+  auto *m = (MeshCollider *)h;
+  std::memcpy(out, m->order.data(), m->order.size() * sizeof(int32_t));
+}
+
+// Batched FirstRayCollision.  org/dir: n*3 float64.  Outputs may be NULL.
+// counters (optional, 2 x int64): total nodes visited, triangles tested.
+void orc_collider_first_hits(void *h, const double *org, const double *dir, int64_t n, double *t,
+                             int32_t *prim, double *normal, double *bary, int64_t *counters,
+                             int nthreads) {
+  auto *m = (MeshCollider *)h;
+  std::atomic<int64_t> cn{0}, ct{0};
+  parallel_for(n, nthreads, [&](int64_t b, int64_t e, int) {
+    Counters c;
+    for (int64_t i = b; i < e; i++) {
+      Ray r{V3(org[i * 3], org[i * 3 + 1], org[i * 3 + 2]), V3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2])};
+      Hit hit;
+      bool ok = m->first_ray_collision(r, hit, counters ? &c : nullptr);
+      if (prim) prim[i] = ok ? hit.prim : -1;
+      if (t) t[i] = ok ? hit.scale : 0;
+      if (normal)
+        for (int k = 0; k < 3; k++) normal[i * 3 + k] = ok ? hit.normal[k] : 0;
+      if (bary)
+        for (int k = 0; k < 3; k++) bary[i * 3 + k] = ok ? hit.bary[k] : 0;
+    }
+    cn += c.nodes;
+    ct += c.tris;
+  });
+  if (counters) {
+    counters[0] = cn;
+    counters[1] = ct;
+  }
+}
+// float32 in (widened), same outputs; used by bench.py's CPU baseline on the same inputs.
+void orc_collider_first_hits_f32(void *h, const float *org, const float *dir, int64_t n, double *t,
+                                 int32_t *prim, double *normal, double *bary, int64_t *counters,
+                                 int nthreads) {
+  auto *m = (MeshCollider *)h;
+  std::atomic<int64_t> cn{0}, ct{0};
+  parallel_for(n, nthreads, [&](int64_t b, int64_t e, int) {
+    Counters c;
+    for (int64_t i = b; i < e; i++) {
+      Ray r{V3(org[i * 3], org[i * 3 + 1], org[i * 3 + 2]), V3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2])};
+      Hit hit;
+      bool ok = m->first_ray_collision(r, hit, counters ? &c : nullptr);
+      if (prim) prim[i] = ok ? hit.prim : -1;
+      if (t) t[i] = ok ? hit.scale : 0;
+      if (normal)
+        for (int k = 0; k < 3; k++) normal[i * 3 + k] = ok ? hit.normal[k] : 0;
+      if (bary)
+        for (int k = 0; k < 3; k++) bary[i * 3 + k] = ok ? hit.bary[k] : 0;
+    }
+    cn += c.nodes;
+    ct += c.tris;
+  });
+  if (counters) {
+    counters[0] = cn;
+    counters[1] = ct;
+  }
+}
+
+// RayCollisions (all hits) for one ray via the BVH (brute == 0) or by testing every
+// triangle (brute == 1).  Returns the count; writes up to cap (t, prim) pairs sorted by t.
+int64_t orc_collider_all_hits(void *h, const double org[3], const double dir[3], int brute,
+                              double *t_out, int32_t *prim_out, int64_t cap) {
+  auto *m = (MeshCollider *)h;
+  Ray r{v3(org), v3(dir)};
+  std::vector<Hit> hits;
+  if (brute)
+    m->brute_collisions(r, hits);
+  else
+    m->ray_collisions(r, hits);
+  std::stable_sort(hits.begin(), hits.end(), [](const Hit &a, const Hit &b) { return a.scale < b.scale; });
+  for (int64_t i = 0; i < (int64_t)hits.size() && i < cap; i++) {
+    t_out[i] = hits[i].scale;
+    prim_out[i] = hits[i].prim;
+  }
+  return (int64_t)hits.size();
+}
+
+// Single-triangle test exposed for edge-case tests (primitives.go:181-249).
+int orc_triangle_first_hit(const double tri[9], const double org[3], const double dir[3], double *t,
+                           double normal[3], double bary[3]) {
+  Triangle tr = mk_tri(v3(tri), v3(tri + 3), v3(tri + 6));
+  Hit h;
+  if (!tri_first_hit(tr, false, Ray{v3(org), v3(dir)}, h)) return 0;
+  *t = h.scale;
+  for (int i = 0; i < 3; i++) {
+    normal[i] = h.normal[i];
+    bary[i] = h.bary[i];
+  }
+  return 1;
+}
+
+// ---- analytic shapes (kind: 1 sphere, 2 rect, 3 cylinder; params as in m3d.h) ---------
+int orc_shape_first_hit(int kind, const double p0[3], const double p1[3], double radius,
+                        const double org[3], const double dir[3], double *t, double normal[3]) {
+  Ray r{v3(org), v3(dir)};
+  Hit h;
+  bool ok = false;
+  if (kind == OBJ_SPHERE) ok = sphere_first_hit(Sphere{v3(p0), radius}, r, h);
+  if (kind == OBJ_RECT) ok = rect_first_hit(Rect{v3(p0), v3(p1)}, r, h);
+  if (kind == OBJ_CYLINDER) ok = cylinder_first_hit(Cylinder{v3(p0), v3(p1), radius}, r, h);
+  if (!ok) return 0;
+  *t = h.scale;
+  for (int i = 0; i < 3; i++) normal[i] = h.normal[i];
+  return 1;
+}
+
+// ---- scene ------------------------------------------------------------------------------
+void *orc_scene_create() { return new Scene(); }
+void orc_scene_destroy(void *s) { delete (Scene *)s; }
+int32_t orc_scene_add_material(void *s, const m3d_material_desc *d) {
+  auto *sc = (Scene *)s;
+  sc->mats.mats.push_back(*d);
+  return (int32_t)sc->mats.mats.size() - 1;
+}
+static void set_xf(Object &o, const m3d_transform *xf) {
+  if (!xf) return;
+  o.has_xf = true;
+  std::memcpy(o.matrix.m, xf->matrix, sizeof(double) * 9);
+  o.inv = inverse(o.matrix);
+  o.offset = v3(xf->offset);
+}
+int32_t orc_scene_add_mesh(void *s, const float *tris, int64_t n, const float *vn, int32_t material,
+                           uint32_t flags, const m3d_transform *xf) {
+  auto *sc = (Scene *)s;
+  Object o;
+  o.kind = OBJ_MESH;
+  o.material = material;
+  o.flags = flags;
+  o.mesh = std::make_shared<MeshCollider>();
+  tris_from_f32(tris, n, vn, o.mesh->tris);
+  o.mesh->interp = vn != nullptr;
+  o.mesh->build(false);
+  set_xf(o, xf);
+  sc->objects.push_back(std::move(o));
+  return (int32_t)sc->objects.size() - 1;
+}
+int32_t orc_scene_add_sphere(void *s, const double c[3], double radius, int32_t material,
+                             uint32_t flags, const m3d_transform *xf) {
+  auto *sc = (Scene *)s;
+  Object o;
+  o.kind = OBJ_SPHERE;
+  o.material = material;
+  o.flags = flags;
+  o.sphere = Sphere{v3(c), radius};
+  set_xf(o, xf);
+  sc->objects.push_back(std::move(o));
+  return (int32_t)sc->objects.size() - 1;
+}
+int32_t orc_scene_add_rect(void *s, const double mn[3], const double mx[3], int32_t material,
+                           uint32_t flags, const m3d_transform *xf) {
+  auto *sc = (Scene *)s;
+  Object o;
+  o.kind = OBJ_RECT;
+  o.material = material;
+  o.flags = flags;
+  o.rect = Rect{v3(mn), v3(mx)};
+  set_xf(o, xf);
+  sc->objects.push_back(std::move(o));
+  return (int32_t)sc->objects.size() - 1;
+}
+int32_t orc_scene_add_cylinder(void *s, const double p1[3], const double p2[3], double radius,
+                               int32_t material, uint32_t flags, const m3d_transform *xf) {
+  auto *sc = (Scene *)s;
+  Object o;
+  o.kind = OBJ_CYLINDER;
+  o.material = material;
+  o.flags = flags;
+  o.cyl = Cylinder{v3(p1), v3(p2), radius};
+  set_xf(o, xf);
+  sc->objects.push_back(std::move(o));
+  return (int32_t)sc->objects.size() - 1;
+}
+
+// Batched Object.Cast over a scene.
+void orc_scene_cast(void *s, const double *org, const double *dir, int64_t n, double *t,
+                    int32_t *obj, int32_t *prim, double *normal, int nthreads) {
+  auto *sc = (Scene *)s;
+  parallel_for(n, nthreads, [&](int64_t b, int64_t e, int) {
+    for (int64_t i = b; i < e; i++) {
+      Ray r{V3(org[i * 3], org[i * 3 + 1], org[i * 3 + 2]), V3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2])};
+      Hit hit;
+      int32_t o = -1;
+      bool ok = sc->cast(r, hit, o);
+      if (obj) obj[i] = ok ? o : -1;
+      if (prim) prim[i] = ok ? hit.prim : -1;
+      if (t) t[i] = ok ? hit.scale : 0;
+      if (normal)
+        for (int k = 0; k < 3; k++) normal[i * 3 + k] = ok ? hit.normal[k] : 0;
+    }
+  });
+}
+
+void orc_camera_at(const double src[3], const double dst[3], double fov, m3d_camera *out) {
+  *out = camera_at(v3(src), v3(dst), fov);
+}
+void orc_camera_rays(const m3d_camera *cam, int W, int H, double *dir_out /*W*H*3*/) {
+  Caster c = make_caster(*cam, double(W) - 1, double(H) - 1);
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      V3 d = c(x, y);
+      for (int k = 0; k < 3; k++) dir_out[(x + y * W) * 3 + k] = d[k];
+    }
+}
+
+void orc_render_raycast(void *s, const m3d_camera *cam, const m3d_point_light *lights, int nl, int W,
+                        int H, double *img, double *t_out, int32_t *obj_out, int32_t *prim_out,
+                        int nthreads) {
+  render_raycast(*(Scene *)s, *cam, lights, nl, W, H, img, t_out, obj_out, prim_out, nthreads);
+}
+
+void orc_srgb8(const double *rgb, int64_t n, uint8_t *out) {
+  for (int64_t i = 0; i < n; i++) out[i] = to_srgb8(rgb[i]);
+}
+double orc_gamma_expand(double u) { return gamma_expand(u); }
+
+// ---- path tracers (render.hpp) ---------------------------------------------------------
+void orc_render_path(void *s, const m3d_camera *cam, const m3d_point_light *lights, int nl,
+                     const m3d_path_params *p, int W, int H, double *mean, double *var_of_mean,
+                     int64_t *rays_cast, int nthreads) {
+  render_path(*(Scene *)s, *cam, lights, nl, *p, W, H, mean, var_of_mean, rays_cast, nthreads);
+}
+void orc_render_bidir(void *s, const m3d_camera *cam, const m3d_area_light *lights, int nl,
+                      const m3d_bidir_params *p, int W, int H, double *mean, double *var_of_mean,
+                      int64_t *rays_cast, int nthreads) {
+  render_bidir(*(Scene *)s, *cam, lights, nl, *p, W, H, mean, var_of_mean, rays_cast, nthreads);
+}
+
+// Material sampling hooks for the restated material tests (material_test.go).
+void orc_material_eval(void *s, int32_t mat, const double normal[3], const double source[3],
+                       const double dest[3], double bsdf[3], double *source_density,
+                       double *dest_density) {
+  auto *sc = (Scene *)s;
+  MatRef m;
+  m.tab = &sc->mats;
+  m.index = mat;
+  V3 b = mat_bsdf(m, mat, v3(normal), v3(source), v3(dest));
+  for (int i = 0; i < 3; i++) bsdf[i] = b[i];
+  *source_density = mat_source_density(m, mat, v3(normal), v3(source), v3(dest));
+  *dest_density = mat_dest_density(m, mat, v3(normal), v3(source), v3(dest));
+}
+void orc_material_sample_source(void *s, int32_t mat, uint64_t seed, const double normal[3],
+                                const double dest[3], int64_t n, double *out /*n*3*/) {
+  auto *sc = (Scene *)s;
+  MatRef m;
+  m.tab = &sc->mats;
+  m.index = mat;
+  Rng g(seed);
+  for (int64_t i = 0; i < n; i++) {
+    V3 v = mat_sample_source(m, mat, g, v3(normal), v3(dest));
+    for (int k = 0; k < 3; k++) out[i * 3 + k] = v[k];
+  }
+}
+void orc_material_sample_dest(void *s, int32_t mat, uint64_t seed, const double normal[3],
+                              const double source[3], int64_t n, double *out /*n*3*/) {
+  auto *sc = (Scene *)s;
+  MatRef m;
+  m.tab = &sc->mats;
+  m.index = mat;
+  Rng g(seed);
+  for (int64_t i = 0; i < n; i++) {
+    V3 v = mat_sample_dest(m, mat, g, v3(normal), v3(source));
+    for (int k = 0; k < 3; k++) out[i * 3 + k] = v[k];
+  }
+}
+
+}  // extern "C"
