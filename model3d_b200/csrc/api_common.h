@@ -1,0 +1,99 @@
+// Shared internals of the C ABI implementation (include/m3d.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/m3d.h"
+#include "kernels.h"
+#include "wide_bvh.h"
+
+namespace m3d {
+
+std::string &last_error_ref();
+int32_t fail(int32_t code, const char *fmt, ...);
+
+#define M3D_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::m3d::fail(_e == cudaErrorMemoryAllocation ? M3D_ERR_OOM : M3D_ERR_CUDA,      \
+                         "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                         __LINE__);                                                         \
+  } while (0)
+
+// RAII device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+struct GpuTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  GpuTimer() {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  ~GpuTimer() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+  void start(cudaStream_t s) { cudaEventRecord(a, s); }
+  void stop(cudaStream_t s) { cudaEventRecord(b, s); }
+  double ms() {
+    float f = 0;
+    cudaEventSynchronize(b);
+    cudaEventElapsedTime(&f, a, b);
+    return f;
+  }
+};
+
+}  // namespace m3d
+
+struct m3d_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t copy_in = nullptr;      // H2D
+  cudaStream_t copy_out = nullptr;     // D2H
+  // scratch reused by host-buffer calls (grown on demand, never shrunk)
+  m3d::DevBuf scratch[8];
+  m3d::DevBuf counters;
+};
+
+struct m3d_mesh {
+  m3d_ctx *ctx = nullptr;
+  m3d::DevBuf nodes, tris, vnormals;
+  m3d::DeviceBVH bvh;
+  m3d_mesh_info info{};
+  double bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
+};
+
+namespace m3d {
+// uploads a built BVH (and optional per-corner normals in caller order, remapped to leaf order)
+int32_t upload_bvh(m3d_ctx *ctx, const WideBVH &bvh, const float *vnormals_by_prim, DevBuf &nodes,
+                   DevBuf &tris, DevBuf &vnormals, DeviceBVH &out);
+}  // namespace m3d

@@ -1,0 +1,354 @@
+// C ABI: library, context and mesh-collider entry points (include/m3d.h).
+// Replaces model3d.MeshToCollider + Collider.FirstRayCollision
+// (model3d/collisions.go:138-142, 275-290) with a device-resident wide BVH and a
+// batched query.  No CPU fallback: every compute call needs a CUDA device.
+#include <cstring>
+
+#include "api_common.h"
+
+namespace m3d {
+
+std::string &last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+
+int32_t fail(int32_t code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+int32_t upload_bvh(m3d_ctx *ctx, const WideBVH &bvh, const float *vnormals_by_prim, DevBuf &nodes,
+                   DevBuf &tris, DevBuf &vnormals, DeviceBVH &out) {
+  const size_t nb = bvh.nodes.size() * sizeof(WideNode);
+  const size_t tb = std::max<size_t>(bvh.tris.size(), 1) * sizeof(TriRecord);
+  M3D_CUDA(nodes.reserve(nb));
+  M3D_CUDA(tris.reserve(tb));
+  M3D_CUDA(cudaMemcpyAsync(nodes.p, bvh.nodes.data(), nb, cudaMemcpyHostToDevice, ctx->stream));
+  if (!bvh.tris.empty())
+    M3D_CUDA(cudaMemcpyAsync(tris.p, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord),
+                             cudaMemcpyHostToDevice, ctx->stream));
+  out.nodes = nodes.as<const uint4>();
+  out.tris = tris.as<const float4>();
+  out.num_nodes = (int64_t)bvh.nodes.size();
+  out.num_tris = (int64_t)bvh.tris.size();
+  out.vnormals = nullptr;
+  std::vector<float> vn;
+  if (vnormals_by_prim && !bvh.tris.empty()) {
+    // leaf order, padded to float4 per corner
+    vn.resize(bvh.tris.size() * 12);
+    for (size_t i = 0; i < bvh.tris.size(); i++) {
+      const float *src = vnormals_by_prim + (size_t)bvh.tris[i].prim * 9;
+      for (int k = 0; k < 3; k++) {
+        vn[i * 12 + k * 4 + 0] = src[k * 3 + 0];
+        vn[i * 12 + k * 4 + 1] = src[k * 3 + 1];
+        vn[i * 12 + k * 4 + 2] = src[k * 3 + 2];
+        vn[i * 12 + k * 4 + 3] = 0.f;
+      }
+    }
+    M3D_CUDA(vnormals.reserve(vn.size() * sizeof(float)));
+    M3D_CUDA(cudaMemcpyAsync(vnormals.p, vn.data(), vn.size() * sizeof(float), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    out.vnormals = vnormals.as<const float4>();
+  }
+  M3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  return M3D_OK;
+}
+
+}  // namespace m3d
+
+using namespace m3d;
+
+extern "C" {
+
+int32_t m3d_abi_version(void) { return M3D_ABI_VERSION; }
+
+const char *m3d_last_error(void) { return last_error_ref().c_str(); }
+
+int32_t m3d_ctx_create(int32_t device, m3d_ctx **out) {
+  if (!out) return fail(M3D_ERR_INVALID_ARG, "m3d_ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(M3D_ERR_CUDA, "no CUDA device available (%s); libm3dgpu has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0) M3D_CUDA(cudaGetDevice(&device));
+  if (device >= count) return fail(M3D_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, count);
+  M3D_CUDA(cudaSetDevice(device));
+  auto *ctx = new m3d_ctx();
+  ctx->device = device;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return fail(M3D_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  *out = ctx;
+  return M3D_OK;
+}
+
+void m3d_ctx_destroy(m3d_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  delete ctx;
+}
+
+int32_t m3d_ctx_device(const m3d_ctx *ctx) { return ctx ? ctx->device : -1; }
+
+int32_t m3d_ctx_synchronize(m3d_ctx *ctx) {
+  if (!ctx) return fail(M3D_ERR_INVALID_ARG, "ctx is NULL");
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  M3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  M3D_CUDA(cudaStreamSynchronize(ctx->copy_in));
+  M3D_CUDA(cudaStreamSynchronize(ctx->copy_out));
+  return M3D_OK;
+}
+
+int32_t m3d_mesh_create(m3d_ctx *ctx, const float *tris, int64_t n, const float *vnormals,
+                        uint32_t build_flags, m3d_mesh **out) {
+  if (!ctx || !out || n < 0 || (n > 0 && !tris))
+    return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_create: bad arguments");
+  if (n > (int64_t)0x7fffff00) return fail(M3D_ERR_INVALID_ARG, "too many triangles (%lld)", (long long)n);
+  *out = nullptr;
+  if (build_flags & M3D_MESH_BUILD_DEVICE_LBVH)
+    return fail(M3D_ERR_UNSUPPORTED, "device LBVH build is not available in this build");
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  for (int64_t i = 0; i < n * 9; i++)
+    if (!(tris[i] == tris[i]) || tris[i] > 3e38f || tris[i] < -3e38f)
+      return fail(M3D_ERR_INVALID_ARG, "non-finite vertex coordinate at float %lld", (long long)i);
+  WideBVH bvh;
+  BuildInput in;
+  in.tris = tris;
+  in.n = n;
+  build_wide_bvh(in, bvh);
+  auto *m = new m3d_mesh();
+  m->ctx = ctx;
+  int32_t rc = upload_bvh(ctx, bvh, vnormals, m->nodes, m->tris, m->vnormals, m->bvh);
+  if (rc != M3D_OK) {
+    delete m;
+    return rc;
+  }
+  m->info.num_triangles = n;
+  m->info.num_nodes = (int64_t)bvh.nodes.size();
+  m->info.node_bytes = sizeof(WideNode);
+  m->info.tri_bytes = sizeof(TriRecord);
+  m->info.device_bytes = (int64_t)(m->nodes.bytes + m->tris.bytes + m->vnormals.bytes);
+  m->info.max_depth = bvh.max_depth;
+  m->info.build_ms = bvh.build_ms;
+  m->info.sah_cost = bvh.sah_cost;
+  for (int k = 0; k < 3; k++) {
+    m->bmin[k] = n ? bvh.bounds_min[k] : 0.0;  // nullCollider bounds are zero (collisions.go:360-366)
+    m->bmax[k] = n ? bvh.bounds_max[k] : 0.0;
+  }
+  *out = m;
+  return M3D_OK;
+}
+
+void m3d_mesh_destroy(m3d_mesh *mesh) {
+  if (!mesh) return;
+  cudaSetDevice(mesh->ctx->device);
+  delete mesh;
+}
+
+int32_t m3d_mesh_get_info(const m3d_mesh *mesh, m3d_mesh_info *info) {
+  if (!mesh || !info) return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_get_info: NULL argument");
+  *info = mesh->info;
+  return M3D_OK;
+}
+
+int32_t m3d_mesh_bounds(const m3d_mesh *mesh, double min_out[3], double max_out[3]) {
+  if (!mesh || !min_out || !max_out) return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_bounds: NULL argument");
+  for (int k = 0; k < 3; k++) {
+    min_out[k] = mesh->bmin[k];
+    max_out[k] = mesh->bmax[k];
+  }
+  return M3D_OK;
+}
+
+int32_t m3d_mesh_first_ray_collisions_device(m3d_mesh *mesh, const void *d_org_tmin,
+                                             const void *d_dir_tmax, int64_t n, void *d_hit0,
+                                             void *d_hit1, uint32_t flags, void *stream,
+                                             m3d_stats *stats) {
+  if (!mesh || n < 0 || (n > 0 && (!d_org_tmin || !d_dir_tmax || !d_hit0 || !d_hit1)))
+    return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_first_ray_collisions_device: bad arguments");
+  m3d_ctx *ctx = mesh->ctx;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  TraceLaunch p;
+  p.org_tmin = (const float4 *)d_org_tmin;
+  p.dir_tmax = (const float4 *)d_dir_tmax;
+  p.n = n;
+  p.hit0 = (float4 *)d_hit0;
+  p.hit1 = (float4 *)d_hit1;
+  p.refine = !(flags & M3D_TRACE_NO_REFINE);
+  p.counters = nullptr;
+  if (flags & M3D_TRACE_COUNTERS) {
+    M3D_CUDA(ctx->counters.reserve(4 * sizeof(unsigned long long)));
+    M3D_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), s));
+    p.counters = ctx->counters.as<unsigned long long>();
+  }
+  if (stats) {
+    GpuTimer tm;
+    tm.start(s);
+    launch_trace_first_hit(mesh->bvh, p, s);
+    tm.stop(s);
+    M3D_CUDA(cudaGetLastError());
+    std::memset(stats, 0, sizeof(*stats));
+    stats->kernel_ms = tm.ms();
+    stats->rays = n;
+    stats->launches = n > 0 ? 1 : 0;
+    if (p.counters) {
+      unsigned long long c[2];
+      M3D_CUDA(cudaMemcpyAsync(c, p.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
+      M3D_CUDA(cudaStreamSynchronize(s));
+      stats->nodes_visited = (int64_t)c[0];
+      stats->tris_tested = (int64_t)c[1];
+    }
+  } else {
+    launch_trace_first_hit(mesh->bvh, p, s);
+    M3D_CUDA(cudaGetLastError());
+  }
+  return M3D_OK;
+}
+
+int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const float *dir, int64_t n,
+                                      float *t, int32_t *prim, float *normal, float *bary,
+                                      uint32_t flags, m3d_stats *stats) {
+  if (!mesh || n < 0 || (n > 0 && (!org || !dir)))
+    return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_first_ray_collisions: bad arguments");
+  m3d_ctx *ctx = mesh->ctx;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n == 0) return M3D_OK;
+
+  // Chunked 3-stage pipeline: H2D (copy_in) -> pack + trace + unpack (stream) -> D2H (copy_out).
+  const int64_t kChunk = 1 << 21;
+  const int nbuf = 2;
+  // per buffer: org3, dir3, org4, dir4, hit0, hit1, out_t, out_prim, out_normal, out_bary
+  const size_t per = (size_t)kChunk;
+  const size_t sz_in3 = per * 3 * sizeof(float), sz_f4 = per * sizeof(float4);
+  const size_t sz_out = per * (sizeof(float) + sizeof(int32_t) + 6 * sizeof(float));
+  const size_t per_buf = 2 * sz_in3 + 4 * sz_f4 + sz_out;
+  const int64_t chunk = n < kChunk ? n : kChunk;
+  (void)chunk;
+  M3D_CUDA(ctx->scratch[0].reserve(per_buf * nbuf));
+  cudaEvent_t ev_in[nbuf], ev_k[nbuf], ev_out[nbuf];
+  for (int b = 0; b < nbuf; b++) {
+    cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming);
+  }
+  unsigned long long *counters = nullptr;
+  if (flags & M3D_TRACE_COUNTERS) {
+    cudaError_t e = ctx->counters.reserve(4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    if (e != cudaSuccess) return fail(M3D_ERR_CUDA, "counter allocation failed");
+    counters = ctx->counters.as<unsigned long long>();
+  }
+  GpuTimer total;
+  cudaEvent_t k0 = nullptr, k1 = nullptr;
+  double kernel_ms = 0;
+  if (stats) {
+    cudaEventCreate(&k0);
+    cudaEventCreate(&k1);
+  }
+  int32_t rc = M3D_OK;
+  int64_t launches = 0;
+  int it = 0;
+  for (int64_t base = 0; base < n && rc == M3D_OK; base += kChunk, it++) {
+    const int b = it % nbuf;
+    const int64_t m = std::min<int64_t>(kChunk, n - base);
+    char *buf = ctx->scratch[0].as<char>() + per_buf * b;
+    float *d_org3 = (float *)buf;
+    float *d_dir3 = (float *)(buf + sz_in3);
+    float4 *d_org4 = (float4 *)(buf + 2 * sz_in3);
+    float4 *d_dir4 = d_org4 + per;
+    float4 *d_hit0 = d_dir4 + per;
+    float4 *d_hit1 = d_hit0 + per;
+    float *d_t = (float *)(d_hit1 + per);
+    int32_t *d_prim = (int32_t *)(d_t + per);
+    float *d_normal = (float *)(d_prim + per);
+    float *d_bary = d_normal + 3 * per;
+    // the previous user of this buffer must have finished its D2H
+    if (it >= nbuf) cudaStreamWaitEvent(ctx->copy_in, ev_out[b], 0);
+    cudaMemcpyAsync(d_org3, org + base * 3, m * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in);
+    cudaMemcpyAsync(d_dir3, dir + base * 3, m * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in);
+    cudaEventRecord(ev_in[b], ctx->copy_in);
+    cudaStreamWaitEvent(ctx->stream, ev_in[b], 0);
+    if (stats) cudaEventRecord(k0, ctx->stream);
+    launch_pack_rays(d_org3, d_dir3, m, 0.f, __builtin_inff(), d_org4, d_dir4, ctx->stream);
+    TraceLaunch p;
+    p.org_tmin = d_org4;
+    p.dir_tmax = d_dir4;
+    p.n = m;
+    p.hit0 = d_hit0;
+    p.hit1 = d_hit1;
+    p.refine = !(flags & M3D_TRACE_NO_REFINE);
+    p.counters = counters;
+    launch_trace_first_hit(mesh->bvh, p, ctx->stream);
+    launch_unpack_hits(d_hit0, d_hit1, m, t ? d_t : nullptr, prim ? d_prim : nullptr, nullptr,
+                       normal ? d_normal : nullptr, bary ? d_bary : nullptr, ctx->stream);
+    launches += 3;
+    if (stats) {
+      cudaEventRecord(k1, ctx->stream);
+    }
+    cudaEventRecord(ev_k[b], ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_out, ev_k[b], 0);
+    if (t) cudaMemcpyAsync(t + base, d_t, m * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out);
+    if (prim) cudaMemcpyAsync(prim + base, d_prim, m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_out);
+    if (normal)
+      cudaMemcpyAsync(normal + base * 3, d_normal, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out);
+    if (bary)
+      cudaMemcpyAsync(bary + base * 3, d_bary, m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_out);
+    cudaEventRecord(ev_out[b], ctx->copy_out);
+    if (stats) {
+      cudaEventSynchronize(k1);
+      float f = 0;
+      cudaEventElapsedTime(&f, k0, k1);
+      kernel_ms += f;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(M3D_ERR_CUDA, "first_ray_collisions pipeline: %s", cudaGetErrorString(e));
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->copy_out);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess && rc == M3D_OK) rc = fail(M3D_ERR_CUDA, "first_ray_collisions: %s", cudaGetErrorString(e));
+  for (int b = 0; b < nbuf; b++) {
+    cudaEventDestroy(ev_in[b]);
+    cudaEventDestroy(ev_k[b]);
+    cudaEventDestroy(ev_out[b]);
+  }
+  if (stats) {
+    cudaEventDestroy(k0);
+    cudaEventDestroy(k1);
+    stats->rays = n;
+    stats->kernel_ms = kernel_ms;
+    stats->launches = launches;
+    stats->h2d_bytes = n * 6 * (int64_t)sizeof(float);
+    stats->d2h_bytes = n * (int64_t)((t ? 4 : 0) + (prim ? 4 : 0) + (normal ? 12 : 0) + (bary ? 12 : 0));
+    if (counters && rc == M3D_OK) {
+      unsigned long long c[2] = {0, 0};
+      cudaMemcpy(c, counters, sizeof(c), cudaMemcpyDeviceToHost);
+      stats->nodes_visited = (int64_t)c[0];
+      stats->tris_tested = (int64_t)c[1];
+    }
+    if (prim && rc == M3D_OK) {
+      int64_t h = 0;
+      for (int64_t i = 0; i < n; i++) h += prim[i] >= 0;
+      stats->hits = h;
+    }
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// Launch wrappers for the sm_100a kernels (definitions in *.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace m3d {
+
+struct DeviceBVH {
+  const uint4 *nodes = nullptr;    // 5 x uint4 per WideNode
+  const float4 *tris = nullptr;    // 3 x float4 per TriRecord
+  const float4 *vnormals = nullptr; // optional, 3 x float4 per triangle (leaf order)
+  int64_t num_nodes = 0, num_tris = 0;
+};
+
+// counters: device pointer to 2 x uint64 (nodes, tris) or nullptr
+struct TraceLaunch {
+  const float4 *org_tmin;
+  const float4 *dir_tmax;
+  int64_t n;
+  float4 *hit0;  // (t, b1, b2, bits(prim))
+  float4 *hit1;  // (nx, ny, nz, bits(object))
+  bool refine;   // float64 re-evaluation of the winning hit
+  unsigned long long *counters;
+};
+
+void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream);
+
+// n*3 float arrays -> float4 SoA with constant tmin/tmax
+void launch_pack_rays(const float *org3, const float *dir3, int64_t n, float tmin, float tmax,
+                      float4 *org_tmin, float4 *dir_tmax, cudaStream_t stream);
+// hit SoA -> the separate arrays of the host ABI (any output may be null)
+void launch_unpack_hits(const float4 *hit0, const float4 *hit1, int64_t n, float *t, int32_t *prim,
+                        int32_t *obj, float *normal3, float *bary3, cudaStream_t stream);
+
+int device_sm_count();
+
+}  // namespace m3d

@@ -1,0 +1,171 @@
+"""Host-side mirror of the reference's collision interface for the GPU path.
+
+Names follow model3d (Go): ``Ray`` / ``RayCollision`` / ``TriangleCollision``
+(model3d/collisions.go:12-46) and the ``Collider`` interface
+(collisions.go:52-72).  ``MeshCollider`` is what ``MeshToCollider(mesh)``
+(collisions.go:138-142) returns here: a device-resident wide BVH queried through
+libm3dgpu's C ABI.  Unsupported queries raise; nothing falls back to the CPU.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+f32p = C.POINTER(C.c_float)
+i32p = C.POINTER(C.c_int32)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+@dataclass
+class Ray:
+    """model3d.Ray (collisions.go:12-15). Direction is not normalised."""
+    Origin: Tuple[float, float, float]
+    Direction: Tuple[float, float, float]
+
+
+@dataclass
+class TriangleCollision:
+    """model3d.TriangleCollision (collisions.go:39-46); Triangle is the id (index in
+    the caller's triangle array) instead of a pointer."""
+    Triangle: int
+    Barycentric: Tuple[float, float, float]
+
+
+@dataclass
+class RayCollision:
+    """model3d.RayCollision (collisions.go:19-35)."""
+    Scale: float
+    Normal: Tuple[float, float, float]
+    Extra: Optional[TriangleCollision] = None
+
+
+@dataclass
+class BatchCollisions:
+    """Result of MeshCollider.FirstRayCollisions: structure-of-arrays RayCollision."""
+    Collides: np.ndarray      # bool  [n]
+    Scale: np.ndarray         # f32   [n]
+    Normal: np.ndarray        # f32   [n,3]
+    Triangle: np.ndarray      # i32   [n]  (-1 == no collision)
+    Barycentric: np.ndarray   # f32   [n,3]
+    Stats: dict = field(default_factory=dict)
+
+
+class UnsupportedError(NotImplementedError):
+    pass
+
+
+class MeshCollider:
+    """GPU-backed model3d.Collider for a triangle mesh.
+
+    ``triangles``: array [n,3,3] (or [n,9]) of float32-representable vertices; the
+    index of a triangle in this array is its id.  ``vertex_normals`` ([n,3,3]) selects
+    MeshToInterpNormalCollider semantics (collisions.go:147-162).
+    """
+
+    def __init__(self, triangles, vertex_normals=None, ctx=None):
+        self.ctx = ctx or N.default_context()
+        tris = np.ascontiguousarray(np.asarray(triangles, dtype=np.float32).reshape(-1, 9))
+        vn = None
+        if vertex_normals is not None:
+            vn = np.ascontiguousarray(np.asarray(vertex_normals, dtype=np.float32).reshape(-1, 9))
+            if vn.shape != tris.shape:
+                raise ValueError("vertex_normals must match triangles")
+        self.num_triangles = int(tris.shape[0])
+        self.h = C.c_void_p()
+        N.check(N.lib().m3d_mesh_create(self.ctx.h, _p(tris, f32p), C.c_int64(self.num_triangles),
+                                        _p(vn, f32p), C.c_uint32(0), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            N.lib().m3d_mesh_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- Bounder ---------------------------------------------------------------
+    def _bounds(self):
+        mn = (C.c_double * 3)()
+        mx = (C.c_double * 3)()
+        N.check(N.lib().m3d_mesh_bounds(self.h, mn, mx))
+        return tuple(mn), tuple(mx)
+
+    def Min(self):
+        return self._bounds()[0]
+
+    def Max(self):
+        return self._bounds()[1]
+
+    def Info(self):
+        info = N.MeshInfo()
+        N.check(N.lib().m3d_mesh_get_info(self.h, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in info._fields_}
+
+    # -- Collider --------------------------------------------------------------
+    def FirstRayCollisions(self, origins, directions, counters=False, refine=True,
+                           want_stats=False) -> BatchCollisions:
+        """Batched FirstRayCollision (collisions.go:275-290) over host arrays [n,3]."""
+        org = np.ascontiguousarray(np.asarray(origins, dtype=np.float32).reshape(-1, 3))
+        dr = np.ascontiguousarray(np.asarray(directions, dtype=np.float32).reshape(-1, 3))
+        if org.shape != dr.shape:
+            raise ValueError("origins and directions must have the same shape")
+        n = int(org.shape[0])
+        t = np.zeros(n, np.float32)
+        prim = np.full(n, -1, np.int32)
+        normal = np.zeros((n, 3), np.float32)
+        bary = np.zeros((n, 3), np.float32)
+        flags = (N.TRACE_COUNTERS if counters else 0) | (0 if refine else N.TRACE_NO_REFINE)
+        stats = N.Stats()
+        N.check(N.lib().m3d_mesh_first_ray_collisions(
+            self.h, _p(org, f32p), _p(dr, f32p), C.c_int64(n), _p(t, f32p), _p(prim, i32p),
+            _p(normal, f32p), _p(bary, f32p), C.c_uint32(flags),
+            C.byref(stats) if (counters or want_stats) else None))
+        st = {k: getattr(stats, k) for k, _ in stats._fields_} if (counters or want_stats) else {}
+        return BatchCollisions(Collides=prim >= 0, Scale=t, Normal=normal, Triangle=prim,
+                               Barycentric=bary, Stats=st)
+
+    def FirstRayCollision(self, r: Ray):
+        """Collider.FirstRayCollision: a batch of one (correct, but use the batch call)."""
+        b = self.FirstRayCollisions([r.Origin], [r.Direction])
+        if not b.Collides[0]:
+            return RayCollision(0.0, (0.0, 0.0, 0.0)), False
+        return RayCollision(
+            Scale=float(b.Scale[0]), Normal=tuple(float(x) for x in b.Normal[0]),
+            Extra=TriangleCollision(int(b.Triangle[0]), tuple(float(x) for x in b.Barycentric[0]))), True
+
+    def FirstRayCollisionsDevice(self, d_org_tmin, d_dir_tmax, n, d_hit0, d_hit1, stream=0,
+                                 counters=False, refine=True, want_stats=False):
+        """Device-resident batch: arguments are raw device pointers (ints) to float4 SoA
+        buffers as documented in include/m3d.h."""
+        flags = (N.TRACE_COUNTERS if counters else 0) | (0 if refine else N.TRACE_NO_REFINE)
+        stats = N.Stats()
+        N.check(N.lib().m3d_mesh_first_ray_collisions_device(
+            self.h, C.c_void_p(d_org_tmin), C.c_void_p(d_dir_tmax), C.c_int64(n),
+            C.c_void_p(d_hit0), C.c_void_p(d_hit1), C.c_uint32(flags), C.c_void_p(stream),
+            C.byref(stats) if (counters or want_stats) else None))
+        return {k: getattr(stats, k) for k, _ in stats._fields_} if (counters or want_stats) else {}
+
+    def RayCollisions(self, r, f=None):
+        raise UnsupportedError("RayCollisions (all hits) is not on the GPU path yet")
+
+    def SphereCollision(self, c, r):
+        raise UnsupportedError("SphereCollision is not on the GPU path")
+
+
+def MeshToCollider(triangles, ctx=None) -> MeshCollider:
+    """model3d.MeshToCollider (collisions.go:138-142)."""
+    return MeshCollider(triangles, ctx=ctx)
+
+
+def MeshToInterpNormalCollider(triangles, vertex_normals, ctx=None) -> MeshCollider:
+    """model3d.MeshToInterpNormalCollider (collisions.go:147-162)."""
+    return MeshCollider(triangles, vertex_normals=vertex_normals, ctx=ctx)

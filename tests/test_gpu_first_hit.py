@@ -1,0 +1,217 @@
+"""GPU parity tests for the first-hit path, through the C ABI (libm3dgpu.so), against the
+float64 oracle on the same seeded inputs.  Contract (BASELINE.json north_star): identical
+first-hit triangle ids except ties / grazing hits within 1e-6 relative t; t and normals
+within 1e-5 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+T_REL = 1e-5
+TIE_REL = 1e-6
+
+
+def rays(rng, n, scale=1.0):
+    o = (rng.normal(size=(n, 3)) * scale).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o, d.astype(np.float32)
+
+
+def check_parity(oracle, tris32, org, d, got, vnormals=None):
+    ref = oracle.Collider(tris32, vnormals).first_hits(org, d, threads=8)
+    hit_o, hit_g = ref["prim"] >= 0, got.Triangle >= 0
+    # a hit/miss flip is only acceptable for grazing hits; we expect none on these inputs
+    assert (hit_o != hit_g).sum() == 0, "hit/miss mismatches: %d" % (hit_o != hit_g).sum()
+    both = hit_o & hit_g
+    same = both & (ref["prim"] == got.Triangle)
+    rel = np.abs(got.Scale - ref["t"]) / np.maximum(np.abs(ref["t"]), 1e-30)
+    assert rel[same].max(initial=0) < T_REL
+    diff = both & ~same
+    assert rel[diff].max(initial=0) <= TIE_REL, "a different triangle won without being a tie"
+    ndot = (got.Normal[same].astype(np.float64) * ref["normal"][same]).sum(1)
+    assert ndot.min(initial=1) > 1 - 1e-6
+    assert np.abs(got.Normal[same] - ref["normal"][same]).max(initial=0) < 1e-5
+    assert np.abs(got.Barycentric[same] - ref["bary"][same]).max(initial=0) < 1e-4
+    return ref, same
+
+
+@pytest.mark.parametrize("mesh", ["polar10", "polar100", "rect", "ico64"])
+def test_first_hit_matches_oracle(built, oracle, mesh):
+    from model3d_b200 import MeshCollider
+    rng = np.random.default_rng(1234)
+    tris = {"polar10": lambda: oracle.mesh_polar(0.5, 0.1, 10),
+            "polar100": lambda: oracle.mesh_polar(0.5, 0.1, 100),
+            "rect": lambda: oracle.mesh_rect((-1, -2, -3), (1, 2, 3)),
+            "ico64": lambda: oracle.mesh_icosphere((0, 0, 0), 1, 64)}[mesh]().astype(np.float32)
+    org, d = rays(rng, 200000)
+    col = MeshCollider(tris)
+    got = col.FirstRayCollisions(org, d)
+    ref, same = check_parity(oracle, tris, org, d, got)
+    assert same.sum() > 1000
+    mn, mx = col.Min(), col.Max()
+    omn, omx = oracle.Collider(tris).bounds()
+    assert np.allclose(mn, omn) and np.allclose(mx, omx)
+
+
+def test_unnormalised_directions_and_scale_units(built, oracle):
+    """t is in units of |d| (camera rays are not unit length, camera.go:77-81)."""
+    from model3d_b200 import MeshCollider
+    rng = np.random.default_rng(5)
+    tris = oracle.mesh_icosphere((0.5, -0.25, 2), 1.5, 24).astype(np.float32)
+    org, d = rays(rng, 50000, 2.0)
+    d = (d * rng.uniform(0.01, 100.0, size=(d.shape[0], 1))).astype(np.float32)
+    got = MeshCollider(tris).FirstRayCollisions(org, d)
+    check_parity(oracle, tris, org, d, got)
+
+
+def test_axis_aligned_rays(built, oracle):
+    """zero direction components: bvh.go:328-333 special-cases rate == 0."""
+    from model3d_b200 import MeshCollider
+    rng = np.random.default_rng(3)
+    tris = oracle.mesh_icosphere((0, 0, 0), 1, 16).astype(np.float32)
+    n = 60000
+    org = rng.uniform(-1.5, 1.5, size=(n, 3)).astype(np.float32)
+    d = np.zeros((n, 3), np.float32)
+    d[np.arange(n), rng.integers(0, 3, n)] = rng.choice([-1.0, 1.0, 2.5], n)
+    got = MeshCollider(tris).FirstRayCollisions(org, d)
+    check_parity(oracle, tris, org, d, got)
+
+
+def test_empty_single_and_degenerate(built, oracle):
+    from model3d_b200 import MeshCollider, Ray
+    rng = np.random.default_rng(8)
+    org, d = rays(rng, 1000)
+    # empty mesh: nullCollider (collisions.go:358-378)
+    col = MeshCollider(np.zeros((0, 3, 3), np.float32))
+    got = col.FirstRayCollisions(org, d)
+    assert not got.Collides.any() and (got.Triangle == -1).all()
+    assert col.Min() == (0.0, 0.0, 0.0) and col.Max() == (0.0, 0.0, 0.0)
+    # empty batch
+    got = MeshCollider(oracle.mesh_rect((0, 0, 0), (1, 1, 1)).astype(np.float32)).FirstRayCollisions(
+        np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert got.Scale.shape == (0,)
+    # one triangle, single-ray Collider.FirstRayCollision
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], np.float32)
+    col = MeshCollider(tri)
+    rc, ok = col.FirstRayCollision(Ray((0.25, 0.25, -1.0), (0, 0, 2.0)))
+    assert ok and abs(rc.Scale - 0.5) < 1e-7 and rc.Extra.Triangle == 0
+    assert np.allclose(rc.Normal, (0, 0, 1)) and np.allclose(rc.Extra.Barycentric, (0.5, 0.25, 0.25))
+    rc, ok = col.FirstRayCollision(Ray((0.25, 0.25, 1.0), (0, 0, 1.0)))
+    assert not ok
+    # hit at t == 0 is accepted (primitives.go:183)
+    rc, ok = col.FirstRayCollision(Ray((0.25, 0.25, 0.0), (0, 0, 1.0)))
+    assert ok and rc.Scale == 0.0
+    # degenerate (zero-area) triangles never report hits and do not break the build
+    tris = oracle.mesh_icosphere((0, 0, 0), 1, 8).astype(np.float32)
+    tris = np.concatenate([tris, np.zeros((5, 3, 3), np.float32), np.ones((3, 3, 3), np.float32)])
+    got = MeshCollider(tris).FirstRayCollisions(org, d)
+    check_parity(oracle, tris, org, d, got)
+    assert got.Triangle.max() < 20 * 64
+
+
+def test_ragged_batch_sizes(built, oracle):
+    """batch sizes around the block size and the pipeline chunk size."""
+    from model3d_b200 import MeshCollider
+    rng = np.random.default_rng(21)
+    tris = oracle.mesh_icosphere((0, 0, 0), 1, 8).astype(np.float32)
+    col = MeshCollider(tris)
+    ocol = oracle.Collider(tris)
+    for n in (1, 31, 127, 128, 129, (1 << 21) - 1, (1 << 21) + 5):
+        org, d = rays(rng, n)
+        got = col.FirstRayCollisions(org, d)
+        ref = ocol.first_hits(org, d, threads=8)
+        assert np.array_equal(got.Triangle >= 0, ref["prim"] >= 0)
+        m = (ref["prim"] >= 0) & (ref["prim"] == got.Triangle)
+        assert m.sum() >= 0.999 * (ref["prim"] >= 0).sum()
+        assert np.allclose(got.Scale[m], ref["t"][m], rtol=1e-5)
+
+
+def test_interp_normal_collider(built, oracle):
+    """MeshToInterpNormalCollider (collisions.go:147-162, primitives.go:499-531)."""
+    from model3d_b200 import MeshToInterpNormalCollider
+    rng = np.random.default_rng(4)
+    tris = oracle.mesh_icosphere((0, 0, 0), 1, 12).astype(np.float32)
+    vn = tris / np.linalg.norm(tris, axis=2, keepdims=True)  # sphere: vertex normal = position
+    org, d = rays(rng, 50000)
+    got = MeshToInterpNormalCollider(tris, vn).FirstRayCollisions(org, d)
+    check_parity(oracle, tris, org, d, got, vnormals=vn.astype(np.float32))
+
+
+def test_no_refine_mode_within_contract(built, oracle):
+    from model3d_b200 import MeshCollider
+    rng = np.random.default_rng(9)
+    tris = oracle.mesh_icosphere((0, 0, 0), 1, 32).astype(np.float32)
+    org, d = rays(rng, 100000)
+    got = MeshCollider(tris).FirstRayCollisions(org, d, refine=False)
+    ref = oracle.Collider(tris).first_hits(org, d, threads=8)
+    same = (ref["prim"] >= 0) & (ref["prim"] == got.Triangle)
+    rel = np.abs(got.Scale - ref["t"])[same] / np.abs(ref["t"][same])
+    assert np.quantile(rel, 0.999) < 1e-5
+
+
+def test_counters_and_device_api(built, oracle):
+    """Device-resident SoA entry point + node/triangle counters (m3d_stats)."""
+    import torch
+    from model3d_b200 import MeshCollider
+    rng = np.random.default_rng(17)
+    tris = oracle.mesh_icosphere((0, 0, 0), 1, 32).astype(np.float32)
+    n = 100000
+    org, d = rays(rng, n)
+    col = MeshCollider(tris)
+    host = col.FirstRayCollisions(org, d, counters=True)
+    assert host.Stats["nodes_visited"] > n and host.Stats["tris_tested"] > 0
+    o4 = torch.zeros((n, 4), dtype=torch.float32)
+    d4 = torch.zeros((n, 4), dtype=torch.float32)
+    o4[:, :3] = torch.from_numpy(org)
+    d4[:, :3] = torch.from_numpy(d)
+    d4[:, 3] = float("inf")
+    o4, d4 = o4.cuda(), d4.cuda()
+    h0 = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    h1 = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    st = col.FirstRayCollisionsDevice(o4.data_ptr(), d4.data_ptr(), n, h0.data_ptr(), h1.data_ptr(),
+                                      stream=torch.cuda.current_stream().cuda_stream, want_stats=True)
+    torch.cuda.synchronize()
+    assert st["kernel_ms"] > 0
+    prim = h0[:, 3].contiguous().view(torch.int32).cpu().numpy()
+    assert np.array_equal(prim, host.Triangle)
+    assert np.array_equal(h0[:, 0].cpu().numpy()[prim >= 0], host.Scale[prim >= 0])
+    assert np.array_equal(h1[:, :3].cpu().numpy()[prim >= 0], host.Normal[prim >= 0])
+
+
+def test_full_size_c2_properties(built, oracle):
+    """BASELINE config 2 at full size (1,003,520-triangle icosphere, 2^24 rays):
+    size-independent properties + oracle parity on a 200k-ray sample."""
+    from model3d_b200 import MeshCollider
+    tris = oracle.mesh_icosphere((0, 0, 0), 1.0, 224).astype(np.float32)
+    assert tris.shape[0] == 1003520
+    rng = np.random.default_rng(20260)
+    n = 1 << 24
+    org = rng.standard_normal((n, 3), dtype=np.float32)
+    d = rng.standard_normal((n, 3), dtype=np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    col = MeshCollider(tris)
+    got = col.FirstRayCollisions(org, d)
+    hit = got.Collides
+    r0 = np.linalg.norm(org.astype(np.float64), axis=1)
+    # closed surface: every ray starting inside the sphere must hit (inradius of the
+    # icosphere > 0.9999), rays pointing away from outside must miss
+    assert hit[r0 < 0.9999].all()
+    away = (r0 > 1.0) & ((org.astype(np.float64) * d).sum(1) > 0)
+    assert not hit[away].any()
+    # hit points lie on the unit sphere up to the facet sagitta, normals are radial
+    p = org[hit].astype(np.float64) + d[hit].astype(np.float64) * got.Scale[hit][:, None].astype(np.float64)
+    rad = np.linalg.norm(p, axis=1)
+    assert rad.min() > 0.9999 and rad.max() < 1.00001
+    ndot = (got.Normal[hit] * (p / rad[:, None])).sum(1)
+    assert ndot.min() > 0.9999
+    # barycentrics reconstruct the hit point (collisions_test.go:63-74)
+    tv = tris[got.Triangle[hit][:100000]].astype(np.float64)
+    pb = (tv * got.Barycentric[hit][:100000][:, :, None]).sum(1)
+    assert np.abs(pb - p[:100000]).max() < 1e-5
+    # oracle parity on a sample
+    idx = rng.choice(n, 200000, replace=False)
+    sub = type(got)(Collides=got.Collides[idx], Scale=got.Scale[idx], Normal=got.Normal[idx],
+                    Triangle=got.Triangle[idx], Barycentric=got.Barycentric[idx])
+    check_parity(oracle, tris, org[idx], d[idx], sub)
