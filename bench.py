@@ -182,7 +182,13 @@ def main():
     o4, d4 = o4.to(dev), d4.to(dev)
     h0 = torch.empty((n, 4), dtype=torch.float32, device=dev)
     h1 = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) torch stream: the library launches on the stream it is
+    # given, and torch.cuda.Event only sees torch's current stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         col.FirstRayCollisionsDevice(o4.data_ptr(), d4.data_ptr(), n, h0.data_ptr(), h1.data_ptr(), stream=stream)
@@ -289,7 +295,7 @@ def main():
                          "bytes_per_ray": bytes_per_ray, "kernel": "trace_first_hit_kernel",
                          "compulsory_stream_GBps": n * RAY_IO_BYTES / (ms_step * 1e-3) / 1e9},
             "clocks": clocks,
-            "gpu_launches": args.steps,
+            "gpu_launches": 2 * args.steps,
         }
         if e2e:
             line["e2e"] = e2e

@@ -81,8 +81,18 @@ struct m3d_ctx {
   cudaStream_t copy_out = nullptr;     // D2H
   // scratch reused by host-buffer calls (grown on demand, never shrunk)
   m3d::DevBuf scratch[8];
-  m3d::DevBuf counters;
+  m3d::DevBuf counters;       // [0..3] node/triangle statistics, then kWorkSlots work counters
+  unsigned work_slot = 0;
+  static constexpr int kWorkSlots = 64;
 };
+
+namespace m3d {
+// Device u64 work counter for one persistent-kernel launch (rotating pool so that launches
+// in flight on different streams never share one).  nullptr on allocation failure.
+unsigned long long *next_work_counter(m3d_ctx *ctx);
+// Device 2 x u64 statistics counters, zeroed on `s`.
+unsigned long long *stats_counters(m3d_ctx *ctx, cudaStream_t s);
+}  // namespace m3d
 
 struct m3d_mesh {
   m3d_ctx *ctx = nullptr;

@@ -23,6 +23,25 @@ int32_t fail(int32_t code, const char *fmt, ...) {
   return code;
 }
 
+static bool ensure_counters(m3d_ctx *ctx) {
+  if (ctx->counters.p) return true;
+  const size_t bytes = (4 + 4 * (size_t)m3d_ctx::kWorkSlots) * sizeof(unsigned long long);
+  if (ctx->counters.reserve(bytes) != cudaSuccess) return false;
+  return cudaMemset(ctx->counters.p, 0, bytes) == cudaSuccess;
+}
+
+unsigned long long *next_work_counter(m3d_ctx *ctx) {
+  if (!ensure_counters(ctx)) return nullptr;
+  const unsigned slot = ctx->work_slot++ % m3d_ctx::kWorkSlots;
+  return ctx->counters.as<unsigned long long>() + 4 + 4 * slot;
+}
+
+unsigned long long *stats_counters(m3d_ctx *ctx, cudaStream_t s) {
+  if (!ensure_counters(ctx)) return nullptr;
+  if (cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), s) != cudaSuccess) return nullptr;
+  return ctx->counters.as<unsigned long long>();
+}
+
 int32_t upload_bvh(m3d_ctx *ctx, const WideBVH &bvh, const float *vnormals_by_prim, DevBuf &nodes,
                    DevBuf &tris, DevBuf &vnormals, DeviceBVH &out) {
   const size_t nb = bvh.nodes.size() * sizeof(WideNode);
@@ -192,10 +211,11 @@ int32_t m3d_mesh_first_ray_collisions_device(m3d_mesh *mesh, const void *d_org_t
   p.hit1 = (float4 *)d_hit1;
   p.refine = !(flags & M3D_TRACE_NO_REFINE);
   p.counters = nullptr;
+  p.ray_counter = next_work_counter(ctx);
+  if (!p.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
   if (flags & M3D_TRACE_COUNTERS) {
-    M3D_CUDA(ctx->counters.reserve(4 * sizeof(unsigned long long)));
-    M3D_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), s));
-    p.counters = ctx->counters.as<unsigned long long>();
+    p.counters = stats_counters(ctx, s);
+    if (!p.counters) return fail(M3D_ERR_CUDA, "counter allocation failed");
   }
   if (stats) {
     GpuTimer tm;
@@ -206,7 +226,7 @@ int32_t m3d_mesh_first_ray_collisions_device(m3d_mesh *mesh, const void *d_org_t
     std::memset(stats, 0, sizeof(*stats));
     stats->kernel_ms = tm.ms();
     stats->rays = n;
-    stats->launches = n > 0 ? 1 : 0;
+    stats->launches = n > 0 ? 2 : 0;
     if (p.counters) {
       unsigned long long c[2];
       M3D_CUDA(cudaMemcpyAsync(c, p.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
@@ -250,12 +270,9 @@ int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const fl
   }
   unsigned long long *counters = nullptr;
   if (flags & M3D_TRACE_COUNTERS) {
-    cudaError_t e = ctx->counters.reserve(4 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream);
-    if (e != cudaSuccess) return fail(M3D_ERR_CUDA, "counter allocation failed");
-    counters = ctx->counters.as<unsigned long long>();
+    counters = stats_counters(ctx, ctx->stream);
+    if (!counters) return fail(M3D_ERR_CUDA, "counter allocation failed");
   }
-  GpuTimer total;
   cudaEvent_t k0 = nullptr, k1 = nullptr;
   double kernel_ms = 0;
   if (stats) {
@@ -295,10 +312,15 @@ int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const fl
     p.hit1 = d_hit1;
     p.refine = !(flags & M3D_TRACE_NO_REFINE);
     p.counters = counters;
+    p.ray_counter = next_work_counter(ctx);
+    if (!p.ray_counter) {
+      rc = fail(M3D_ERR_OOM, "work counter allocation failed");
+      break;
+    }
     launch_trace_first_hit(mesh->bvh, p, ctx->stream);
     launch_unpack_hits(d_hit0, d_hit1, m, t ? d_t : nullptr, prim ? d_prim : nullptr, nullptr,
                        normal ? d_normal : nullptr, bary ? d_bary : nullptr, ctx->stream);
-    launches += 3;
+    launches += 4;
     if (stats) {
       cudaEventRecord(k1, ctx->stream);
     }

@@ -20,7 +20,8 @@ struct TraceLaunch {
   float4 *hit0;  // (t, b1, b2, bits(prim))
   float4 *hit1;  // (nx, ny, nz, bits(object))
   bool refine;   // float64 re-evaluation of the winning hit
-  unsigned long long *counters;
+  unsigned long long *counters;     // optional device 2 x u64 (nodes, tris)
+  unsigned long long *ray_counter;  // device u64 work counter of the persistent kernel
 };
 
 void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream);

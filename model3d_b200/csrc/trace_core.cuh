@@ -104,6 +104,18 @@ M3D_HD float add_rn(float a, float b) {
 #endif
 }
 
+// 1-ulp reciprocal (one MUFU.RCP on the device instead of the IEEE division sequence);
+// only used for slab-test slopes and 1/|d|^2, both of which are consumed with slack.
+M3D_HD float rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+
 struct F3 {
   float x, y, z;
 };
@@ -142,6 +154,34 @@ struct TraceCounters {
 
 #define M3D_STACK_SIZE 32
 
+M3D_HD float max3f(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+#else
+  return fmaxf(fmaxf(a, b), c);
+#endif
+}
+M3D_HD float min3f(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+#else
+  return fminf(fminf(a, b), c);
+#endif
+}
+// byte j of q placed in mantissa bits 8..15 of 1.0f: value == 1 + q_j * 2^-15 exactly.
+// One PRMT on the device instead of a byte extract + integer->float conversion.
+M3D_HD float unit_plus_byte(uint32_t q, int j) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(__byte_perm(q, 0x3f800000u, 0x7604u | ((uint32_t)j << 4)));
+#else
+  return f_from_bits(0x3f800000u | (((q >> (8 * j)) & 0xffu) << 8));
+#endif
+}
+
 // float32 edge-function test.  Accepts t in [tmin, tmax], bary inclusive, no culling
 // (primitives.go:183,232,238 accept scale >= 0 and inclusive barycentrics).
 M3D_HD bool intersect_tri_f32(const float4 *__restrict__ tri, float ox, float oy, float oz, F3 d,
@@ -159,7 +199,7 @@ M3D_HD bool intersect_tri_f32(const float4 *__restrict__ tri, float ox, float oy
   if (det == 0.f) return false;
   // hit point relative to the origin is (U*A + V*B + W*C)/det; project on d
   float T = U * dot_sym(A, d) + V * dot_sym(B, d) + W * dot_sym(C, d);
-  float rdet = 1.0f / det;
+  float rdet = rcp_fast(det);
   float t = T * rdet * inv_dd;
   if (!(t >= tmin && t <= tmax)) return false;
   t_out = t;
@@ -168,110 +208,214 @@ M3D_HD bool intersect_tri_f32(const float4 *__restrict__ tri, float ox, float oy
   return true;
 }
 
-// Traverse.  nodes: 5 x uint4 per node.  tris: 3 x float4 per triangle.
-// skip_tri: triangle index to ignore (self-intersection guard for secondary rays), -1 none.
-// ANY_HIT: return at the first accepted hit (shadow / visibility rays).
+// The reference's Moeller-Trumbore in float64 (primitives.go:207-249) on the float32
+// inputs widened exactly: the arbiter for rays that pass so close to a triangle edge that
+// the float32 edge functions cannot decide.  Kept out of line: it runs for ~0.1 % of the
+// triangle tests and must not cost registers on the hot path.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+bool tri_decide_f64(const float4 *__restrict__ tri, float oxf, float oyf, float ozf, float dxf,
+                    float dyf, float dzf, float tmin, float tmax, float &t_out, float &b1, float &b2) {
+  const float4 q0 = tri[0], q1 = tri[1], q2 = tri[2];
+  const double dx = dxf, dy = dyf, dz = dzf;
+  const double v1x = (double)q1.x - q0.x, v1y = (double)q1.y - q0.y, v1z = (double)q1.z - q0.z;
+  const double v2x = (double)q2.x - q0.x, v2y = (double)q2.y - q0.y, v2z = (double)q2.z - q0.z;
+  const double c1x = dy * v2z - dz * v2y, c1y = dz * v2x - dx * v2z, c1z = dx * v2y - dy * v2x;
+  const double det = c1x * v1x + c1y * v1y + c1z * v1z;
+  if (det == 0.0) return false;
+  const double inv = 1.0 / det;
+  const double px = (double)oxf - q0.x, py = (double)oyf - q0.y, pz = (double)ozf - q0.z;
+  const double bary1 = inv * (px * c1x + py * c1y + pz * c1z);
+  if (bary1 < 0 || bary1 > 1) return false;
+  const double c2x = py * v1z - pz * v1y, c2y = pz * v1x - px * v1z, c2z = px * v1y - py * v1x;
+  const double bary2 = inv * (dx * c2x + dy * c2y + dz * c2z);
+  if (bary2 < 0 || bary1 + bary2 > 1) return false;
+  const double t = inv * (v2x * c2x + v2y * c2y + v2z * c2z);
+  if (!(t >= (double)tmin && t <= (double)tmax)) return false;
+  t_out = (float)t;
+  b1 = (float)bary1;
+  b2 = (float)bary2;
+  return true;
+}
+
+// Per-ray constants of the traversal.
+struct RayPre {
+  float ox, oy, oz;
+  F3 d;
+  float idx, idy, idz;  // reciprocal direction (zero components replaced by +-2^-64)
+  float inv_dd;         // 1 / |d|^2
+  float err2;           // (2^-20)^2 * |d|^2: squared relative error bound of an edge function
+  float tmin;
+  uint32_t octinv4;     // (7 - octant) replicated in four bytes
+  uint32_t neg;         // bit0: dx<0, bit1: dy<0, bit2: dz<0
+};
+
+M3D_HD RayPre precompute_ray(const RayF &ray) {
+  RayPre rp;
+  const float ooeps = 5.421010862e-20f;  // 2^-64 (bvh.go:328-333 handles rate == 0 exactly)
+  const float dx = fabsf(ray.dx) > ooeps ? ray.dx : copysignf(ooeps, ray.dx);
+  const float dy = fabsf(ray.dy) > ooeps ? ray.dy : copysignf(ooeps, ray.dy);
+  const float dz = fabsf(ray.dz) > ooeps ? ray.dz : copysignf(ooeps, ray.dz);
+  rp.ox = ray.ox;
+  rp.oy = ray.oy;
+  rp.oz = ray.oz;
+  rp.d = mk3(ray.dx, ray.dy, ray.dz);
+  rp.idx = rcp_fast(dx);
+  rp.idy = rcp_fast(dy);
+  rp.idz = rcp_fast(dz);
+  rp.inv_dd = rcp_fast(ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz);
+  rp.tmin = ray.tmin;
+  rp.err2 = 9.094947e-13f * (ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz);
+  const uint32_t octinv = ((ray.dx < 0.f ? 0u : 4u) | (ray.dy < 0.f ? 0u : 2u) | (ray.dz < 0.f ? 0u : 1u));
+  rp.octinv4 = octinv * 0x01010101u;
+  rp.neg = (ray.dx < 0.f ? 1u : 0u) | (ray.dy < 0.f ? 2u : 0u) | (ray.dz < 0.f ? 4u : 0u);
+  return rp;
+}
+
+// Ray/triangle test of the traversal: float32 edge functions (watertight, see above); when
+// an edge function is within its own rounding-error bound of zero the decision is taken
+// by tri_decide_f64, so that triangle ids agree with the float64 reference except for
+// exact ties.  Accepts t in [tmin, tmax], barycentrics inclusive, no back-face culling
+// (primitives.go:183,232,238).
+M3D_HD bool intersect_tri(const float4 *__restrict__ tri, const RayPre &rp, float tmax, float &t_out,
+                          float &b1, float &b2) {
+#if defined(__CUDA_ARCH__)
+  const float4 q0 = __ldg(tri), q1 = __ldg(tri + 1), q2 = __ldg(tri + 2);
+#else
+  const float4 q0 = tri[0], q1 = tri[1], q2 = tri[2];
+#endif
+  const F3 A = mk3(q0.x - rp.ox, q0.y - rp.oy, q0.z - rp.oz);
+  const F3 B = mk3(q1.x - rp.ox, q1.y - rp.oy, q1.z - rp.oz);
+  const F3 C = mk3(q2.x - rp.ox, q2.y - rp.oy, q2.z - rp.oz);
+  const float U = dot_sym(rp.d, cross_sym(B, C));  // weight of v0
+  const float V = dot_sym(rp.d, cross_sym(C, A));  // weight of v1
+  const float W = dot_sym(rp.d, cross_sym(A, B));  // weight of v2
+  // rounding-error bound of an edge function: ~16 ulp of |d| * max|vertex - origin|^2
+  const float m2 = max3f(A.x * A.x + A.y * A.y + A.z * A.z, B.x * B.x + B.y * B.y + B.z * B.z,
+                         C.x * C.x + C.y * C.y + C.z * C.z);
+  const float bound2 = rp.err2 * m2 * m2;
+  if (min3f(U * U, V * V, W * W) <= bound2) {
+    // too close to an edge (or degenerate): let the float64 reference arithmetic decide,
+    // unless the ray is clearly outside with respect to another edge
+    const float s = sqrtf(bound2);
+    const bool out_pos = (U > s || V > s || W > s), out_neg = (U < -s || V < -s || W < -s);
+    if (out_pos && out_neg) return false;
+    return tri_decide_f64(tri, rp.ox, rp.oy, rp.oz, rp.d.x, rp.d.y, rp.d.z, rp.tmin, tmax, t_out, b1, b2);
+  }
+  if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) return false;
+  const float det = U + V + W;
+  // hit point relative to the origin is (U*A + V*B + W*C)/det; project on d
+  const float T = U * dot_sym(A, rp.d) + V * dot_sym(B, rp.d) + W * dot_sym(C, rp.d);
+  const float rdet = rcp_fast(det);
+  const float t = T * rdet * rp.inv_dd;
+  if (!(t >= rp.tmin && t <= tmax)) return false;
+  t_out = t;
+  b1 = V * rdet;
+  b2 = W * rdet;
+  return true;
+}
+
+// Fetch one wide node (five 16-byte loads) and slab-test its eight quantised child boxes.
+// Outputs the node group (x = child base, y = internal hit bits 24..31 | imask) and the
+// triangle group (x = triangle base, y = leaf hit bits 0..23).
+//
+// Quantised plane q on axis a sits at origin_a + q * 2^e_a.  With v = 1 + q * 2^-15
+// (unit_plus_byte) the ray parameter of the plane is  v * S + b  where
+// S = 2^(e_a+15) / d_a and b = (origin_a - o_a) / d_a - S: one PRMT and one FMA per plane.
+// b absorbs a rounding error of at most ulp(S)/2, so near planes are moved back and far
+// planes forward by |S| * 2^-22 (0.8 % of a grid step) to stay conservative.
+M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index, const RayPre &rp,
+                           float tmax, uint2 &ngroup, uint2 &tgroup) {
+  const uint4 *np = nodes + (size_t)node_index * 5;
+#if defined(__CUDA_ARCH__)
+  const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+#else
+  const uint4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+#endif
+  const uint32_t e = n0.w;
+  const float Sx = f_from_bits((e & 0xffu) << 23) * (32768.0f * rp.idx);
+  const float Sy = f_from_bits(((e >> 8) & 0xffu) << 23) * (32768.0f * rp.idy);
+  const float Sz = f_from_bits(((e >> 16) & 0xffu) << 23) * (32768.0f * rp.idz);
+  const float bx = (f_from_bits(n0.x) - rp.ox) * rp.idx - Sx;
+  const float by = (f_from_bits(n0.y) - rp.oy) * rp.idy - Sy;
+  const float bz = (f_from_bits(n0.z) - rp.oz) * rp.idz - Sz;
+  const float kSlack = 2.384185791e-7f;  // 2^-22
+  const float gx = fabsf(Sx) * kSlack, gy = fabsf(Sy) * kSlack, gz = fabsf(Sz) * kSlack;
+  const float bnx = bx - gx, bfx = bx + gx;
+  const float bny = by - gy, bfy = by + gy;
+  const float bnz = bz - gz, bfz = bz + gz;
+  const float tmax_w = tmax * 1.0000005f + 1e-30f;  // few-ulp widening of the far bound
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const uint32_t meta4 = half == 0 ? n1.z : n1.w;
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (rp.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const uint32_t qlox = half == 0 ? n2.x : n2.y, qloy = half == 0 ? n2.z : n2.w;
+    const uint32_t qloz = half == 0 ? n3.x : n3.y, qhix = half == 0 ? n3.z : n3.w;
+    const uint32_t qhiy = half == 0 ? n4.x : n4.y, qhiz = half == 0 ? n4.z : n4.w;
+    const uint32_t xn = (rp.neg & 1u) ? qhix : qlox, xf = (rp.neg & 1u) ? qlox : qhix;
+    const uint32_t yn = (rp.neg & 2u) ? qhiy : qloy, yf = (rp.neg & 2u) ? qloy : qhiy;
+    const uint32_t zn = (rp.neg & 4u) ? qhiz : qloz, zf = (rp.neg & 4u) ? qloz : qhiz;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float t0x = fmaf(unit_plus_byte(xn, j), Sx, bnx);
+      const float t0y = fmaf(unit_plus_byte(yn, j), Sy, bny);
+      const float t0z = fmaf(unit_plus_byte(zn, j), Sz, bnz);
+      const float t1x = fmaf(unit_plus_byte(xf, j), Sx, bfx);
+      const float t1y = fmaf(unit_plus_byte(yf, j), Sy, bfy);
+      const float t1z = fmaf(unit_plus_byte(zf, j), Sz, bfz);
+      const float cmin = fmaxf(max3f(t0x, t0y, t0z), rp.tmin);
+      const float cmax = fminf(min3f(t1x, t1y, t1z), tmax_w);
+      if (cmin <= cmax) {
+        const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
+        const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
+        hitmask |= cb << bi;
+      }
+    }
+  }
+  ngroup.x = n1.x;
+  ngroup.y = (hitmask & 0xff000000u) | (e >> 24);
+  tgroup.x = n1.y;
+  tgroup.y = hitmask & 0x00ffffffu;
+}
+
+// Pop the nearest pending child of a node group: returns its node index and clears its
+// hit bit (the caller pushes the remainder if bits 24..31 are still non-zero).
+M3D_HD uint32_t take_nearest_child(uint2 &ngroup, uint32_t octinv4) {
+  const uint32_t hits_imask = ngroup.y;
+  const int bit = bfind32(hits_imask);
+  ngroup.y &= ~(1u << bit);
+  const uint32_t slot = (uint32_t)(bit - 24) ^ (octinv4 & 7u);
+  const uint32_t rel = (uint32_t)popc32(hits_imask & ~(0xffffffffu << slot) & 0xffu);
+  return ngroup.x + rel;
+}
+
+// Scalar traversal of one ray (used by the CPU-side tests through tests/emul and by the
+// shading kernels for single secondary rays).  nodes: 5 x uint4 per node.  tris: 3 x
+// float4 per triangle.  skip_tri: triangle index to ignore (self-intersection guard for
+// secondary rays), -1 none.  ANY_HIT: return at the first accepted hit.
 template <bool COUNT, bool ANY_HIT>
 M3D_HD void trace_bvh(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
                       const RayF &ray, int32_t skip_tri, HitF &hit, TraceCounters *cnt) {
-  const float ooeps = 5.421010862e-20f;  // 2^-64: avoid 1/0 (bvh.go:328-333 handles rate==0 exactly)
-  float dx = fabsf(ray.dx) > ooeps ? ray.dx : copysignf(ooeps, ray.dx);
-  float dy = fabsf(ray.dy) > ooeps ? ray.dy : copysignf(ooeps, ray.dy);
-  float dz = fabsf(ray.dz) > ooeps ? ray.dz : copysignf(ooeps, ray.dz);
-  const float idx = 1.0f / dx, idy = 1.0f / dy, idz = 1.0f / dz;
-  const F3 d = mk3(ray.dx, ray.dy, ray.dz);
-  const float inv_dd = 1.0f / (ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz);
-  const uint32_t octinv = ((ray.dx < 0.f ? 0u : 4u) | (ray.dy < 0.f ? 0u : 2u) | (ray.dz < 0.f ? 0u : 1u));
-  const uint32_t octinv4 = octinv * 0x01010101u;
-  const float tmin = ray.tmin;
+  const RayPre rp = precompute_ray(ray);
   float tmax = ray.tmax;
-
   hit.tri = -1;
   hit.t = tmax;
   hit.b1 = hit.b2 = 0.f;
 
   uint2 stack[M3D_STACK_SIZE];
   int sp = 0;
-
-  // node group: x = child base index, y = (hit bits 24..31) | imask (bits 0..7)
-  // tri group:  x = triangle base index, y = hit bits 0..23
   uint2 ngroup, tgroup;
-  ngroup.x = 0;
-  ngroup.y = 0x80000000u;  // root: pretend slot (7 ^ octinv) of a virtual parent, see below
-  tgroup.x = 0;
-  tgroup.y = 0;
-  bool root_pending = true;
-
+  uint32_t node_index = 0;  // root
   for (;;) {
-    if (ngroup.y & 0xff000000u) {
-      uint32_t node_index;
-      if (root_pending) {
-        root_pending = false;
-        node_index = 0;
-        ngroup.y = 0;
-      } else {
-        const uint32_t hits_imask = ngroup.y;
-        const int bit = bfind32(hits_imask);
-        ngroup.y &= ~(1u << bit);
-        if (ngroup.y & 0xff000000u) {
-          if (sp < M3D_STACK_SIZE) stack[sp++] = ngroup;
-        }
-        const uint32_t slot = (uint32_t)(bit - 24) ^ (octinv & 7u);
-        const uint32_t rel = (uint32_t)popc32(hits_imask & ~(0xffffffffu << slot) & 0xffu);
-        node_index = ngroup.x + rel;
-      }
-      if (COUNT) cnt->nodes++;
-
-      const uint4 *np = nodes + (size_t)node_index * 5;
-      const uint4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
-      const uint32_t e = n0.w;
-      const float sx = f_from_bits((e & 0xffu) << 23) * idx;
-      const float sy = f_from_bits(((e >> 8) & 0xffu) << 23) * idy;
-      const float sz = f_from_bits(((e >> 16) & 0xffu) << 23) * idz;
-      const float bx = (f_from_bits(n0.x) - ray.ox) * idx;
-      const float by = (f_from_bits(n0.y) - ray.oy) * idy;
-      const float bz = (f_from_bits(n0.z) - ray.oz) * idz;
-      uint32_t hitmask = 0;
-#pragma unroll
-      for (int half = 0; half < 2; half++) {
-        const uint32_t meta4 = half == 0 ? n1.z : n1.w;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlox = half == 0 ? n2.x : n2.y, qloy = half == 0 ? n2.z : n2.w;
-        const uint32_t qloz = half == 0 ? n3.x : n3.y, qhix = half == 0 ? n3.z : n3.w;
-        const uint32_t qhiy = half == 0 ? n4.x : n4.y, qhiz = half == 0 ? n4.z : n4.w;
-        const uint32_t xn = ray.dx < 0.f ? qhix : qlox, xf = ray.dx < 0.f ? qlox : qhix;
-        const uint32_t yn = ray.dy < 0.f ? qhiy : qloy, yf = ray.dy < 0.f ? qloy : qhiy;
-        const uint32_t zn = ray.dz < 0.f ? qhiz : qloz, zf = ray.dz < 0.f ? qloz : qhiz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int sh = 8 * j;
-          const float t0x = (float)((xn >> sh) & 0xffu) * sx + bx;
-          const float t0y = (float)((yn >> sh) & 0xffu) * sy + by;
-          const float t0z = (float)((zn >> sh) & 0xffu) * sz + bz;
-          const float t1x = (float)((xf >> sh) & 0xffu) * sx + bx;
-          const float t1y = (float)((yf >> sh) & 0xffu) * sy + by;
-          const float t1z = (float)((zf >> sh) & 0xffu) * sz + bz;
-          const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-          const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-          // widen by a few ulp: the quantised slab arithmetic is not exactly conservative
-          if (cmin <= cmax * 1.0000005f + 1e-30f) {
-            const uint32_t cb = (child_bits4 >> sh) & 0xffu;
-            const uint32_t bi = (bit_index4 >> sh) & 0xffu;
-            hitmask |= cb << bi;
-          }
-        }
-      }
-      ngroup.x = n1.x;
-      ngroup.y = (hitmask & 0xff000000u) | (e >> 24);
-      tgroup.x = n1.y;
-      tgroup.y = hitmask & 0x00ffffffu;
-    }
-    // (ngroup always carries pending internal hits here: it is either the root, a
-    // freshly decoded node, or a popped stack entry)
-
+    if (COUNT) cnt->nodes++;
+    intersect_node(nodes, node_index, rp, tmax, ngroup, tgroup);
     while (tgroup.y) {
       const int bit = bfind32(tgroup.y);
       tgroup.y &= ~(1u << bit);
@@ -279,8 +423,7 @@ M3D_HD void trace_bvh(const uint4 *__restrict__ nodes, const float4 *__restrict_
       if (ti == skip_tri) continue;
       if (COUNT) cnt->tris++;
       float t, b1, b2;
-      if (intersect_tri_f32(tris + (size_t)ti * 3, ray.ox, ray.oy, ray.oz, d, inv_dd, tmin, tmax, t,
-                            b1, b2)) {
+      if (intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
         tmax = t;
         hit.t = t;
         hit.b1 = b1;
@@ -289,11 +432,12 @@ M3D_HD void trace_bvh(const uint4 *__restrict__ nodes, const float4 *__restrict_
         if (ANY_HIT) return;
       }
     }
-
     if ((ngroup.y & 0xff000000u) == 0) {
       if (sp == 0) break;
       ngroup = stack[--sp];
     }
+    node_index = take_nearest_child(ngroup, rp.octinv4);
+    if ((ngroup.y & 0xff000000u) && sp < M3D_STACK_SIZE) stack[sp++] = ngroup;
   }
 }
 
