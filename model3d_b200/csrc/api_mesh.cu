@@ -57,6 +57,10 @@ int32_t upload_bvh(m3d_ctx *ctx, const WideBVH &bvh, const float *vnormals_by_pr
   out.num_nodes = (int64_t)bvh.nodes.size();
   out.num_tris = (int64_t)bvh.tris.size();
   out.vnormals = nullptr;
+  for (int k = 0; k < 3; k++) {
+    out.bmin[k] = bvh.bounds_min[k];
+    out.bmax[k] = bvh.bounds_max[k];
+  }
   std::vector<float> vn;
   if (vnormals_by_prim && !bvh.tris.empty()) {
     // leaf order, padded to float4 per corner
@@ -200,6 +204,8 @@ int32_t m3d_mesh_first_ray_collisions_device(m3d_mesh *mesh, const void *d_org_t
                                              m3d_stats *stats) {
   if (!mesh || n < 0 || (n > 0 && (!d_org_tmin || !d_dir_tmax || !d_hit0 || !d_hit1)))
     return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_first_ray_collisions_device: bad arguments");
+  if (n > (int64_t)0x7ff00000)
+    return fail(M3D_ERR_INVALID_ARG, "batch too large (%lld rays); split it", (long long)n);
   m3d_ctx *ctx = mesh->ctx;
   M3D_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;

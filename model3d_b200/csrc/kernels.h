@@ -10,6 +10,7 @@ struct DeviceBVH {
   const float4 *tris = nullptr;    // 3 x float4 per TriRecord
   const float4 *vnormals = nullptr; // optional, 3 x float4 per triangle (leaf order)
   int64_t num_nodes = 0, num_tris = 0;
+  float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};  // bounds of all vertices
 };
 
 // counters: device pointer to 2 x uint64 (nodes, tris) or nullptr

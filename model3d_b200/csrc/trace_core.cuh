@@ -7,8 +7,10 @@
 // Differences that are allowed by the parity contract (ties / grazing only):
 //   * children are visited near-to-far with tmax pruning (the reference visits every
 //     child whose box the ray enters, unordered);
-//   * the float32 triangle test is an edge-function (scalar triple product) test whose
-//     shared-edge values are exact negations of each other, i.e. watertight;
+//   * the float32 triangle test is the reference's Moeller-Trumbore with an explicit
+//     rounding-error band; rays inside the band of an edge are decided in float64 with
+//     the reference's own arithmetic, so no crack can open that the reference does not
+//     have, and triangle ids match except for exact ties;
 //   * the winning hit is re-evaluated in float64 with the reference's own
 //     Moeller-Trumbore arithmetic (refine_hit_f64), so Scale / Barycentric / Normal
 //     match the float64 oracle to float rounding.
@@ -182,36 +184,10 @@ M3D_HD float unit_plus_byte(uint32_t q, int j) {
 #endif
 }
 
-// float32 edge-function test.  Accepts t in [tmin, tmax], bary inclusive, no culling
-// (primitives.go:183,232,238 accept scale >= 0 and inclusive barycentrics).
-M3D_HD bool intersect_tri_f32(const float4 *__restrict__ tri, float ox, float oy, float oz, F3 d,
-                              float inv_dd, float tmin, float tmax, float &t_out, float &b1,
-                              float &b2) {
-  float4 q0 = tri[0], q1 = tri[1], q2 = tri[2];
-  F3 A = mk3(q0.x - ox, q0.y - oy, q0.z - oz);
-  F3 B = mk3(q1.x - ox, q1.y - oy, q1.z - oz);
-  F3 C = mk3(q2.x - ox, q2.y - oy, q2.z - oz);
-  float U = dot_sym(d, cross_sym(B, C));  // weight of v0
-  float V = dot_sym(d, cross_sym(C, A));  // weight of v1
-  float W = dot_sym(d, cross_sym(A, B));  // weight of v2
-  if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) return false;
-  float det = U + V + W;
-  if (det == 0.f) return false;
-  // hit point relative to the origin is (U*A + V*B + W*C)/det; project on d
-  float T = U * dot_sym(A, d) + V * dot_sym(B, d) + W * dot_sym(C, d);
-  float rdet = rcp_fast(det);
-  float t = T * rdet * inv_dd;
-  if (!(t >= tmin && t <= tmax)) return false;
-  t_out = t;
-  b1 = V * rdet;
-  b2 = W * rdet;
-  return true;
-}
-
 // The reference's Moeller-Trumbore in float64 (primitives.go:207-249) on the float32
-// inputs widened exactly: the arbiter for rays that pass so close to a triangle edge that
-// the float32 edge functions cannot decide.  Kept out of line: it runs for ~0.1 % of the
-// triangle tests and must not cost registers on the hot path.
+// inputs widened exactly: the arbiter for rays that pass so close to a triangle edge (or
+// are so nearly parallel to it) that the float32 test cannot decide.  Kept out of line: it
+// runs for well under 1 % of the triangle tests and must not cost registers on the hot path.
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #else
@@ -223,6 +199,13 @@ bool tri_decide_f64(const float4 *__restrict__ tri, float oxf, float oyf, float 
   const double dx = dxf, dy = dyf, dz = dzf;
   const double v1x = (double)q1.x - q0.x, v1y = (double)q1.y - q0.y, v1z = (double)q1.z - q0.z;
   const double v2x = (double)q2.x - q0.x, v2y = (double)q2.y - q0.y, v2z = (double)q2.z - q0.z;
+  {
+    // primitives.go:208: |normalize(v1 x v2) . normalize(d)| < 1e-8 -> parallel, no hit
+    const double nx = v1y * v2z - v1z * v2y, ny = v1z * v2x - v1x * v2z, nz = v1x * v2y - v1y * v2x;
+    const double nn = 1.0 / sqrt(nx * nx + ny * ny + nz * nz), dn = 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+    const double c = (nx * nn) * (dx * dn) + (ny * nn) * (dy * dn) + (nz * nn) * (dz * dn);
+    if (!(c >= 1e-8 || c <= -1e-8)) return false;
+  }
   const double c1x = dy * v2z - dz * v2y, c1y = dz * v2x - dx * v2z, c1z = dx * v2y - dy * v2x;
   const double det = c1x * v1x + c1y * v1y + c1z * v1z;
   if (det == 0.0) return false;
@@ -246,14 +229,14 @@ struct RayPre {
   float ox, oy, oz;
   F3 d;
   float idx, idy, idz;  // reciprocal direction (zero components replaced by +-2^-64)
-  float inv_dd;         // 1 / |d|^2
-  float err2;           // (2^-20)^2 * |d|^2: squared relative error bound of an edge function
   float tmin;
-  uint32_t octinv4;     // (7 - octant) replicated in four bytes
-  uint32_t neg;         // bit0: dx<0, bit1: dy<0, bit2: dz<0
+  float err;            // float32 error scale of the triangle test: 3e-6 * |d| * Dmax
+  uint32_t octinv4;     // (7 - octant) replicated in four bytes; bit 2/1/0 clear <=> dx/dy/dz < 0
 };
 
-M3D_HD RayPre precompute_ray(const RayF &ray) {
+// scene_min/max: bounds of all triangle vertices (for the error bound: no vertex is
+// farther than Dmax from the origin in the infinity norm).
+M3D_HD RayPre precompute_ray(const RayF &ray, const float *scene_min, const float *scene_max) {
   RayPre rp;
   const float ooeps = 5.421010862e-20f;  // 2^-64 (bvh.go:328-333 handles rate == 0 exactly)
   const float dx = fabsf(ray.dx) > ooeps ? ray.dx : copysignf(ooeps, ray.dx);
@@ -266,19 +249,23 @@ M3D_HD RayPre precompute_ray(const RayF &ray) {
   rp.idx = rcp_fast(dx);
   rp.idy = rcp_fast(dy);
   rp.idz = rcp_fast(dz);
-  rp.inv_dd = rcp_fast(ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz);
   rp.tmin = ray.tmin;
-  rp.err2 = 9.094947e-13f * (ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz);
+  const float dmax = max3f(fmaxf(fabsf(ray.ox - scene_min[0]), fabsf(ray.ox - scene_max[0])),
+                           fmaxf(fabsf(ray.oy - scene_min[1]), fabsf(ray.oy - scene_max[1])),
+                           fmaxf(fabsf(ray.oz - scene_min[2]), fabsf(ray.oz - scene_max[2])));
+  rp.err = 3e-6f * dmax * sqrtf(ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz);
   const uint32_t octinv = ((ray.dx < 0.f ? 0u : 4u) | (ray.dy < 0.f ? 0u : 2u) | (ray.dz < 0.f ? 0u : 1u));
   rp.octinv4 = octinv * 0x01010101u;
-  rp.neg = (ray.dx < 0.f ? 1u : 0u) | (ray.dy < 0.f ? 2u : 0u) | (ray.dz < 0.f ? 4u : 0u);
   return rp;
 }
 
-// Ray/triangle test of the traversal: float32 edge functions (watertight, see above); when
-// an edge function is within its own rounding-error bound of zero the decision is taken
-// by tri_decide_f64, so that triangle ids agree with the float64 reference except for
-// exact ties.  Accepts t in [tmin, tmax], barycentrics inclusive, no back-face culling
+// Ray/triangle test of the traversal: the reference's Moeller-Trumbore (primitives.go:
+// 207-249) in float32.  Its barycentrics carry an absolute error of a few ulp of
+// |o - v0| * |d| * |edge| / det, far larger than 1 ulp for small, distant triangles, so a
+// ray whose barycentric (or det) lies within that bound of the accept/reject boundary is
+// re-decided by tri_decide_f64: triangle ids then agree with the float64 reference except
+// for exact ties.  tri[2].w carries the triangle's longest edge (infinity norm) for the
+// bound.  Accepts t in [tmin, tmax], barycentrics inclusive, no back-face culling
 // (primitives.go:183,232,238).
 M3D_HD bool intersect_tri(const float4 *__restrict__ tri, const RayPre &rp, float tmax, float &t_out,
                           float &b1, float &b2) {
@@ -287,34 +274,30 @@ M3D_HD bool intersect_tri(const float4 *__restrict__ tri, const RayPre &rp, floa
 #else
   const float4 q0 = tri[0], q1 = tri[1], q2 = tri[2];
 #endif
-  const F3 A = mk3(q0.x - rp.ox, q0.y - rp.oy, q0.z - rp.oz);
-  const F3 B = mk3(q1.x - rp.ox, q1.y - rp.oy, q1.z - rp.oz);
-  const F3 C = mk3(q2.x - rp.ox, q2.y - rp.oy, q2.z - rp.oz);
-  const float U = dot_sym(rp.d, cross_sym(B, C));  // weight of v0
-  const float V = dot_sym(rp.d, cross_sym(C, A));  // weight of v1
-  const float W = dot_sym(rp.d, cross_sym(A, B));  // weight of v2
-  // rounding-error bound of an edge function: ~16 ulp of |d| * max|vertex - origin|^2
-  const float m2 = max3f(A.x * A.x + A.y * A.y + A.z * A.z, B.x * B.x + B.y * B.y + B.z * B.z,
-                         C.x * C.x + C.y * C.y + C.z * C.z);
-  const float bound2 = rp.err2 * m2 * m2;
-  if (min3f(U * U, V * V, W * W) <= bound2) {
-    // too close to an edge (or degenerate): let the float64 reference arithmetic decide,
-    // unless the ray is clearly outside with respect to another edge
-    const float s = sqrtf(bound2);
-    const bool out_pos = (U > s || V > s || W > s), out_neg = (U < -s || V < -s || W < -s);
-    if (out_pos && out_neg) return false;
+  const float e1x = q1.x - q0.x, e1y = q1.y - q0.y, e1z = q1.z - q0.z;
+  const float e2x = q2.x - q0.x, e2y = q2.y - q0.y, e2z = q2.z - q0.z;
+  const float c1x = rp.d.y * e2z - rp.d.z * e2y, c1y = rp.d.z * e2x - rp.d.x * e2z,
+              c1z = rp.d.x * e2y - rp.d.y * e2x;  // d x e2
+  const float det = c1x * e1x + c1y * e1y + c1z * e1z;
+  const float px = rp.ox - q0.x, py = rp.oy - q0.y, pz = rp.oz - q0.z;
+  const float n1 = px * c1x + py * c1y + pz * c1z;  // bary1 * det
+  const float c2x = py * e1z - pz * e1y, c2y = pz * e1x - px * e1z, c2z = px * e1y - py * e1x;  // o x e1
+  const float n2 = rp.d.x * c2x + rp.d.y * c2y + rp.d.z * c2z;  // bary2 * det
+  const float n0 = det - (n1 + n2);                             // bary0 * det
+  const float band = rp.err * q2.w;  // error bound of n0, n1, n2 and det
+  const float adet = fabsf(det);
+  // clearly outside (beyond the band) with respect to some edge: no hit
+  const float sgn = det < 0.f ? -1.f : 1.f;
+  const float m = min3f(n0 * sgn, n1 * sgn, n2 * sgn);
+  if (m < -band) return false;
+  if (m <= band || adet <= band)
     return tri_decide_f64(tri, rp.ox, rp.oy, rp.oz, rp.d.x, rp.d.y, rp.d.z, rp.tmin, tmax, t_out, b1, b2);
-  }
-  if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) return false;
-  const float det = U + V + W;
-  // hit point relative to the origin is (U*A + V*B + W*C)/det; project on d
-  const float T = U * dot_sym(A, rp.d) + V * dot_sym(B, rp.d) + W * dot_sym(C, rp.d);
-  const float rdet = rcp_fast(det);
-  const float t = T * rdet * rp.inv_dd;
+  const float inv = rcp_fast(det);
+  const float t = (e2x * c2x + e2y * c2y + e2z * c2z) * inv;
   if (!(t >= rp.tmin && t <= tmax)) return false;
   t_out = t;
-  b1 = V * rdet;
-  b2 = W * rdet;
+  b1 = n1 * inv;
+  b2 = n2 * inv;
   return true;
 }
 
@@ -359,9 +342,9 @@ M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index,
     const uint32_t qlox = half == 0 ? n2.x : n2.y, qloy = half == 0 ? n2.z : n2.w;
     const uint32_t qloz = half == 0 ? n3.x : n3.y, qhix = half == 0 ? n3.z : n3.w;
     const uint32_t qhiy = half == 0 ? n4.x : n4.y, qhiz = half == 0 ? n4.z : n4.w;
-    const uint32_t xn = (rp.neg & 1u) ? qhix : qlox, xf = (rp.neg & 1u) ? qlox : qhix;
-    const uint32_t yn = (rp.neg & 2u) ? qhiy : qloy, yf = (rp.neg & 2u) ? qloy : qhiy;
-    const uint32_t zn = (rp.neg & 4u) ? qhiz : qloz, zf = (rp.neg & 4u) ? qloz : qhiz;
+    const uint32_t xn = (rp.octinv4 & 4u) ? qlox : qhix, xf = (rp.octinv4 & 4u) ? qhix : qlox;
+    const uint32_t yn = (rp.octinv4 & 2u) ? qloy : qhiy, yf = (rp.octinv4 & 2u) ? qhiy : qloy;
+    const uint32_t zn = (rp.octinv4 & 1u) ? qloz : qhiz, zf = (rp.octinv4 & 1u) ? qhiz : qloz;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const float t0x = fmaf(unit_plus_byte(xn, j), Sx, bnx);
@@ -402,8 +385,9 @@ M3D_HD uint32_t take_nearest_child(uint2 &ngroup, uint32_t octinv4) {
 // secondary rays), -1 none.  ANY_HIT: return at the first accepted hit.
 template <bool COUNT, bool ANY_HIT>
 M3D_HD void trace_bvh(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
-                      const RayF &ray, int32_t skip_tri, HitF &hit, TraceCounters *cnt) {
-  const RayPre rp = precompute_ray(ray);
+                      const float *scene_min, const float *scene_max, const RayF &ray,
+                      int32_t skip_tri, HitF &hit, TraceCounters *cnt) {
+  const RayPre rp = precompute_ray(ray, scene_min, scene_max);
   float tmax = ray.tmax;
   hit.tri = -1;
   hit.t = tmax;

@@ -5,6 +5,8 @@
 //                              (Ray{Origin,Direction}, collisions.go:12-15;
 //                              RayCollision / TriangleCollision, collisions.go:19-46)
 //                              and the device float4 SoA layout.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "trace_core.cuh"
 
@@ -28,24 +30,20 @@ constexpr int kRayBatch = 32 * 6; // rays a warp claims per global atomic
 // body is "one node visit, then that node's triangles" for all lanes together.
 // The trace kernel only writes the raw float32 hit (t, b1, b2, triangle index);
 // finish_hits_kernel re-evaluates hits in float64 in a separate, fully coherent pass.
-template <bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock, 8)
-trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned long long *__restrict__ ray_counter) {
+template <bool COUNT, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kTraceBlock, MIN_BLOCKS)
+trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ ray_counter) {
   __shared__ uint2 s_stack[kSmemStack][kTraceBlock];
   uint2 l_stack[kLocalStack];
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned lane_lt = (1u << lane) - 1u;
   const uint4 *__restrict__ nodes = bvh.nodes;
   const float4 *__restrict__ tris = bvh.tris;
+  const int n = (int)p.n;
 
-  long long batch_next = 0, batch_end = 0;  // warp-uniform
-  bool exhausted = false;                   // warp-uniform: the global counter ran past n
-
-  bool active = false;
-  long long ray_idx = 0;
+  int batch_next = 0, batch_end = 0;  // warp-uniform; batch_end < 0: the global counter ran past n
+  int ray_idx = -1;                   // < 0: the lane has no ray
   RayPre rp;
   float tmax = 0.f;
-  float hit_t = 0.f, hit_b1 = 0.f, hit_b2 = 0.f;
   int hit_tri = -1;
   uint2 ngroup = make_uint2(0u, 0u);
   uint2 tq = make_uint2(0u, 0u), tq2 = make_uint2(0u, 0u);  // pending leaf-triangle groups
@@ -56,33 +54,34 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned long long *__restr
 
   for (;;) {
     // ---- refill idle lanes ----------------------------------------------------------
-    const unsigned need = __ballot_sync(0xffffffffu, !active);
+    const unsigned need = __ballot_sync(0xffffffffu, ray_idx < 0);
     if (need) {
-      if (batch_next >= batch_end && !exhausted) {
-        long long base = 0;
-        if (lane == 0) base = (long long)atomicAdd(ray_counter, (unsigned long long)kRayBatch);
+      if (batch_next >= batch_end && batch_end >= 0) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(ray_counter, (unsigned)kRayBatch);
         base = __shfl_sync(0xffffffffu, base, 0);
-        batch_next = base;
-        batch_end = base + kRayBatch < p.n ? base + kRayBatch : p.n;
-        if (base >= p.n) exhausted = true;
-        // pull the batch's rays towards the SM now; lanes pick them up one by one later
-        for (long long r = batch_next + 4 * (long long)lane; r < batch_end; r += 128) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.org_tmin + r));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dir_tmax + r));
+        if (base >= (unsigned)n) {
+          batch_end = -1;
+        } else {
+          batch_next = (int)base;
+          batch_end = (int)base + kRayBatch < n ? (int)base + kRayBatch : n;
+          // pull the batch's rays towards the SM now; lanes pick them up one by one later
+          for (int r = batch_next + 4 * (int)lane; r < batch_end; r += 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.org_tmin + r));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dir_tmax + r));
+          }
         }
       }
-      if (!active) {
-        const long long idx = batch_next + (long long)__popc(need & lane_lt);
+      if (ray_idx < 0) {
+        const int idx = batch_next + __popc(need & ((1u << lane) - 1u));
         if (idx < batch_end) {
           const float4 o = __ldg(p.org_tmin + idx);
           const float4 d = __ldg(p.dir_tmax + idx);
           RayF ray;
           ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmin = o.w;
           ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.tmax = d.w;
-          rp = precompute_ray(ray);
+          rp = precompute_ray(ray, bvh.bmin, bvh.bmax);
           tmax = d.w;
-          hit_t = d.w;
-          hit_b1 = hit_b2 = 0.f;
           hit_tri = -1;
           // virtual parent whose only child is the root: child base 0, slot (7 ^ octinv)
           // of an all-internal imask so that take_nearest_child() yields node 0
@@ -92,14 +91,13 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned long long *__restr
           tq2.y = 0u;
           sp = 0;
           ray_idx = idx;
-          active = true;
         }
       }
       batch_next += __popc(need);
-      if (exhausted && __ballot_sync(0xffffffffu, active) == 0u) break;
+      if (batch_end < 0 && __ballot_sync(0xffffffffu, ray_idx >= 0) == 0u) break;
     }
 
-    if (active) {
+    if (ray_idx >= 0) {
       // ---- phase A: one node visit (skipped only while both triangle slots are full) ---
       bool have_node = (ngroup.y & 0xff000000u) != 0u;
       if (!have_node && sp > 0 && tq2.y == 0u) {
@@ -140,29 +138,27 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned long long *__restr
         float t, b1, b2;
         if (intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
           tmax = t;
-          hit_t = t;
-          hit_b1 = b1;
-          hit_b2 = b2;
           hit_tri = ti;
         }
       }
       // ---- ray finished? (checked here so that the lane is refilled before the next A) --
       if ((ngroup.y & 0xff000000u) == 0u && sp == 0 && tq.y == 0u && tq2.y == 0u) {
-        p.hit0[ray_idx] = make_float4(hit_t, hit_b1, hit_b2, __int_as_float(hit_tri));
-        active = false;
+        // raw hit: float32 t and the triangle's index; finish_hits_kernel does the rest
+        p.hit0[ray_idx] = make_float4(tmax, 0.f, 0.f, __int_as_float(hit_tri));
+        ray_idx = -1;
       }
     }
   }
 
   if (COUNT) {
-    unsigned long long n = cnt.nodes, t = cnt.tris;
+    unsigned long long nn = cnt.nodes, tt = cnt.tris;
     for (int off = 16; off > 0; off >>= 1) {
-      n += __shfl_down_sync(0xffffffffu, n, off);
-      t += __shfl_down_sync(0xffffffffu, t, off);
+      nn += __shfl_down_sync(0xffffffffu, nn, off);
+      tt += __shfl_down_sync(0xffffffffu, tt, off);
     }
     if (lane == 0) {
-      atomicAdd(p.counters, n);
-      atomicAdd(p.counters + 1, t);
+      atomicAdd(p.counters, nn);
+      atomicAdd(p.counters + 1, tt);
     }
   }
 }
@@ -207,16 +203,24 @@ finish_hits_kernel(DeviceBVH bvh, TraceLaunch p) {
       const float e1x = q1.x - q0.x, e1y = q1.y - q0.y, e1z = q1.z - q0.z;
       const float e2x = q2.x - q0.x, e2y = q2.y - q0.y, e2z = q2.z - q0.z;
       float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+      // float32 barycentrics (Moeller-Trumbore, as in the traversal)
+      const float4 o = __ldg(p.org_tmin + i);
+      const float4 d = __ldg(p.dir_tmax + i);
+      const float c1x = d.y * e2z - d.z * e2y, c1y = d.z * e2x - d.x * e2z, c1z = d.x * e2y - d.y * e2x;
+      const float inv = 1.0f / (c1x * e1x + c1y * e1y + c1z * e1z);
+      const float px = o.x - q0.x, py = o.y - q0.y, pz = o.z - q0.z;
+      const float fb1 = inv * (px * c1x + py * c1y + pz * c1z);
+      const float fb2 = inv * (d.x * (py * e1z - pz * e1y) + d.y * (pz * e1x - px * e1z) + d.z * (px * e1y - py * e1x));
       if (bvh.vnormals) {
         const float4 *vn = bvh.vnormals + (size_t)tri_idx * 3;
         const float4 a = __ldg(vn), b = __ldg(vn + 1), c = __ldg(vn + 2);
-        const float b0 = 1.f - (raw.y + raw.z);
-        nx = b0 * a.x + raw.y * b.x + raw.z * c.x;
-        ny = b0 * a.y + raw.y * b.y + raw.z * c.y;
-        nz = b0 * a.z + raw.y * b.z + raw.z * c.z;
+        const float b0 = 1.f - (fb1 + fb2);
+        nx = b0 * a.x + fb1 * b.x + fb2 * c.x;
+        ny = b0 * a.y + fb1 * b.y + fb2 * c.y;
+        nz = b0 * a.z + fb1 * b.z + fb2 * c.z;
       }
       const float s = rsqrtf(nx * nx + ny * ny + nz * nz);
-      h0 = make_float4(raw.x, raw.y, raw.z, __int_as_float(prim));
+      h0 = make_float4(raw.x, fb1, fb2, __int_as_float(prim));
       h1 = make_float4(nx * s, ny * s, nz * s, __int_as_float(obj));
     }
   }
@@ -258,27 +262,42 @@ __global__ void unpack_hits_kernel(const float4 *__restrict__ hit0, const float4
 
 }  // namespace
 
-void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
-  if (p.n <= 0) return;
-  // persistent grid: as many blocks as stay resident (8 per SM at <= 64 registers)
-  static int blocks_per_sm[2] = {0, 0};
-  const int which = p.counters ? 1 : 0;
-  if (!blocks_per_sm[which]) {
+template <bool COUNT, int MIN_BLOCKS>
+static void launch_trace_variant(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
+  // persistent grid: as many blocks as stay resident
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
     int b = 0;
-    if (which)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_first_hit_kernel<true>, kTraceBlock, 0);
-    else
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_first_hit_kernel<false>, kTraceBlock, 0);
-    blocks_per_sm[which] = b > 0 ? b : 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_first_hit_kernel<COUNT, MIN_BLOCKS>, kTraceBlock, 0);
+    blocks_per_sm = b > 0 ? b : 1;
   }
   long long want = (p.n + kTraceBlock - 1) / kTraceBlock;
-  long long grid = (long long)device_sm_count() * blocks_per_sm[which];
+  long long grid = (long long)device_sm_count() * blocks_per_sm;
   if (grid > want) grid = want;
+  unsigned int *rc32 = reinterpret_cast<unsigned int *>(p.ray_counter);
+  trace_first_hit_kernel<COUNT, MIN_BLOCKS><<<(unsigned)grid, kTraceBlock, 0, stream>>>(bvh, p, rc32);
+}
+
+void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
+  if (p.n <= 0) return;
+  // register budget of the traversal kernel: 6 resident blocks/SM (80 registers, no spills)
+  // measured best on B200; M3D_TRACE_MINB=7|8 selects the tighter variants for tuning runs
+  static int minb = 0;
+  if (!minb) {
+    const char *e = getenv("M3D_TRACE_MINB");
+    minb = e ? atoi(e) : 6;
+    if (minb < 6 || minb > 8) minb = 6;
+  }
   cudaMemsetAsync(p.ray_counter, 0, sizeof(unsigned long long), stream);
-  if (p.counters)
-    trace_first_hit_kernel<true><<<(unsigned)grid, kTraceBlock, 0, stream>>>(bvh, p, p.ray_counter);
-  else
-    trace_first_hit_kernel<false><<<(unsigned)grid, kTraceBlock, 0, stream>>>(bvh, p, p.ray_counter);
+  if (p.counters) {
+    launch_trace_variant<true, 6>(bvh, p, stream);
+  } else if (minb == 8) {
+    launch_trace_variant<false, 8>(bvh, p, stream);
+  } else if (minb == 7) {
+    launch_trace_variant<false, 7>(bvh, p, stream);
+  } else {
+    launch_trace_variant<false, 6>(bvh, p, stream);
+  }
   finish_hits_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(bvh, p);
 }
 

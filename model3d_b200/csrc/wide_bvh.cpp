@@ -419,7 +419,17 @@ void build_wide_bvh(const BuildInput &in, WideBVH &out, int num_threads) {
           std::memcpy(tr.v2, v + 6, 12);
           tr.prim = in.prim_ids ? in.prim_ids[t] : t;
           tr.object = in.obj_ids ? in.obj_ids[t] : 0;
-          tr.pad = 0;
+          {
+            // longest edge (infinity norm), rounded up: scale of the float32 error bound
+            float em = 0.f;
+            for (int k = 0; k < 3; k++) {
+              em = std::max(em, std::fabs(v[3 + k] - v[k]));
+              em = std::max(em, std::fabs(v[6 + k] - v[k]));
+              em = std::max(em, std::fabs(v[6 + k] - v[3 + k]));
+            }
+            em *= 1.0000002f;
+            std::memcpy(&tr.pad, &em, 4);
+          }
           out.tris.push_back(tr);
         }
         tri_off += cnt;

@@ -28,14 +28,15 @@ static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
 
 // One triangle record: three float4.  The w lanes carry ids so that the winning hit
 // needs no second lookup: v0.w = bits(prim id in the caller's array),
-// v1.w = bits(object id), v2.w = 0.
+// v1.w = bits(object id), v2.w = longest edge length (float, infinity norm; the scale
+// of the float32 error bound of the triangle test).
 struct alignas(16) TriRecord {
   float v0[3];
   int32_t prim;
   float v1[3];
   int32_t object;
   float v2[3];
-  int32_t pad;
+  int32_t pad;  // float bits: longest edge
 };
 static_assert(sizeof(TriRecord) == 48, "TriRecord must be 48 bytes");
 

@@ -44,7 +44,7 @@ void emul_trace(void *h, const float *org, const float *dir, int64_t n, float *t
     r.dx = dir[3 * i]; r.dy = dir[3 * i + 1]; r.dz = dir[3 * i + 2]; r.tmax = __builtin_inff();
     HitF hit;
     TraceCounters c{0, 0};
-    trace_bvh<true, false>(nodes, tris, r, -1, hit, &c);
+    trace_bvh<true, false>(nodes, tris, e->bvh.bounds_min, e->bvh.bounds_max, r, -1, hit, &c);
     cn += c.nodes; ct += c.tris;
     prim[i] = -1; t[i] = 0;
     if (hit.tri >= 0) {
