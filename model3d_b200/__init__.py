@@ -9,5 +9,7 @@ from .model3d import (BatchCollisions, MeshCollider, MeshToCollider,  # noqa: F4
                       MeshToInterpNormalCollider, Ray, RayCollision, TriangleCollision,
                       UnsupportedError)
 
-__all__ = ["MeshCollider", "MeshToCollider", "MeshToInterpNormalCollider", "Ray", "RayCollision",
+from . import render3d  # noqa: F401,E402
+
+__all__ = ["render3d", "MeshCollider", "MeshToCollider", "MeshToInterpNormalCollider", "Ray", "RayCollision",
            "TriangleCollision", "BatchCollisions", "UnsupportedError"]

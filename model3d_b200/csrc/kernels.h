@@ -23,8 +23,12 @@ struct TraceLaunch {
   bool refine;   // float64 re-evaluation of the winning hit
   unsigned long long *counters;     // optional device 2 x u64 (nodes, tris)
   unsigned long long *ray_counter;  // device u64 work counter of the persistent kernel
+  const int32_t *skip_tris = nullptr;  // optional per ray: leaf-order triangle index to ignore
 };
 
+// BVH traversal only: hit0 = (t_f32, 0, 0, bits(leaf-order triangle index | -1))
+void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream);
+// traversal + finish pass (float64 refine) for a plain mesh
 void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream);
 
 // n*3 float arrays -> float4 SoA with constant tmin/tmax

@@ -189,9 +189,9 @@ M3D_HD float unit_plus_byte(uint32_t q, int j) {
 // are so nearly parallel to it) that the float32 test cannot decide.  Kept out of line: it
 // runs for well under 1 % of the triangle tests and must not cost registers on the hot path.
 #if defined(__CUDACC__)
-__host__ __device__ __noinline__
+static __host__ __device__ __noinline__
 #else
-inline
+static inline
 #endif
 bool tri_decide_f64(const float4 *__restrict__ tri, float oxf, float oyf, float ozf, float dxf,
                     float dyf, float dzf, float tmin, float tmax, float &t_out, float &b1, float &b2) {

@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "scene.h"
 #include "trace_core.cuh"
 
 namespace m3d {
@@ -45,6 +46,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
   RayPre rp;
   float tmax = 0.f;
   int hit_tri = -1;
+  int skip_tri = -1;
   uint2 ngroup = make_uint2(0u, 0u);
   uint2 tq = make_uint2(0u, 0u), tq2 = make_uint2(0u, 0u);  // pending leaf-triangle groups
   int sp = 0;
@@ -75,14 +77,15 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
       if (ray_idx < 0) {
         const int idx = batch_next + __popc(need & ((1u << lane) - 1u));
         if (idx < batch_end) {
-          const float4 o = __ldg(p.org_tmin + idx);
-          const float4 d = __ldg(p.dir_tmax + idx);
+          const float4 o = __ldcs(p.org_tmin + idx);  // streaming: keep the BVH in L2
+          const float4 d = __ldcs(p.dir_tmax + idx);
           RayF ray;
           ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmin = o.w;
           ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.tmax = d.w;
           rp = precompute_ray(ray, bvh.bmin, bvh.bmax);
           tmax = d.w;
           hit_tri = -1;
+          skip_tri = p.skip_tris ? __ldg(p.skip_tris + idx) : -1;
           // virtual parent whose only child is the root: child base 0, slot (7 ^ octinv)
           // of an all-internal imask so that take_nearest_child() yields node 0
           ngroup.x = 0u;
@@ -136,7 +139,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
         const int ti = (int)(tq.x + (uint32_t)bit);
         if (COUNT) cnt.tris++;
         float t, b1, b2;
-        if (intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
+        if (ti != skip_tri && intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
           tmax = t;
           hit_tri = ti;
         }
@@ -144,7 +147,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
       // ---- ray finished? (checked here so that the lane is refilled before the next A) --
       if ((ngroup.y & 0xff000000u) == 0u && sp == 0 && tq.y == 0u && tq2.y == 0u) {
         // raw hit: float32 t and the triangle's index; finish_hits_kernel does the rest
-        p.hit0[ray_idx] = make_float4(tmax, 0.f, 0.f, __int_as_float(hit_tri));
+        __stcs(p.hit0 + ray_idx, make_float4(tmax, 0.f, 0.f, __int_as_float(hit_tri)));
         ray_idx = -1;
       }
     }
@@ -161,71 +164,6 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
       atomicAdd(p.counters + 1, tt);
     }
   }
-}
-
-// Coherent second pass: turn raw hits (t, b1, b2, triangle index) into the final records
-//   hit0 = (Scale, bary1, bary2, bits(prim id)),  hit1 = (Normal, bits(object id))
-// re-evaluating the winning triangle in float64 with the reference's arithmetic
-// (primitives.go:27-33,207-249; InterpNormal primitives.go:508-516).
-__global__ void __launch_bounds__(256)
-finish_hits_kernel(DeviceBVH bvh, TraceLaunch p) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= p.n) return;
-  const float4 raw = p.hit0[i];
-  const int tri_idx = __float_as_int(raw.w);
-  float4 h0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-  float4 h1 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-  if (tri_idx >= 0) {
-    const float4 *tri = bvh.tris + (size_t)tri_idx * 3;
-    const int prim = __float_as_int(__ldg(&tri[0].w));
-    const int obj = __float_as_int(__ldg(&tri[1].w));
-    if (p.refine) {
-      const float4 o = __ldg(p.org_tmin + i);
-      const float4 d = __ldg(p.dir_tmax + i);
-      const HitD r = refine_hit_f64(tri, o.x, o.y, o.z, d.x, d.y, d.z);
-      const double t = r.t >= 0.0 ? r.t : (double)raw.x;
-      double nx = r.nx, ny = r.ny, nz = r.nz;
-      if (bvh.vnormals) {
-        const float4 *vn = bvh.vnormals + (size_t)tri_idx * 3;
-        const float4 a = __ldg(vn), b = __ldg(vn + 1), c = __ldg(vn + 2);
-        nx = r.b0 * a.x + r.b1 * b.x + r.b2 * c.x;
-        ny = r.b0 * a.y + r.b1 * b.y + r.b2 * c.y;
-        nz = r.b0 * a.z + r.b1 * b.z + r.b2 * c.z;
-        const double s = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
-        nx *= s;
-        ny *= s;
-        nz *= s;
-      }
-      h0 = make_float4((float)t, (float)r.b1, (float)r.b2, __int_as_float(prim));
-      h1 = make_float4((float)nx, (float)ny, (float)nz, __int_as_float(obj));
-    } else {
-      const float4 q0 = __ldg(tri), q1 = __ldg(tri + 1), q2 = __ldg(tri + 2);
-      const float e1x = q1.x - q0.x, e1y = q1.y - q0.y, e1z = q1.z - q0.z;
-      const float e2x = q2.x - q0.x, e2y = q2.y - q0.y, e2z = q2.z - q0.z;
-      float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
-      // float32 barycentrics (Moeller-Trumbore, as in the traversal)
-      const float4 o = __ldg(p.org_tmin + i);
-      const float4 d = __ldg(p.dir_tmax + i);
-      const float c1x = d.y * e2z - d.z * e2y, c1y = d.z * e2x - d.x * e2z, c1z = d.x * e2y - d.y * e2x;
-      const float inv = 1.0f / (c1x * e1x + c1y * e1y + c1z * e1z);
-      const float px = o.x - q0.x, py = o.y - q0.y, pz = o.z - q0.z;
-      const float fb1 = inv * (px * c1x + py * c1y + pz * c1z);
-      const float fb2 = inv * (d.x * (py * e1z - pz * e1y) + d.y * (pz * e1x - px * e1z) + d.z * (px * e1y - py * e1x));
-      if (bvh.vnormals) {
-        const float4 *vn = bvh.vnormals + (size_t)tri_idx * 3;
-        const float4 a = __ldg(vn), b = __ldg(vn + 1), c = __ldg(vn + 2);
-        const float b0 = 1.f - (fb1 + fb2);
-        nx = b0 * a.x + fb1 * b.x + fb2 * c.x;
-        ny = b0 * a.y + fb1 * b.y + fb2 * c.y;
-        nz = b0 * a.z + fb1 * b.z + fb2 * c.z;
-      }
-      const float s = rsqrtf(nx * nx + ny * ny + nz * nz);
-      h0 = make_float4(raw.x, fb1, fb2, __int_as_float(prim));
-      h1 = make_float4(nx * s, ny * s, nz * s, __int_as_float(obj));
-    }
-  }
-  p.hit0[i] = h0;
-  p.hit1[i] = h1;
 }
 
 __global__ void pack_rays_kernel(const float *__restrict__ org3, const float *__restrict__ dir3,
@@ -278,7 +216,7 @@ static void launch_trace_variant(const DeviceBVH &bvh, const TraceLaunch &p, cud
   trace_first_hit_kernel<COUNT, MIN_BLOCKS><<<(unsigned)grid, kTraceBlock, 0, stream>>>(bvh, p, rc32);
 }
 
-void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
+void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
   if (p.n <= 0) return;
   // register budget of the traversal kernel: 6 resident blocks/SM (80 registers, no spills)
   // measured best on B200; M3D_TRACE_MINB=7|8 selects the tighter variants for tuning runs
@@ -298,7 +236,22 @@ void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStre
   } else {
     launch_trace_variant<false, 6>(bvh, p, stream);
   }
-  finish_hits_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(bvh, p);
+}
+
+void launch_trace_scene(const DeviceScene &scene, const SceneTraceLaunch &p, cudaStream_t stream) {
+  if (p.t.n <= 0) return;
+  TraceLaunch t = p.t;
+  t.skip_tris = p.skip_ids;  // negative ids (shapes / none) never match a triangle index
+  launch_trace_bvh_only(scene.bvh, t, stream);
+  launch_finish_scene_hits(scene, p, stream);
+}
+
+void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
+  DeviceScene sc;
+  sc.bvh = bvh;
+  SceneTraceLaunch sp;
+  sp.t = p;
+  launch_trace_scene(sc, sp, stream);
 }
 
 void launch_pack_rays(const float *org3, const float *dir3, int64_t n, float tmin, float tmax,

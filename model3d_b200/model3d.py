@@ -77,6 +77,9 @@ class MeshCollider:
             if vn.shape != tris.shape:
                 raise ValueError("vertex_normals must match triangles")
         self.num_triangles = int(tris.shape[0])
+        # host copy: scenes merge the triangles of all mesh objects into one BVH
+        self.triangles = tris.reshape(-1, 3, 3)
+        self.vertex_normals = None if vn is None else vn.reshape(-1, 3, 3)
         self.h = C.c_void_p()
         N.check(N.lib().m3d_mesh_create(self.ctx.h, _p(tris, f32p), C.c_int64(self.num_triangles),
                                         _p(vn, f32p), C.c_uint32(0), C.byref(self.h)))

@@ -1,0 +1,432 @@
+"""Host-side mirror of the reference's ``render3d`` interface for the GPU path.
+
+Same names and field meanings as render3d (Go): ``Camera`` / ``NewCameraAt``
+(render3d/camera.go:19-66), ``PointLight`` (light.go:57-66), ``LambertMaterial`` /
+``PhongMaterial`` / ``RefractMaterial`` / ``JoinedMaterial`` (material.go:119-631),
+``ColliderObject`` / ``JoinedObject`` / ``Translate`` / ``MatrixMultiply`` (object.go:26-153,
+transform.go:6-85), ``Image`` (image.go:17-47), ``RayCaster`` (raycast.go:9-39),
+``RecursiveRayTracer`` (raytrace.go:14-119), ``BidirPathTracer`` (bidir.go:14-84).
+Objects are compiled by a type switch into a device scene through libm3dgpu's C ABI;
+unsupported object / collider / material types raise ``UnsupportedError`` -- there is no
+CPU fallback.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .model3d import MeshCollider, UnsupportedError
+
+Vec = Tuple[float, float, float]
+f32p = C.POINTER(C.c_float)
+i32p = C.POINTER(C.c_int32)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+# ---- colours (light.go:19-55) -------------------------------------------------------
+def NewColor(b):
+    return (float(b), float(b), float(b))
+
+
+def _gamma_expand(u):
+    return u / 12.92 if u <= 0.04045 else math.pow((u + 0.055) / 1.055, 2.4)
+
+
+def NewColorRGB(r, g, b):
+    return (_gamma_expand(r), _gamma_expand(g), _gamma_expand(b))
+
+
+def _scale(c, s):
+    return (c[0] * s, c[1] * s, c[2] * s)
+
+
+# ---- analytic colliders (model3d/shapes.go) ------------------------------------------
+@dataclass
+class Sphere:
+    Center: Vec = (0.0, 0.0, 0.0)
+    Radius: float = 1.0
+
+
+@dataclass
+class Rect:
+    MinVal: Vec = (0.0, 0.0, 0.0)
+    MaxVal: Vec = (1.0, 1.0, 1.0)
+
+
+@dataclass
+class Cylinder:
+    P1: Vec = (0.0, 0.0, 0.0)
+    P2: Vec = (0.0, 0.0, 1.0)
+    Radius: float = 1.0
+
+
+# ---- materials (material.go) ------------------------------------------------------------
+ZERO = (0.0, 0.0, 0.0)
+
+
+@dataclass(eq=False)
+class LambertMaterial:
+    DiffuseColor: Vec = ZERO
+    AmbientColor: Vec = ZERO
+    EmissionColor: Vec = ZERO
+
+
+@dataclass(eq=False)
+class PhongMaterial:
+    Alpha: float = 0.0
+    SpecularColor: Vec = ZERO
+    DiffuseColor: Vec = ZERO
+    EmissionColor: Vec = ZERO
+    AmbientColor: Vec = ZERO
+    NoFluxCorrection: bool = False
+
+
+@dataclass(eq=False)
+class RefractMaterial:
+    IndexOfRefraction: float = 1.0
+    RefractColor: Vec = ZERO
+    SpecularColor: Vec = ZERO
+
+
+@dataclass(eq=False)
+class JoinedMaterial:
+    Materials: List[object] = field(default_factory=list)
+    Probs: List[float] = field(default_factory=list)
+
+
+@dataclass(eq=False)
+class CheckerLambertMaterial:
+    """Declarative form of showcase's FloorObject (examples/renderings/showcase/room.go:61-75):
+    Lambert whose diffuse colour is Color2 where int(mod(x+300,2)) == int(mod(y+301,2)),
+    else Color1."""
+    Color1: Vec = ZERO
+    Color2: Vec = ZERO
+
+
+@dataclass(eq=False)
+class ZGradientPhongMaterial:
+    """Declarative form of showcase's VaseObject (models.go:79-97): Phong whose diffuse colour
+    is Color1*frac + Color2*(1-frac), frac = z / MaxZ."""
+    Alpha: float = 0.0
+    SpecularColor: Vec = ZERO
+    Color1: Vec = ZERO
+    Color2: Vec = ZERO
+    MaxZ: float = 1.0
+
+
+def material_desc(m, index_of):
+    """render3d.Material -> m3d_material_desc (raises UnsupportedError)."""
+    d = N.MaterialDesc()
+
+    def put(dst, c):
+        dst[:] = [float(x) for x in c]
+
+    if isinstance(m, LambertMaterial):
+        d.kind = N.MAT_LAMBERT
+        put(d.diffuse, m.DiffuseColor)
+        put(d.ambient, m.AmbientColor)
+        put(d.emission, m.EmissionColor)
+    elif isinstance(m, PhongMaterial):
+        d.kind = N.MAT_PHONG
+        d.alpha = m.Alpha
+        put(d.specular, m.SpecularColor)
+        put(d.diffuse, m.DiffuseColor)
+        put(d.emission, m.EmissionColor)
+        put(d.ambient, m.AmbientColor)
+        if m.NoFluxCorrection:
+            d.flags |= N.MAT_NO_FLUX_CORRECTION
+    elif isinstance(m, RefractMaterial):
+        d.kind = N.MAT_REFRACT
+        d.index_of_refraction = m.IndexOfRefraction
+        put(d.refract, m.RefractColor)
+        put(d.specular, m.SpecularColor)
+    elif isinstance(m, JoinedMaterial):
+        if len(m.Probs) != len(m.Materials):
+            raise ValueError("mismatched probabilities and materials")  # material.go:573-575
+        if len(m.Materials) > 4:
+            raise UnsupportedError("JoinedMaterial with more than 4 parts")
+        d.kind = N.MAT_JOINED
+        d.num_sub = len(m.Materials)
+        for i, sub in enumerate(m.Materials):
+            d.sub[i] = index_of(sub)
+            d.sub_prob[i] = float(m.Probs[i])
+    elif isinstance(m, CheckerLambertMaterial):
+        d.kind = N.MAT_LAMBERT
+        d.flags |= N.MAT_CHECKER
+        put(d.diffuse, m.Color1)
+        put(d.diffuse2, m.Color2)
+    elif isinstance(m, ZGradientPhongMaterial):
+        d.kind = N.MAT_PHONG
+        d.flags |= N.MAT_Z_GRADIENT
+        d.alpha = m.Alpha
+        put(d.specular, m.SpecularColor)
+        put(d.diffuse, m.Color1)
+        put(d.diffuse2, m.Color2)
+        d.proc_param = m.MaxZ
+    else:
+        raise UnsupportedError("material type %s is not supported on the GPU path" % type(m).__name__)
+    return d
+
+
+# ---- objects (object.go, transform.go) ----------------------------------------------------
+@dataclass(eq=False)
+class ColliderObject:
+    Collider: object = None
+    Material: object = None
+    FlipNormals: bool = False  # declarative form of showcase's DomeObject (room.go:40-44)
+
+
+class JoinedObject(list):
+    """render3d.JoinedObject ([]Object)."""
+
+
+@dataclass(eq=False)
+class _Transformed:
+    Object: object
+    Matrix: Optional[Sequence[float]]  # row-major 3x3 (model3d/matrix.go:11-12)
+    Offset: Vec
+
+
+def Translate(obj, offset):
+    """render3d.Translate (transform.go:6-31)."""
+    return _Transformed(obj, None, tuple(float(x) for x in offset))
+
+
+def MatrixMultiply(obj, m):
+    """render3d.MatrixMultiply (transform.go:48-85); m is row-major 3x3."""
+    return _Transformed(obj, [float(x) for x in np.asarray(m, np.float64).reshape(9)], (0.0, 0.0, 0.0))
+
+
+def _compose(outer, inner):
+    """x -> outer(inner(x)) for (matrix|None, offset) pairs."""
+    if outer is None:
+        return inner
+    if inner is None:
+        return outer
+    mo = np.eye(3) if outer[0] is None else np.asarray(outer[0], np.float64).reshape(3, 3)
+    mi = np.eye(3) if inner[0] is None else np.asarray(inner[0], np.float64).reshape(3, 3)
+    return ((mo @ mi).reshape(9).tolist(), tuple((mo @ np.asarray(inner[1]) + np.asarray(outer[1])).tolist()))
+
+
+class Scene:
+    """A render3d.Object compiled to a device scene (m3d_scene)."""
+
+    def __init__(self, obj, ctx=None):
+        self.ctx = ctx or N.default_context()
+        L = N.lib()
+        b = C.c_void_p()
+        N.check(L.m3d_scene_builder_create(self.ctx.h, C.byref(b)))
+        self.materials = []      # python material objects, index == device index
+        self._mat_index = {}
+        self.objects = []        # leaf objects in device order
+        try:
+            self._add(b, obj, None)
+            self.h = C.c_void_p()
+            N.check(L.m3d_scene_build(b, C.c_uint32(0), C.byref(self.h)))
+        finally:
+            L.m3d_scene_builder_destroy(b)
+
+    def _material(self, b, m):
+        if id(m) in self._mat_index:
+            return self._mat_index[id(m)]
+        d = material_desc(m, lambda sub: self._material(b, sub))
+        idx = C.c_int32(-1)
+        N.check(N.lib().m3d_scene_add_material(b, C.byref(d), C.byref(idx)))
+        self._mat_index[id(m)] = idx.value
+        self.materials.append(m)
+        assert idx.value == len(self.materials) - 1
+        return idx.value
+
+    def _add(self, b, obj, xf):
+        L = N.lib()
+        if isinstance(obj, (list, tuple)):
+            for o in obj:
+                self._add(b, o, xf)
+            return
+        if isinstance(obj, _Transformed):
+            self._add(b, obj.Object, _compose(xf, (obj.Matrix, obj.Offset)))
+            return
+        if not isinstance(obj, ColliderObject):
+            raise UnsupportedError("object type %s is not supported on the GPU path" % type(obj).__name__)
+        mat = self._material(b, obj.Material)
+        flags = N.OBJ_FLIP_NORMAL if obj.FlipNormals else 0
+        t = None
+        if xf is not None:
+            t = N.Transform()
+            t.matrix[:] = [1, 0, 0, 0, 1, 0, 0, 0, 1] if xf[0] is None else xf[0]
+            t.offset[:] = list(xf[1])
+        tp = C.byref(t) if t is not None else None
+        c = obj.Collider
+        idx = C.c_int32(-1)
+        if isinstance(c, Sphere):
+            N.check(L.m3d_scene_add_sphere(b, _d3(c.Center), C.c_double(c.Radius), C.c_int32(mat),
+                                           C.c_uint32(flags), tp, C.byref(idx)))
+        elif isinstance(c, Rect):
+            N.check(L.m3d_scene_add_rect(b, _d3(c.MinVal), _d3(c.MaxVal), C.c_int32(mat),
+                                         C.c_uint32(flags), tp, C.byref(idx)))
+        elif isinstance(c, Cylinder):
+            N.check(L.m3d_scene_add_cylinder(b, _d3(c.P1), _d3(c.P2), C.c_double(c.Radius), C.c_int32(mat),
+                                             C.c_uint32(flags), tp, C.byref(idx)))
+        elif isinstance(c, MeshCollider) or isinstance(c, np.ndarray):
+            tris = c.triangles if isinstance(c, MeshCollider) else c
+            vn = c.vertex_normals if isinstance(c, MeshCollider) else None
+            tris = np.ascontiguousarray(np.asarray(tris, np.float32).reshape(-1, 9))
+            vn = None if vn is None else np.ascontiguousarray(np.asarray(vn, np.float32).reshape(-1, 9))
+            N.check(L.m3d_scene_add_mesh(b, _p(tris, f32p), C.c_int64(tris.shape[0]), _p(vn, f32p),
+                                         C.c_int32(mat), C.c_uint32(flags), tp, C.byref(idx)))
+        else:
+            raise UnsupportedError("collider type %s is not supported on the GPU path" % type(c).__name__)
+        self.objects.append(obj)
+
+    def close(self):
+        if getattr(self, "h", None):
+            N.lib().m3d_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def Min(self):
+        return self._bounds()[0]
+
+    def Max(self):
+        return self._bounds()[1]
+
+    def _bounds(self):
+        mn, mx = (C.c_double * 3)(), (C.c_double * 3)()
+        N.check(N.lib().m3d_scene_bounds(self.h, mn, mx))
+        return tuple(mn), tuple(mx)
+
+    def Cast(self, origins, directions, counters=False):
+        """Batched Object.Cast (object.go:141-153): dict(t, obj, prim, normal)."""
+        org = np.ascontiguousarray(np.asarray(origins, np.float32).reshape(-1, 3))
+        dr = np.ascontiguousarray(np.asarray(directions, np.float32).reshape(-1, 3))
+        n = org.shape[0]
+        t = np.zeros(n, np.float32)
+        obj = np.full(n, -1, np.int32)
+        prim = np.full(n, -1, np.int32)
+        normal = np.zeros((n, 3), np.float32)
+        stats = N.Stats()
+        N.check(N.lib().m3d_scene_cast(self.h, _p(org, f32p), _p(dr, f32p), C.c_int64(n), _p(t, f32p),
+                                       _p(obj, i32p), _p(prim, i32p), _p(normal, f32p),
+                                       C.c_uint32(N.TRACE_COUNTERS if counters else 0), C.byref(stats)))
+        return dict(t=t, obj=obj, prim=prim, normal=normal,
+                    stats={k: getattr(stats, k) for k, _ in stats._fields_})
+
+
+def _as_scene(obj, ctx=None):
+    if isinstance(obj, Scene):
+        return obj
+    cached = getattr(obj, "_m3d_scene", None) if not isinstance(obj, (list, tuple)) or isinstance(obj, JoinedObject) else None
+    if cached is not None:
+        return cached
+    sc = Scene(obj, ctx)
+    try:
+        obj._m3d_scene = sc
+    except Exception:
+        pass
+    return sc
+
+
+# ---- camera (camera.go) --------------------------------------------------------------------
+DefaultFieldOfView = math.pi / 2
+
+
+@dataclass
+class Camera:
+    Origin: Vec
+    ScreenX: Vec
+    ScreenY: Vec
+    FieldOfView: float
+
+    def _c(self):
+        c = N.Camera()
+        c.origin[:] = list(self.Origin)
+        c.screen_x[:] = list(self.ScreenX)
+        c.screen_y[:] = list(self.ScreenY)
+        c.field_of_view = self.FieldOfView
+        return c
+
+
+def NewCameraAt(source, dest, fov=0.0):
+    """render3d.NewCameraAt (camera.go:48-66), float64 host arithmetic."""
+    if fov == 0:
+        fov = DefaultFieldOfView
+    s, d = np.asarray(source, np.float64), np.asarray(dest, np.float64)
+    z = d - s
+    z = z * (1 / math.sqrt(float(z @ z)))
+    x = np.array([z[1], -z[0], 0.0])
+    if math.sqrt(float(x @ x)) < 1e-5:
+        ex = np.array([1.0, 0.0, 0.0])
+        x = ex - z * float(z @ ex)  # X(1).ProjectOut(zAxis); z is unit
+    x = x * (1 / math.sqrt(float(x @ x)))
+    y = np.cross(z, x)
+    return Camera(tuple(s.tolist()), tuple(x.tolist()), tuple(y.tolist()), float(fov))
+
+
+@dataclass
+class PointLight:
+    Origin: Vec
+    Color: Vec
+    QuadDropoff: bool = False
+
+    def _c(self):
+        l = N.PointLight()
+        l.origin[:] = list(self.Origin)
+        l.color[:] = list(self.Color)
+        l.quad_dropoff = 1 if self.QuadDropoff else 0
+        return l
+
+
+class Image:
+    """render3d.Image (image.go:17-47): Data is [Height, Width, 3] linear RGB."""
+
+    def __init__(self, width, height):
+        self.Width, self.Height = int(width), int(height)
+        self.Data = np.zeros((self.Height, self.Width, 3), np.float32)
+
+    def RGBA8(self):
+        """8-bit sRGB like Image.RGBA (image.go:125-145, light.go:41-47)."""
+        c = np.clip(self.Data.astype(np.float64), 0.0, 1.0)
+        s = np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055)
+        return (s * (256.0 - 0.001)).astype(np.uint8)
+
+
+def _lights(lights):
+    arr = (N.PointLight * max(1, len(lights)))(*[l._c() for l in lights])
+    return arr
+
+
+@dataclass
+class RayCaster:
+    """render3d.RayCaster (raycast.go:9-39)."""
+    Camera: Camera = None
+    Lights: List[PointLight] = field(default_factory=list)
+
+    def Render(self, img: Image, obj, partition=None):
+        sc = _as_scene(obj)
+        cam = self.Camera._c()
+        data = np.ascontiguousarray(img.Data, np.float32)
+        stats = N.Stats()
+        part = None
+        if partition is not None:
+            part = N.Partition(int(partition[0]), int(partition[1]), 0)
+        N.check(N.lib().m3d_render_raycast(sc.h, C.byref(cam), _lights(self.Lights), C.c_int32(len(self.Lights)),
+                                           C.c_int32(img.Width), C.c_int32(img.Height),
+                                           C.byref(part) if part is not None else None,
+                                           _p(data, f32p), C.byref(stats)))
+        img.Data = data
+        return {k: getattr(stats, k) for k, _ in stats._fields_}
