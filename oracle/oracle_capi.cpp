@@ -364,4 +364,21 @@ void orc_material_sample_dest(void *s, int32_t mat, uint64_t seed, const double 
   }
 }
 
+// Batched material evaluation (restated material_test.go integrals run over many directions).
+void orc_material_eval_batch(void *s, int32_t mat, const double normal[3], const double *sources,
+                             const double *dests, int64_t n, double *bsdf /*n*3*/,
+                             double *source_density /*n*/, double *dest_density /*n*/) {
+  auto *sc = (Scene *)s;
+  MatRef m;
+  m.tab = &sc->mats;
+  m.index = mat;
+  for (int64_t i = 0; i < n; i++) {
+    V3 src = v3(sources + 3 * i), dst = v3(dests + 3 * i);
+    V3 b = mat_bsdf(m, mat, v3(normal), src, dst);
+    for (int k = 0; k < 3; k++) bsdf[i * 3 + k] = b[k];
+    source_density[i] = mat_source_density(m, mat, v3(normal), src, dst);
+    dest_density[i] = mat_dest_density(m, mat, v3(normal), src, dst);
+  }
+}
+
 }  // extern "C"

@@ -323,6 +323,15 @@ class Scene:
                                 _p(bsdf, f64p), C.byref(sd), C.byref(dd))
         return bsdf, sd.value, dd.value
 
+    def material_eval_batch(self, mat, normal, sources, dests):
+        sources = np.ascontiguousarray(sources, np.float64)
+        dests = np.ascontiguousarray(np.broadcast_to(dests, sources.shape), np.float64)
+        n = sources.shape[0]
+        bsdf, sd, dd = np.zeros((n, 3)), np.zeros(n), np.zeros(n)
+        lib().orc_material_eval_batch(self.h, C.c_int32(mat), _d3(normal), _p(sources, f64p), _p(dests, f64p),
+                                      C.c_int64(n), _p(bsdf, f64p), _p(sd, f64p), _p(dd, f64p))
+        return bsdf, sd, dd
+
     def material_sample_source(self, mat, seed, normal, dest, n):
         out = np.zeros((n, 3))
         lib().orc_material_sample_source(self.h, C.c_int32(mat), C.c_uint64(seed), _d3(normal),
