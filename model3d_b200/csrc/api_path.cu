@@ -1,0 +1,249 @@
+// C ABI: (*RecursiveRayTracer).Render (include/m3d.h, m3d_render_path*).
+// Replaces render3d/raytrace.go:98-229 + render3d/ray_renderer.go:25-151 with a wavefront
+// pipeline: raygen -> [trace -> shade/compact (-> shadow trace -> shadow resolve)] x depth
+// -> flush, batch by batch, all enqueued on one stream with device-side queue lengths
+// (no host round trip between bounces).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "api_common.h"
+#include "path.h"
+#include "scene.h"
+
+using namespace m3d;
+
+namespace m3d {
+const DeviceScene &scene_device(const m3d_scene *s);
+m3d_ctx *scene_ctx(const m3d_scene *s);
+DeviceCamera device_camera(const m3d_camera &c, int W, int H);
+const std::vector<m3d_material_desc> &scene_materials(const m3d_scene *s);
+}  // namespace m3d
+
+namespace {
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Carves the path-state arrays out of one scratch allocation.
+int32_t carve_path_buffers(m3d_ctx *ctx, int64_t cap, int num_lights, PathBuffers &b) {
+  const size_t c = (size_t)cap, nl = (size_t)num_lights;
+  size_t total = 0;
+  auto take = [&](size_t bytes) {
+    const size_t off = total;
+    total += align256(bytes);
+    return off;
+  };
+  size_t o_org[2], o_dir[2], o_skip[2], o_queue[2];
+  for (int i = 0; i < 2; i++) {
+    o_org[i] = take(c * 16);
+    o_dir[i] = take(c * 16);
+    o_skip[i] = take(c * 4);
+    o_queue[i] = take(c * 4);
+  }
+  const size_t o_raw = take(c * 16), o_thr = take(c * 16), o_acc = take(c * 16);
+  const size_t o_sorg = take(c * nl * 16), o_sdir = take(c * nl * 16), o_sraw = take(c * nl * 16),
+               o_spay = take(c * nl * 16), o_sskip = take(c * nl * 4);
+  const size_t o_counts = take(64);
+  M3D_CUDA(ctx->scratch[4].reserve(total));
+  char *p = ctx->scratch[4].as<char>();
+  b.cap = cap;
+  for (int i = 0; i < 2; i++) {
+    b.org[i] = (float4 *)(p + o_org[i]);
+    b.dir[i] = (float4 *)(p + o_dir[i]);
+    b.skip[i] = (int32_t *)(p + o_skip[i]);
+    b.queue[i] = (int32_t *)(p + o_queue[i]);
+  }
+  b.raw = (float4 *)(p + o_raw);
+  b.thr = (float4 *)(p + o_thr);
+  b.accum = (float4 *)(p + o_acc);
+  b.sorg = (float4 *)(p + o_sorg);
+  b.sdir = (float4 *)(p + o_sdir);
+  b.sraw = (float4 *)(p + o_sraw);
+  b.spay = (float4 *)(p + o_spay);
+  b.sskip = (int32_t *)(p + o_sskip);
+  b.counts = (int *)(p + o_counts);
+  b.ray_total = (unsigned long long *)(p + o_counts + 32);
+  return M3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
+                               int32_t num_lights, const m3d_path_params *params, int32_t width,
+                               int32_t height, const m3d_partition *part, int32_t sample_count,
+                               void *d_rgb_sum, void *d_rgb_sumsq, void *stream, m3d_stats *stats) {
+  if (!scene || !cam || !params || width <= 0 || height <= 0 || !d_rgb_sum || num_lights < 0 ||
+      (num_lights > 0 && !lights) || sample_count < 0)
+    return fail(M3D_ERR_INVALID_ARG, "m3d_render_path: bad arguments");
+  if (params->num_focus_points < 0 || params->num_focus_points > M3D_MAX_FOCUS_POINTS)
+    return fail(M3D_ERR_UNSUPPORTED, "at most %d focus points are supported", M3D_MAX_FOCUS_POINTS);
+  if (params->min_samples != 0 && params->max_stddev != 0)
+    return fail(M3D_ERR_UNSUPPORTED,
+                "adaptive sampling (MinSamples/MaxStddev) is not supported on the GPU path: render "
+                "fixed-size sample shards and test convergence on the reduced sums");
+  if (params->max_depth < 0 || params->max_depth > 1000) return fail(M3D_ERR_INVALID_ARG, "bad max_depth");
+  if ((int64_t)width * height > (int64_t)0x7fffffff / 4) return fail(M3D_ERR_INVALID_ARG, "frame too large");
+  m3d_ctx *ctx = scene_ctx(scene);
+  const DeviceScene &sc = scene_device(scene);
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  int row_begin = 0, row_end = height;
+  int64_t sample_begin = 0;
+  if (part) {
+    if (!(part->row_begin == 0 && part->row_end == 0)) {
+      row_begin = part->row_begin;
+      row_end = part->row_end;
+      if (row_begin < 0 || row_end > height || row_begin > row_end)
+        return fail(M3D_ERR_INVALID_ARG, "bad row partition [%d,%d) of %d rows", row_begin, row_end, height);
+    }
+    sample_begin = part->sample_begin;
+    if (sample_begin < 0 || sample_begin + sample_count > (int64_t)0xffffffffll)
+      return fail(M3D_ERR_INVALID_ARG, "sample range out of bounds");
+  }
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  const int64_t npix = (int64_t)width * (row_end - row_begin);
+  if (npix == 0 || sample_count == 0) return M3D_OK;
+
+  DevicePathParams pp;
+  std::memset(&pp, 0, sizeof(pp));
+  pp.max_depth = params->max_depth;
+  pp.num_focus = params->num_focus_points;
+  pp.num_lights = num_lights;
+  pp.cutoff = (float)params->cutoff;
+  pp.antialias = (float)params->antialias;
+  pp.seed = params->seed;
+  for (int i = 0; i < pp.num_focus; i++) {
+    const m3d_focus_point &f = params->focus[i];
+    if (f.kind != M3D_FOCUS_PHONG && f.kind != M3D_FOCUS_SPHERE)
+      return fail(M3D_ERR_UNSUPPORTED, "focus point kind %d is not supported on the GPU path", f.kind);
+    pp.focus[i].kind = f.kind;
+    for (int k = 0; k < 3; k++) pp.focus[i].target[k] = (float)f.target[k];
+    pp.focus[i].alpha = (float)f.alpha;
+    pp.focus[i].radius = (float)f.radius;
+    pp.focus[i].prob = (float)f.prob;
+    pp.focus[i].mask = f.material_mask;
+  }
+  if (pp.cutoff > 1.f) return M3D_OK;  // recurse() returns black at depth 0 (raytrace.go:139-142)
+
+  // batch geometry: nP pixels x S samples <= cap slots
+  const int64_t kMaxSlots = (int64_t)1 << 22;
+  const int64_t total = npix * sample_count;
+  const int64_t cap = std::min(total, std::max<int64_t>(kMaxSlots, 1));
+  const int64_t nP_max = std::min(npix, cap);
+  PathBuffers buf;
+  if (int32_t rc = carve_path_buffers(ctx, cap, num_lights, buf)) return rc;
+  DevicePointLight *d_lights = nullptr;
+  std::vector<DevicePointLight> hl(num_lights);
+  if (num_lights) {
+    M3D_CUDA(ctx->scratch[5].reserve(hl.size() * sizeof(DevicePointLight)));
+    d_lights = ctx->scratch[5].as<DevicePointLight>();
+    for (int i = 0; i < num_lights; i++) {
+      for (int k = 0; k < 3; k++) {
+        hl[i].origin[k] = (float)lights[i].origin[k];
+        hl[i].color[k] = (float)lights[i].color[k];
+      }
+      hl[i].quad_dropoff = lights[i].quad_dropoff;
+    }
+    M3D_CUDA(cudaMemcpyAsync(d_lights, hl.data(), hl.size() * sizeof(DevicePointLight), cudaMemcpyHostToDevice, s));
+  }
+  M3D_CUDA(cudaMemsetAsync(buf.ray_total, 0, sizeof(unsigned long long), s));
+  const DeviceCamera dc = device_camera(*cam, width, height);
+
+  GpuTimer tm;
+  tm.start(s);
+  int64_t launches = 0;
+  for (int64_t p0 = 0; p0 < npix; p0 += nP_max) {
+    const int64_t nP = std::min(nP_max, npix - p0);
+    const int64_t S_max = std::max<int64_t>(1, cap / nP);
+    for (int64_t s0 = 0; s0 < sample_count; s0 += S_max) {
+      PathBatch b;
+      b.W = width;
+      b.pix0 = (int32_t)((int64_t)row_begin * width + p0);
+      b.nP = (int32_t)nP;
+      b.S = (int32_t)std::min<int64_t>(S_max, sample_count - s0);
+      b.sample0 = (uint32_t)(sample_begin + s0);
+      const int64_t n = (int64_t)b.nP * b.S;
+      launch_path_raygen(dc, pp, b, buf, s);
+      launches++;
+      int cur = 0;
+      for (int depth = 0; depth <= pp.max_depth; depth++) {
+        TraceLaunch t;
+        t.org_tmin = buf.org[cur];
+        t.dir_tmax = buf.dir[cur];
+        t.n = n;
+        t.n_ptr = buf.counts + cur;
+        t.hit0 = buf.raw;
+        t.hit1 = nullptr;
+        t.refine = false;
+        t.counters = nullptr;
+        t.skip_tris = buf.skip[cur];
+        t.ray_counter = next_work_counter(ctx);
+        if (!t.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
+        launch_trace_bvh_only(sc.bvh, t, s);
+        launch_path_shade(sc, pp, d_lights, b, buf, cur, depth, s);
+        launches += 2;
+        if (num_lights > 0) {
+          TraceLaunch ts;
+          ts.org_tmin = buf.sorg;
+          ts.dir_tmax = buf.sdir;
+          ts.n = n * num_lights;
+          ts.n_ptr = buf.counts + 2;
+          ts.hit0 = buf.sraw;
+          ts.hit1 = nullptr;
+          ts.refine = false;
+          ts.counters = nullptr;
+          ts.skip_tris = buf.sskip;
+          ts.ray_counter = next_work_counter(ctx);
+          if (!ts.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
+          launch_trace_bvh_only(sc.bvh, ts, s);
+          launch_path_shadow_resolve(sc, pp, buf, cur, s);
+          launches += 2;
+        }
+        // the consumed queue becomes the next output queue
+        M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
+        cur ^= 1;
+      }
+      launch_path_flush(b, buf, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
+      launches++;
+    }
+  }
+  tm.stop(s);
+  // host-side tables (lights) must outlive the async copies; stats need the counters
+  unsigned long long rays = 0;
+  M3D_CUDA(cudaMemcpyAsync(&rays, buf.ray_total, sizeof(rays), cudaMemcpyDeviceToHost, s));
+  M3D_CUDA(cudaStreamSynchronize(s));
+  M3D_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->rays = (int64_t)rays;
+    stats->kernel_ms = tm.ms();
+    stats->launches = launches;
+  }
+  return M3D_OK;
+}
+
+int32_t m3d_render_path(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
+                        int32_t num_lights, const m3d_path_params *params, int32_t width, int32_t height,
+                        const m3d_partition *part, int32_t sample_count, float *rgb_sum, float *rgb_sumsq,
+                        m3d_stats *stats) {
+  if (!scene || !rgb_sum || width <= 0 || height <= 0)
+    return fail(M3D_ERR_INVALID_ARG, "m3d_render_path: bad arguments");
+  m3d_ctx *ctx = scene_ctx(scene);
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)width * height * 3 * sizeof(float);
+  M3D_CUDA(ctx->scratch[3].reserve(bytes * 2));
+  float *d_sum = ctx->scratch[3].as<float>();
+  float *d_sq = rgb_sumsq ? d_sum + (size_t)width * height * 3 : nullptr;
+  M3D_CUDA(cudaMemsetAsync(d_sum, 0, bytes * (rgb_sumsq ? 2 : 1), ctx->stream));
+  int32_t rc = m3d_render_path_device(scene, cam, lights, num_lights, params, width, height, part, sample_count,
+                                      d_sum, d_sq, ctx->stream, stats);
+  if (rc != M3D_OK) return rc;
+  M3D_CUDA(cudaMemcpyAsync(rgb_sum, d_sum, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (rgb_sumsq) M3D_CUDA(cudaMemcpyAsync(rgb_sumsq, d_sq, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  M3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (stats) stats->d2h_bytes = (int64_t)(bytes * (rgb_sumsq ? 2 : 1));
+  return M3D_OK;
+}
+
+}  // extern "C"

@@ -24,6 +24,8 @@ struct TraceLaunch {
   unsigned long long *counters;     // optional device 2 x u64 (nodes, tris)
   unsigned long long *ray_counter;  // device u64 work counter of the persistent kernel
   const int32_t *skip_tris = nullptr;  // optional per ray: leaf-order triangle index to ignore
+  const int *n_ptr = nullptr;          // optional device count (<= n): wavefront queues whose
+                                       // length is only known on the device
 };
 
 // BVH traversal only: hit0 = (t_f32, 0, 0, bits(leaf-order triangle index | -1))

@@ -157,4 +157,230 @@ __device__ __forceinline__ V3f shade_collision(const DevicePointLight &l, V3f n,
   return color * density;
 }
 
+// ---- random numbers: Philox4x32-10, counter based ------------------------------------------
+// The reference draws from Go's math/rand per goroutine (concurrency.go:33-35), so parity is
+// statistical.  Here every (pixel, sample) owns a Philox stream keyed by the seed: the image
+// is independent of how samples are partitioned over GPUs or batches.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+struct Rng {
+  uint2 key;
+  uint32_t pixel, sample, block, domain;
+  uint4 buf;
+  int have;
+  __device__ __forceinline__ void init(uint64_t seed, uint32_t pixel_, uint32_t sample_, uint32_t domain_) {
+    key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    pixel = pixel_;
+    sample = sample_;
+    domain = domain_;
+    block = 0;
+    have = 0;
+  }
+  __device__ __forceinline__ uint32_t bits() {
+    if (have == 0) {
+      buf = philox4x32_10(make_uint4(pixel, sample, block++, domain), key);
+      have = 4;
+    }
+    const uint32_t r = have == 4 ? buf.x : (have == 3 ? buf.y : (have == 2 ? buf.z : buf.w));
+    have--;
+    return r;
+  }
+  // uniform in [0, 1) with 24 bits
+  __device__ __forceinline__ float f32() { return (float)(bits() >> 8) * 5.9604644775390625e-8f; }
+};
+
+// ---- sampling (material.go) ---------------------------------------------------------------
+constexpr float kTwoPi = 6.283185307179586f;
+
+// Tag of the direction a sampler produced: which Dirac lobe(s) of which sub-material.
+constexpr int kLobeRefract = 1, kLobeReflect = 2;  // bits 0..1; sub-material index in bits 2..3
+
+// material.go:136-151
+__device__ __forceinline__ V3f lambert_sample(Rng &g, V3f normal) {
+  const float u = g.f32();
+  const float cos_lat = sqrtf(u), sin_lat = sqrtf(1.f - u);
+  float sl, cl;
+  sincosf(g.f32() * kTwoPi, &sl, &cl);
+  V3f xa, za;
+  ortho_basis(normal, xa, za);
+  const V3f lon_point = xa * cl + za * sl;
+  return normal * -cos_lat + lon_point * sin_lat;
+}
+// material.go:153-159
+__device__ __forceinline__ float lambert_density(V3f normal, V3f source) {
+  const float nd = -dot(normal, source);
+  return nd < 0.f ? 0.f : 4.f * nd;
+}
+// material.go:274-323
+__device__ __forceinline__ V3f sample_around_direction(Rng &g, float alpha, V3f direction) {
+  V3f xa, za;
+  ortho_basis(direction, xa, za);
+  const float u = g.f32(), v = g.f32();
+  float sl, cl;
+  sincosf(kTwoPi * u, &sl, &cl);
+  const float cos_lat = powf(v, 1.f / (alpha + 1.f));
+  const float sin_lat = sqrtf(fmaxf(0.f, 1.f - cos_lat * cos_lat));
+  const V3f lon_point = xa * cl + za * sl;
+  return direction * cos_lat + lon_point * sin_lat;
+}
+// material.go:328-335: 2(a+1) / v^(1/(a+1) - 1) with v = d^(a+1), i.e. 2(a+1) d^a
+__device__ __forceinline__ float density_around_direction(float alpha, V3f direction, V3f sample) {
+  const float d = dot(direction, sample);
+  if (d < 0.f) return 0.f;
+  return 2.f * (alpha + 1.f) * powf(d, alpha);
+}
+
+// material.go:360-378; tir: total internal reflection (the result is the mirror direction)
+__device__ __forceinline__ V3f refract_dir(float ior, V3f normal, V3f source, bool &tir) {
+  V3f sine_part = source - normal * dot(normal, source);  // ProjectOut (normal is unit)
+  float sine_scale = ior;
+  V3f cosine_part = normal;
+  if (dot(normal, source) < 0.f) {
+    sine_scale = 1.f / sine_scale;
+    cosine_part = cosine_part * -1.f;
+  }
+  sine_part = sine_part * sine_scale;
+  const float sine_norm = norm(sine_part);
+  tir = sine_norm > 1.f;
+  if (tir) return reflect_about(normal, source) * -1.f;
+  return sine_part + cosine_part * sqrtf(1.f - sine_norm * sine_norm);
+}
+__device__ __forceinline__ V3f refract_inverse(float ior, V3f normal, V3f dest, bool &tir) {
+  return refract_dir(ior, normal, dest * -1.f, tir) * -1.f;
+}
+// material.go:384-389
+__device__ __forceinline__ float reflect_amount(float ior, V3f normal, V3f source) {
+  const float x = (ior - 1.f) / (ior + 1.f);
+  const float r0 = x * x;
+  const float c = 1.f - fabsf(dot(normal, source));
+  return r0 * (1.f - r0) * (c * c * c * c * c);
+}
+
+// SampleSource of a non-joined material; lobe: Dirac lobes the direction belongs to.
+__device__ __forceinline__ V3f simple_sample_source(const DeviceMaterial &d, V3f diffuse, Rng &g, V3f normal,
+                                                    V3f dest, int &lobe) {
+  lobe = 0;
+  if (d.kind == M3D_MAT_LAMBERT) return lambert_sample(g, normal);
+  if (d.kind == M3D_MAT_PHONG) {  // material.go:230-236,251-256
+    if (is_zero(diffuse) || (g.bits() & 1u) == 0u) {
+      const V3f reflection = reflect_about(normal, dest) * -1.f;
+      return sample_around_direction(g, d.alpha, reflection);
+    }
+    return lambert_sample(g, normal);
+  }
+  // RefractMaterial material.go:425-439
+  bool tir;
+  const V3f refracted = refract_inverse(d.ior, normal, dest, tir);
+  if (is_zero(v3f(d.specular))) {
+    lobe = kLobeRefract;
+    return refracted;
+  }
+  const float refl = reflect_amount(d.ior, normal, dest);
+  if (g.f32() > refl) {
+    lobe = tir ? (kLobeRefract | kLobeReflect) : kLobeRefract;
+    return refracted;
+  }
+  lobe = tir ? (kLobeRefract | kLobeReflect) : kLobeReflect;
+  return reflect_about(normal, dest) * -1.f;
+}
+
+struct Density {
+  float fin;  // finite part
+  float del;  // coefficient of 2/cosineEpsilon
+};
+
+// SourceDensity of a non-joined material for a direction tagged `lobe`
+// (material.go:153-159, 240-247, 441-462).
+__device__ __forceinline__ Density simple_source_density(const DeviceMaterial &d, V3f diffuse, V3f normal,
+                                                         V3f source, V3f dest, int lobe) {
+  Density r;
+  r.fin = 0.f;
+  r.del = 0.f;
+  if (d.kind == M3D_MAT_LAMBERT) {
+    r.fin = lambert_density(normal, source);
+  } else if (d.kind == M3D_MAT_PHONG) {
+    const V3f reflection = reflect_about(normal, dest) * -1.f;
+    const float pw = density_around_direction(d.alpha, reflection, source);
+    r.fin = is_zero(diffuse) ? pw : 0.5f * (pw + lambert_density(normal, source));
+  } else if (d.kind == M3D_MAT_REFRACT) {
+    if (is_zero(v3f(d.specular))) {
+      r.del = (lobe & kLobeRefract) ? 1.f : 0.f;
+    } else {
+      const float refl = reflect_amount(d.ior, normal, dest);
+      r.del = ((lobe & kLobeRefract) ? 1.f - refl : 0.f) + ((lobe & kLobeReflect) ? refl : 0.f);
+    }
+  }
+  return r;
+}
+
+// Dirac part of the BSDF of a non-joined material, as a coefficient of 2/cosineEpsilon
+// (material.go:391-423); the finite part is simple_bsdf().
+__device__ __forceinline__ V3f simple_bsdf_delta(const DeviceMaterial &d, V3f normal, V3f source, V3f dest,
+                                                 int lobe) {
+  if (d.kind != M3D_MAT_REFRACT || lobe == 0) return v3f(0.f, 0.f, 0.f);
+  const float s_refr = 1.f / fmaxf(kCosEps, fabsf(dot(dest, normal)));
+  if (is_zero(v3f(d.specular))) return (lobe & kLobeRefract) ? v3f(d.refract) * s_refr : v3f(0.f, 0.f, 0.f);
+  const float ra = reflect_amount(d.ior, normal, source);
+  V3f r = v3f(0.f, 0.f, 0.f);
+  if (lobe & kLobeRefract) r = r + v3f(d.refract) * ((1.f - ra) * s_refr);
+  if (lobe & kLobeReflect) r = r + v3f(d.specular) * (ra / maximum_cosine(dot(dest, normal), dot(source, normal)));
+  return r;
+}
+
+// Material.SampleSource incl. JoinedMaterial (material.go:573-586); tag = lobe | sub << 2.
+__device__ __forceinline__ V3f mat_sample_source(const DeviceScene &sc, const MatAt &m, Rng &g, V3f normal,
+                                                 V3f dest, int &tag) {
+  const DeviceMaterial &d = sc.materials[m.index];
+  if (d.kind != M3D_MAT_JOINED) return simple_sample_source(d, m.diffuse, g, normal, dest, tag);
+  float p = g.f32();
+  int pick = d.num_sub - 1;
+  for (int i = 0; i < d.num_sub; i++) {
+    p -= d.sub_prob[i];
+    if (p < 0.f) {
+      pick = i;
+      break;
+    }
+  }
+  const DeviceMaterial &s = sc.materials[d.sub[pick]];
+  int lobe;
+  const V3f r = simple_sample_source(s, v3f(s.diffuse), g, normal, dest, lobe);
+  tag = lobe | (pick << 2);
+  return r;
+}
+
+__device__ __forceinline__ Density mat_source_density(const DeviceScene &sc, const MatAt &m, V3f normal,
+                                                      V3f source, V3f dest, int tag) {
+  const DeviceMaterial &d = sc.materials[m.index];
+  if (d.kind != M3D_MAT_JOINED) return simple_source_density(d, m.diffuse, normal, source, dest, tag & 3);
+  Density r;
+  r.fin = 0.f;
+  r.del = 0.f;
+  for (int i = 0; i < d.num_sub; i++) {  // material.go:588-594
+    const DeviceMaterial &s = sc.materials[d.sub[i]];
+    const Density x = simple_source_density(s, v3f(s.diffuse), normal, source, dest, (tag >> 2) == i ? (tag & 3) : 0);
+    r.fin += d.sub_prob[i] * x.fin;
+    r.del += d.sub_prob[i] * x.del;
+  }
+  return r;
+}
+
+__device__ __forceinline__ V3f mat_bsdf_delta(const DeviceScene &sc, const MatAt &m, V3f normal, V3f source,
+                                              V3f dest, int tag) {
+  const DeviceMaterial &d = sc.materials[m.index];
+  if (d.kind != M3D_MAT_JOINED) return simple_bsdf_delta(d, normal, source, dest, tag & 3);
+  const int pick = tag >> 2;
+  if ((tag & 3) == 0 || pick >= d.num_sub) return v3f(0.f, 0.f, 0.f);
+  return simple_bsdf_delta(sc.materials[d.sub[pick]], normal, source, dest, tag & 3);
+}
+
 }  // namespace m3d

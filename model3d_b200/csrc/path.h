@@ -1,0 +1,64 @@
+// Wavefront path tracer: device-side parameter blocks and launch wrappers.
+// Replaces rayRenderer.Render / estimateColor (render3d/ray_renderer.go:25-151) and
+// RecursiveRayTracer.recurse (render3d/raytrace.go:138-229), which the reference runs as one
+// goroutine-scheduled recursion per pixel (render3d/concurrency.go:17-43).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "scene.h"
+
+namespace m3d {
+
+struct DeviceFocus {  // render3d/focus_point.go:30-44, 73-85
+  int32_t kind;       // M3D_FOCUS_PHONG / M3D_FOCUS_SPHERE
+  float target[3];
+  float alpha, radius, prob;
+  uint64_t mask;      // bit i: MaterialFilter(material i) (pre-evaluated by the wrapper)
+};
+
+struct DevicePathParams {
+  int32_t max_depth;
+  int32_t num_focus;
+  int32_t num_lights;
+  float cutoff, antialias;
+  uint64_t seed;
+  DeviceFocus focus[4];
+};
+
+// One batch = nP consecutive pixels (frame-linear index pix0 .. pix0+nP) x S samples
+// (absolute sample indices sample0 .. sample0+S).  Path slot = s * nP + p.
+struct PathBatch {
+  int32_t W;
+  int32_t pix0, nP, S;
+  uint32_t sample0;
+};
+
+// Structure-of-arrays path state, capacity `cap` slots.  Rays / raw hits / skip ids / queue
+// entries are stored in QUEUE order (compacted, ping-pong [2]); throughput and accumulated
+// colour are stored by SLOT and stay in place for the whole batch.
+struct PathBuffers {
+  int64_t cap;
+  float4 *org[2], *dir[2];
+  int32_t *skip[2], *queue[2];
+  float4 *raw;
+  float4 *thr, *accum;
+  // shadow rays towards point lights (num_lights per queue entry, fixed positions)
+  float4 *sorg, *sdir, *sraw, *spay;
+  int32_t *sskip;
+  int *counts;                    // [0],[1]: queue lengths (ping-pong); [2]: shadow rays
+  unsigned long long *ray_total;  // rays cast (statistics)
+};
+
+void launch_path_raygen(const DeviceCamera &cam, const DevicePathParams &pp, const PathBatch &b,
+                        const PathBuffers &buf, cudaStream_t stream);
+// one bounce: resolve hits of queue `cur`, shade, emit shadow rays, sample and enqueue into 1-cur
+void launch_path_shade(const DeviceScene &sc, const DevicePathParams &pp, const DevicePointLight *lights,
+                       const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream);
+void launch_path_shadow_resolve(const DeviceScene &sc, const DevicePathParams &pp, const PathBuffers &buf,
+                                int cur, cudaStream_t stream);
+// per pixel: add the S per-sample colours (and their squares) into the frame accumulators
+void launch_path_flush(const PathBatch &b, const PathBuffers &buf, float *rgb_sum, float *rgb_sumsq,
+                       cudaStream_t stream);
+
+}  // namespace m3d

@@ -1,0 +1,342 @@
+// Wavefront path tracer kernels (sm_100a):
+//   path_raygen_kernel          rayRenderer.Render's per-sample camera ray with antialias
+//                               jitter (render3d/ray_renderer.go:29-31,118-124, camera.go:74-82)
+//   path_shade_kernel           one level of RecursiveRayTracer.recurse (raytrace.go:138-181):
+//                               JoinedObject.Cast closest-of + float64 hit refinement, emission /
+//                               ambient, point-light shadow rays, sampleNextSource /
+//                               sourceDensity with focus points (raytrace.go:183-215,
+//                               focus_point.go:44-177), throughput update, cutoff, and
+//                               ballot/popc compaction of the surviving paths into the next queue
+//   path_shadow_resolve_kernel  shadow test `hit && Scale < 1` (raytrace.go:157-163)
+//   path_flush_kernel           colorSum (+ squares) per pixel (ray_renderer.go:125-127,150)
+// Traversal between the stages is trace_first_hit_kernel (trace_kernels.cu).
+#include "materials.cuh"
+#include "path.h"
+#include "scene_hit.cuh"
+
+namespace m3d {
+
+namespace {
+
+constexpr int kShadeBlock = 128;
+
+__device__ __forceinline__ bool focus_applies(const DeviceFocus &f, int material) {
+  return material < 64 ? ((f.mask >> material) & 1ull) != 0ull : false;
+}
+
+// focus_point.go:155-163
+__device__ __forceinline__ V3f sample_around_uniform(Rng &g, float min_cos, V3f direction) {
+  const float cos_lat = 1.f - g.f32() * (1.f - min_cos);
+  const float sin_lat = sqrtf(fmaxf(0.f, 1.f - cos_lat * cos_lat));
+  float sl, cl;
+  sincosf(g.f32() * kTwoPi, &sl, &cl);
+  V3f xa, za;
+  ortho_basis(direction, xa, za);
+  return direction * cos_lat + (xa * cl + za * sl) * sin_lat;
+}
+
+// Whether focus point f overrides the material's sampler at `point`, and its direction info.
+// PhongFocusPoint (focus_point.go:46-64): falls back when Target == point or the filter
+// rejects; SphereFocusPoint (focus_point.go:87-153): when inside the sphere or rejected.
+__device__ __forceinline__ bool focus_active(const DeviceFocus &f, int material, V3f point, V3f &dir,
+                                             float &min_cos) {
+  if (!focus_applies(f, material)) return false;
+  const V3f diff = point - v3f(f.target);
+  const float d = norm(diff);
+  if (f.kind == M3D_FOCUS_PHONG) {
+    if (d == 0.f) return false;
+    dir = diff * (1.f / d);
+    min_cos = 0.f;
+    return true;
+  }
+  if (d < f.radius) return false;
+  const float ratio = f.radius / d;
+  min_cos = sqrtf(fmaxf(0.f, 1.f - ratio * ratio));
+  dir = diff * (1.f / d);
+  return true;
+}
+
+__device__ __forceinline__ float focus_density(const DeviceFocus &f, V3f dir, float min_cos, V3f source) {
+  if (f.kind == M3D_FOCUS_PHONG) return density_around_direction(f.alpha, dir, source);
+  // focus_point.go:172-177
+  return dot(dir, source) < min_cos ? 0.f : 2.f / (1.f - min_cos);
+}
+
+__global__ void __launch_bounds__(256)
+path_raygen_kernel(DeviceCamera cam, DevicePathParams pp, PathBatch b, PathBuffers buf) {
+  const int64_t n = (int64_t)b.nP * b.S;
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot == 0) {
+    buf.counts[0] = (int)n;
+    buf.counts[1] = 0;
+    buf.counts[2] = 0;
+  }
+  if (slot >= n) return;
+  const int p = (int)(slot % b.nP), s = (int)(slot / b.nP);
+  const int pix = b.pix0 + p;
+  const int x = pix % b.W, y = pix / b.W;
+  double fx = (double)x, fy = (double)y;
+  if (pp.antialias != 0.f) {  // ray_renderer.go:118-124
+    Rng g;
+    g.init(pp.seed, (uint32_t)pix, b.sample0 + (uint32_t)s, 0xA11A5u);
+    fx += (double)(pp.antialias * (g.f32() - 0.5f));
+    fy += (double)(pp.antialias * (g.f32() - 0.5f));
+  }
+  fx = (fx - cam.cx) / cam.cx;
+  fy = (fy - cam.cy) / cam.cy;
+  buf.org[0][slot] = make_float4((float)cam.origin[0], (float)cam.origin[1], (float)cam.origin[2], 0.f);
+  buf.dir[0][slot] = make_float4((float)(cam.x[0] * fx + cam.y[0] * fy + cam.z[0]),
+                                 (float)(cam.x[1] * fx + cam.y[1] * fy + cam.z[1]),
+                                 (float)(cam.x[2] * fx + cam.y[2] * fy + cam.z[2]), INFINITY);
+  buf.skip[0][slot] = -1;
+  buf.queue[0][slot] = (int32_t)slot;
+  buf.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+  buf.accum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(kShadeBlock)
+path_shade_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *__restrict__ lights, PathBatch b,
+                  PathBuffers buf, int cur, int depth) {
+  const int n = buf.counts[cur];
+  const unsigned lane = threadIdx.x & 31u;
+  const int warps_total = (gridDim.x * kShadeBlock) >> 5;
+  const int warp_id = (blockIdx.x * kShadeBlock + threadIdx.x) >> 5;
+  const float4 *__restrict__ org_in = buf.org[cur];
+  const float4 *__restrict__ dir_in = buf.dir[cur];
+  const int32_t *__restrict__ skip_in = buf.skip[cur];
+  const int32_t *__restrict__ queue_in = buf.queue[cur];
+  const int nxt = cur ^ 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(buf.ray_total, (unsigned long long)n);
+    buf.counts[2] = n * pp.num_lights;
+  }
+
+  for (int base = warp_id * 32; base < n; base += warps_total * 32) {
+    const int q = base + (int)lane;
+    bool alive = false;
+    int slot = 0, surf = -1;
+    V3f point = v3f(0.f, 0.f, 0.f), next_dir = v3f(0.f, 0.f, 1.f);
+    float4 thr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < n) {
+      slot = queue_in[q];
+      const float4 o = __ldcs(org_in + q), d = __ldcs(dir_in + q), raw = __ldcs(buf.raw + q);
+      const SceneHit h = resolve_scene_hit(sc, o, d, raw, skip_in[q], true);
+      if (pp.num_lights > 0 && h.obj < 0) {
+        // no shadow rays for a miss: give the slots an empty parameter interval
+        for (int l = 0; l < pp.num_lights; l++) {
+          const size_t si = (size_t)q * pp.num_lights + l;
+          buf.sorg[si] = make_float4(0.f, 0.f, 0.f, 1.f);
+          buf.sdir[si] = make_float4(0.f, 0.f, 1.f, -1.f);
+          buf.sskip[si] = -1;
+          buf.spay[si] = make_float4(0.f, 0.f, 0.f, __int_as_float(slot));
+        }
+      }
+      if (h.obj >= 0) {
+        const V3f org = v3f(o.x, o.y, o.z), dir = v3f(d.x, d.y, d.z), nrm = v3f(h.nx, h.ny, h.nz);
+        point = org + dir * h.t;
+        surf = h.surf;
+        const MatAt m = material_at(sc, h.obj, point);
+        const V3f dest = normalize(dir) * -1.f;
+        thr = buf.thr[slot];
+        const V3f tv = v3f(thr.x, thr.y, thr.z);
+        // raytrace.go:150-155
+        V3f color = mat_emission(sc, m);
+        if (depth == 0) color = color + mat_ambient(sc, m);
+        if (!is_zero(color)) {
+          float4 a = buf.accum[slot];
+          a.x += tv.x * color.x;
+          a.y += tv.y * color.y;
+          a.z += tv.z * color.z;
+          buf.accum[slot] = a;
+        }
+        // raytrace.go:156-168: one shadow ray per point light, un-normalised direction,
+        // occluded iff a hit has Scale < 1
+        for (int l = 0; l < pp.num_lights; l++) {
+          const DevicePointLight lt = lights[l];
+          const V3f lo = v3f(lt.origin);
+          const V3f light_dir = lo - point;
+          const V3f brdf = mat_bsdf(sc, m, nrm, normalize(point - lo), dest);
+          const V3f c = shade_collision(lt, nrm, light_dir) * brdf * tv;
+          const size_t si = (size_t)q * pp.num_lights + l;
+          const bool useful = !is_zero(c);
+          buf.sorg[si] = make_float4(point.x, point.y, point.z, useful ? 0.f : 1.f);
+          buf.sdir[si] = make_float4(light_dir.x, light_dir.y, light_dir.z, useful ? 1.f : -1.f);
+          buf.sskip[si] = surf;
+          buf.spay[si] = make_float4(c.x, c.y, c.z, __int_as_float(slot));
+        }
+        if (depth < pp.max_depth) {
+          Rng g;
+          g.init(pp.seed, (uint32_t)(b.pix0 + slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP), (uint32_t)depth);
+          // sampleNextSource (raytrace.go:183-199)
+          V3f source;
+          int tag = 0;
+          int chosen = -1;
+          if (pp.num_focus > 0) {
+            float u = g.f32();
+            for (int i = 0; i < pp.num_focus; i++) {
+              u -= pp.focus[i].prob;
+              if (u < 0.f) {
+                chosen = i;
+                break;
+              }
+            }
+          }
+          bool from_focus = false;
+          if (chosen >= 0) {
+            V3f fdir;
+            float min_cos;
+            if (focus_active(pp.focus[chosen], m.index, point, fdir, min_cos)) {
+              from_focus = true;
+              source = pp.focus[chosen].kind == M3D_FOCUS_PHONG
+                           ? sample_around_direction(g, pp.focus[chosen].alpha, fdir)
+                           : sample_around_uniform(g, min_cos, fdir);
+            }
+          }
+          if (!from_focus) source = mat_sample_source(sc, m, g, nrm, dest, tag);
+          // sourceDensity (raytrace.go:201-215): mixture of focus densities and the material's
+          const Density md = mat_source_density(sc, m, nrm, source, dest, tag);
+          float dens_fin = md.fin, dens_del = md.del;
+          if (pp.num_focus > 0) {
+            float mat_prob = 1.f, fin = 0.f;
+            for (int i = 0; i < pp.num_focus; i++) {
+              V3f fdir;
+              float min_cos;
+              if (focus_active(pp.focus[i], m.index, point, fdir, min_cos)) {
+                fin += pp.focus[i].prob * focus_density(pp.focus[i], fdir, min_cos, source);
+                mat_prob -= pp.focus[i].prob;
+              }
+            }
+            dens_fin = fin + mat_prob * md.fin;
+            dens_del = mat_prob * md.del;
+          }
+          // weight = |cos| / density; mask = BSDF * weight (raytrace.go:170-176).  A direction
+          // drawn from a Dirac lobe carries bsdf and density proportional to 2/cosineEpsilon:
+          // their ratio is taken analytically (the finite parts are 1e-8 relative).
+          const float cosv = fabsf(dot(source, nrm));
+          V3f mask;
+          if (dens_del > 0.f)
+            mask = mat_bsdf_delta(sc, m, nrm, source, dest, tag) * (cosv / dens_del);
+          else
+            mask = mat_bsdf(sc, m, nrm, source, dest) * (dens_fin > 0.f ? cosv / dens_fin : 0.f);
+          const V3f nt = tv * mask;
+          const float mean = (nt.x + nt.y + nt.z) * (1.f / 3.f);
+          // recurse() entry test (raytrace.go:139-142); a zero / non-finite throughput can
+          // never contribute again
+          if (mean >= pp.cutoff && mean > 0.f && mean < INFINITY) {
+            alive = true;
+            thr = make_float4(nt.x, nt.y, nt.z, 0.f);
+            next_dir = source * -1.f;
+          }
+        }
+      }
+    }
+    // compaction: surviving lanes take consecutive positions of the next queue
+    const unsigned live = __ballot_sync(0xffffffffu, alive);
+    if (live) {
+      int pos0 = 0;
+      if (lane == (unsigned)(__ffs(live) - 1)) pos0 = atomicAdd(buf.counts + nxt, __popc(live));
+      pos0 = __shfl_sync(0xffffffffu, pos0, __ffs(live) - 1);
+      if (alive) {
+        const int pos = pos0 + __popc(live & ((1u << lane) - 1u));
+        buf.org[nxt][pos] = make_float4(point.x, point.y, point.z, 0.f);
+        buf.dir[nxt][pos] = make_float4(next_dir.x, next_dir.y, next_dir.z, INFINITY);
+        buf.skip[nxt][pos] = surf;
+        buf.queue[nxt][pos] = slot;
+        buf.thr[slot] = thr;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+path_shadow_resolve_kernel(DeviceScene sc, DevicePathParams pp, PathBuffers buf, int cur) {
+  const int n = buf.counts[cur];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0) atomicAdd(buf.ray_total, (unsigned long long)n * pp.num_lights);
+  if (q >= n) return;
+  float3 add = make_float3(0.f, 0.f, 0.f);
+  int slot = 0;
+  for (int l = 0; l < pp.num_lights; l++) {
+    const size_t si = (size_t)q * pp.num_lights + l;
+    const float4 pay = buf.spay[si];
+    slot = __float_as_int(pay.w);
+    const float4 d = buf.sdir[si];
+    if (d.w < 0.f) continue;
+    const SceneHit h = resolve_scene_hit(sc, buf.sorg[si], d, buf.sraw[si], buf.sskip[si], false);
+    if (h.obj >= 0) continue;  // occluded (tmax == 1 bounds the query)
+    add.x += pay.x;
+    add.y += pay.y;
+    add.z += pay.z;
+  }
+  if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {
+    float4 a = buf.accum[slot];
+    a.x += add.x;
+    a.y += add.y;
+    a.z += add.z;
+    buf.accum[slot] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+path_flush_kernel(PathBatch b, PathBuffers buf, float *__restrict__ rgb_sum, float *__restrict__ rgb_sumsq) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= b.nP) return;
+  float sx = 0.f, sy = 0.f, sz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+  for (int s = 0; s < b.S; s++) {
+    const float4 a = __ldcs(buf.accum + (size_t)s * b.nP + p);
+    sx += a.x;
+    sy += a.y;
+    sz += a.z;
+    qx += a.x * a.x;
+    qy += a.y * a.y;
+    qz += a.z * a.z;
+  }
+  const size_t o = (size_t)(b.pix0 + p) * 3;
+  rgb_sum[o] += sx;
+  rgb_sum[o + 1] += sy;
+  rgb_sum[o + 2] += sz;
+  if (rgb_sumsq) {
+    rgb_sumsq[o] += qx;
+    rgb_sumsq[o + 1] += qy;
+    rgb_sumsq[o + 2] += qz;
+  }
+}
+
+}  // namespace
+
+void launch_path_raygen(const DeviceCamera &cam, const DevicePathParams &pp, const PathBatch &b,
+                        const PathBuffers &buf, cudaStream_t stream) {
+  const int64_t n = (int64_t)b.nP * b.S;
+  if (n <= 0) return;
+  path_raygen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cam, pp, b, buf);
+}
+
+void launch_path_shade(const DeviceScene &sc, const DevicePathParams &pp, const DevicePointLight *lights,
+                       const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream) {
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    int x = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&x, path_shade_kernel, kShadeBlock, 0);
+    blocks_per_sm = x > 0 ? x : 1;
+  }
+  const int64_t n = (int64_t)b.nP * b.S;
+  int64_t grid = (int64_t)device_sm_count() * blocks_per_sm;
+  const int64_t want = (n + kShadeBlock - 1) / kShadeBlock;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  path_shade_kernel<<<(unsigned)grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth);
+}
+
+void launch_path_shadow_resolve(const DeviceScene &sc, const DevicePathParams &pp, const PathBuffers &buf,
+                                int cur, cudaStream_t stream) {
+  if (buf.cap <= 0) return;
+  path_shadow_resolve_kernel<<<(unsigned)((buf.cap + 255) / 256), 256, 0, stream>>>(sc, pp, buf, cur);
+}
+
+void launch_path_flush(const PathBatch &b, const PathBuffers &buf, float *rgb_sum, float *rgb_sumsq,
+                       cudaStream_t stream) {
+  if (b.nP <= 0) return;
+  path_flush_kernel<<<(unsigned)((b.nP + 255) / 256), 256, 0, stream>>>(b, buf, rgb_sum, rgb_sumsq);
+}
+
+}  // namespace m3d

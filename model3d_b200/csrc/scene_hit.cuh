@@ -1,0 +1,297 @@
+// Device functions shared by the scene-level kernels: analytic shapes in float64
+// (model3d/shapes.go:35-93,177-247,601-705,816-856), the float64 re-evaluation of the
+// winning triangle (model3d/primitives.go:27-33,207-249,508-516) and JoinedObject's
+// closest-of rule (render3d/object.go:141-153).
+#pragma once
+#include "scene.h"
+#include "trace_core.cuh"
+
+namespace m3d {
+
+struct D3 {
+  double x, y, z;
+};
+__device__ __forceinline__ D3 d3(double x, double y, double z) {
+  D3 r;
+  r.x = x;
+  r.y = y;
+  r.z = z;
+  return r;
+}
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return d3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double dnorm(D3 a) { return sqrt(ddot(a, a)); }
+__device__ __forceinline__ D3 dnormalize(D3 a) { return a * (1.0 / dnorm(a)); }
+__device__ __forceinline__ double comp(D3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// Every analytic test takes t_floor: hits with t < t_floor are ignored (0 for primary rays;
+// a small positive value when the ray starts on this very shape, standing in for the
+// reference's 1e-8 origin offset which float32 origins cannot express).
+
+// shapes.go:52-93 (first root >= 0; discriminant <= 0 misses; outward normal)
+__device__ inline bool sphere_hit(const DeviceShape &s, D3 o, D3 d, double t_floor, double &t, D3 &n) {
+  const D3 c = d3(s.p0[0], s.p0[1], s.p0[2]);
+  const D3 oc = o - c;
+  const double a = ddot(d, d), b = 2 * ddot(d, oc), cc = ddot(oc, oc) - s.radius * s.radius;
+  const double disc = b * b - 4 * a * cc;
+  if (disc <= 0) return false;
+  const double sq = sqrt(disc);
+  double t1 = (-b + sq) / (2 * a), t2 = (-b - sq) / (2 * a);
+  if (t1 > t2) {
+    const double tmp = t1;
+    t1 = t2;
+    t2 = tmp;
+  }
+  double tt;
+  if (t1 >= t_floor)
+    tt = t1;
+  else if (t2 >= t_floor)
+    tt = t2;
+  else
+    return false;
+  t = tt;
+  n = dnormalize((o + d * tt) - c);
+  return true;
+}
+
+// bvh.go:322-351
+__device__ inline void ray_bounds(D3 o, D3 d, D3 mn, D3 mx, double &min_frac, double &max_frac) {
+  min_frac = -INFINITY;
+  max_frac = INFINITY;
+  for (int axis = 0; axis < 3; axis++) {
+    const double origin = comp(o, axis), rate = comp(d, axis);
+    if (rate == 0) {
+      if (origin < comp(mn, axis) || origin > comp(mx, axis)) {
+        min_frac = 0;
+        max_frac = -1;
+        return;
+      }
+      continue;
+    }
+    double t1 = (comp(mn, axis) - origin) / rate, t2 = (comp(mx, axis) - origin) / rate;
+    if (t1 > t2) {
+      const double tmp = t1;
+      t1 = t2;
+      t2 = tmp;
+    }
+    if (t2 < 0) {
+      min_frac = 0;
+      max_frac = -1;
+      return;
+    }
+    if (t1 > min_frac) min_frac = t1;
+    if (t2 < max_frac) max_frac = t2;
+  }
+}
+
+// shapes.go:177-196, 221-247
+__device__ inline bool rect_hit(const DeviceShape &s, D3 o, D3 d, double t_floor, double &t, D3 &n) {
+  const D3 mn = d3(s.p0[0], s.p0[1], s.p0[2]), mx = d3(s.p1[0], s.p1[1], s.p1[2]);
+  double tmin, tmax;
+  ray_bounds(o, d, mn, mx, tmin, tmax);
+  if (tmax < tmin || tmax < t_floor) return false;
+  double tt = tmin;
+  if (tt < t_floor) tt = tmax;
+  t = tt;
+  const D3 c = o + d * tt;
+  int axis = 0;
+  double sign = 0, min_dist = INFINITY;
+  for (int i = 0; i < 3; i++) {
+    double dd = fabs(comp(c, i) - comp(mn, i));
+    if (dd < min_dist) {
+      min_dist = dd;
+      sign = -1;
+      axis = i;
+    }
+    dd = fabs(comp(c, i) - comp(mx, i));
+    if (dd < min_dist) {
+      min_dist = dd;
+      sign = 1;
+      axis = i;
+    }
+  }
+  n = d3(axis == 0 ? sign : 0.0, axis == 1 ? sign : 0.0, axis == 2 ? sign : 0.0);
+  return true;
+}
+
+// shapes.go:816-856
+__device__ inline bool circle_hit(D3 normal, D3 center, double radius, D3 o, D3 d, double t_floor, double &t) {
+  const double ddn = ddot(d, normal);
+  if (fabs(ddn) < 1e-8 * dnorm(d) * dnorm(normal)) return false;
+  const double tt = (ddot(normal, center) - ddot(o, normal)) / ddn;
+  if (tt < t_floor) return false;
+  const D3 p = o + d * tt;
+  if (dnorm(p - center) > radius) return false;
+  t = tt;
+  return true;
+}
+
+// shapes.go:601-705: minimum over side roots and the two caps (first strictly smaller wins)
+__device__ inline bool cylinder_hit(const DeviceShape &s, D3 o_in, D3 d, double t_floor, double &t, D3 &n) {
+  const D3 p1 = d3(s.p0[0], s.p0[1], s.p0[2]), p2 = d3(s.p1[0], s.p1[1], s.p1[2]);
+  bool ok = false;
+  const D3 v = dnormalize(p2 - p1);
+  const D3 o = o_in - p1;
+  const D3 v1 = v * ddot(o, v) - o;
+  const D3 v2 = v * ddot(d, v) - d;
+  const double a = ddot(v2, v2), b = 2 * ddot(v1, v2), cv = ddot(v1, v1) - s.radius * s.radius;
+  const double disc = b * b - 4 * a * cv;
+  if (disc > 0) {
+    const double sq = sqrt(disc);
+    const double max_scale = dnorm(p2 - p1);
+    for (int k = 0; k < 2; k++) {
+      const double sign = k == 0 ? -1.0 : 1.0;
+      const double tt = (-b + sign * sq) / (2 * a);
+      if (tt < t_floor) continue;
+      const D3 p = o + d * tt;
+      const double frac = ddot(v, p);
+      if (frac >= 0 && frac < max_scale && (!ok || tt < t)) {
+        t = tt;
+        n = dnormalize(p - v * frac);
+        ok = true;
+      }
+    }
+  }
+  for (int i = 0; i < 2; i++) {
+    const D3 tip = i == 0 ? p1 : p2;
+    const D3 nn = i == 0 ? v * -1.0 : v;
+    double tt;
+    if (circle_hit(nn, tip, s.radius, o_in, d, t_floor, tt) && (!ok || tt < t)) {
+      t = tt;
+      n = nn;
+      ok = true;
+    }
+  }
+  return ok;
+}
+
+// Result of resolving one scene ray: the closest of the BVH's raw triangle hit and the
+// analytic shapes.  surf: leaf-order triangle index, or -2-shape index, or -1 (miss).
+struct SceneHit {
+  float t;
+  float b1, b2;
+  float nx, ny, nz;
+  int32_t prim, obj, surf;
+};
+
+// o = (origin, tmin), d = (direction, tmax); raw = trace_first_hit_kernel's output
+// (t_f32, -, -, bits(leaf-order triangle | -1)); skip = surface the ray starts on.
+__device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, float4 d, float4 raw, int skip,
+                                             bool refine) {
+  SceneHit h;
+  h.t = 0.f;
+  h.b1 = h.b2 = 0.f;
+  h.nx = h.ny = h.nz = 0.f;
+  h.prim = -1;
+  h.obj = -1;
+  h.surf = -1;
+  const int tri_idx = __float_as_int(raw.w);
+  double best_t = INFINITY;
+  int best_obj = 0x7fffffff;
+  if (tri_idx >= 0) {
+    const float4 *tri = sc.bvh.tris + (size_t)tri_idx * 3;
+    const int prim = __float_as_int(__ldg(&tri[0].w));
+    const int obj = __float_as_int(__ldg(&tri[1].w));
+    h.surf = tri_idx;
+    h.prim = prim;
+    h.obj = obj;
+    if (refine) {
+      const HitD r = refine_hit_f64(tri, o.x, o.y, o.z, d.x, d.y, d.z);
+      const double t = r.t >= 0.0 ? r.t : (double)raw.x;
+      double nx = r.nx, ny = r.ny, nz = r.nz;
+      if (sc.bvh.vnormals) {
+        // InterpNormalTriangle.InterpNormal (primitives.go:508-516)
+        const float4 *vn = sc.bvh.vnormals + (size_t)tri_idx * 3;
+        const float4 a = __ldg(vn), b = __ldg(vn + 1), c = __ldg(vn + 2);
+        nx = r.b0 * a.x + r.b1 * b.x + r.b2 * c.x;
+        ny = r.b0 * a.y + r.b1 * b.y + r.b2 * c.y;
+        nz = r.b0 * a.z + r.b1 * b.z + r.b2 * c.z;
+        const double s = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+        nx *= s;
+        ny *= s;
+        nz *= s;
+      }
+      best_t = t;
+      h.t = (float)t;
+      h.b1 = (float)r.b1;
+      h.b2 = (float)r.b2;
+      h.nx = (float)nx;
+      h.ny = (float)ny;
+      h.nz = (float)nz;
+    } else {
+      const float4 q0 = __ldg(tri), q1 = __ldg(tri + 1), q2 = __ldg(tri + 2);
+      const float e1x = q1.x - q0.x, e1y = q1.y - q0.y, e1z = q1.z - q0.z;
+      const float e2x = q2.x - q0.x, e2y = q2.y - q0.y, e2z = q2.z - q0.z;
+      float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+      // float32 barycentrics (Moeller-Trumbore, as in the traversal)
+      const float c1x = d.y * e2z - d.z * e2y, c1y = d.z * e2x - d.x * e2z, c1z = d.x * e2y - d.y * e2x;
+      const float inv = 1.0f / (c1x * e1x + c1y * e1y + c1z * e1z);
+      const float px = o.x - q0.x, py = o.y - q0.y, pz = o.z - q0.z;
+      const float fb1 = inv * (px * c1x + py * c1y + pz * c1z);
+      const float fb2 =
+          inv * (d.x * (py * e1z - pz * e1y) + d.y * (pz * e1x - px * e1z) + d.z * (px * e1y - py * e1x));
+      if (sc.bvh.vnormals) {
+        const float4 *vn = sc.bvh.vnormals + (size_t)tri_idx * 3;
+        const float4 a = __ldg(vn), b = __ldg(vn + 1), c = __ldg(vn + 2);
+        const float b0 = 1.f - (fb1 + fb2);
+        nx = b0 * a.x + fb1 * b.x + fb2 * c.x;
+        ny = b0 * a.y + fb1 * b.y + fb2 * c.y;
+        nz = b0 * a.z + fb1 * b.z + fb2 * c.z;
+      }
+      const float s = rsqrtf(nx * nx + ny * ny + nz * nz);
+      best_t = raw.x;
+      h.t = raw.x;
+      h.b1 = fb1;
+      h.b2 = fb2;
+      h.nx = nx * s;
+      h.ny = ny * s;
+      h.nz = nz * s;
+    }
+    best_obj = obj;
+  }
+  if (sc.num_shapes > 0) {
+    const D3 od = d3(o.x, o.y, o.z), dd = d3(d.x, d.y, d.z);
+    const double t_hi = (double)d.w;  // ray tmax (shadow / visibility rays)
+    const double inv_len = 1.0 / dnorm(dd);
+    for (int s = 0; s < sc.num_shapes; s++) {
+      const DeviceShape &sh = sc.shapes[s];
+      double t_floor = (double)o.w;
+      if (skip == -2 - s) {
+        double size = sh.radius;
+        if (sh.kind == SHAPE_RECT)
+          size = fmax(fmax(sh.p1[0] - sh.p0[0], sh.p1[1] - sh.p0[1]), sh.p1[2] - sh.p0[2]);
+        t_floor = fmax(t_floor, 1e-4 * size * inv_len);
+      }
+      double t;
+      D3 n;
+      bool ok = false;
+      if (sh.kind == SHAPE_SPHERE) ok = sphere_hit(sh, od, dd, t_floor, t, n);
+      else if (sh.kind == SHAPE_RECT) ok = rect_hit(sh, od, dd, t_floor, t, n);
+      else if (sh.kind == SHAPE_CYLINDER) ok = cylinder_hit(sh, od, dd, t_floor, t, n);
+      if (!ok || t > t_hi) continue;
+      // JoinedObject.Cast: strict '<' in object order, the first object wins ties
+      if (t < best_t || (t == best_t && sh.object < best_obj)) {
+        best_t = t;
+        best_obj = sh.object;
+        h.surf = -2 - s;
+        h.t = (float)t;
+        h.b1 = h.b2 = 0.f;
+        h.prim = 0;
+        h.obj = sh.object;
+        h.nx = (float)n.x;
+        h.ny = (float)n.y;
+        h.nz = (float)n.z;
+      }
+    }
+  }
+  if (sc.objects && h.obj >= 0 && (sc.objects[h.obj].flags & M3D_OBJ_FLIP_NORMAL)) {
+    h.nx = -h.nx;  // showcase DomeObject (room.go:40-44)
+    h.ny = -h.ny;
+    h.nz = -h.nz;
+  }
+  return h;
+}
+
+}  // namespace m3d

@@ -39,7 +39,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
   const unsigned lane = threadIdx.x & 31u;
   const uint4 *__restrict__ nodes = bvh.nodes;
   const float4 *__restrict__ tris = bvh.tris;
-  const int n = (int)p.n;
+  const int n = p.n_ptr ? min(__ldg(p.n_ptr), (int)p.n) : (int)p.n;
 
   int batch_next = 0, batch_end = 0;  // warp-uniform; batch_end < 0: the global counter ran past n
   int ray_idx = -1;                   // < 0: the lane has no ray

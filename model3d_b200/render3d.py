@@ -430,3 +430,148 @@ class RayCaster:
                                            _p(data, f32p), C.byref(stats)))
         img.Data = data
         return {k: getattr(stats, k) for k, _ in stats._fields_}
+
+
+# ---- focus points (focus_point.go) ----------------------------------------------------------
+@dataclass(eq=False)
+class PhongFocusPoint:
+    """render3d.PhongFocusPoint (focus_point.go:30-71)."""
+    Target: Vec = (0.0, 0.0, 0.0)
+    Alpha: float = 0.0
+    MaterialFilter: Optional[Callable[[object], bool]] = None
+
+
+@dataclass(eq=False)
+class SphereFocusPoint:
+    """render3d.SphereFocusPoint (focus_point.go:73-153)."""
+    Center: Vec = (0.0, 0.0, 0.0)
+    Radius: float = 0.0
+    MaterialFilter: Optional[Callable[[object], bool]] = None
+
+
+def _focus_desc(fp, prob, materials):
+    """FocusPoint -> m3d_focus_point.  MaterialFilter closures cannot cross the C ABI: the
+    filter is evaluated once per scene material into a bit mask (include/m3d.h)."""
+    d = N.FocusPoint()
+    if isinstance(fp, PhongFocusPoint):
+        d.kind = N.FOCUS_PHONG
+        d.target[:] = [float(x) for x in fp.Target]
+        d.alpha = float(fp.Alpha)
+    elif isinstance(fp, SphereFocusPoint):
+        d.kind = N.FOCUS_SPHERE
+        d.target[:] = [float(x) for x in fp.Center]
+        d.radius = float(fp.Radius)
+    else:
+        raise UnsupportedError("focus point type %s is not supported on the GPU path" % type(fp).__name__)
+    if len(materials) > 64:
+        raise UnsupportedError("focus-point material filters support at most 64 scene materials")
+    mask = 0
+    for i, m in enumerate(materials):
+        if fp.MaterialFilter is None or fp.MaterialFilter(m):
+            mask |= 1 << i
+    d.material_mask = mask
+    d.prob = float(prob)
+    return d
+
+
+def _samples_partition(partition):
+    """(row_begin, row_end, sample_begin) or None -> m3d_partition pointer (or None)."""
+    if partition is None:
+        return None
+    return N.Partition(int(partition[0]), int(partition[1]), int(partition[2]))
+
+
+@dataclass
+class RecursiveRayTracer:
+    """render3d.RecursiveRayTracer (raytrace.go:14-119): same exported fields.
+
+    Render() runs the wavefront path tracer of libm3dgpu (m3d_render_path).  Adaptive early
+    stopping (MinSamples/MaxStddev/Convergence) is not available on the GPU path and raises
+    UnsupportedError: sample counts are fixed so that shards can be summed across GPUs."""
+    Camera: Camera = None
+    Lights: List[PointLight] = field(default_factory=list)
+    FocusPoints: List[object] = field(default_factory=list)
+    FocusPointProbs: List[float] = field(default_factory=list)
+    MaxDepth: int = 0
+    NumSamples: int = 0
+    MinSamples: int = 0
+    MaxStddev: float = 0.0
+    OversaturatedStddevs: float = 0.0
+    Convergence: Optional[Callable] = None
+    Cutoff: float = 0.0
+    Antialias: float = 0.0
+    Epsilon: float = 0.0
+    LogFunc: Optional[Callable[[float, float], None]] = None
+    Seed: int = 0  # Philox key (the reference seeds math/rand from the global source)
+
+    def _params(self, sc, num_samples):
+        if self.NumSamples == 0 and num_samples == 0:
+            raise ValueError("must set NumSamples to non-zero for rayRenderer")  # ray_renderer.go:26-28
+        if len(self.FocusPoints) != len(self.FocusPointProbs):
+            raise ValueError("FocusPoints and FocusPointProbs must match in length")  # raytrace.go:186-188
+        if (self.MinSamples != 0 and self.MaxStddev != 0) or self.Convergence is not None:
+            raise UnsupportedError("adaptive sampling (MinSamples/MaxStddev/Convergence) is not "
+                                   "supported on the GPU path")
+        if len(self.FocusPoints) > 4:
+            raise UnsupportedError("at most 4 focus points are supported on the GPU path")
+        p = N.PathParams()
+        p.max_depth = int(self.MaxDepth)
+        p.num_samples = int(num_samples or self.NumSamples)
+        p.cutoff = float(self.Cutoff)
+        p.antialias = float(self.Antialias)
+        p.epsilon = float(self.Epsilon)
+        p.num_focus_points = len(self.FocusPoints)
+        for i, (fp, prob) in enumerate(zip(self.FocusPoints, self.FocusPointProbs)):
+            p.focus[i] = _focus_desc(fp, prob, sc.materials)
+        p.seed = int(self.Seed)
+        return p
+
+    def RenderSums(self, width, height, obj, partition=None, sample_count=None, variance=False,
+                   antialias=None):
+        """Per-pixel SUMS (and sums of squares) over `sample_count` samples of this shard:
+        the quantity that adds up across GPUs.  partition = (row_begin, row_end,
+        sample_begin)."""
+        sc = _as_scene(obj)
+        n = int(self.NumSamples if sample_count is None else sample_count)
+        p = self._params(sc, n)
+        if antialias is not None:
+            p.antialias = float(antialias)
+        cam = self.Camera._c()
+        rgb = np.zeros((height, width, 3), np.float32)
+        sq = np.zeros((height, width, 3), np.float32) if variance else None
+        stats = N.Stats()
+        part = _samples_partition(partition)
+        N.check(N.lib().m3d_render_path(sc.h, C.byref(cam), _lights(self.Lights), C.c_int32(len(self.Lights)),
+                                        C.byref(p), C.c_int32(width), C.c_int32(height),
+                                        C.byref(part) if part is not None else None, C.c_int32(n),
+                                        _p(rgb, f32p), _p(sq, f32p), C.byref(stats)))
+        return rgb, sq, {k: getattr(stats, k) for k, _ in stats._fields_}
+
+    def Render(self, img: Image, obj):
+        """(*RecursiveRayTracer).Render (raytrace.go:98-100)."""
+        rgb, _, stats = self.RenderSums(img.Width, img.Height, obj)
+        img.Data = rgb / np.float32(self.NumSamples)  # colorSum.Scale(1/numSamples) ray_renderer.go:150
+        if self.LogFunc is not None:
+            self.LogFunc(1.0, float(self.NumSamples))
+        return stats
+
+    def RenderVariance(self, img: Image, obj, numSamples, antialias=None):
+        """rayRenderer.RenderVariance (ray_renderer.go:59-67,90-110): per-pixel sample variance
+        with Bessel's correction, clamped at zero."""
+        if numSamples < 2:
+            raise ValueError("need to take at least two samples")
+        rgb, sq, stats = self.RenderSums(img.Width, img.Height, obj, sample_count=numSamples, variance=True,
+                                         antialias=antialias)
+        n = float(numSamples)
+        mean = rgb.astype(np.float64) / n
+        var = (sq.astype(np.float64) / n - mean * mean) * (n / (n - 1))
+        img.Data = np.maximum(var, 0.0).astype(np.float32)
+        return stats
+
+    def RayVariance(self, obj, width, height, samples):
+        """rayRenderer.RayVariance (ray_renderer.go:69-88): mean variance, no antialiasing."""
+        if samples < 2:
+            raise ValueError("need to take at least two samples")
+        img = Image(width, height)
+        self.RenderVariance(img, obj, samples, antialias=0.0)
+        return float(img.Data.astype(np.float64).sum() / (3 * width * height))

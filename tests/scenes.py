@@ -245,3 +245,81 @@ def testing_scene():
                 area_lights=[dict(object=1, emission=gray(100.0)), dict(object=2, emission=gray(130.0))],
                 focus=[dict(kind="sphere", target=(0, -19, 5), radius=1.0, prob=0.2, applies=lambda m: True),
                        dict(kind="sphere", target=(3, -19, 5), radius=0.5, prob=0.1, applies=lambda m: True)])
+
+
+# ---- renderer parameter builders (oracle / product) from one spec ----------------------------
+def all_materials(spec):
+    """Materials of the spec in first-use order, sub-materials of joined ones first (the order
+    both builders register them in)."""
+    out = []
+
+    def visit(m):
+        if any(m is x for x in out):
+            return
+        if m["kind"] == "joined":
+            for s in m["mats"]:
+                visit(s)
+        out.append(m)
+
+    for o in spec["objects"]:
+        visit(o["material"])
+    return out
+
+
+def oracle_path_params(spec, osc, max_depth, num_samples, cutoff=0.0, antialias=0.0, seed=1):
+    from oracle import pyoracle as O
+    pp = O.PathParams()
+    pp.max_depth, pp.num_samples, pp.cutoff, pp.antialias, pp.seed = max_depth, num_samples, cutoff, antialias, seed
+    focus = spec.get("focus", [])
+    pp.num_focus_points = len(focus)
+    for i, f in enumerate(focus):
+        pp.focus[i].kind = 0 if f["kind"] == "phong" else 1
+        pp.focus[i].target[:] = f["target"]
+        pp.focus[i].alpha = f.get("alpha", 0.0)
+        pp.focus[i].radius = f.get("radius", 0.0)
+        pp.focus[i].prob = f["prob"]
+        mask = 0
+        for m in all_materials(spec):
+            if f["applies"](m):
+                mask |= 1 << osc.material_index(m)
+        pp.focus[i].material_mask = mask
+    return pp
+
+
+def product_tracer(spec, psc, max_depth, num_samples, cutoff=0.0, antialias=0.0, seed=1, lights=()):
+    from model3d_b200 import render3d as R
+    cam = spec["camera"]
+    fps, probs = [], []
+    for f in spec.get("focus", []):
+        ok = [psc.material_of(m) for m in all_materials(spec) if f["applies"](m)]
+        flt = (lambda mats: (lambda m: any(m is x for x in mats)))(ok)
+        if f["kind"] == "phong":
+            fps.append(R.PhongFocusPoint(Target=f["target"], Alpha=f["alpha"], MaterialFilter=flt))
+        else:
+            fps.append(R.SphereFocusPoint(Center=f["target"], Radius=f["radius"], MaterialFilter=flt))
+        probs.append(f["prob"])
+    return R.RecursiveRayTracer(Camera=R.NewCameraAt(cam["src"], cam["dst"], cam["fov"]), Lights=list(lights),
+                                FocusPoints=fps, FocusPointProbs=probs, MaxDepth=max_depth,
+                                NumSamples=num_samples, Cutoff=cutoff, Antialias=antialias, Seed=seed)
+
+
+def glass_scene():
+    """Refraction with Fresnel reflection (RefractMaterial with SpecularColor), a glass ball
+    and a glass slab inside a lit Lambert room: exercises every Dirac-lobe branch
+    (refract / reflect / total internal reflection) of material.go:343-479."""
+    m_wall = lambert(diffuse=gray(0.5))
+    m_light = lambert(emission=gray(12.0))
+    m_glass = refract(1.5, gray(0.95), specular=gray(0.9))
+    m_clear = refract(1.2, (0.9, 0.95, 1.0))
+    walls = mesh_rect_tris((-4, -4, -2), (4, 6, 4)) * np.array([-1.0, 1.0, 1.0])
+    light = mesh_rect_tris((-1.5, 0, 3.8), (1.5, 3, 3.9))
+    slab = mesh_rect_tris((-3.0, 3.0, -1.5), (-1.0, 3.4, 1.5))
+    objs = [
+        dict(kind="mesh", tris=walls.astype(np.float32), material=m_wall),
+        dict(kind="mesh", tris=light.astype(np.float32), material=m_light),
+        dict(kind="sphere", center=(0.8, 2.0, -0.8), radius=1.2, material=m_glass),
+        dict(kind="mesh", tris=slab.astype(np.float32), material=m_clear),
+        dict(kind="cylinder", p1=(2.5, 4.0, -2.0), p2=(2.5, 4.0, 0.5), radius=0.6,
+             material=phong(30.0, specular=gray(0.3), diffuse=(0.1, 0.3, 0.5))),
+    ]
+    return dict(objects=objs, camera=dict(src=(0, -3.5, 1.0), dst=(0, 4, 0.2), fov=math.pi / 3.0))

@@ -1,0 +1,154 @@
+"""GPU parity tests for the wavefront path tracer (m3d_render_path behind
+render3d.RecursiveRayTracer) against the float64 oracle (oracle/render.hpp).
+
+Random streams differ (Philox vs the oracle's mt19937; the reference itself uses Go's
+math/rand), so parity is statistical: the per-pixel means must agree within 3 sigma of the
+combined Monte-Carlo noise (BASELINE north_star), checked as z-scores over all pixels and
+channels plus block averages that shrink the noise."""
+import numpy as np
+import pytest
+
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def z_scores(got_mean, got_var, ref_mean, ref_var):
+    # float32-vs-float64 floor (1e-4 relative + 1e-6) under the Monte-Carlo noise, so that
+    # (nearly) deterministic pixels are compared at rounding tolerance instead of 0/0
+    floor = 1e-4 * np.abs(ref_mean) + 1e-6
+    s = np.sqrt(got_var + ref_var + floor ** 2)
+    return (got_mean - ref_mean) / s
+
+
+def check_statistical_parity(got_mean, got_var, ref_mean, ref_var, block=4):
+    z = z_scores(got_mean, got_var, ref_mean, ref_var)
+    frac3 = (np.abs(z) > 3).mean()
+    # Monte-Carlo pixel noise is heavy tailed: allow a little more than the Gaussian 0.27 %
+    assert frac3 < 0.02, "fraction of |z| > 3: %.4f" % frac3
+    # deterministic silhouette / shadow-edge pixels may flip between float32 and float64
+    assert (np.abs(z) > 8).sum() <= max(3, z.size // 400), ((np.abs(z) > 8).sum(), np.abs(z).max())
+    assert abs(z.mean()) < 0.15, "systematic bias: mean z %.3f" % z.mean()
+    # block means: noise shrinks by `block`, a bias would not
+    H, W, _ = got_mean.shape
+    Hb, Wb = H // block * block, W // block * block
+
+    def blk(a):
+        return a[:Hb, :Wb].reshape(Hb // block, block, Wb // block, block, 3).mean(axis=(1, 3))
+
+    zb = z_scores(blk(got_mean), blk(got_var) / block ** 2, blk(ref_mean), blk(ref_var) / block ** 2)
+    assert (np.abs(zb) > 3).mean() < 0.03, (np.abs(zb) > 3).mean()
+    tot_g, tot_r = got_mean.mean(), ref_mean.mean()
+    tot_s = np.sqrt((got_var.sum() + ref_var.sum())) / got_mean.size
+    assert abs(tot_g - tot_r) < 4 * tot_s + 1e-6, (tot_g, tot_r, tot_s)
+
+
+def gpu_mean_var(tracer, psc, W, H, n):
+    rgb, sq, stats = tracer.RenderSums(W, H, psc, sample_count=n, variance=True)
+    mean = rgb.astype(np.float64) / n
+    var = np.maximum(sq.astype(np.float64) / n - mean * mean, 0.0) * n / (n - 1)
+    return mean, var / n, stats
+
+
+def run_case(oracle, spec, W, H, n_gpu, n_ref, max_depth, cutoff=0.0, antialias=0.0, lights=()):
+    from model3d_b200 import render3d as R
+    osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
+    cam = spec["camera"]
+    ocam = oracle.camera_at(cam["src"], cam["dst"], cam["fov"])
+    pp = scenes.oracle_path_params(spec, osc, max_depth, n_ref, cutoff=cutoff, antialias=antialias, seed=3)
+    olights = []
+    plights = []
+    for l in lights:
+        ol = oracle.PointLight()
+        ol.origin[:], ol.color[:], ol.quad_dropoff = l["origin"], l["color"], int(l.get("quad", False))
+        olights.append(ol)
+        plights.append(R.PointLight(Origin=tuple(l["origin"]), Color=tuple(l["color"]), QuadDropoff=bool(l.get("quad", False))))
+    ref = osc.render_path(ocam, olights, pp, W, H, threads=8)
+    tr = scenes.product_tracer(spec, psc, max_depth, n_gpu, cutoff=cutoff, antialias=antialias, seed=9,
+                               lights=plights)
+    mean, var, stats = gpu_mean_var(tr, psc, W, H, n_gpu)
+    assert np.isfinite(mean).all()
+    assert stats["rays"] > W * H * n_gpu
+    check_statistical_parity(mean, var, ref["mean"], ref["var_of_mean"])
+    return mean, ref, stats
+
+
+def test_path_cornell_box(built, oracle):
+    """BASELINE config 3 (cornell_box, RecursiveRayTracer, MaxDepth 5, Cutoff 1e-4, Antialias 1,
+    PhongFocusPoint prob 0.3 with the material filter of cornell_box/main.go:98-108) at a
+    test-sized resolution."""
+    spec = scenes.cornell_box()
+    mean, ref, stats = run_case(oracle, spec, 48, 48, n_gpu=1024, n_ref=512, max_depth=5, cutoff=1e-4, antialias=1.0)
+    assert ref["mean"].mean() > 0.05  # the scene is lit
+
+
+def test_path_testing_scene_sphere_focus(built, oracle):
+    """render3d/bidir_test.go:12-42: testingScene with two SphereFocusPoints, MaxDepth 10."""
+    spec = scenes.testing_scene()
+    run_case(oracle, spec, 16, 16, n_gpu=8192, n_ref=4096, max_depth=10)
+
+
+def test_path_glass_scene(built, oracle):
+    """Dirac lobes: refraction, Fresnel reflection, total internal reflection, on a sphere, a
+    mesh slab and next to a Phong cylinder."""
+    spec = scenes.glass_scene()
+    run_case(oracle, spec, 40, 32, n_gpu=2048, n_ref=1024, max_depth=8, cutoff=1e-3)
+
+
+def test_path_point_lights_and_shadows(built, oracle):
+    """Point lights with shadow rays (raytrace.go:156-168) on the mixed scene (all collider
+    kinds + a transformed sphere), MaxDepth 2, including depth-0 ambient."""
+    spec = scenes.mixed_scene()
+    spec["camera"] = dict(src=(4.0, -6.0, 3.0), dst=(0.0, 0.0, 0.0), fov=np.pi / 3.6)
+    lights = [dict(origin=(30.0, -40.0, 50.0), color=(1.0, 0.9, 0.8)),
+              dict(origin=(-3.0, -4.0, 6.0), color=(40.0, 40.0, 60.0), quad=True)]
+    run_case(oracle, spec, 40, 30, n_gpu=512, n_ref=256, max_depth=2, lights=lights)
+
+
+def test_path_depth0_equals_shadowed_raycast(built, oracle):
+    """MaxDepth 0 is deterministic (no sampling): must match the oracle to float32 rounding."""
+    spec = scenes.mixed_scene()
+    spec["camera"] = dict(src=(4.0, -6.0, 3.0), dst=(0.0, 0.0, 0.0), fov=np.pi / 3.6)
+    lights = [dict(origin=(30.0, -40.0, 50.0), color=(1.0, 0.9, 0.8))]
+    from model3d_b200 import render3d as R
+    osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
+    cam = spec["camera"]
+    ocam = oracle.camera_at(cam["src"], cam["dst"], cam["fov"])
+    pp = scenes.oracle_path_params(spec, osc, 0, 2)
+    ol = oracle.PointLight()
+    ol.origin[:], ol.color[:], ol.quad_dropoff = lights[0]["origin"], lights[0]["color"], 0
+    ref = osc.render_path(ocam, [ol], pp, 64, 48, threads=8)["mean"]
+    tr = scenes.product_tracer(spec, psc, 0, 2, lights=[R.PointLight(Origin=lights[0]["origin"], Color=lights[0]["color"])])
+    img = R.Image(64, 48)
+    tr.Render(img, psc)
+    diff = np.abs(img.Data - ref)
+    # a handful of pixels sit on shadow / silhouette edges where float32 flips the outcome
+    assert (diff > 1e-4).sum() <= 12, (diff > 1e-4).sum()
+    assert np.median(diff) < 1e-6
+
+
+def test_path_partitions_add_up(built):
+    """Sample shards and row bands (the multi-GPU partitioning) reproduce the single-call sums:
+    the Philox stream is keyed by absolute (pixel, sample)."""
+    spec = scenes.cornell_box()
+    psc = scenes.build_product(spec)
+    tr = scenes.product_tracer(spec, psc, 4, 64, cutoff=1e-4, antialias=1.0, seed=5)
+    W, H = 32, 24
+    full, _, _ = tr.RenderSums(W, H, psc)
+    a, _, _ = tr.RenderSums(W, H, psc, partition=(0, 0, 0), sample_count=24)
+    b, _, _ = tr.RenderSums(W, H, psc, partition=(0, 0, 24), sample_count=40)
+    assert np.allclose(a + b, full, rtol=1e-4, atol=1e-4)
+    top, _, _ = tr.RenderSums(W, H, psc, partition=(0, 10, 0))
+    bot, _, _ = tr.RenderSums(W, H, psc, partition=(10, H, 0))
+    assert np.abs(top[10:]).max() == 0 and np.abs(bot[:10]).max() == 0
+    assert np.allclose(top + bot, full, rtol=1e-4, atol=1e-4)
+
+
+def test_path_unsupported_adaptive(built):
+    from model3d_b200 import UnsupportedError
+    spec = scenes.testing_scene()
+    psc = scenes.build_product(spec)
+    tr = scenes.product_tracer(spec, psc, 3, 100)
+    tr.MinSamples, tr.MaxStddev = 10, 0.01
+    with pytest.raises(UnsupportedError):
+        tr.RenderSums(4, 4, psc)
