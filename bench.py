@@ -39,10 +39,9 @@ def make_rays(n, seed):
 
 
 def make_mesh():
-    # Synthetic mesh generator lives with the oracle (restated NewMeshIcosphere); it is
-    # input synthesis, not part of the measured path.
-    from oracle import pyoracle as O
-    return O.mesh_icosphere((0, 0, 0), 1.0, ICO_N).astype(np.float32)
+    # NewMeshIcosphere(0, 1, 224) restated in numpy on the product side (model3d_b200/meshes.py)
+    from model3d_b200 import meshes
+    return meshes.NewMeshIcosphere((0, 0, 0), 1.0, ICO_N).astype(np.float32).reshape(-1, 9)
 
 
 class ClockSampler:
@@ -139,6 +138,143 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+C3_WORKLOAD = "C3 cornell_box (examples/renderings/cornell_box), RecursiveRayTracer MaxDepth 5, Cutoff 1e-4, Antialias 1, PhongFocusPoint 0.3"
+
+
+def cornell_tracer(spp, seed=1234):
+    from model3d_b200 import examples
+    spec = examples.cornell_box()
+    psc = examples.build_product(spec)
+    tr = examples.product_tracer(spec, psc, 5, spp, cutoff=1e-4, antialias=1.0, seed=seed)
+    return spec, psc, tr
+
+
+def run_path(args):
+    """BASELINE configs[2]: cornell_box, RecursiveRayTracer, 1024x1024 at --spp samples per pixel
+    per step.  N GPUs: samples sharded by index (strong scaling), per-pixel sums reduced to
+    rank 0 with one NCCL reduce, inside the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    from model3d_b200 import _native as N
+    N.default_context(local_rank)
+    W = H = args.size
+    spp = args.spp
+    spec, psc, tr = cornell_tracer(spp)
+    from model3d_b200 import distributed as D
+    part, my_spp = D.sample_shard(spp, rank, world)
+    acc = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    rays = [0]
+    launches = [0]
+
+    def step():
+        acc.zero_()
+        st = tr.RenderSumsDevice(W, H, psc, acc.data_ptr(), partition=part, sample_count=my_spp,
+                                 stream=tstream.cuda_stream)
+        rays[0] = st["rays"]
+        launches[0] = st["launches"]
+        D.reduce_sums(acc, dst=0)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, float(rays[0])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, total_rays = float(tmax[0].item()), float(t[1].item())
+    else:
+        total_rays = float(rays[0])
+    ms_step = ms / args.steps
+    samples = W * H * spp
+    value = samples / (ms_step * 1e-3) / 1e6
+    if rank == 0:
+        # end to end: the host-buffer call (sums copied back to host memory every step)
+        e2e = None
+        if world == 1 and not args.no_e2e:
+            t0 = time.perf_counter()
+            k = max(1, args.steps // 2)
+            for _ in range(k):
+                tr.RenderSums(W, H, psc)
+            dt = (time.perf_counter() - t0) / k
+            e2e = {"value": samples / dt / 1e6, "unit": "Msamples/s", "ms_per_step": dt * 1e3,
+                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 12,
+                   "api": "m3d_render_path (host image buffers)"}
+        line = {
+            "metric": "path_traced_Msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": C3_WORKLOAD, "width": W, "height": H, "spp": spp,
+                       "rays_per_sample": total_rays / samples, "Mrays_per_s": total_rays / (ms_step * 1e-3) / 1e6,
+                       "sharding": "sample index, NCCL reduce of the W*H*3 float32 sums to rank 0",
+                       "l2": "scene is 72 triangles + 2 spheres (L1-resident); path state streams through HBM"},
+            "clocks": clocks, "gpu_launches": int(launches[0]) * args.steps,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_path(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenes
+    from oracle import pyoracle as O
+    threads = O.hardware_threads()
+    spec = scenes.cornell_box()
+    osc = scenes.build_oracle(spec)
+    cam = spec["camera"]
+    ocam = O.camera_at(cam["src"], cam["dst"], cam["fov"])
+    W = H = 256
+    spp = 8
+    pp = scenes.oracle_path_params(spec, osc, 5, spp, cutoff=1e-4, antialias=1.0, seed=3)
+    t0 = time.perf_counter()
+    k = max(1, args.steps)
+    for _ in range(k):
+        osc.render_path(ocam, [], pp, W, H, threads=threads)
+    dt = (time.perf_counter() - t0) / k
+    rate = W * H * spp / dt / 1e6
+    line = {"impl": "reference", "metric": "path_traced_Msamples_per_s", "value": rate, "unit": "Msamples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": C3_WORKLOAD},
+            "cpu_baseline": {"value": rate, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                             "sample": "%dx%d at %d spp per step" % (W, H, spp)},
+            "e2e": {"value": rate, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -148,9 +284,19 @@ def main():
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2: raw first-hit ray batch (headline); c3: cornell_box RecursiveRayTracer 1024x1024")
+    ap.add_argument("--spp", type=int, default=256, help="samples per pixel per step (c3)")
+    ap.add_argument("--size", type=int, default=1024, help="frame width == height (c3)")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        if args.workload == "c3":
+            run_reference_path(args)
+        else:
+            run_reference(args)
+        return
+    if args.workload == "c3":
+        run_path(args)
         return
 
     import torch

@@ -547,6 +547,22 @@ class RecursiveRayTracer:
                                         _p(rgb, f32p), _p(sq, f32p), C.byref(stats)))
         return rgb, sq, {k: getattr(stats, k) for k, _ in stats._fields_}
 
+    def RenderSumsDevice(self, width, height, obj, d_rgb_sum, d_rgb_sumsq=0, partition=None,
+                         sample_count=None, stream=0):
+        """Like RenderSums on device buffers (pointers to W*H*3 float32 accumulators that the
+        call ADDS into); what a multi-GPU driver reduces with NCCL."""
+        sc = _as_scene(obj)
+        n = int(self.NumSamples if sample_count is None else sample_count)
+        p = self._params(sc, n)
+        cam = self.Camera._c()
+        stats = N.Stats()
+        part = _samples_partition(partition)
+        N.check(N.lib().m3d_render_path_device(
+            sc.h, C.byref(cam), _lights(self.Lights), C.c_int32(len(self.Lights)), C.byref(p),
+            C.c_int32(width), C.c_int32(height), C.byref(part) if part is not None else None, C.c_int32(n),
+            C.c_void_p(d_rgb_sum), C.c_void_p(d_rgb_sumsq or None), C.c_void_p(stream or None), C.byref(stats)))
+        return {k: getattr(stats, k) for k, _ in stats._fields_}
+
     def Render(self, img: Image, obj):
         """(*RecursiveRayTracer).Render (raytrace.go:98-100)."""
         rgb, _, stats = self.RenderSums(img.Width, img.Height, obj)
