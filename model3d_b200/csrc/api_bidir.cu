@@ -1,0 +1,311 @@
+// C ABI: (*BidirPathTracer).Render (include/m3d.h, m3d_render_bidir*).
+// Replaces render3d/bidir.go:66-576 with a wavefront pipeline per batch of samples:
+//   eye raygen -> [trace -> eye shade] x MaxDepth
+//   light raygen -> [trace -> light shade] x (MaxLightDepth-1)
+//   for every eye prefix length: connect (MIS in float64) -> trace visibility rays -> resolve
+//   flush
+// all on one stream with device-side queue lengths.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "api_common.h"
+#include "bidir.h"
+#include "scene_host.h"
+
+using namespace m3d;
+
+namespace m3d {
+DeviceCamera device_camera(const m3d_camera &c, int W, int H);
+}
+
+namespace {
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int32_t carve_bidir_buffers(m3d_ctx *ctx, int64_t cap, int De, int Dl, BidirBuffers &b) {
+  const size_t c = (size_t)cap;
+  size_t total = 0;
+  auto take = [&](size_t bytes) {
+    const size_t off = total;
+    total += align256(bytes);
+    return off;
+  };
+  const size_t o_ev = take(c * 16 * kBidirVertexFields * De), o_lv = take(c * 16 * kBidirVertexFields * Dl);
+  const size_t o_ne = take(c * 4), o_nl = take(c * 4);
+  size_t o_org[2], o_dir[2], o_skip[2], o_queue[2];
+  for (int i = 0; i < 2; i++) {
+    o_org[i] = take(c * 16);
+    o_dir[i] = take(c * 16);
+    o_skip[i] = take(c * 4);
+    o_queue[i] = take(c * 4);
+  }
+  const size_t o_raw = take(c * 16), o_ef = take(c * 16), o_er = take(c * 16), o_acc = take(c * 16);
+  const size_t o_es = take(c * 32);
+  const size_t cc = c * (size_t)Dl;
+  const size_t o_corg = take(cc * 16), o_cdir = take(cc * 16), o_craw = take(cc * 16), o_cpay = take(cc * 16),
+               o_cskip = take(cc * 4);
+  const size_t o_counts = take(64);
+  M3D_CUDA(ctx->scratch[6].reserve(total));
+  char *p = ctx->scratch[6].as<char>();
+  b.cap = cap;
+  b.De = De;
+  b.Dl = Dl;
+  b.ev = (float4 *)(p + o_ev);
+  b.lv = (float4 *)(p + o_lv);
+  b.ne = (int32_t *)(p + o_ne);
+  b.nl = (int32_t *)(p + o_nl);
+  for (int i = 0; i < 2; i++) {
+    b.org[i] = (float4 *)(p + o_org[i]);
+    b.dir[i] = (float4 *)(p + o_dir[i]);
+    b.skip[i] = (int32_t *)(p + o_skip[i]);
+    b.queue[i] = (int32_t *)(p + o_queue[i]);
+  }
+  b.raw = (float4 *)(p + o_raw);
+  b.ender_full = (float4 *)(p + o_ef);
+  b.ender_roul = (float4 *)(p + o_er);
+  b.accum = (float4 *)(p + o_acc);
+  b.eye_state = (double *)(p + o_es);
+  b.corg = (float4 *)(p + o_corg);
+  b.cdir = (float4 *)(p + o_cdir);
+  b.craw = (float4 *)(p + o_craw);
+  b.cpay = (float4 *)(p + o_cpay);
+  b.cskip = (int32_t *)(p + o_cskip);
+  b.counts = (int *)(p + o_counts);
+  b.ray_total = (unsigned long long *)(p + o_counts + 32);
+  return M3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m3d_area_light *lights,
+                                int32_t num_lights, const m3d_bidir_params *params, int32_t width,
+                                int32_t height, const m3d_partition *part, int32_t sample_count,
+                                void *d_rgb_sum, void *d_rgb_sumsq, void *stream, m3d_stats *stats) {
+  if (!scene || !cam || !params || !lights || num_lights <= 0 || width <= 0 || height <= 0 || !d_rgb_sum ||
+      sample_count < 0)
+    return fail(M3D_ERR_INVALID_ARG, "m3d_render_bidir: bad arguments");
+  const int max_depth = params->max_depth;
+  const int max_ld = params->max_light_depth != 0 ? params->max_light_depth : max_depth;  // bidir.go:257-262
+  if (max_depth < 1 || max_ld < 1) return fail(M3D_ERR_INVALID_ARG, "MaxDepth and MaxLightDepth must be >= 1");
+  if (max_depth > kBidirMaxDepth || max_ld > kBidirMaxDepth)
+    return fail(M3D_ERR_UNSUPPORTED, "BidirPathTracer depths above %d are not supported on the GPU path",
+                kBidirMaxDepth);
+  if ((int64_t)width * height > (int64_t)0x7fffffff / 4) return fail(M3D_ERR_INVALID_ARG, "frame too large");
+  m3d_ctx *ctx = scene->ctx;
+  const DeviceScene &sc = scene->dev;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  int row_begin = 0, row_end = height;
+  int64_t sample_begin = 0;
+  if (part) {
+    if (!(part->row_begin == 0 && part->row_end == 0)) {
+      row_begin = part->row_begin;
+      row_end = part->row_end;
+      if (row_begin < 0 || row_end > height || row_begin > row_end)
+        return fail(M3D_ERR_INVALID_ARG, "bad row partition [%d,%d) of %d rows", row_begin, row_end, height);
+    }
+    sample_begin = part->sample_begin;
+    if (sample_begin < 0 || sample_begin + sample_count > (int64_t)0xffffffffll)
+      return fail(M3D_ERR_INVALID_ARG, "sample range out of bounds");
+  }
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  const int64_t npix = (int64_t)width * (row_end - row_begin);
+  if (npix == 0 || sample_count == 0) return M3D_OK;
+
+  // ---- area-light tables (light.go:131-161, 237-252, 283-301) ------------------------------
+  std::vector<DeviceAreaLight> hl((size_t)num_lights);
+  std::vector<DeviceLightTri> ht;
+  double total_light = 0;
+  for (int i = 0; i < num_lights; i++) {
+    const m3d_area_light &a = lights[i];
+    if (a.object < 0 || a.object >= (int32_t)scene->object_kind.size())
+      return fail(M3D_ERR_INVALID_ARG, "area light %d refers to object %d which does not exist", i, a.object);
+    DeviceAreaLight &L = hl[(size_t)i];
+    std::memset(&L, 0, sizeof(L));
+    L.object = a.object;
+    const double esum = a.emission[0] + a.emission[1] + a.emission[2];
+    for (int k = 0; k < 3; k++) L.emission[k] = (float)a.emission[k];
+    const int kind = scene->object_kind[(size_t)a.object];
+    double total = 0;
+    if (kind == SHAPE_SPHERE) {
+      int si = -1;
+      for (size_t q = 0; q < scene->host_shapes.size(); q++)
+        if (scene->host_shapes[q].object == a.object) si = (int)q;
+      const DeviceShape &sh = scene->host_shapes[(size_t)si];
+      L.kind = SHAPE_SPHERE;
+      L.surf = -2 - si;
+      for (int k = 0; k < 3; k++) L.center[k] = (float)sh.p0[k];
+      L.radius = (float)sh.radius;
+      total = esum * 4 * M_PI * sh.radius * sh.radius;  // light.go:159-161
+    } else if (kind == 0) {
+      L.kind = 0;
+      L.tri_begin = (int32_t)ht.size();
+      const int64_t t0 = scene->object_tri_begin[(size_t)a.object], tn = scene->object_tri_count[(size_t)a.object];
+      if (tn == 0) return fail(M3D_ERR_INVALID_ARG, "area light %d is an empty mesh", i);
+      L.tri_count = (int32_t)tn;
+      double area_sum = 0;
+      for (int64_t t = 0; t < tn; t++) {
+        const float *v = scene->merged_tris.data() + (size_t)(t0 + t) * 9;
+        DeviceLightTri T;
+        std::memset(&T, 0, sizeof(T));
+        for (int k = 0; k < 9; k++) T.v[k] = v[k];
+        const double e1[3] = {(double)v[3] - v[0], (double)v[4] - v[1], (double)v[5] - v[2]};
+        const double e2[3] = {(double)v[6] - v[0], (double)v[7] - v[1], (double)v[8] - v[2]};
+        const double c[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2],
+                             e1[0] * e2[1] - e1[1] * e2[0]};
+        const double cn = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+        area_sum += cn / 2;  // Triangle.Area (primitives.go:21-23)
+        T.cumu_area = area_sum;
+        for (int k = 0; k < 3; k++) T.n[k] = (float)(c[k] * (1.0 / cn));
+        T.leaf_index = scene->leaf_of_merged[(size_t)(t0 + t)];
+        ht.push_back(T);
+      }
+      L.total_area = area_sum;
+      total = area_sum * esum;  // light.go:272-274
+    } else {
+      return fail(M3D_ERR_UNSUPPORTED, "area lights must be mesh or sphere objects (light %d is object kind %d)", i,
+                  kind);
+    }
+    total_light += total;
+    L.cumu_total = total_light;
+  }
+  if (!(total_light > 0)) return fail(M3D_ERR_INVALID_ARG, "the area lights emit nothing");
+
+  DeviceBidirParams bp;
+  std::memset(&bp, 0, sizeof(bp));
+  bp.max_depth = max_depth;
+  bp.max_light_depth = max_ld;
+  bp.min_depth = params->min_depth;
+  bp.cutoff = (float)params->cutoff;
+  bp.antialias = (float)params->antialias;
+  bp.roulette_delta = params->roulette_delta;
+  bp.power_heuristic = params->power_heuristic;
+  bp.seed = params->seed;
+  bp.num_lights = num_lights;
+  bp.total_light = total_light;
+
+  const size_t lights_bytes = align256(hl.size() * sizeof(DeviceAreaLight));
+  M3D_CUDA(ctx->scratch[7].reserve(lights_bytes + std::max<size_t>(1, ht.size()) * sizeof(DeviceLightTri)));
+  DeviceAreaLight *d_lights = ctx->scratch[7].as<DeviceAreaLight>();
+  DeviceLightTri *d_tris = (DeviceLightTri *)(ctx->scratch[7].as<char>() + lights_bytes);
+  M3D_CUDA(cudaMemcpyAsync(d_lights, hl.data(), hl.size() * sizeof(DeviceAreaLight), cudaMemcpyHostToDevice, s));
+  if (!ht.empty())
+    M3D_CUDA(cudaMemcpyAsync(d_tris, ht.data(), ht.size() * sizeof(DeviceLightTri), cudaMemcpyHostToDevice, s));
+
+  // batch geometry: per-slot footprint is dominated by the stored path vertices
+  const size_t per_slot = (size_t)16 * kBidirVertexFields * (max_depth + max_ld) + (size_t)max_ld * 68 + 256;
+  int64_t cap = (int64_t)std::min<size_t>((size_t)1 << 20, ((size_t)6 << 30) / per_slot);
+  const int64_t total = npix * sample_count;
+  cap = std::max<int64_t>(1, std::min(cap, total));
+  const int64_t nP_max = std::min(npix, cap);
+  BidirBuffers buf;
+  if (int32_t rc = carve_bidir_buffers(ctx, cap, max_depth, max_ld, buf)) return rc;
+  M3D_CUDA(cudaMemsetAsync(buf.ray_total, 0, sizeof(unsigned long long), s));
+  const DeviceCamera dc = device_camera(*cam, width, height);
+
+  auto trace = [&](const float4 *org, const float4 *dir, const int32_t *skip, float4 *raw, int64_t n_max,
+                   const int *n_ptr) -> int32_t {
+    TraceLaunch t;
+    t.org_tmin = org;
+    t.dir_tmax = dir;
+    t.n = n_max;
+    t.n_ptr = n_ptr;
+    t.hit0 = raw;
+    t.hit1 = nullptr;
+    t.refine = false;
+    t.counters = nullptr;
+    t.skip_tris = skip;
+    t.ray_counter = next_work_counter(ctx);
+    if (!t.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
+    launch_trace_bvh_only(sc.bvh, t, s);
+    return M3D_OK;
+  };
+
+  GpuTimer tm;
+  tm.start(s);
+  int64_t launches = 0;
+  for (int64_t p0 = 0; p0 < npix; p0 += nP_max) {
+    const int64_t nP = std::min(nP_max, npix - p0);
+    const int64_t S_max = std::max<int64_t>(1, cap / nP);
+    for (int64_t s0 = 0; s0 < sample_count; s0 += S_max) {
+      PathBatch b;
+      b.W = width;
+      b.pix0 = (int32_t)((int64_t)row_begin * width + p0);
+      b.nP = (int32_t)nP;
+      b.S = (int32_t)std::min<int64_t>(S_max, sample_count - s0);
+      b.sample0 = (uint32_t)(sample_begin + s0);
+      const int64_t n = (int64_t)b.nP * b.S;
+      // eye sub-paths
+      launch_bidir_eye_raygen(dc, bp, b, buf, s);
+      launches++;
+      int cur = 0;
+      for (int depth = 0; depth < max_depth; depth++) {
+        if (int32_t rc = trace(buf.org[cur], buf.dir[cur], buf.skip[cur], buf.raw, n, buf.counts + cur)) return rc;
+        launch_bidir_eye_shade(sc, bp, b, buf, cur, depth, s);
+        M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
+        cur ^= 1;
+        launches += 2;
+      }
+      // light sub-paths
+      launch_bidir_light_raygen(sc, bp, d_lights, d_tris, b, buf, s);
+      launches++;
+      cur = 0;
+      for (int depth = 0; depth + 1 < max_ld; depth++) {
+        if (int32_t rc = trace(buf.org[cur], buf.dir[cur], buf.skip[cur], buf.raw, n, buf.counts + cur)) return rc;
+        launch_bidir_light_shade(sc, bp, b, buf, cur, depth, s);
+        M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
+        cur ^= 1;
+        launches += 2;
+      }
+      // connections
+      for (int i = 1; i <= max_depth; i++) {
+        M3D_CUDA(cudaMemsetAsync(buf.counts + 2, 0, sizeof(int), s));
+        launch_bidir_connect(sc, bp, b, buf, i, s);
+        if (int32_t rc = trace(buf.corg, buf.cdir, buf.cskip, buf.craw, n * max_ld, buf.counts + 2)) return rc;
+        launch_bidir_connect_resolve(sc, buf, s);
+        launches += 3;
+      }
+      launch_path_flush(b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
+      launches++;
+    }
+  }
+  tm.stop(s);
+  unsigned long long rays = 0;
+  M3D_CUDA(cudaMemcpyAsync(&rays, buf.ray_total, sizeof(rays), cudaMemcpyDeviceToHost, s));
+  M3D_CUDA(cudaStreamSynchronize(s));  // also keeps the host light tables alive for the copies
+  M3D_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->rays = (int64_t)rays;
+    stats->kernel_ms = tm.ms();
+    stats->launches = launches;
+  }
+  return M3D_OK;
+}
+
+int32_t m3d_render_bidir(m3d_scene *scene, const m3d_camera *cam, const m3d_area_light *lights, int32_t num_lights,
+                         const m3d_bidir_params *params, int32_t width, int32_t height,
+                         const m3d_partition *part, int32_t sample_count, float *rgb_sum, float *rgb_sumsq,
+                         m3d_stats *stats) {
+  if (!scene || !rgb_sum || width <= 0 || height <= 0)
+    return fail(M3D_ERR_INVALID_ARG, "m3d_render_bidir: bad arguments");
+  m3d_ctx *ctx = scene->ctx;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)width * height * 3 * sizeof(float);
+  M3D_CUDA(ctx->scratch[3].reserve(bytes * 2));
+  float *d_sum = ctx->scratch[3].as<float>();
+  float *d_sq = rgb_sumsq ? d_sum + (size_t)width * height * 3 : nullptr;
+  M3D_CUDA(cudaMemsetAsync(d_sum, 0, bytes * (rgb_sumsq ? 2 : 1), ctx->stream));
+  int32_t rc = m3d_render_bidir_device(scene, cam, lights, num_lights, params, width, height, part, sample_count,
+                                       d_sum, d_sq, ctx->stream, stats);
+  if (rc != M3D_OK) return rc;
+  M3D_CUDA(cudaMemcpyAsync(rgb_sum, d_sum, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (rgb_sumsq) M3D_CUDA(cudaMemcpyAsync(rgb_sumsq, d_sq, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  M3D_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (stats) stats->d2h_bytes = (int64_t)(bytes * (rgb_sumsq ? 2 : 1));
+  return M3D_OK;
+}
+
+}  // extern "C"

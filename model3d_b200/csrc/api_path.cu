@@ -205,7 +205,7 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
         M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
         cur ^= 1;
       }
-      launch_path_flush(b, buf, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
+      launch_path_flush(b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
       launches++;
     }
   }

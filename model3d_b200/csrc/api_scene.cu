@@ -8,6 +8,7 @@
 
 #include "api_common.h"
 #include "scene.h"
+#include "scene_host.h"
 
 using namespace m3d;
 
@@ -28,21 +29,6 @@ struct m3d_scene_builder {
   m3d_ctx *ctx = nullptr;
   std::vector<m3d_material_desc> materials;
   std::vector<BuilderObject> objects;
-};
-
-struct m3d_scene {
-  m3d_ctx *ctx = nullptr;
-  DevBuf nodes, tris, vnormals, shapes, objects, materials;
-  DeviceScene dev;
-  std::vector<DeviceShape> host_shapes;
-  std::vector<m3d_material_desc> host_materials;
-  std::vector<int32_t> object_material;
-  std::vector<int32_t> object_kind;           // 0 mesh / ShapeKind
-  std::vector<int64_t> object_tri_begin;      // for mesh objects: range in the merged input
-  std::vector<int64_t> object_tri_count;
-  std::vector<float> merged_tris;             // world-space triangles of all mesh objects
-  double bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
-  m3d_mesh_info info{};
 };
 
 namespace {
@@ -361,6 +347,9 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
   in.prim_ids = prim_ids.data();
   in.obj_ids = obj_ids.data();
   build_wide_bvh(in, bvh);
+  sc->leaf_of_merged.assign((size_t)ntri, -1);
+  for (size_t li = 0; li < bvh.tris.size(); li++)
+    sc->leaf_of_merged[(size_t)(sc->object_tri_begin[bvh.tris[li].object] + bvh.tris[li].prim)] = (int32_t)li;
   // upload_bvh remaps vnormals through TriRecord.prim, which is per-object here: give it a
   // table indexed by merged position instead
   std::vector<float> vn_by_leaf;

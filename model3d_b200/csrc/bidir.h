@@ -1,0 +1,82 @@
+// Bidirectional path tracer: device-side parameter blocks and launch wrappers.
+// Replaces BidirPathTracer.rayColor and helpers (render3d/bidir.go:101-576) and the area
+// lights it samples (render3d/light.go:104-314).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "path.h"
+#include "scene.h"
+
+namespace m3d {
+
+constexpr int kBidirMaxDepth = 16;  // per sub-path; joined paths have at most 32 vertices
+
+struct DeviceBidirParams {
+  int32_t max_depth, max_light_depth, min_depth;
+  float cutoff, antialias;
+  double roulette_delta, power_heuristic;
+  uint64_t seed;
+  int32_t num_lights;
+  double total_light;  // AreaLight.TotalEmission of the joined light (light.go:313-314)
+};
+
+// One emitter of the joined area light (light.go:104-161, 227-274).
+struct DeviceAreaLight {
+  int32_t kind;       // 0 mesh, SHAPE_SPHERE
+  int32_t object;
+  int32_t surf;       // sphere: -2 - shape index (self-intersection guard id)
+  int32_t tri_begin, tri_count;  // range in the light-triangle table (mesh lights)
+  float emission[3];
+  float center[3], radius;
+  double cumu_total;  // cumulative TotalEmission up to and including this light
+  double total_area;
+};
+
+// One triangle of a mesh light: vertices, flat normal, cumulative area inside its light,
+// and its leaf-order index in the scene BVH (self-intersection guard id).
+struct DeviceLightTri {
+  float v[9];
+  float n[3];
+  double cumu_area;
+  int32_t leaf_index;
+  int32_t pad;
+};
+
+// SoA path-vertex storage: field f of vertex `depth` of slot s lives at
+// verts[(f * D + depth) * cap + s]; 7 float4 fields per vertex (see bidir_kernels.cu).
+constexpr int kBidirVertexFields = 7;
+
+struct BidirBuffers {
+  int64_t cap;
+  int32_t De, Dl;  // vertex capacity of the eye / light sub-paths
+  float4 *ev, *lv;
+  int32_t *ne, *nl;
+  float4 *org[2], *dir[2];
+  int32_t *skip[2], *queue[2];
+  float4 *raw;
+  float4 *ender_full, *ender_roul;  // PathEnder state: (fullMask, currentRoulette), rouletteMask
+  float4 *accum;
+  double *eye_state;  // 4 doubles per slot: eyeDensity, eyeBSDF.xyz
+  // connection (visibility) rays of one round, compacted
+  float4 *corg, *cdir, *craw, *cpay;
+  int32_t *cskip;
+  int *counts;  // [0],[1] queue lengths, [2] connection rays
+  unsigned long long *ray_total;
+};
+
+void launch_bidir_eye_raygen(const DeviceCamera &cam, const DeviceBidirParams &bp, const PathBatch &b,
+                             const BidirBuffers &buf, cudaStream_t stream);
+void launch_bidir_eye_shade(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
+                            const BidirBuffers &buf, int cur, int depth, cudaStream_t stream);
+void launch_bidir_light_raygen(const DeviceScene &sc, const DeviceBidirParams &bp, const DeviceAreaLight *lights,
+                               const DeviceLightTri *tris, const PathBatch &b, const BidirBuffers &buf,
+                               cudaStream_t stream);
+void launch_bidir_light_shade(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
+                              const BidirBuffers &buf, int cur, int depth, cudaStream_t stream);
+// connections of eye prefix length i (1-based) with every light prefix; emits visibility rays
+void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
+                          const BidirBuffers &buf, int i, cudaStream_t stream);
+void launch_bidir_connect_resolve(const DeviceScene &sc, const BidirBuffers &buf, cudaStream_t stream);
+
+}  // namespace m3d

@@ -1,0 +1,622 @@
+// Bidirectional path tracer kernels (sm_100a), a wavefront restatement of
+// render3d/bidir.go:
+//   bidir_eye_raygen / bidir_eye_shade      sampleEyePath        bidir.go:161-189
+//   bidir_light_raygen / bidir_light_shade  sampleLightPath      bidir.go:191-234
+//                                           (+ SampleLight light.go:142-157,254-270,303-311)
+//   bidir_connect                           allPathCombinations  bidir.go:476-530, combinePaths
+//                                           :532-572, densities :421-471, the MIS weighting and
+//                                           Russian roulette of rayColor :101-159
+//   bidir_connect_resolve                   the visibility test  bidir.go:144-152
+// Path vertices (bptPathVertex bidir.go:311-346) live in HBM as SoA float4 fields.
+//
+// Numerics: traversal, hit points and BSDF values are float32.  Densities, path throughputs
+// and MIS weights are products over up to 2*depth vertices and include the reference's
+// Dirac-lobe magnitude 2/cosineEpsilon = 2e8 per specular vertex (material.go:401-462), which
+// overflows float32 after 5 vertices: they are carried as (finite, delta-coefficient) pairs per
+// vertex and combined in float64, exactly like the reference's float64 arithmetic.
+#include "bidir.h"
+#include "materials.cuh"
+#include "scene_hit.cuh"
+
+namespace m3d {
+
+namespace {
+
+constexpr int kBlock = 128;
+constexpr double kDeltaMag = 2.0e8;  // 2 / cosineEpsilon
+constexpr double kFourPi = 12.566370614359172;
+
+struct BVert {
+  V3f point, normal, source, dest;
+  V3f bsdf_fin, bsdf_del, emission;
+  float sd_fin, sd_del, dd_fin, dd_del;
+  float roulette;
+  int32_t obj;   // < 0: the emitter vertex of a light path (no material, bidir.go:338-342)
+  int32_t surf;  // surface id for the self-intersection guard
+};
+
+__device__ __forceinline__ size_t vidx(int field, int D, int64_t cap, int depth, int slot) {
+  return ((size_t)field * D + depth) * (size_t)cap + slot;
+}
+
+__device__ __forceinline__ void store_vertex(float4 *__restrict__ verts, int D, int64_t cap, int depth, int slot,
+                                             const BVert &v) {
+  verts[vidx(0, D, cap, depth, slot)] = make_float4(v.point.x, v.point.y, v.point.z, v.roulette);
+  verts[vidx(1, D, cap, depth, slot)] = make_float4(v.normal.x, v.normal.y, v.normal.z, __int_as_float(v.obj));
+  verts[vidx(2, D, cap, depth, slot)] = make_float4(v.source.x, v.source.y, v.source.z, v.sd_fin);
+  verts[vidx(3, D, cap, depth, slot)] = make_float4(v.dest.x, v.dest.y, v.dest.z, v.dd_fin);
+  verts[vidx(4, D, cap, depth, slot)] = make_float4(v.bsdf_fin.x, v.bsdf_fin.y, v.bsdf_fin.z, v.sd_del);
+  verts[vidx(5, D, cap, depth, slot)] = make_float4(v.bsdf_del.x, v.bsdf_del.y, v.bsdf_del.z, v.dd_del);
+  verts[vidx(6, D, cap, depth, slot)] = make_float4(v.emission.x, v.emission.y, v.emission.z, __int_as_float(v.surf));
+}
+
+__device__ __forceinline__ BVert load_vertex(const float4 *__restrict__ verts, int D, int64_t cap, int depth,
+                                             int slot) {
+  const float4 f0 = verts[vidx(0, D, cap, depth, slot)], f1 = verts[vidx(1, D, cap, depth, slot)],
+               f2 = verts[vidx(2, D, cap, depth, slot)], f3 = verts[vidx(3, D, cap, depth, slot)],
+               f4 = verts[vidx(4, D, cap, depth, slot)], f5 = verts[vidx(5, D, cap, depth, slot)],
+               f6 = verts[vidx(6, D, cap, depth, slot)];
+  BVert v;
+  v.point = v3f(f0.x, f0.y, f0.z);
+  v.roulette = f0.w;
+  v.normal = v3f(f1.x, f1.y, f1.z);
+  v.obj = __float_as_int(f1.w);
+  v.source = v3f(f2.x, f2.y, f2.z);
+  v.sd_fin = f2.w;
+  v.dest = v3f(f3.x, f3.y, f3.z);
+  v.dd_fin = f3.w;
+  v.bsdf_fin = v3f(f4.x, f4.y, f4.z);
+  v.sd_del = f4.w;
+  v.bsdf_del = v3f(f5.x, f5.y, f5.z);
+  v.dd_del = f5.w;
+  v.emission = v3f(f6.x, f6.y, f6.z);
+  v.surf = __float_as_int(f6.w);
+  return v;
+}
+
+// bptPathVertex.EvalMaterial (bidir.go:338-346); tag: Dirac lobe linking source and dest
+__device__ __forceinline__ void eval_vertex(const DeviceScene &sc, BVert &v, int tag) {
+  v.sd_fin = v.sd_del = v.dd_fin = v.dd_del = 0.f;
+  v.bsdf_fin = v.bsdf_del = v3f(0.f, 0.f, 0.f);
+  if (v.obj < 0) {
+    v.dd_fin = 4.f * fmaxf(0.f, dot(v.dest, v.normal));
+    return;
+  }
+  const MatAt m = material_at(sc, v.obj, v.point);
+  const Density sd = mat_source_density(sc, m, v.normal, v.source, v.dest, tag);
+  const Density dd = mat_dest_density(sc, m, v.normal, v.source, v.dest, tag);
+  v.sd_fin = sd.fin;
+  v.sd_del = sd.del;
+  v.dd_fin = dd.fin;
+  v.dd_del = dd.del;
+  v.bsdf_fin = mat_bsdf(sc, m, v.normal, v.source, v.dest);
+  v.bsdf_del = mat_bsdf_delta(sc, m, v.normal, v.source, v.dest, tag);
+}
+
+__device__ __forceinline__ float source_dot(const BVert &v) { return fabsf(dot(v.normal, v.source)); }
+__device__ __forceinline__ float dest_dot(const BVert &v) { return fabsf(dot(v.normal, v.dest)); }
+__device__ __forceinline__ double full_sd(const BVert &v) { return (double)v.sd_fin + (double)v.sd_del * kDeltaMag; }
+__device__ __forceinline__ double full_dd(const BVert &v) { return (double)v.dd_fin + (double)v.dd_del * kDeltaMag; }
+
+// pathEnder.End (bidir.go:282-309).  full = (fullMask, currentRoulette), roul = rouletteMask.
+__device__ __forceinline__ bool ender_end(float4 &full, float4 &roul, Rng &g, int i, V3f mask, int min_length,
+                                          float cutoff) {
+  full.x *= mask.x;
+  full.y *= mask.y;
+  full.z *= mask.z;
+  const float mean = (full.x + full.y + full.z) * (1.f / 3.f);
+  if (!(mean == mean) || mean == INFINITY) return true;  // degenerate density: nothing can be carried on
+  if (mean < cutoff) {
+    const float keep = mean / cutoff;
+    if (g.f32() > keep) return true;
+    full.w *= 1.f / keep;
+  }
+  if (min_length != 0 && i + 1 >= min_length) {
+    roul.x *= mask.x;
+    roul.y *= mask.y;
+    roul.z *= mask.z;
+    const float mv = fmaxf(fmaxf(roul.x, roul.y), roul.z);
+    if (mv < 1.f) {
+      roul = make_float4(1.f, 1.f, 1.f, 0.f);
+      const float keep = mv;
+      if (g.f32() > keep) return true;
+      full.w *= 1.f / keep;
+    }
+  }
+  return false;
+}
+
+// BSDF * cos / density of the sampled direction; Dirac lobes cancel analytically.
+__device__ __forceinline__ V3f sampled_mask(V3f bsdf_fin, V3f bsdf_del, float d_fin, float d_del, float cosv) {
+  if (d_del > 0.f) return bsdf_del * (cosv / d_del);
+  return bsdf_fin * (cosv / d_fin);  // d_fin == 0 -> inf / NaN, caught by ender_end
+}
+
+__device__ __forceinline__ int warp_aggregated_alloc(int *counter) {
+  const unsigned m = __activemask();
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bidir_eye_raygen_kernel(DeviceCamera cam, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
+  const int64_t n = (int64_t)b.nP * b.S;
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot == 0) {
+    buf.counts[0] = (int)n;
+    buf.counts[1] = 0;
+    buf.counts[2] = 0;
+  }
+  if (slot >= n) return;
+  const int p = (int)(slot % b.nP), s = (int)(slot / b.nP);
+  const int pix = b.pix0 + p;
+  const int x = pix % b.W, y = pix / b.W;
+  double fx = (double)x, fy = (double)y;
+  if (bp.antialias != 0.f) {  // ray_renderer.go:118-124
+    Rng g;
+    g.init(bp.seed, (uint32_t)pix, b.sample0 + (uint32_t)s, 0xA11A5u);
+    fx += (double)(bp.antialias * (g.f32() - 0.5f));
+    fy += (double)(bp.antialias * (g.f32() - 0.5f));
+  }
+  fx = (fx - cam.cx) / cam.cx;
+  fy = (fy - cam.cy) / cam.cy;
+  buf.org[0][slot] = make_float4((float)cam.origin[0], (float)cam.origin[1], (float)cam.origin[2], 0.f);
+  buf.dir[0][slot] = make_float4((float)(cam.x[0] * fx + cam.y[0] * fy + cam.z[0]),
+                                 (float)(cam.x[1] * fx + cam.y[1] * fy + cam.z[1]),
+                                 (float)(cam.x[2] * fx + cam.y[2] * fy + cam.z[2]), INFINITY);
+  buf.skip[0][slot] = -1;
+  buf.queue[0][slot] = (int32_t)slot;
+  buf.ne[slot] = 0;
+  buf.nl[slot] = 0;
+  buf.ender_full[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
+  buf.ender_roul[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+  buf.accum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// One step of sampleEyePath (EYE) or sampleLightPath's loop (!EYE): resolve the hit, build and
+// store the vertex, sample the continuation, apply pathEnder, compact survivors.
+template <bool EYE>
+__global__ void __launch_bounds__(kBlock)
+bidir_shade_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf, int cur, int depth) {
+  const int n = buf.counts[cur];
+  const unsigned lane = threadIdx.x & 31u;
+  const int warps_total = (gridDim.x * kBlock) >> 5;
+  const int warp_id = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+  const int nxt = cur ^ 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(buf.ray_total, (unsigned long long)n);
+  const int max_vertices = EYE ? bp.max_depth : bp.max_light_depth;
+  const int vdepth = EYE ? depth : depth + 1;  // index of the vertex this step creates
+  float4 *__restrict__ verts = EYE ? buf.ev : buf.lv;
+  const int D = EYE ? buf.De : buf.Dl;
+
+  for (int base = warp_id * 32; base < n; base += warps_total * 32) {
+    const int q = base + (int)lane;
+    bool alive = false;
+    int slot = 0;
+    BVert v;
+    V3f next_dir = v3f(0.f, 0.f, 1.f);
+    v.point = v3f(0.f, 0.f, 0.f);
+    v.surf = -1;
+    if (q < n) {
+      slot = buf.queue[cur][q];
+      const float4 o = __ldcs(buf.org[cur] + q), d = __ldcs(buf.dir[cur] + q), raw = __ldcs(buf.raw + q);
+      const SceneHit h = resolve_scene_hit(sc, o, d, raw, buf.skip[cur][q], true);
+      if (h.obj >= 0) {
+        const V3f org = v3f(o.x, o.y, o.z), dir = v3f(d.x, d.y, d.z);
+        v.point = org + dir * h.t;
+        v.normal = v3f(h.nx, h.ny, h.nz);
+        v.obj = h.obj;
+        v.surf = h.surf;
+        const MatAt m = material_at(sc, h.obj, v.point);
+        v.emission = mat_emission(sc, m);
+        Rng g;
+        g.init(bp.seed, (uint32_t)(b.pix0 + slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP),
+               (EYE ? 0x100u : 0x300u) + (uint32_t)depth);
+        int tag = 0;
+        if (EYE) {
+          v.dest = normalize(dir) * -1.f;                                // bidir.go:171
+          v.source = mat_sample_source(sc, m, g, v.normal, v.dest, tag);  // bidir.go:172
+          next_dir = v.source * -1.f;
+        } else {
+          v.source = dir;                                                // bidir.go:213
+          v.dest = mat_sample_dest(sc, m, g, v.normal, v.source, tag);    // bidir.go:214
+          next_dir = v.dest;
+        }
+        float4 full = buf.ender_full[slot], roul = buf.ender_roul[slot];
+        v.roulette = full.w;
+        eval_vertex(sc, v, tag);
+        store_vertex(verts, D, buf.cap, vdepth, slot, v);
+        (EYE ? buf.ne : buf.nl)[slot] = vdepth + 1;
+        const V3f mask = EYE ? sampled_mask(v.bsdf_fin, v.bsdf_del, v.sd_fin, v.sd_del, source_dot(v))
+                             : sampled_mask(v.bsdf_fin, v.bsdf_del, v.dd_fin, v.dd_del, dest_dot(v));
+        const bool ended = ender_end(full, roul, g, depth, mask, bp.min_depth, bp.cutoff);
+        if (!ended && vdepth + 1 < max_vertices) {
+          alive = true;
+          buf.ender_full[slot] = full;
+          buf.ender_roul[slot] = roul;
+        }
+      }
+    }
+    const unsigned live = __ballot_sync(0xffffffffu, alive);
+    if (live) {
+      int pos0 = 0;
+      if (lane == (unsigned)(__ffs(live) - 1)) pos0 = atomicAdd(buf.counts + nxt, __popc(live));
+      pos0 = __shfl_sync(0xffffffffu, pos0, __ffs(live) - 1);
+      if (alive) {
+        const int pos = pos0 + __popc(live & ((1u << lane) - 1u));
+        buf.org[nxt][pos] = make_float4(v.point.x, v.point.y, v.point.z, 0.f);
+        buf.dir[nxt][pos] = make_float4(next_dir.x, next_dir.y, next_dir.z, INFINITY);
+        buf.skip[nxt][pos] = v.surf;
+        buf.queue[nxt][pos] = slot;
+      }
+    }
+  }
+}
+
+// Box-Muller pair from two uniforms
+__device__ __forceinline__ void gauss2(Rng &g, float &a, float &b) {
+  const float u1 = fmaxf(g.f32(), 5.9604644775390625e-8f), u2 = g.f32();
+  const float r = sqrtf(-2.f * logf(u1));
+  float s, c;
+  sincosf(kTwoPi * u2, &s, &c);
+  a = r * c;
+  b = r * s;
+}
+
+// sampleLightPath up to its first ray (bidir.go:191-208)
+__global__ void __launch_bounds__(256)
+bidir_light_raygen_kernel(DeviceScene sc, DeviceBidirParams bp, const DeviceAreaLight *__restrict__ lights,
+                          const DeviceLightTri *__restrict__ tris, PathBatch b, BidirBuffers buf) {
+  const int64_t n = (int64_t)b.nP * b.S;
+  const int64_t slot64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot64 == 0) {
+    buf.counts[0] = bp.max_light_depth > 1 ? (int)n : 0;
+    buf.counts[1] = 0;
+  }
+  if (slot64 >= n) return;
+  const int slot = (int)slot64;
+  Rng g;
+  g.init(bp.seed, (uint32_t)(b.pix0 + slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP), 0x200u);
+  // joinedAreaLight.SampleLight (light.go:303-311): light chosen in proportion to TotalEmission
+  int li = 0;
+  if (bp.num_lights > 1) {
+    const double x = (double)g.f32() * bp.total_light;
+    int lo = 0, hi = bp.num_lights;  // sort.SearchFloat64s: smallest index with cumu >= x
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (lights[mid].cumu_total < x) lo = mid + 1; else hi = mid;
+    }
+    li = lo == bp.num_lights ? lo - 1 : lo;
+  }
+  const DeviceAreaLight L = lights[li];
+  BVert v;
+  v.obj = -1;
+  v.emission = v3f(L.emission);
+  v.roulette = 1.f;
+  if (L.kind == SHAPE_SPHERE) {  // SphereAreaLight.SampleLight (light.go:142-157)
+    V3f nrm;
+    for (;;) {
+      float a, bb, c, dmy;
+      gauss2(g, a, bb);
+      gauss2(g, c, dmy);
+      nrm = v3f(a, bb, c);
+      const float len = norm(nrm);
+      if (len > 0.01f && len < 100.f) {
+        nrm = nrm * (1.f / len);
+        break;
+      }
+    }
+    v.normal = nrm;
+    v.point = v3f(L.center) + nrm * L.radius;
+    v.surf = L.surf;
+  } else {  // MeshAreaLight.SampleLight (light.go:254-270)
+    const double x = (double)g.f32() * L.total_area;
+    int lo = 0, hi = L.tri_count;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (tris[L.tri_begin + mid].cumu_area < x) lo = mid + 1; else hi = mid;
+    }
+    const int ti = L.tri_begin + (lo == L.tri_count ? lo - 1 : lo);
+    const DeviceLightTri T = tris[ti];
+    const float r1 = sqrtf(g.f32()), r2 = g.f32();
+    const float w0 = 1.f - r1, w1 = r1 * (1.f - r2), w2 = r1 * r2;
+    v.point = v3f(T.v[0] * w0 + T.v[3] * w1 + T.v[6] * w2, T.v[1] * w0 + T.v[4] * w1 + T.v[7] * w2,
+                  T.v[2] * w0 + T.v[5] * w1 + T.v[8] * w2);
+    v.normal = v3f(T.n);
+    v.surf = T.leaf_index;
+  }
+  v.source = v.normal * -1.f;
+  v.dest = lambert_sample(g, v.normal) * -1.f;  // sampleAngularDest (bidir.go:574-576)
+  eval_vertex(sc, v, 0);
+  store_vertex(buf.lv, buf.Dl, buf.cap, 0, slot, v);
+  buf.nl[slot] = 1;
+  buf.org[0][slot] = make_float4(v.point.x, v.point.y, v.point.z, 0.f);
+  buf.dir[0][slot] = make_float4(v.dest.x, v.dest.y, v.dest.z, INFINITY);
+  buf.skip[0][slot] = v.surf;
+  buf.queue[0][slot] = slot;
+  buf.ender_full[slot] = make_float4(1.f, 1.f, 1.f, 1.f);
+  buf.ender_roul[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+}
+
+// Per-vertex scalars of the MIS computation (bidir.go:421-471).
+struct Mis {
+  double sd, dd;
+  float sdot, ddot;
+  float px, py, pz;
+};
+__device__ __forceinline__ Mis mis_of(const BVert &v) {
+  Mis m;
+  m.sd = full_sd(v);
+  m.dd = full_dd(v);
+  m.sdot = source_dot(v);
+  m.ddot = dest_dot(v);
+  m.px = v.point.x;
+  m.py = v.point.y;
+  m.pz = v.point.z;
+  return m;
+}
+__device__ __forceinline__ double out_area(const Mis &a, const Mis &b) {
+  const double dx = (double)a.px - b.px, dy = (double)a.py - b.py, dz = (double)a.pz - b.pz;
+  return kFourPi * (dx * dx + dy * dy + dz * dz);
+}
+
+struct D3c {
+  double x, y, z;
+};
+
+// allPathCombinations for one eye prefix length i (bidir.go:476-530) + rayColor's callback
+// (bidir.go:113-158).  One thread per sample.
+__global__ void __launch_bounds__(kBlock)
+bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf, int i) {
+  const int n_slots = b.nP * b.S;
+  const int slot = blockIdx.x * kBlock + threadIdx.x;
+  if (slot >= n_slots) return;
+  const int ne = buf.ne[slot];
+  if (i > ne) return;
+  const int nl = buf.nl[slot];
+
+  // eye prefix state: eyeDensity, eyeBSDF (bidir.go:482-483, 527-528)
+  double eye_density = 1.0;
+  D3c eye_bsdf = {1.0, 1.0, 1.0};
+  if (i > 1) {
+    const double *st = buf.eye_state + (size_t)slot * 4;
+    eye_density = st[0];
+    eye_bsdf.x = st[1];
+    eye_bsdf.y = st[2];
+    eye_bsdf.z = st[3];
+  }
+
+  Mis E[kBidirMaxDepth], L[kBidirMaxDepth];
+  for (int k = 0; k < i; k++) E[k] = mis_of(load_vertex(buf.ev, buf.De, buf.cap, k, slot));
+  for (int k = 0; k < nl; k++) L[k] = mis_of(load_vertex(buf.lv, buf.Dl, buf.cap, k, slot));
+  const BVert ev = load_vertex(buf.ev, buf.De, buf.cap, i - 1, slot);
+  const BVert l0 = load_vertex(buf.lv, buf.Dl, buf.cap, 0, slot);
+  const double l0_sum = (double)l0.emission.x + l0.emission.y + l0.emission.z;
+  const int max_ld = bp.max_light_depth;  // already defaulted to max_depth by the host
+  const double ph = bp.power_heuristic;
+
+  float3 add = make_float3(0.f, 0.f, 0.f);
+
+  // MIS weight of the joined path made of light[0..j-2], JL, JE, eye[i-2..0] (j >= 1) or
+  // eye[i-1..0] (j == 0): sum over every way of splitting it into a light and an eye part.
+  auto mis_weight = [&](int j, const Mis &JL, const Mis &JE, double density, double emis0_sum) -> double {
+    const int n = i + j;
+    auto at = [&](int k) -> Mis {
+      if (j == 0) return E[i - 1 - k];
+      if (k < j - 1) return L[k];
+      if (k == j - 1) return JL;
+      if (k == j) return JE;
+      return E[i - 1 - (k - j)];
+    };
+    const double s = ph == 0.0 ? 1.0 : (ph == 2.0 ? rsqrt(density) : pow(density, -(ph - 1.0) / ph));
+    double weight = 0.0;
+    auto f = [&](double d) {
+      if (ph == 0.0) weight += d;
+      else if (ph == 2.0) weight += (d * s) * (d * s);
+      else weight += pow(d * s, ph);
+    };
+    double acc[2 * kBidirMaxDepth];
+    double sdp = 1.0;
+    for (int k = n - 1; k > 0; k--) {
+      acc[k] = sdp;
+      sdp *= at(k).sd;
+    }
+    if (n <= bp.max_depth) f(sdp);
+    if (n > 1) {
+      double ld = emis0_sum / bp.total_light;
+      Mis m0 = at(0), m1 = at(1);
+      if (n - 1 <= bp.max_depth) f(ld * acc[1] * out_area(m0, m1) / (double)m0.ddot);
+      for (int k = 0; k + 2 < n; k++) {
+        if (k + 1 >= max_ld) break;
+        const Mis m2 = at(k + 2);
+        ld *= m0.dd;
+        ld *= (double)m1.sdot / (double)m0.ddot;
+        if (n - (k + 2) <= bp.max_depth) f(acc[k + 2] * ld * out_area(m1, m2) / (double)m1.ddot);
+        m0 = m1;
+        m1 = m2;
+      }
+    }
+    return weight;
+  };
+
+  const Mis EV = mis_of(ev);
+  // ---- j == 0: the eye path itself reached an emitter (bidir.go:486-491)
+  if (!is_zero(ev.emission)) {
+    const double r = (double)ev.roulette;
+    const D3c cur = {ev.emission.x * eye_bsdf.x * r, ev.emission.y * eye_bsdf.y * r, ev.emission.z * eye_bsdf.z * r};
+    if (cur.x + cur.y + cur.z >= 1e-8) {
+      const double es = (double)ev.emission.x + ev.emission.y + ev.emission.z;
+      const double w = mis_weight(0, EV, EV, eye_density, es);
+      if (w > 0.0 && w < INFINITY) {
+        add.x += (float)(cur.x / w);
+        add.y += (float)(cur.y / w);
+        add.z += (float)(cur.z / w);
+      }
+    }
+  }
+  // ---- j >= 1 (bidir.go:493-525)
+  double density = eye_density * l0_sum / bp.total_light;
+  D3c light_bsdf = {l0.emission.x, l0.emission.y, l0.emission.z};
+  BVert prev = l0;  // light[j-2] inside the loop
+  BVert lj = l0;    // light[j-1]
+  for (int j = 1; j <= nl; j++) {
+    if (j > 1) {
+      lj = load_vertex(buf.lv, buf.Dl, buf.cap, j - 1, slot);
+      density *= full_dd(prev);
+      density *= (double)source_dot(lj) / (double)dest_dot(prev);
+      if (j > 2) {
+        light_bsdf.x *= (double)prev.bsdf_fin.x + (double)prev.bsdf_del.x * kDeltaMag;
+        light_bsdf.y *= (double)prev.bsdf_fin.y + (double)prev.bsdf_del.y * kDeltaMag;
+        light_bsdf.z *= (double)prev.bsdf_fin.z + (double)prev.bsdf_del.z * kDeltaMag;
+      }
+      const double sdj = (double)source_dot(lj);
+      light_bsdf.x *= sdj;
+      light_bsdf.y *= sdj;
+      light_bsdf.z *= sdj;
+    }
+    const V3f diff = lj.point - ev.point;
+    const float dist2 = dot(diff, diff);
+    // combinePaths (bidir.go:544-566): both junction vertices re-evaluated for the new edge
+    BVert jl = lj;
+    const float dist = sqrtf(dist2);
+    jl.dest = (ev.point - lj.point) * (1.f / dist);
+    eval_vertex(sc, jl, 0);
+    BVert je = ev;
+    je.source = jl.dest;
+    eval_vertex(sc, je, 0);
+    const float dd = dest_dot(jl);
+    const float sd = source_dot(je);
+    if (dd > 0.f && sd > 0.f && dist > 0.f) {
+      const double cur_density = density * (kFourPi * (double)dist2) / (double)dd;
+      const double scale = (double)sd * (double)lj.roulette * (double)ev.roulette;
+      D3c inten = {eye_bsdf.x * light_bsdf.x * scale * (double)je.bsdf_fin.x,
+                   eye_bsdf.y * light_bsdf.y * scale * (double)je.bsdf_fin.y,
+                   eye_bsdf.z * light_bsdf.z * scale * (double)je.bsdf_fin.z};
+      if (j > 1) {
+        inten.x *= (double)jl.bsdf_fin.x;
+        inten.y *= (double)jl.bsdf_fin.y;
+        inten.z *= (double)jl.bsdf_fin.z;
+      }
+      if (inten.x + inten.y + inten.z >= 1e-8) {
+        const double w = mis_weight(j, mis_of(jl), mis_of(je), cur_density, l0_sum);
+        if (w > 0.0 && w < INFINITY) {
+          D3c color = {inten.x / w, inten.y / w, inten.z / w};
+          bool keep_it = true;
+          const double brightness = fmax(fmax(color.x, color.y), color.z);
+          if (bp.roulette_delta > 0.0 && brightness < bp.roulette_delta) {  // bidir.go:133-142
+            const double keep = brightness / bp.roulette_delta;
+            Rng g;
+            g.init(bp.seed, (uint32_t)(b.pix0 + slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP),
+                   0x1000u + (uint32_t)(i * 64 + j));
+            if ((double)g.f32() > keep) keep_it = false;
+            color.x /= keep;
+            color.y /= keep;
+            color.z /= keep;
+          }
+          if (keep_it && (color.x > 0.0 || color.y > 0.0 || color.z > 0.0)) {
+            // visibility ray eye vertex -> light vertex (bidir.go:144-152): blocked iff something
+            // lies strictly between the end points; both end surfaces are excluded (start: skip
+            // id, end: parameter interval) since float32 cannot express the 1e-8 offsets
+            const int pos = warp_aggregated_alloc(buf.counts + 2);
+            const V3f dirn = (lj.point - ev.point) * (1.f / dist);
+            buf.corg[pos] = make_float4(ev.point.x, ev.point.y, ev.point.z, 0.f);
+            buf.cdir[pos] = make_float4(dirn.x, dirn.y, dirn.z, dist * (1.f - 2e-4f));
+            buf.cskip[pos] = ev.surf;
+            buf.cpay[pos] = make_float4((float)color.x, (float)color.y, (float)color.z, __int_as_float(slot));
+          }
+        }
+      }
+    }
+    prev = lj;
+  }
+  if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {
+    float4 a = buf.accum[slot];
+    a.x += add.x;
+    a.y += add.y;
+    a.z += add.z;
+    buf.accum[slot] = a;
+  }
+  // bidir.go:527-528
+  {
+    double *st = buf.eye_state + (size_t)slot * 4;
+    const double sdv = (double)source_dot(ev);
+    st[0] = eye_density * full_sd(ev);
+    st[1] = eye_bsdf.x * ((double)ev.bsdf_fin.x + (double)ev.bsdf_del.x * kDeltaMag) * sdv;
+    st[2] = eye_bsdf.y * ((double)ev.bsdf_fin.y + (double)ev.bsdf_del.y * kDeltaMag) * sdv;
+    st[3] = eye_bsdf.z * ((double)ev.bsdf_fin.z + (double)ev.bsdf_del.z * kDeltaMag) * sdv;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bidir_connect_resolve_kernel(DeviceScene sc, BidirBuffers buf) {
+  const int n = buf.counts[2];
+  const int stride = gridDim.x * blockDim.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(buf.ray_total, (unsigned long long)n);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+    const float4 pay = buf.cpay[q];
+    const SceneHit h = resolve_scene_hit(sc, buf.corg[q], buf.cdir[q], buf.craw[q], buf.cskip[q], false);
+    if (h.obj >= 0) continue;  // blocked
+    float *a = reinterpret_cast<float *>(buf.accum + __float_as_int(pay.w));
+    atomicAdd(a, pay.x);
+    atomicAdd(a + 1, pay.y);
+    atomicAdd(a + 2, pay.z);
+  }
+}
+
+template <class K>
+int persistent_grid(K kernel, int block, int64_t n) {
+  int x = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&x, kernel, block, 0);
+  int64_t grid = (int64_t)device_sm_count() * (x > 0 ? x : 1);
+  const int64_t want = (n + block - 1) / block;
+  if (grid > want) grid = want;
+  return (int)(grid < 1 ? 1 : grid);
+}
+
+}  // namespace
+
+void launch_bidir_eye_raygen(const DeviceCamera &cam, const DeviceBidirParams &bp, const PathBatch &b,
+                             const BidirBuffers &buf, cudaStream_t stream) {
+  const int64_t n = (int64_t)b.nP * b.S;
+  if (n <= 0) return;
+  bidir_eye_raygen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cam, bp, b, buf);
+}
+
+void launch_bidir_eye_shade(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
+                            const BidirBuffers &buf, int cur, int depth, cudaStream_t stream) {
+  const int grid = persistent_grid(bidir_shade_kernel<true>, kBlock, (int64_t)b.nP * b.S);
+  bidir_shade_kernel<true><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf, cur, depth);
+}
+
+void launch_bidir_light_raygen(const DeviceScene &sc, const DeviceBidirParams &bp, const DeviceAreaLight *lights,
+                               const DeviceLightTri *tris, const PathBatch &b, const BidirBuffers &buf,
+                               cudaStream_t stream) {
+  const int64_t n = (int64_t)b.nP * b.S;
+  if (n <= 0) return;
+  bidir_light_raygen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sc, bp, lights, tris, b, buf);
+}
+
+void launch_bidir_light_shade(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
+                              const BidirBuffers &buf, int cur, int depth, cudaStream_t stream) {
+  const int grid = persistent_grid(bidir_shade_kernel<false>, kBlock, (int64_t)b.nP * b.S);
+  bidir_shade_kernel<false><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf, cur, depth);
+}
+
+void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
+                          const BidirBuffers &buf, int i, cudaStream_t stream) {
+  const int64_t n = (int64_t)b.nP * b.S;
+  if (n <= 0) return;
+  bidir_connect_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, stream>>>(sc, bp, b, buf, i);
+}
+
+void launch_bidir_connect_resolve(const DeviceScene &sc, const BidirBuffers &buf, cudaStream_t stream) {
+  const int grid = device_sm_count() * 8;
+  bidir_connect_resolve_kernel<<<grid, 256, 0, stream>>>(sc, buf);
+}
+
+}  // namespace m3d

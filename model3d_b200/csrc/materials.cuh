@@ -383,4 +383,53 @@ __device__ __forceinline__ V3f mat_bsdf_delta(const DeviceScene &sc, const MatAt
   return simple_bsdf_delta(sc.materials[d.sub[pick]], normal, source, dest, tag & 3);
 }
 
+// ---- destination-side sampling (light paths of the bidirectional tracer) --------------------
+// Generic rule (material.go:97-116): SampleDest(n, src) = -SampleSource(n, -src) and
+// DestDensity(n, src, dst) = SourceDensity(n, -dst, -src); RefractMaterial flips the normal
+// instead (material.go:464-471); JoinedMaterial mixes its parts (material.go:596-616).
+__device__ __forceinline__ V3f simple_sample_dest(const DeviceMaterial &d, V3f diffuse, Rng &g, V3f normal,
+                                                  V3f source, int &lobe) {
+  if (d.kind == M3D_MAT_REFRACT) return simple_sample_source(d, diffuse, g, normal * -1.f, source, lobe);
+  return simple_sample_source(d, diffuse, g, normal, source * -1.f, lobe) * -1.f;
+}
+__device__ __forceinline__ Density simple_dest_density(const DeviceMaterial &d, V3f diffuse, V3f normal, V3f source,
+                                                       V3f dest, int lobe) {
+  if (d.kind == M3D_MAT_REFRACT) return simple_source_density(d, diffuse, normal * -1.f, dest, source, lobe);
+  return simple_source_density(d, diffuse, normal, dest * -1.f, source * -1.f, 0);
+}
+__device__ __forceinline__ V3f mat_sample_dest(const DeviceScene &sc, const MatAt &m, Rng &g, V3f normal, V3f source,
+                                               int &tag) {
+  const DeviceMaterial &d = sc.materials[m.index];
+  if (d.kind != M3D_MAT_JOINED) return simple_sample_dest(d, m.diffuse, g, normal, source, tag);
+  float p = g.f32();
+  int pick = d.num_sub - 1;
+  for (int i = 0; i < d.num_sub; i++) {
+    p -= d.sub_prob[i];
+    if (p < 0.f) {
+      pick = i;
+      break;
+    }
+  }
+  const DeviceMaterial &s = sc.materials[d.sub[pick]];
+  int lobe;
+  const V3f r = simple_sample_dest(s, v3f(s.diffuse), g, normal, source, lobe);
+  tag = lobe | (pick << 2);
+  return r;
+}
+__device__ __forceinline__ Density mat_dest_density(const DeviceScene &sc, const MatAt &m, V3f normal, V3f source,
+                                                    V3f dest, int tag) {
+  const DeviceMaterial &d = sc.materials[m.index];
+  if (d.kind != M3D_MAT_JOINED) return simple_dest_density(d, m.diffuse, normal, source, dest, tag & 3);
+  Density r;
+  r.fin = 0.f;
+  r.del = 0.f;
+  for (int i = 0; i < d.num_sub; i++) {
+    const DeviceMaterial &s = sc.materials[d.sub[i]];
+    const Density x = simple_dest_density(s, v3f(s.diffuse), normal, source, dest, (tag >> 2) == i ? (tag & 3) : 0);
+    r.fin += d.sub_prob[i] * x.fin;
+    r.del += d.sub_prob[i] * x.del;
+  }
+  return r;
+}
+
 }  // namespace m3d

@@ -58,7 +58,7 @@ void launch_path_shade(const DeviceScene &sc, const DevicePathParams &pp, const 
 void launch_path_shadow_resolve(const DeviceScene &sc, const DevicePathParams &pp, const PathBuffers &buf,
                                 int cur, cudaStream_t stream);
 // per pixel: add the S per-sample colours (and their squares) into the frame accumulators
-void launch_path_flush(const PathBatch &b, const PathBuffers &buf, float *rgb_sum, float *rgb_sumsq,
+void launch_path_flush(const PathBatch &b, const float4 *accum, float *rgb_sum, float *rgb_sumsq,
                        cudaStream_t stream);
 
 }  // namespace m3d

@@ -278,12 +278,13 @@ path_shadow_resolve_kernel(DeviceScene sc, DevicePathParams pp, PathBuffers buf,
 }
 
 __global__ void __launch_bounds__(256)
-path_flush_kernel(PathBatch b, PathBuffers buf, float *__restrict__ rgb_sum, float *__restrict__ rgb_sumsq) {
+path_flush_kernel(PathBatch b, const float4 *__restrict__ accum, float *__restrict__ rgb_sum,
+                  float *__restrict__ rgb_sumsq) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= b.nP) return;
   float sx = 0.f, sy = 0.f, sz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
   for (int s = 0; s < b.S; s++) {
-    const float4 a = __ldcs(buf.accum + (size_t)s * b.nP + p);
+    const float4 a = __ldcs(accum + (size_t)s * b.nP + p);
     sx += a.x;
     sy += a.y;
     sz += a.z;
@@ -333,10 +334,10 @@ void launch_path_shadow_resolve(const DeviceScene &sc, const DevicePathParams &p
   path_shadow_resolve_kernel<<<(unsigned)((buf.cap + 255) / 256), 256, 0, stream>>>(sc, pp, buf, cur);
 }
 
-void launch_path_flush(const PathBatch &b, const PathBuffers &buf, float *rgb_sum, float *rgb_sumsq,
+void launch_path_flush(const PathBatch &b, const float4 *accum, float *rgb_sum, float *rgb_sumsq,
                        cudaStream_t stream) {
   if (b.nP <= 0) return;
-  path_flush_kernel<<<(unsigned)((b.nP + 255) / 256), 256, 0, stream>>>(b, buf, rgb_sum, rgb_sumsq);
+  path_flush_kernel<<<(unsigned)((b.nP + 255) / 256), 256, 0, stream>>>(b, accum, rgb_sum, rgb_sumsq);
 }
 
 }  // namespace m3d

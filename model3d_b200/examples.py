@@ -90,7 +90,8 @@ def build_product(spec):
         return r
 
     objs = R.JoinedObject()
-    for o in spec["objects"]:
+    light_of = {l["object"]: l for l in spec.get("area_lights", [])}
+    for oi, o in enumerate(spec["objects"]):
         m = mat(o["material"])
         if o["kind"] == "mesh":
             c = np.asarray(o["tris"], np.float32)
@@ -100,13 +101,19 @@ def build_product(spec):
             c = R.Rect(tuple(o["min"]), tuple(o["max"]))
         elif o["kind"] == "cylinder":
             c = R.Cylinder(tuple(o["p1"]), tuple(o["p2"]), o["radius"])
-        obj = R.ColliderObject(Collider=c, Material=m, FlipNormals=bool(o.get("flip")))
+        if oi in light_of:
+            # an emitter sampled by the BidirPathTracer: AreaLight object (light.go:131-140,237-252)
+            obj = R.AreaLight(c, light_of[oi]["emission"])
+        else:
+            obj = R.ColliderObject(Collider=c, Material=m, FlipNormals=bool(o.get("flip")))
         xf = o.get("xf")
         if xf is not None:
             obj = R.Translate(R.MatrixMultiply(obj, xf[0]), xf[1])
         objs.append(obj)
     scene = R.Scene(objs)
     scene.material_of = lambda m: cache[id(m)]
+    scene.area_light = R.JoinAreaLights(*[objs[l["object"]] for l in spec.get("area_lights", [])]) \
+        if spec.get("area_lights") else None
     return scene
 
 
@@ -175,7 +182,7 @@ def cornell_box(area_light_mesh=True):
     return dict(objects=objs, camera=dict(src=(0, -7, 2.5), dst=(0, 10, 2.5), fov=math.pi / 3.6),
                 focus=[dict(kind="phong", target=(0, 6, 6.9), alpha=40.0, prob=0.3,
                             applies=lambda m: m["kind"] == "lambert" or (m["kind"] == "phong" and sum(m["diffuse"]) > 0))],
-                light_object=4, light_emission=gray(25.0))
+                area_lights=[dict(object=4, emission=gray(25.0))])
 
 
 def testing_scene():
@@ -229,6 +236,16 @@ def product_tracer(spec, psc, max_depth, num_samples, cutoff=0.0, antialias=0.0,
                                 NumSamples=num_samples, Cutoff=cutoff, Antialias=antialias, Seed=seed)
 
 
+def product_bidir(spec, psc, max_depth, num_samples, min_depth=0, roulette_delta=0.0, power_heuristic=0.0,
+                  cutoff=0.0, antialias=0.0, max_light_depth=0, seed=1):
+    from . import render3d as R
+    cam = spec["camera"]
+    return R.BidirPathTracer(Camera=R.NewCameraAt(cam["src"], cam["dst"], cam["fov"]), Light=psc.area_light,
+                             MaxDepth=max_depth, MaxLightDepth=max_light_depth, MinDepth=min_depth,
+                             RouletteDelta=roulette_delta, PowerHeuristic=power_heuristic, NumSamples=num_samples,
+                             Cutoff=cutoff, Antialias=antialias, Seed=seed)
+
+
 def glass_scene():
     """Refraction with Fresnel reflection (RefractMaterial with SpecularColor), a glass ball
     and a glass slab inside a lit Lambert room: exercises every Dirac-lobe branch
@@ -248,4 +265,5 @@ def glass_scene():
         dict(kind="cylinder", p1=(2.5, 4.0, -2.0), p2=(2.5, 4.0, 0.5), radius=0.6,
              material=phong(30.0, specular=gray(0.3), diffuse=(0.1, 0.3, 0.5))),
     ]
-    return dict(objects=objs, camera=dict(src=(0, -3.5, 1.0), dst=(0, 4, 0.2), fov=math.pi / 3.0))
+    return dict(objects=objs, camera=dict(src=(0, -3.5, 1.0), dst=(0, 4, 0.2), fov=math.pi / 3.0),
+                area_lights=[dict(object=1, emission=gray(12.0))])

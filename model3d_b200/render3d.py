@@ -591,3 +591,144 @@ class RecursiveRayTracer:
         img = Image(width, height)
         self.RenderVariance(img, obj, samples, antialias=0.0)
         return float(img.Data.astype(np.float64).sum() / (3 * width * height))
+
+
+# ---- area lights (light.go:104-314) -----------------------------------------------------------
+class AreaLight(ColliderObject):
+    """render3d.AreaLight: an Object that can also be sampled as an emitter.  Created by
+    NewSphereAreaLight / NewMeshAreaLight; its material is Lambert with only an emission
+    colour, like the reference (light.go:131-140, 237-252)."""
+
+    def __init__(self, collider, emission):
+        super().__init__(Collider=collider, Material=LambertMaterial(EmissionColor=tuple(emission)))
+        self.Emission = tuple(float(x) for x in emission)
+
+
+def NewSphereAreaLight(sphere: Sphere, emission):
+    """render3d.NewSphereAreaLight (light.go:131-140)."""
+    return AreaLight(sphere, emission)
+
+
+def NewMeshAreaLight(mesh, emission):
+    """render3d.NewMeshAreaLight (light.go:237-252); mesh: triangle array [n,3,3] or MeshCollider."""
+    return AreaLight(mesh, emission)
+
+
+class JoinedAreaLight(JoinedObject):
+    """render3d.JoinAreaLights (light.go:283-301): the lights are also scene objects."""
+
+
+def JoinAreaLights(*lights):
+    for l in lights:
+        if not isinstance(l, AreaLight):
+            raise UnsupportedError("area light type %s is not supported on the GPU path" % type(l).__name__)
+    return JoinedAreaLight(lights)
+
+
+def _area_lights(sc, light):
+    """AreaLight | JoinedAreaLight -> m3d_area_light[] (scene object indices by identity)."""
+    leaves = list(light) if isinstance(light, (list, tuple)) else [light]
+    arr = (N.AreaLight * max(1, len(leaves)))()
+    for i, l in enumerate(leaves):
+        if not isinstance(l, AreaLight):
+            raise UnsupportedError("area light type %s is not supported on the GPU path" % type(l).__name__)
+        idx = [k for k, o in enumerate(sc.objects) if o is l]
+        if not idx:
+            raise ValueError("the BidirPathTracer's Light must be part of the rendered scene")
+        arr[i].object = idx[0]
+        arr[i].emission[:] = list(l.Emission)
+    return arr, len(leaves)
+
+
+@dataclass
+class BidirPathTracer:
+    """render3d.BidirPathTracer (bidir.go:14-84): same exported fields; Render() runs
+    libm3dgpu's wavefront bidirectional path tracer (m3d_render_bidir)."""
+    Camera: Camera = None
+    Light: object = None
+    MaxDepth: int = 0
+    MaxLightDepth: int = 0
+    MinDepth: int = 0
+    RouletteDelta: float = 0.0
+    PowerHeuristic: float = 0.0
+    NumSamples: int = 0
+    MinSamples: int = 0
+    MaxStddev: float = 0.0
+    OversaturatedStddevs: float = 0.0
+    Convergence: Optional[Callable] = None
+    Cutoff: float = 0.0
+    Antialias: float = 0.0
+    Epsilon: float = 0.0
+    LogFunc: Optional[Callable[[float, float], None]] = None
+    Seed: int = 0
+
+    def _params(self, num_samples):
+        if self.NumSamples == 0 and num_samples == 0:
+            raise ValueError("must set NumSamples to non-zero for rayRenderer")
+        if (self.MinSamples != 0 and self.MaxStddev != 0) or self.Convergence is not None:
+            raise UnsupportedError("adaptive sampling (MinSamples/MaxStddev/Convergence) is not "
+                                   "supported on the GPU path")
+        p = N.BidirParams()
+        p.max_depth, p.max_light_depth, p.min_depth = int(self.MaxDepth), int(self.MaxLightDepth), int(self.MinDepth)
+        p.num_samples = int(num_samples or self.NumSamples)
+        p.roulette_delta, p.power_heuristic = float(self.RouletteDelta), float(self.PowerHeuristic)
+        p.cutoff, p.antialias, p.epsilon = float(self.Cutoff), float(self.Antialias), float(self.Epsilon)
+        p.seed = int(self.Seed)
+        return p
+
+    def RenderSums(self, width, height, obj, partition=None, sample_count=None, variance=False, antialias=None):
+        sc = _as_scene(obj)
+        n = int(self.NumSamples if sample_count is None else sample_count)
+        p = self._params(n)
+        if antialias is not None:
+            p.antialias = float(antialias)
+        cam = self.Camera._c()
+        lights, nl = _area_lights(sc, self.Light)
+        rgb = np.zeros((height, width, 3), np.float32)
+        sq = np.zeros((height, width, 3), np.float32) if variance else None
+        stats = N.Stats()
+        part = _samples_partition(partition)
+        N.check(N.lib().m3d_render_bidir(sc.h, C.byref(cam), lights, C.c_int32(nl), C.byref(p), C.c_int32(width),
+                                         C.c_int32(height), C.byref(part) if part is not None else None,
+                                         C.c_int32(n), _p(rgb, f32p), _p(sq, f32p), C.byref(stats)))
+        return rgb, sq, {k: getattr(stats, k) for k, _ in stats._fields_}
+
+    def RenderSumsDevice(self, width, height, obj, d_rgb_sum, d_rgb_sumsq=0, partition=None, sample_count=None,
+                         stream=0):
+        sc = _as_scene(obj)
+        n = int(self.NumSamples if sample_count is None else sample_count)
+        p = self._params(n)
+        cam = self.Camera._c()
+        lights, nl = _area_lights(sc, self.Light)
+        stats = N.Stats()
+        part = _samples_partition(partition)
+        N.check(N.lib().m3d_render_bidir_device(
+            sc.h, C.byref(cam), lights, C.c_int32(nl), C.byref(p), C.c_int32(width), C.c_int32(height),
+            C.byref(part) if part is not None else None, C.c_int32(n), C.c_void_p(d_rgb_sum),
+            C.c_void_p(d_rgb_sumsq or None), C.c_void_p(stream or None), C.byref(stats)))
+        return {k: getattr(stats, k) for k, _ in stats._fields_}
+
+    def Render(self, img: Image, obj):
+        """(*BidirPathTracer).Render (bidir.go:66-68)."""
+        rgb, _, stats = self.RenderSums(img.Width, img.Height, obj)
+        img.Data = rgb / np.float32(self.NumSamples)
+        if self.LogFunc is not None:
+            self.LogFunc(1.0, float(self.NumSamples))
+        return stats
+
+    def RenderVariance(self, img: Image, obj, numSamples, antialias=None):
+        """rayRenderer.RenderVariance (ray_renderer.go:59-67,90-110)."""
+        if numSamples < 2:
+            raise ValueError("need to take at least two samples")
+        rgb, sq, stats = self.RenderSums(img.Width, img.Height, obj, sample_count=numSamples, variance=True,
+                                         antialias=antialias)
+        n = float(numSamples)
+        mean = rgb.astype(np.float64) / n
+        img.Data = np.maximum((sq.astype(np.float64) / n - mean * mean) * (n / (n - 1)), 0.0).astype(np.float32)
+        return stats
+
+    def RayVariance(self, obj, width, height, samples):
+        """rayRenderer.RayVariance (ray_renderer.go:69-88)."""
+        img = Image(width, height)
+        self.RenderVariance(img, obj, samples, antialias=0.0)
+        return float(img.Data.astype(np.float64).sum() / (3 * width * height))

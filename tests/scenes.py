@@ -82,3 +82,19 @@ def oracle_path_params(spec, osc, max_depth, num_samples, cutoff=0.0, antialias=
     return pp
 
 
+
+
+def oracle_bidir_params(spec, max_depth, num_samples, min_depth=0, roulette_delta=0.0, power_heuristic=0.0,
+                        cutoff=0.0, antialias=0.0, max_light_depth=0, seed=1):
+    from oracle import pyoracle as O
+    bp = O.BidirParams()
+    bp.max_depth, bp.max_light_depth, bp.min_depth, bp.num_samples = max_depth, max_light_depth, min_depth, num_samples
+    bp.roulette_delta, bp.power_heuristic, bp.cutoff, bp.antialias, bp.seed = (
+        roulette_delta, power_heuristic, cutoff, antialias, seed)
+    lights = []
+    for l in spec["area_lights"]:
+        a = O.AreaLight()
+        a.object = l["object"]
+        a.emission[:] = l["emission"]
+        lights.append(a)
+    return bp, lights
