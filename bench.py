@@ -141,11 +141,18 @@ def run_reference(args):
 C3_WORKLOAD = "C3 cornell_box (examples/renderings/cornell_box), RecursiveRayTracer MaxDepth 5, Cutoff 1e-4, Antialias 1, PhongFocusPoint 0.3"
 
 
-def cornell_tracer(spp, seed=1234):
+C5_WORKLOAD = "C5 cornell_box with the ceiling light as MeshAreaLight, BidirPathTracer MaxDepth 10, MinDepth 3, RouletteDelta 0.2, PowerHeuristic 2, Antialias 1, Cutoff 1e-4"
+C5_KW = dict(max_depth=10, min_depth=3, roulette_delta=0.2, power_heuristic=2.0, antialias=1.0, cutoff=1e-4)
+
+
+def cornell_tracer(spp, workload="c3", seed=1234):
     from model3d_b200 import examples
     spec = examples.cornell_box()
     psc = examples.build_product(spec)
-    tr = examples.product_tracer(spec, psc, 5, spp, cutoff=1e-4, antialias=1.0, seed=seed)
+    if workload == "c5":
+        tr = examples.product_bidir(spec, psc, num_samples=spp, seed=seed, **C5_KW)
+    else:
+        tr = examples.product_tracer(spec, psc, 5, spp, cutoff=1e-4, antialias=1.0, seed=seed)
     return spec, psc, tr
 
 
@@ -167,7 +174,7 @@ def run_path(args):
     N.default_context(local_rank)
     W = H = args.size
     spp = args.spp
-    spec, psc, tr = cornell_tracer(spp)
+    spec, psc, tr = cornell_tracer(spp, args.workload)
     from model3d_b200 import distributed as D
     part, my_spp = D.sample_shard(spp, rank, world)
     acc = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
@@ -225,12 +232,13 @@ def run_path(args):
             dt = (time.perf_counter() - t0) / k
             e2e = {"value": samples / dt / 1e6, "unit": "Msamples/s", "ms_per_step": dt * 1e3,
                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 12,
-                   "api": "m3d_render_path (host image buffers)"}
+                   "api": "m3d_render_%s (host image buffers)" % ("bidir" if args.workload == "c5" else "path")}
         line = {
             "metric": "path_traced_Msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": C3_WORKLOAD, "width": W, "height": H, "spp": spp,
+            "config": {"workload": C5_WORKLOAD if args.workload == "c5" else C3_WORKLOAD, "width": W, "height": H,
+                       "spp": spp,
                        "rays_per_sample": total_rays / samples, "Mrays_per_s": total_rays / (ms_step * 1e-3) / 1e6,
                        "sharding": "sample index, NCCL reduce of the W*H*3 float32 sums to rank 0",
                        "l2": "scene is 72 triangles + 2 spheres (L1-resident); path state streams through HBM"},
@@ -257,17 +265,24 @@ def run_reference_path(args):
     ocam = O.camera_at(cam["src"], cam["dst"], cam["fov"])
     W = H = 256
     spp = 8
-    pp = scenes.oracle_path_params(spec, osc, 5, spp, cutoff=1e-4, antialias=1.0, seed=3)
+    if args.workload == "c5":
+        W = H = 128
+        bp, lights = scenes.oracle_bidir_params(spec, num_samples=spp, seed=3, **C5_KW)
+    else:
+        pp = scenes.oracle_path_params(spec, osc, 5, spp, cutoff=1e-4, antialias=1.0, seed=3)
     t0 = time.perf_counter()
     k = max(1, args.steps)
     for _ in range(k):
-        osc.render_path(ocam, [], pp, W, H, threads=threads)
+        if args.workload == "c5":
+            osc.render_bidir(ocam, lights, bp, W, H, threads=threads)
+        else:
+            osc.render_path(ocam, [], pp, W, H, threads=threads)
     dt = (time.perf_counter() - t0) / k
     rate = W * H * spp / dt / 1e6
     line = {"impl": "reference", "metric": "path_traced_Msamples_per_s", "value": rate, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": C3_WORKLOAD},
+            "config": {"workload": C5_WORKLOAD if args.workload == "c5" else C3_WORKLOAD},
             "cpu_baseline": {"value": rate, "unit": "Msamples/s", "cores": threads, "kind": "port",
                              "sample": "%dx%d at %d spp per step" % (W, H, spp)},
             "e2e": {"value": rate, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -284,18 +299,19 @@ def main():
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2: raw first-hit ray batch (headline); c3: cornell_box RecursiveRayTracer 1024x1024")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2: raw first-hit ray batch (headline); c3: cornell_box RecursiveRayTracer 1024x1024; "
+                         "c5: cornell_box BidirPathTracer 1024x1024")
     ap.add_argument("--spp", type=int, default=256, help="samples per pixel per step (c3)")
     ap.add_argument("--size", type=int, default=1024, help="frame width == height (c3)")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.workload == "c3":
+        if args.workload in ("c3", "c5"):
             run_reference_path(args)
         else:
             run_reference(args)
         return
-    if args.workload == "c3":
+    if args.workload in ("c3", "c5"):
         run_path(args)
         return
 
