@@ -181,7 +181,7 @@ bidir_eye_raygen_kernel(DeviceCamera cam, DeviceBidirParams bp, PathBatch b, Bid
 // One step of sampleEyePath (EYE) or sampleLightPath's loop (!EYE): resolve the hit, build and
 // store the vertex, sample the continuation, apply pathEnder, compact survivors.
 template <bool EYE>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 8)
 bidir_shade_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf, int cur, int depth) {
   const int n = buf.counts[cur];
   const unsigned lane = threadIdx.x & 31u;
@@ -261,9 +261,9 @@ bidir_shade_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffe
 // Box-Muller pair from two uniforms
 __device__ __forceinline__ void gauss2(Rng &g, float &a, float &b) {
   const float u1 = fmaxf(g.f32(), 5.9604644775390625e-8f), u2 = g.f32();
-  const float r = sqrtf(-2.f * logf(u1));
+  const float r = sqrtf(-2.f * __logf(u1));
   float s, c;
-  sincosf(kTwoPi * u2, &s, &c);
+  sincos_2pi(u2, &s, &c);
   a = r * c;
   b = r * s;
 }
@@ -371,7 +371,7 @@ struct D3c {
 
 // allPathCombinations for one eye prefix length i (bidir.go:476-530) + rayColor's callback
 // (bidir.go:113-158).  One thread per sample.
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 8)
 bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf, int i) {
   const int n_slots = b.nP * b.S;
   const int slot = blockIdx.x * kBlock + threadIdx.x;

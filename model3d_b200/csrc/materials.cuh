@@ -48,7 +48,7 @@ __device__ __forceinline__ float sum3(V3f a) { return a.x + a.y + a.z; }
 __device__ __forceinline__ V3f reflect_about(V3f n, V3f c1) { return (c1 + n * (-2.f * dot(n, c1))) * -1.f; }
 
 // coords.go:388-421
-__device__ __forceinline__ void ortho_basis(V3f c, V3f &b1o, V3f &b2o) {
+static __device__ __noinline__ void ortho_basis(V3f c, V3f &b1o, V3f &b2o) {
   const float ax = fabsf(c.x), ay = fabsf(c.y), az = fabsf(c.z);
   V3f b1 = v3f(0.f, 0.f, 0.f);
   if (ax > ay && ax > az) {
@@ -63,6 +63,17 @@ __device__ __forceinline__ void ortho_basis(V3f c, V3f &b1o, V3f &b2o) {
   b1o = normalize(b1);
   b2o = normalize(b2);
 }
+
+// x^y for x in [0, 1], y >= 0 through the SFU (lg2.approx / ex2.approx): a dozen instructions
+// instead of powf's ~150, relative error ~ y * 2^-22 (1e-4 at alpha = 400) -- far below the
+// Monte-Carlo noise these sampling formulas feed, and the same function is used by the sampler
+// and by its density so the estimator stays consistent.
+__device__ __forceinline__ float pow_unit(float x, float y) {
+  if (y == 0.f) return 1.f;  // pow(0, 0) == 1 like math.Pow
+  return exp2f(y * __log2f(x));
+}
+// sin and cos of 2*pi*u without libm's large-argument slow path
+__device__ __forceinline__ void sincos_2pi(float u, float *s, float *c) { sincospif(2.f * u, s, c); }
 
 constexpr float kCosEps = 1e-8f;  // cosineEpsilon material.go:10
 
@@ -94,7 +105,7 @@ __device__ __forceinline__ float maximum_cosine(float c1, float c2) {
 }
 
 // Finite part of the BSDF of a non-joined material (delta lobes excluded, see header).
-__device__ __forceinline__ V3f simple_bsdf(const DeviceMaterial &d, V3f diffuse, V3f n, V3f src, V3f dst) {
+static __device__ __noinline__ V3f simple_bsdf(const DeviceMaterial &d, V3f diffuse, V3f n, V3f src, V3f dst) {
   if (d.kind == M3D_MAT_LAMBERT) {  // material.go:125-134
     if (dot(dst, n) < 0.f || dot(src, n) > 0.f) return v3f(0.f, 0.f, 0.f);
     return diffuse * 4.f;
@@ -107,7 +118,7 @@ __device__ __forceinline__ V3f simple_bsdf(const DeviceMaterial &d, V3f diffuse,
     const V3f reflection = reflect_about(n, src) * -1.f;
     const float ref_dot = dot(reflection, dst);
     if (ref_dot < 0.f) return color;
-    float intensity = powf(ref_dot, d.alpha) * (1.f + d.alpha);
+    float intensity = pow_unit(ref_dot, d.alpha) * (1.f + d.alpha);
     if (!(d.flags & M3D_MAT_NO_FLUX_CORRECTION)) intensity /= maximum_cosine(source_dot, dest_dot);
     return color + v3f(d.specular) * (2.f * intensity);
   }
@@ -186,11 +197,12 @@ struct Rng {
     block = 0;
     have = 0;
   }
+  __device__ __noinline__ void refill() {
+    buf = philox4x32_10(make_uint4(pixel, sample, block++, domain), key);
+    have = 4;
+  }
   __device__ __forceinline__ uint32_t bits() {
-    if (have == 0) {
-      buf = philox4x32_10(make_uint4(pixel, sample, block++, domain), key);
-      have = 4;
-    }
+    if (have == 0) refill();
     const uint32_t r = have == 4 ? buf.x : (have == 3 ? buf.y : (have == 2 ? buf.z : buf.w));
     have--;
     return r;
@@ -202,15 +214,16 @@ struct Rng {
 // ---- sampling (material.go) ---------------------------------------------------------------
 constexpr float kTwoPi = 6.283185307179586f;
 
+
 // Tag of the direction a sampler produced: which Dirac lobe(s) of which sub-material.
 constexpr int kLobeRefract = 1, kLobeReflect = 2;  // bits 0..1; sub-material index in bits 2..3
 
 // material.go:136-151
-__device__ __forceinline__ V3f lambert_sample(Rng &g, V3f normal) {
+static __device__ __noinline__ V3f lambert_sample(Rng &g, V3f normal) {
   const float u = g.f32();
   const float cos_lat = sqrtf(u), sin_lat = sqrtf(1.f - u);
   float sl, cl;
-  sincosf(g.f32() * kTwoPi, &sl, &cl);
+  sincos_2pi(g.f32(), &sl, &cl);
   V3f xa, za;
   ortho_basis(normal, xa, za);
   const V3f lon_point = xa * cl + za * sl;
@@ -222,13 +235,13 @@ __device__ __forceinline__ float lambert_density(V3f normal, V3f source) {
   return nd < 0.f ? 0.f : 4.f * nd;
 }
 // material.go:274-323
-__device__ __forceinline__ V3f sample_around_direction(Rng &g, float alpha, V3f direction) {
+static __device__ __noinline__ V3f sample_around_direction(Rng &g, float alpha, V3f direction) {
   V3f xa, za;
   ortho_basis(direction, xa, za);
   const float u = g.f32(), v = g.f32();
   float sl, cl;
-  sincosf(kTwoPi * u, &sl, &cl);
-  const float cos_lat = powf(v, 1.f / (alpha + 1.f));
+  sincos_2pi(u, &sl, &cl);
+  const float cos_lat = pow_unit(v, 1.f / (alpha + 1.f));
   const float sin_lat = sqrtf(fmaxf(0.f, 1.f - cos_lat * cos_lat));
   const V3f lon_point = xa * cl + za * sl;
   return direction * cos_lat + lon_point * sin_lat;
@@ -237,7 +250,7 @@ __device__ __forceinline__ V3f sample_around_direction(Rng &g, float alpha, V3f 
 __device__ __forceinline__ float density_around_direction(float alpha, V3f direction, V3f sample) {
   const float d = dot(direction, sample);
   if (d < 0.f) return 0.f;
-  return 2.f * (alpha + 1.f) * powf(d, alpha);
+  return 2.f * (alpha + 1.f) * pow_unit(d, alpha);
 }
 
 // material.go:360-378; tir: total internal reflection (the result is the mirror direction)
@@ -267,7 +280,7 @@ __device__ __forceinline__ float reflect_amount(float ior, V3f normal, V3f sourc
 }
 
 // SampleSource of a non-joined material; lobe: Dirac lobes the direction belongs to.
-__device__ __forceinline__ V3f simple_sample_source(const DeviceMaterial &d, V3f diffuse, Rng &g, V3f normal,
+static __device__ __noinline__ V3f simple_sample_source(const DeviceMaterial &d, V3f diffuse, Rng &g, V3f normal,
                                                     V3f dest, int &lobe) {
   lobe = 0;
   if (d.kind == M3D_MAT_LAMBERT) return lambert_sample(g, normal);
@@ -301,7 +314,7 @@ struct Density {
 
 // SourceDensity of a non-joined material for a direction tagged `lobe`
 // (material.go:153-159, 240-247, 441-462).
-__device__ __forceinline__ Density simple_source_density(const DeviceMaterial &d, V3f diffuse, V3f normal,
+static __device__ __noinline__ Density simple_source_density(const DeviceMaterial &d, V3f diffuse, V3f normal,
                                                          V3f source, V3f dest, int lobe) {
   Density r;
   r.fin = 0.f;
@@ -325,7 +338,7 @@ __device__ __forceinline__ Density simple_source_density(const DeviceMaterial &d
 
 // Dirac part of the BSDF of a non-joined material, as a coefficient of 2/cosineEpsilon
 // (material.go:391-423); the finite part is simple_bsdf().
-__device__ __forceinline__ V3f simple_bsdf_delta(const DeviceMaterial &d, V3f normal, V3f source, V3f dest,
+static __device__ __noinline__ V3f simple_bsdf_delta(const DeviceMaterial &d, V3f normal, V3f source, V3f dest,
                                                  int lobe) {
   if (d.kind != M3D_MAT_REFRACT || lobe == 0) return v3f(0.f, 0.f, 0.f);
   const float s_refr = 1.f / fmaxf(kCosEps, fabsf(dot(dest, normal)));

@@ -29,7 +29,7 @@ __device__ __forceinline__ V3f sample_around_uniform(Rng &g, float min_cos, V3f 
   const float cos_lat = 1.f - g.f32() * (1.f - min_cos);
   const float sin_lat = sqrtf(fmaxf(0.f, 1.f - cos_lat * cos_lat));
   float sl, cl;
-  sincosf(g.f32() * kTwoPi, &sl, &cl);
+  sincos_2pi(g.f32(), &sl, &cl);
   V3f xa, za;
   ortho_basis(direction, xa, za);
   return direction * cos_lat + (xa * cl + za * sl) * sin_lat;
@@ -94,7 +94,7 @@ path_raygen_kernel(DeviceCamera cam, DevicePathParams pp, PathBatch b, PathBuffe
   buf.accum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-__global__ void __launch_bounds__(kShadeBlock)
+__global__ void __launch_bounds__(kShadeBlock, 8)
 path_shade_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *__restrict__ lights, PathBatch b,
                   PathBuffers buf, int cur, int depth) {
   const int n = buf.counts[cur];

@@ -31,7 +31,7 @@ __device__ __forceinline__ double comp(D3 a, int i) { return i == 0 ? a.x : (i =
 // reference's 1e-8 origin offset which float32 origins cannot express).
 
 // shapes.go:52-93 (first root >= 0; discriminant <= 0 misses; outward normal)
-__device__ inline bool sphere_hit(const DeviceShape &s, D3 o, D3 d, double t_floor, double &t, D3 &n) {
+static __device__ __noinline__ bool sphere_hit(const DeviceShape &s, D3 o, D3 d, double t_floor, double &t, D3 &n) {
   const D3 c = d3(s.p0[0], s.p0[1], s.p0[2]);
   const D3 oc = o - c;
   const double a = ddot(d, d), b = 2 * ddot(d, oc), cc = ddot(oc, oc) - s.radius * s.radius;
@@ -57,7 +57,7 @@ __device__ inline bool sphere_hit(const DeviceShape &s, D3 o, D3 d, double t_flo
 }
 
 // bvh.go:322-351
-__device__ inline void ray_bounds(D3 o, D3 d, D3 mn, D3 mx, double &min_frac, double &max_frac) {
+static __device__ __noinline__ void ray_bounds(D3 o, D3 d, D3 mn, D3 mx, double &min_frac, double &max_frac) {
   min_frac = -INFINITY;
   max_frac = INFINITY;
   for (int axis = 0; axis < 3; axis++) {
@@ -87,7 +87,7 @@ __device__ inline void ray_bounds(D3 o, D3 d, D3 mn, D3 mx, double &min_frac, do
 }
 
 // shapes.go:177-196, 221-247
-__device__ inline bool rect_hit(const DeviceShape &s, D3 o, D3 d, double t_floor, double &t, D3 &n) {
+static __device__ __noinline__ bool rect_hit(const DeviceShape &s, D3 o, D3 d, double t_floor, double &t, D3 &n) {
   const D3 mn = d3(s.p0[0], s.p0[1], s.p0[2]), mx = d3(s.p1[0], s.p1[1], s.p1[2]);
   double tmin, tmax;
   ray_bounds(o, d, mn, mx, tmin, tmax);
@@ -117,7 +117,7 @@ __device__ inline bool rect_hit(const DeviceShape &s, D3 o, D3 d, double t_floor
 }
 
 // shapes.go:816-856
-__device__ inline bool circle_hit(D3 normal, D3 center, double radius, D3 o, D3 d, double t_floor, double &t) {
+static __device__ __noinline__ bool circle_hit(D3 normal, D3 center, double radius, D3 o, D3 d, double t_floor, double &t) {
   const double ddn = ddot(d, normal);
   if (fabs(ddn) < 1e-8 * dnorm(d) * dnorm(normal)) return false;
   const double tt = (ddot(normal, center) - ddot(o, normal)) / ddn;
@@ -129,7 +129,7 @@ __device__ inline bool circle_hit(D3 normal, D3 center, double radius, D3 o, D3 
 }
 
 // shapes.go:601-705: minimum over side roots and the two caps (first strictly smaller wins)
-__device__ inline bool cylinder_hit(const DeviceShape &s, D3 o_in, D3 d, double t_floor, double &t, D3 &n) {
+static __device__ __noinline__ bool cylinder_hit(const DeviceShape &s, D3 o_in, D3 d, double t_floor, double &t, D3 &n) {
   const D3 p1 = d3(s.p0[0], s.p0[1], s.p0[2]), p2 = d3(s.p1[0], s.p1[1], s.p1[2]);
   bool ok = false;
   const D3 v = dnormalize(p2 - p1);
@@ -165,6 +165,40 @@ __device__ inline bool cylinder_hit(const DeviceShape &s, D3 o_in, D3 d, double 
     }
   }
   return ok;
+}
+
+// Conservative float32 pre-test: true only if the ray's supporting line provably misses the
+// shape's bounding sphere (sphere: the shape itself).  Margin 1e-4 relative covers float32
+// rounding of the discriminant with two orders of magnitude to spare.
+__device__ __forceinline__ bool shape_certainly_missed(const DeviceShape &sh, float4 o, float4 d) {
+  float cx, cy, cz, r;
+  if (sh.kind == SHAPE_SPHERE) {
+    cx = (float)sh.p0[0];
+    cy = (float)sh.p0[1];
+    cz = (float)sh.p0[2];
+    r = (float)sh.radius;
+  } else {
+    // rect: centre and half diagonal; cylinder: segment midpoint, half length + radius
+    cx = 0.5f * (float)(sh.p0[0] + sh.p1[0]);
+    cy = 0.5f * (float)(sh.p0[1] + sh.p1[1]);
+    cz = 0.5f * (float)(sh.p0[2] + sh.p1[2]);
+    const float hx = 0.5f * (float)(sh.p1[0] - sh.p0[0]), hy = 0.5f * (float)(sh.p1[1] - sh.p0[1]),
+                hz = 0.5f * (float)(sh.p1[2] - sh.p0[2]);
+    r = sqrtf(hx * hx + hy * hy + hz * hz) + (sh.kind == SHAPE_CYLINDER ? (float)sh.radius : 0.f);
+  }
+  r *= 1.001f;
+  const float ox = o.x - cx, oy = o.y - cy, oz = o.z - cz;
+  const float a = d.x * d.x + d.y * d.y + d.z * d.z;
+  const float b = ox * d.x + oy * d.y + oz * d.z;
+  const float oo = ox * ox + oy * oy + oz * oz;
+  const float c = oo - r * r;
+  // discriminant / 4 of a t^2 + 2 b t + c; every term is bounded by a * oo
+  const float disc = b * b - a * c;
+  const float margin = 1e-4f * (a * oo + a * r * r);
+  if (disc < -margin) return true;
+  // both roots behind the origin: outside the sphere and pointing away
+  if (c > margin && b > 0.f && b * b > 1e-4f * a * oo) return true;
+  return false;
 }
 
 // Result of resolving one scene ray: the closest of the BVH's raw triangle hit and the
@@ -264,6 +298,9 @@ __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, fl
           size = fmax(fmax(sh.p1[0] - sh.p0[0], sh.p1[1] - sh.p0[1]), sh.p1[2] - sh.p0[2]);
         t_floor = fmax(t_floor, 1e-4 * size * inv_len);
       }
+      // cheap float32 rejection with a generous error margin: most rays miss most shapes, and
+      // the float64 tests (sqrt / divisions) are an order of magnitude more instructions
+      if (shape_certainly_missed(sh, o, d)) continue;
       double t;
       D3 n;
       bool ok = false;
