@@ -145,8 +145,18 @@ C5_WORKLOAD = "C5 cornell_box with the ceiling light as MeshAreaLight, BidirPath
 C5_KW = dict(max_depth=10, min_depth=3, roulette_delta=0.2, power_heuristic=2.0, antialias=1.0, cutoff=1e-4)
 
 
+C4_WORKLOAD = "C4 showcase (examples/renderings/showcase, 326,136 triangles in 7 meshes + 2 spheres + rect + cylinder, vase omitted: asset missing), RecursiveRayTracer MaxDepth 10, Cutoff 1e-4, Antialias 1, SphereFocusPoint 0.3, fixed spp"
+WORKLOAD_NAME = {"c3": C3_WORKLOAD, "c4": C4_WORKLOAD, "c5": C5_WORKLOAD}
+
+
 def cornell_tracer(spp, workload="c3", seed=1234):
     from model3d_b200 import examples
+    if workload == "c4":
+        spec = examples.showcase(hd=True)
+        psc = examples.build_product(spec)
+        tr = examples.product_tracer(spec, psc, spec["max_depth"], spp, cutoff=spec["cutoff"],
+                                     antialias=spec["antialias"], seed=seed)
+        return spec, psc, tr
     spec = examples.cornell_box()
     psc = examples.build_product(spec)
     if workload == "c5":
@@ -175,6 +185,8 @@ def run_path(args):
     W = H = args.size
     spp = args.spp
     spec, psc, tr = cornell_tracer(spp, args.workload)
+    if args.workload == "c4":
+        W, H = spec["size"]  # "HD" 960x640 (showcase/main.go:61-69)
     from model3d_b200 import distributed as D
     part, my_spp = D.sample_shard(spp, rank, world)
     acc = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
@@ -237,11 +249,11 @@ def run_path(args):
             "metric": "path_traced_Msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": C5_WORKLOAD if args.workload == "c5" else C3_WORKLOAD, "width": W, "height": H,
+            "config": {"workload": WORKLOAD_NAME[args.workload], "width": W, "height": H,
                        "spp": spp,
                        "rays_per_sample": total_rays / samples, "Mrays_per_s": total_rays / (ms_step * 1e-3) / 1e6,
                        "sharding": "sample index, NCCL reduce of the W*H*3 float32 sums to rank 0",
-                       "l2": "scene is 72 triangles + 2 spheres (L1-resident); path state streams through HBM"},
+                       "l2": "path state streams through HBM (> L2 per batch); scene BVH is L2/L1 resident"},
             "clocks": clocks, "gpu_launches": int(launches[0]) * args.steps,
         }
         if e2e:
@@ -259,15 +271,19 @@ def run_reference_path(args):
     import scenes
     from oracle import pyoracle as O
     threads = O.hardware_threads()
-    spec = scenes.cornell_box()
+    spec = scenes.showcase(hd=True) if args.workload == "c4" else scenes.cornell_box()
     osc = scenes.build_oracle(spec)
     cam = spec["camera"]
     ocam = O.camera_at(cam["src"], cam["dst"], cam["fov"])
     W = H = 256
     spp = 8
+    if args.workload == "c4":
+        W, H, spp = 240, 160, 4
     if args.workload == "c5":
         W = H = 128
         bp, lights = scenes.oracle_bidir_params(spec, num_samples=spp, seed=3, **C5_KW)
+    elif args.workload == "c4":
+        pp = scenes.oracle_path_params(spec, osc, 10, spp, cutoff=1e-4, antialias=1.0, seed=3)
     else:
         pp = scenes.oracle_path_params(spec, osc, 5, spp, cutoff=1e-4, antialias=1.0, seed=3)
     t0 = time.perf_counter()
@@ -282,7 +298,7 @@ def run_reference_path(args):
     line = {"impl": "reference", "metric": "path_traced_Msamples_per_s", "value": rate, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": C5_WORKLOAD if args.workload == "c5" else C3_WORKLOAD},
+            "config": {"workload": WORKLOAD_NAME[args.workload]},
             "cpu_baseline": {"value": rate, "unit": "Msamples/s", "cores": threads, "kind": "port",
                              "sample": "%dx%d at %d spp per step" % (W, H, spp)},
             "e2e": {"value": rate, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -299,19 +315,19 @@ def main():
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2: raw first-hit ray batch (headline); c3: cornell_box RecursiveRayTracer 1024x1024; "
                          "c5: cornell_box BidirPathTracer 1024x1024")
     ap.add_argument("--spp", type=int, default=256, help="samples per pixel per step (c3)")
     ap.add_argument("--size", type=int, default=1024, help="frame width == height (c3)")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.workload in ("c3", "c5"):
+        if args.workload in ("c3", "c4", "c5"):
             run_reference_path(args)
         else:
             run_reference(args)
         return
-    if args.workload in ("c3", "c5"):
+    if args.workload in ("c3", "c4", "c5"):
         run_path(args)
         return
 

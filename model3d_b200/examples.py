@@ -267,3 +267,87 @@ def glass_scene():
     ]
     return dict(objects=objs, camera=dict(src=(0, -3.5, 1.0), dst=(0, 4, 0.2), fov=math.pi / 3.0),
                 area_lights=[dict(object=1, emission=gray(12.0))])
+
+
+def checker(color1, color2):
+    """showcase FloorObject (room.go:61-75): Lambert, color2 where the checker test holds."""
+    return dict(kind="checker", color1=color1, color2=color2)
+
+
+def showcase_models():
+    """The seven meshes of examples/renderings/showcase/models (tests/golden/showcase_models.npz,
+    written by tests/golden/make_fixtures.py from the reference's *.stl.gz), float64 [n,3,3]."""
+    z = np.load(os.path.join(GOLDEN, "showcase_models.npz"))
+    names = sorted(k[:-2] for k in z.files if k.endswith("_v"))
+    return {n: z[n + "_v"][z[n + "_f"]].astype(np.float64) for n in names}
+
+
+def showcase(hd=False):
+    """BASELINE config 4: examples/renderings/showcase (main.go, room.go, models.go,
+    constants.go).  The vase is omitted: vase.stl.gz is not part of the reference checkout.
+    Go closures become declarative materials / flags: FloorObject -> checker Lambert,
+    DomeObject -> flipped normals, the focus point's MaterialFilter -> Lambert/Phong kinds."""
+    M = showcase_models()
+    light_dir = np.array([2.0, -3.0, 3.0])
+    light_dir = light_dir * (1.0 / math.sqrt(float(light_dir @ light_dir)))
+    light_center = tuple((light_dir * (1.0 / math.sqrt(float(light_dir @ light_dir))) * 50.0).tolist())
+    room_radius, light_radius = 100.0, 5.0
+
+    def bounds(t):
+        p = t.reshape(-1, 3)
+        return p.min(axis=0), p.max(axis=0)
+
+    def rot(t, axis, angle):
+        return (t.reshape(-1, 3) @ rotation(axis, angle).T).reshape(-1, 3, 3)
+
+    def f32(t):
+        return np.ascontiguousarray(t, np.float32)
+
+    objs = []
+    # NewFloorObject / NewDomeObject / NewLightObject (room.go)
+    objs.append(dict(kind="rect", min=(-room_radius, -room_radius, -0.01), max=(room_radius, room_radius, 0.0),
+                     material=checker(gray(0.6), gray(0.1))))
+    sky = tuple(0.15 * c + 0.15 for c in NewColorRGB(0.5, 0.8, 0.95))
+    objs.append(dict(kind="sphere", center=(0.0, 0.0, 0.0), radius=room_radius, material=lambert(diffuse=sky),
+                     flip=True))
+    objs.append(dict(kind="sphere", center=light_center, radius=light_radius,
+                     material=lambert(emission=gray(300.0))))
+    # ReadRose (models.go:33-59)
+    t = M["rose"]
+    mn, mx = bounds(t)
+    t = t - (mn + mx) / 2
+    t = rot(t, (1, 0, 0), math.pi / 4) + np.array([5.0, 11.0, 7.0])
+    objs.append(dict(kind="mesh", tris=f32(t),
+                     material=lambert(diffuse=tuple(0.5 * c for c in NewColorRGB(0.95, 0.2, 0.2)))))
+    objs.append(dict(kind="cylinder", p1=(5.0, 11.0, 0.0), p2=(5.0, 11.0, 7.0), radius=0.15,
+                     material=lambert(diffuse=tuple(0.5 * c for c in NewColorRGB(0.1, 0.55, 0.0)))))
+    # ReadWineGlass (models.go:144-176)
+    t = M["wine_glass"]
+    mn, mx = bounds(t)
+    t = t - mn
+    t = t + np.array([-5.0 - (mx[0] - mn[0]) / 2, 10.5 - (mx[1] - mn[1]) / 2, 1e-4])
+    glass = joined([refract(1.3, gray(0.95)), phong(100.0, specular=gray(0.05))], [0.8, 0.2])
+    objs.append(dict(kind="mesh", tris=f32(t), material=glass))
+    # ReadPumpkin (models.go:113-142)
+    colors = [NewColorRGB(255.0 / 255, 206.0 / 255, 107.0 / 255), NewColorRGB(214.0 / 255, 143.0 / 255, 0),
+              NewColorRGB(79.0 / 255, 53.0 / 255, 0)]
+    for name, col in zip(["pumpkin_inside", "pumpkin_outside", "pumpkin_stem"], colors):
+        t = M[name] + np.array([-2.0, 10.0, 1.1942578125000005])
+        objs.append(dict(kind="mesh", tris=f32(t), material=lambert(diffuse=tuple(0.5 * c for c in col))))
+    # ReadRocks (models.go:100-111)
+    t = M["rocks"]
+    mn, mx = bounds(t)
+    t = t + np.array([-(mx[0] + mn[0]) / 2, 15.0 - mn[1], 0.0])
+    objs.append(dict(kind="mesh", tris=f32(t), material=lambert(diffuse=gray(0.3))))
+    # ReadCurvyThing (models.go:14-31)
+    t = M["curvy_thing"]
+    mn, mx = bounds(t)
+    inv_mid = -(mn + mx) / 2
+    inv_mid[2] = -mn[2]
+    t = rot(t + inv_mid, (0, 0, 1), -math.pi / 4) + np.array([1.8, 9.0, 0.0])
+    objs.append(dict(kind="mesh", tris=f32(t), material=phong(20.0, specular=gray(0.05), diffuse=gray(0.3))))
+    size = (960, 640) if hd else (480, 320)
+    return dict(objects=objs, camera=dict(src=(0.0, -5.0, 4.0), dst=(0.0, room_radius, 4.0), fov=math.pi / 3.6),
+                focus=[dict(kind="sphere", target=light_center, radius=light_radius, prob=0.3,
+                            applies=lambda m: m["kind"] in ("lambert", "phong", "checker", "zgradient"))],
+                size=size, max_depth=10, cutoff=1e-4, antialias=1.0)

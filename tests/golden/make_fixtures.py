@@ -6,6 +6,10 @@ The GPU box has no /root/reference; tests only read the .npy files written here.
   diamond_tris.npy   the 46 triangles of examples/renderings/cornell_box/diamond.stl
                      (binary STL: 80-byte header, uint32 count, 50 B/triangle, float32 LE --
                      fileformats/stl.go:121-133,243-261), float32 [46,3,3].
+  showcase_models.npz  the seven meshes of examples/renderings/showcase/models/*.stl.gz
+                     (BASELINE config 4; vase.stl.gz is missing from the reference checkout),
+                     each stored indexed: <name>_v float32 [V,3] unique vertices in first-use
+                     order, <name>_f int32 [n,3]; triangles = v[f] in file order.
 """
 import os
 import struct
@@ -26,7 +30,35 @@ def read_binary_stl(path):
     return tris
 
 
+SHOWCASE = ["curvy_thing", "pumpkin_inside", "pumpkin_outside", "pumpkin_stem", "rocks", "rose", "wine_glass"]
+
+
+def read_stl_gz_indexed(path):
+    import gzip
+    data = gzip.decompress(open(path, "rb").read())
+    (n,) = struct.unpack_from("<I", data, 80)
+    rec = np.dtype([("normal", "<f4", (3,)), ("verts", "<f4", (3, 3)), ("attr", "<u2")])
+    tris = np.frombuffer(data, dtype=rec, count=n, offset=84)["verts"].reshape(-1, 3)
+    # unique vertices in first-use order (bit patterns, so -0.0 and 0.0 stay distinct)
+    keys = np.ascontiguousarray(tris).view(np.dtype((np.void, 12))).ravel()
+    _, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+    order = np.argsort(first)
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    verts = tris[first[order]]
+    faces = rank[inv].astype(np.int32).reshape(n, 3)
+    assert np.array_equal(verts[faces].reshape(-1, 3).view(np.uint32), tris.view(np.uint32))
+    return verts.astype(np.float32), faces
+
+
 if __name__ == "__main__":
+    out = {}
+    for name in SHOWCASE:
+        v, f = read_stl_gz_indexed(os.path.join(REF, "examples/renderings/showcase/models", name + ".stl.gz"))
+        out[name + "_v"], out[name + "_f"] = v, f
+        print(name, f.shape[0], "triangles", v.shape[0], "vertices")
+    np.savez_compressed(os.path.join(HERE, "showcase_models.npz"), **out)
+
     tris = read_binary_stl(os.path.join(REF, "examples/renderings/cornell_box/diamond.stl"))
     assert tris.shape == (46, 3, 3), tris.shape
     np.save(os.path.join(HERE, "diamond_tris.npy"), tris)

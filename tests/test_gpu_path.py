@@ -152,3 +152,25 @@ def test_path_unsupported_adaptive(built):
     tr.MinSamples, tr.MaxStddev = 10, 0.01
     with pytest.raises(UnsupportedError):
         tr.RenderSums(4, 4, psc)
+
+
+def test_showcase_cast_and_path(built, oracle):
+    """BASELINE config 4 (examples/renderings/showcase, 326,136 triangles in 7 meshes + 2 spheres
+    + rect + cylinder; checker floor, flipped dome, refractive glass): primary-ray hits identical
+    to the oracle, then RecursiveRayTracer MaxDepth 10 statistical parity at test size."""
+    spec = scenes.showcase()
+    osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
+    cam = spec["camera"]
+    ocam = oracle.camera_at(cam["src"], cam["dst"], cam["fov"])
+    W, H = 240, 160
+    dirs = oracle.camera_rays(ocam, W, H)
+    org = np.tile(np.asarray(cam["src"], np.float64), (W * H, 1))
+    got = psc.Cast(org, dirs)
+    ref = osc.cast(org.astype(np.float32), dirs.astype(np.float32), threads=8)
+    assert (got["obj"] >= 0).all() and (ref["obj"] >= 0).all()  # closed room
+    same = (ref["obj"] == got["obj"]) & (ref["prim"] == got["prim"])
+    assert same.sum() >= W * H - 8, W * H - same.sum()
+    rel = np.abs(got["t"] - ref["t"]) / np.abs(ref["t"])
+    assert rel[same].max() < 1e-5
+    assert len(np.unique(got["obj"])) >= 10
+    run_case(oracle, spec, 60, 40, n_gpu=512, n_ref=192, max_depth=10, cutoff=1e-4, antialias=1.0)
