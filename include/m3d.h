@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define M3D_ABI_VERSION 1
+#define M3D_ABI_VERSION 2
 
 typedef enum {
   M3D_OK = 0,
@@ -69,6 +69,7 @@ typedef struct {
   double h2d_ms, d2h_ms; /* host<->device copy time (host-buffer calls)  */
   int64_t h2d_bytes, d2h_bytes;
   int64_t launches;      /* kernels of this library launched by the call */
+  int64_t samples;       /* renderers: samples taken (adaptive mode stops per pixel) */
 } m3d_stats;
 
 /* ---- mesh collider ----------------------------------------------------------
@@ -267,7 +268,10 @@ typedef struct {
 typedef struct {
   int32_t max_depth;
   int32_t num_samples;
-  int32_t min_samples;           /* adaptive stop (ray_renderer.go:128-148) */
+  int32_t min_samples;           /* adaptive stop (ray_renderer.go:128-148): with max_stddev != 0
+                                    every pixel stops at the reference's sample; the call must
+                                    then cover all samples (no sample sharding, rows may be
+                                    banded) and rgb_sum holds mean * num_samples */
   int32_t num_focus_points;
   double max_stddev;
   double oversaturated_stddevs;
@@ -314,6 +318,11 @@ typedef struct {
   double antialias;
   double epsilon;
   uint64_t seed;
+  /* adaptive stop, as in m3d_path_params (bidir.go:45-52) */
+  int32_t min_samples;
+  int32_t _pad;
+  double max_stddev;
+  double oversaturated_stddevs;
 } m3d_bidir_params;
 
 /* (*BidirPathTracer).Render (render3d/bidir.go:66-68,101-159). Sums, as above. */

@@ -32,7 +32,7 @@ class Stats(C.Structure):
     _fields_ = [("rays", C.c_int64), ("hits", C.c_int64), ("nodes_visited", C.c_int64),
                 ("tris_tested", C.c_int64), ("kernel_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("launches", C.c_int64)]
+                ("launches", C.c_int64), ("samples", C.c_int64)]
 
 
 class MeshInfo(C.Structure):
@@ -92,7 +92,8 @@ class BidirParams(C.Structure):
                 ("min_depth", C.c_int32), ("num_samples", C.c_int32),
                 ("roulette_delta", C.c_double), ("power_heuristic", C.c_double),
                 ("cutoff", C.c_double), ("antialias", C.c_double), ("epsilon", C.c_double),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("min_samples", C.c_int32), ("_pad", C.c_int32),
+                ("max_stddev", C.c_double), ("oversaturated_stddevs", C.c_double)]
 
 
 # every symbol include/m3d.h declares (tests check that the library exports all of them)

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "adaptive.h"
 #include "api_common.h"
 #include "bidir.h"
 #include "scene_host.h"
@@ -114,6 +115,13 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
   if (stats) std::memset(stats, 0, sizeof(*stats));
   const int64_t npix = (int64_t)width * (row_end - row_begin);
   if (npix == 0 || sample_count == 0) return M3D_OK;
+  // BidirPathTracer.MinSamples / MaxStddev / OversaturatedStddevs (bidir.go:45-52) arrive in the
+  // trailing fields of m3d_bidir_params
+  const bool adaptive = params->min_samples != 0 && params->max_stddev != 0;
+  if (adaptive && (sample_begin != 0 || sample_count != params->num_samples || d_rgb_sumsq))
+    return fail(M3D_ERR_INVALID_ARG,
+                "adaptive sampling (MinSamples/MaxStddev) stops per pixel: it cannot be sharded by sample index "
+                "(sample_begin must be 0 and sample_count == num_samples; shard by rows) and has no sumsq output");
 
   // ---- area-light tables (light.go:131-161, 237-252, 283-301) ------------------------------
   std::vector<DeviceAreaLight> hl((size_t)num_lights);
@@ -227,49 +235,66 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
   GpuTimer tm;
   tm.start(s);
   int64_t launches = 0;
-  for (int64_t p0 = 0; p0 < npix; p0 += nP_max) {
-    const int64_t nP = std::min(nP_max, npix - p0);
-    const int64_t S_max = std::max<int64_t>(1, cap / nP);
-    for (int64_t s0 = 0; s0 < sample_count; s0 += S_max) {
-      PathBatch b;
-      b.W = width;
-      b.pix0 = (int32_t)((int64_t)row_begin * width + p0);
-      b.nP = (int32_t)nP;
-      b.S = (int32_t)std::min<int64_t>(S_max, sample_count - s0);
-      b.sample0 = (uint32_t)(sample_begin + s0);
-      const int64_t n = (int64_t)b.nP * b.S;
-      // eye sub-paths
-      launch_bidir_eye_raygen(dc, bp, b, buf, s);
-      launches++;
-      int cur = 0;
-      for (int depth = 0; depth < max_depth; depth++) {
-        if (int32_t rc = trace(buf.org[cur], buf.dir[cur], buf.skip[cur], buf.raw, n, buf.counts + cur)) return rc;
-        launch_bidir_eye_shade(sc, bp, b, buf, cur, depth, s);
-        M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
-        cur ^= 1;
-        launches += 2;
+  // traces one batch of samples; leaves one colour per slot in buf.accum
+  auto run_batch = [&](const PathBatch &b) -> int32_t {
+    const int64_t n = (int64_t)b.nP * b.S;
+    // eye sub-paths
+    launch_bidir_eye_raygen(dc, bp, b, buf, s);
+    launches++;
+    int cur = 0;
+    for (int depth = 0; depth < max_depth; depth++) {
+      if (int32_t rc = trace(buf.org[cur], buf.dir[cur], buf.skip[cur], buf.raw, n, buf.counts + cur)) return rc;
+      launch_bidir_eye_shade(sc, bp, b, buf, cur, depth, s);
+      M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
+      cur ^= 1;
+      launches += 2;
+    }
+    // light sub-paths
+    launch_bidir_light_raygen(sc, bp, d_lights, d_tris, b, buf, s);
+    launches++;
+    cur = 0;
+    for (int depth = 0; depth + 1 < max_ld; depth++) {
+      if (int32_t rc = trace(buf.org[cur], buf.dir[cur], buf.skip[cur], buf.raw, n, buf.counts + cur)) return rc;
+      launch_bidir_light_shade(sc, bp, b, buf, cur, depth, s);
+      M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
+      cur ^= 1;
+      launches += 2;
+    }
+    // connections
+    for (int i = 1; i <= max_depth; i++) {
+      M3D_CUDA(cudaMemsetAsync(buf.counts + 2, 0, sizeof(int), s));
+      launch_bidir_connect(sc, bp, b, buf, i, s);
+      if (int32_t rc = trace(buf.corg, buf.cdir, buf.cskip, buf.craw, n * max_ld, buf.counts + 2)) return rc;
+      launch_bidir_connect_resolve(sc, buf, s);
+      launches += 3;
+    }
+    return M3D_OK;
+  };
+  int64_t samples_taken = npix * sample_count;
+  if (adaptive) {
+    AdaptiveParams ap;
+    ap.num_samples = params->num_samples;
+    ap.min_samples = params->min_samples;
+    ap.max_stddev = params->max_stddev;
+    ap.oversaturated_stddevs = params->oversaturated_stddevs;
+    if (int32_t rc = run_adaptive(ctx, s, width, (int32_t)((int64_t)row_begin * width), (int32_t)npix, cap, ap,
+                                  buf.accum, (float *)d_rgb_sum, run_batch, &samples_taken))
+      return rc;
+  } else {
+    for (int64_t p0 = 0; p0 < npix; p0 += nP_max) {
+      const int64_t nP = std::min(nP_max, npix - p0);
+      const int64_t S_max = std::max<int64_t>(1, cap / nP);
+      for (int64_t s0 = 0; s0 < sample_count; s0 += S_max) {
+        PathBatch b;
+        b.W = width;
+        b.pix0 = (int32_t)((int64_t)row_begin * width + p0);
+        b.nP = (int32_t)nP;
+        b.S = (int32_t)std::min<int64_t>(S_max, sample_count - s0);
+        b.sample0 = (uint32_t)(sample_begin + s0);
+        if (int32_t rc = run_batch(b)) return rc;
+        launch_path_flush(b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
+        launches++;
       }
-      // light sub-paths
-      launch_bidir_light_raygen(sc, bp, d_lights, d_tris, b, buf, s);
-      launches++;
-      cur = 0;
-      for (int depth = 0; depth + 1 < max_ld; depth++) {
-        if (int32_t rc = trace(buf.org[cur], buf.dir[cur], buf.skip[cur], buf.raw, n, buf.counts + cur)) return rc;
-        launch_bidir_light_shade(sc, bp, b, buf, cur, depth, s);
-        M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
-        cur ^= 1;
-        launches += 2;
-      }
-      // connections
-      for (int i = 1; i <= max_depth; i++) {
-        M3D_CUDA(cudaMemsetAsync(buf.counts + 2, 0, sizeof(int), s));
-        launch_bidir_connect(sc, bp, b, buf, i, s);
-        if (int32_t rc = trace(buf.corg, buf.cdir, buf.cskip, buf.craw, n * max_ld, buf.counts + 2)) return rc;
-        launch_bidir_connect_resolve(sc, buf, s);
-        launches += 3;
-      }
-      launch_path_flush(b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
-      launches++;
     }
   }
   tm.stop(s);
@@ -281,6 +306,7 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
     stats->rays = (int64_t)rays;
     stats->kernel_ms = tm.ms();
     stats->launches = launches;
+    stats->samples = samples_taken;
   }
   return M3D_OK;
 }

@@ -80,7 +80,7 @@ struct m3d_ctx {
   cudaStream_t copy_in = nullptr;      // H2D
   cudaStream_t copy_out = nullptr;     // D2H
   // scratch reused by host-buffer calls (grown on demand, never shrunk)
-  m3d::DevBuf scratch[8];
+  m3d::DevBuf scratch[12];
   m3d::DevBuf counters;       // [0..3] node/triangle statistics, then kWorkSlots work counters
   unsigned work_slot = 0;
   static constexpr int kWorkSlots = 64;

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "adaptive.h"
 #include "api_common.h"
 #include "path.h"
 #include "scene.h"
@@ -79,10 +80,8 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
     return fail(M3D_ERR_INVALID_ARG, "m3d_render_path: bad arguments");
   if (params->num_focus_points < 0 || params->num_focus_points > M3D_MAX_FOCUS_POINTS)
     return fail(M3D_ERR_UNSUPPORTED, "at most %d focus points are supported", M3D_MAX_FOCUS_POINTS);
-  if (params->min_samples != 0 && params->max_stddev != 0)
-    return fail(M3D_ERR_UNSUPPORTED,
-                "adaptive sampling (MinSamples/MaxStddev) is not supported on the GPU path: render "
-                "fixed-size sample shards and test convergence on the reduced sums");
+  // rayRenderer.HasConvergenceCheck (ray_renderer.go:153-155) without the Convergence callback
+  const bool adaptive = params->min_samples != 0 && params->max_stddev != 0;
   if (params->max_depth < 0 || params->max_depth > 1000) return fail(M3D_ERR_INVALID_ARG, "bad max_depth");
   if ((int64_t)width * height > (int64_t)0x7fffffff / 4) return fail(M3D_ERR_INVALID_ARG, "frame too large");
   m3d_ctx *ctx = scene_ctx(scene);
@@ -105,6 +104,10 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   if (stats) std::memset(stats, 0, sizeof(*stats));
   const int64_t npix = (int64_t)width * (row_end - row_begin);
   if (npix == 0 || sample_count == 0) return M3D_OK;
+  if (adaptive && (sample_begin != 0 || sample_count != params->num_samples || d_rgb_sumsq))
+    return fail(M3D_ERR_INVALID_ARG,
+                "adaptive sampling (MinSamples/MaxStddev) stops per pixel: it cannot be sharded by sample index "
+                "(sample_begin must be 0 and sample_count == num_samples; shard by rows) and has no sumsq output");
 
   DevicePathParams pp;
   std::memset(&pp, 0, sizeof(pp));
@@ -154,59 +157,77 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   GpuTimer tm;
   tm.start(s);
   int64_t launches = 0;
-  for (int64_t p0 = 0; p0 < npix; p0 += nP_max) {
-    const int64_t nP = std::min(nP_max, npix - p0);
-    const int64_t S_max = std::max<int64_t>(1, cap / nP);
-    for (int64_t s0 = 0; s0 < sample_count; s0 += S_max) {
-      PathBatch b;
-      b.W = width;
-      b.pix0 = (int32_t)((int64_t)row_begin * width + p0);
-      b.nP = (int32_t)nP;
-      b.S = (int32_t)std::min<int64_t>(S_max, sample_count - s0);
-      b.sample0 = (uint32_t)(sample_begin + s0);
-      const int64_t n = (int64_t)b.nP * b.S;
-      launch_path_raygen(dc, pp, b, buf, s);
-      launches++;
-      int cur = 0;
-      for (int depth = 0; depth <= pp.max_depth; depth++) {
-        TraceLaunch t;
-        t.org_tmin = buf.org[cur];
-        t.dir_tmax = buf.dir[cur];
-        t.n = n;
-        t.n_ptr = buf.counts + cur;
-        t.hit0 = buf.raw;
-        t.hit1 = nullptr;
-        t.refine = false;
-        t.counters = nullptr;
-        t.skip_tris = buf.skip[cur];
-        t.ray_counter = next_work_counter(ctx);
-        if (!t.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
-        launch_trace_bvh_only(sc.bvh, t, s);
-        launch_path_shade(sc, pp, d_lights, b, buf, cur, depth, s);
+  // traces one batch: raygen -> [trace -> shade (-> shadow trace -> resolve)] x depth; leaves one
+  // colour per slot in buf.accum
+  auto run_batch = [&](const PathBatch &b) -> int32_t {
+    const int64_t n = (int64_t)b.nP * b.S;
+    launch_path_raygen(dc, pp, b, buf, s);
+    launches++;
+    int cur = 0;
+    for (int depth = 0; depth <= pp.max_depth; depth++) {
+      TraceLaunch t;
+      t.org_tmin = buf.org[cur];
+      t.dir_tmax = buf.dir[cur];
+      t.n = n;
+      t.n_ptr = buf.counts + cur;
+      t.hit0 = buf.raw;
+      t.hit1 = nullptr;
+      t.refine = false;
+      t.counters = nullptr;
+      t.skip_tris = buf.skip[cur];
+      t.ray_counter = next_work_counter(ctx);
+      if (!t.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
+      launch_trace_bvh_only(sc.bvh, t, s);
+      launch_path_shade(sc, pp, d_lights, b, buf, cur, depth, s);
+      launches += 2;
+      if (num_lights > 0) {
+        TraceLaunch ts;
+        ts.org_tmin = buf.sorg;
+        ts.dir_tmax = buf.sdir;
+        ts.n = n * num_lights;
+        ts.n_ptr = buf.counts + 2;
+        ts.hit0 = buf.sraw;
+        ts.hit1 = nullptr;
+        ts.refine = false;
+        ts.counters = nullptr;
+        ts.skip_tris = buf.sskip;
+        ts.ray_counter = next_work_counter(ctx);
+        if (!ts.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
+        launch_trace_bvh_only(sc.bvh, ts, s);
+        launch_path_shadow_resolve(sc, pp, buf, cur, s);
         launches += 2;
-        if (num_lights > 0) {
-          TraceLaunch ts;
-          ts.org_tmin = buf.sorg;
-          ts.dir_tmax = buf.sdir;
-          ts.n = n * num_lights;
-          ts.n_ptr = buf.counts + 2;
-          ts.hit0 = buf.sraw;
-          ts.hit1 = nullptr;
-          ts.refine = false;
-          ts.counters = nullptr;
-          ts.skip_tris = buf.sskip;
-          ts.ray_counter = next_work_counter(ctx);
-          if (!ts.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
-          launch_trace_bvh_only(sc.bvh, ts, s);
-          launch_path_shadow_resolve(sc, pp, buf, cur, s);
-          launches += 2;
-        }
-        // the consumed queue becomes the next output queue
-        M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
-        cur ^= 1;
       }
-      launch_path_flush(b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
-      launches++;
+      // the consumed queue becomes the next output queue
+      M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
+      cur ^= 1;
+    }
+    return M3D_OK;
+  };
+  int64_t samples_taken = npix * sample_count;
+  if (adaptive) {
+    AdaptiveParams ap;
+    ap.num_samples = params->num_samples;
+    ap.min_samples = params->min_samples;
+    ap.max_stddev = params->max_stddev;
+    ap.oversaturated_stddevs = params->oversaturated_stddevs;
+    if (int32_t rc = run_adaptive(ctx, s, width, (int32_t)((int64_t)row_begin * width), (int32_t)npix, cap, ap,
+                                  buf.accum, (float *)d_rgb_sum, run_batch, &samples_taken))
+      return rc;
+  } else {
+    for (int64_t p0 = 0; p0 < npix; p0 += nP_max) {
+      const int64_t nP = std::min(nP_max, npix - p0);
+      const int64_t S_max = std::max<int64_t>(1, cap / nP);
+      for (int64_t s0 = 0; s0 < sample_count; s0 += S_max) {
+        PathBatch b;
+        b.W = width;
+        b.pix0 = (int32_t)((int64_t)row_begin * width + p0);
+        b.nP = (int32_t)nP;
+        b.S = (int32_t)std::min<int64_t>(S_max, sample_count - s0);
+        b.sample0 = (uint32_t)(sample_begin + s0);
+        if (int32_t rc = run_batch(b)) return rc;
+        launch_path_flush(b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
+        launches++;
+      }
     }
   }
   tm.stop(s);
@@ -219,6 +240,7 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
     stats->rays = (int64_t)rays;
     stats->kernel_ms = tm.ms();
     stats->launches = launches;
+    stats->samples = samples_taken;
   }
   return M3D_OK;
 }

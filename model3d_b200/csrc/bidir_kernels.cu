@@ -154,7 +154,7 @@ bidir_eye_raygen_kernel(DeviceCamera cam, DeviceBidirParams bp, PathBatch b, Bid
   }
   if (slot >= n) return;
   const int p = (int)(slot % b.nP), s = (int)(slot / b.nP);
-  const int pix = b.pix0 + p;
+  const int pix = batch_pixel(b, p);
   const int x = pix % b.W, y = pix / b.W;
   double fx = (double)x, fy = (double)y;
   if (bp.antialias != 0.f) {  // ray_renderer.go:118-124
@@ -215,7 +215,7 @@ bidir_shade_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffe
         const MatAt m = material_at(sc, h.obj, v.point);
         v.emission = mat_emission(sc, m);
         Rng g;
-        g.init(bp.seed, (uint32_t)(b.pix0 + slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP),
+        g.init(bp.seed, (uint32_t)batch_pixel(b, slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP),
                (EYE ? 0x100u : 0x300u) + (uint32_t)depth);
         int tag = 0;
         if (EYE) {
@@ -281,7 +281,7 @@ bidir_light_raygen_kernel(DeviceScene sc, DeviceBidirParams bp, const DeviceArea
   if (slot64 >= n) return;
   const int slot = (int)slot64;
   Rng g;
-  g.init(bp.seed, (uint32_t)(b.pix0 + slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP), 0x200u);
+  g.init(bp.seed, (uint32_t)batch_pixel(b, slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP), 0x200u);
   // joinedAreaLight.SampleLight (light.go:303-311): light chosen in proportion to TotalEmission
   int li = 0;
   if (bp.num_lights > 1) {
@@ -511,7 +511,7 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
           if (bp.roulette_delta > 0.0 && brightness < bp.roulette_delta) {  // bidir.go:133-142
             const double keep = brightness / bp.roulette_delta;
             Rng g;
-            g.init(bp.seed, (uint32_t)(b.pix0 + slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP),
+            g.init(bp.seed, (uint32_t)batch_pixel(b, slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP),
                    0x1000u + (uint32_t)(i * 64 + j));
             if ((double)g.f32() > keep) keep_it = false;
             color.x /= keep;

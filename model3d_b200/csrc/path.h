@@ -32,7 +32,13 @@ struct PathBatch {
   int32_t W;
   int32_t pix0, nP, S;
   uint32_t sample0;
+  // optional explicit pixel list (frame-linear indices, device memory) instead of the range
+  // pix0 .. pix0+nP: the still-unconverged pixels of an adaptive render
+  const int32_t *pixels = nullptr;
 };
+#if defined(__CUDACC__)
+__device__ __forceinline__ int batch_pixel(const PathBatch &b, int p) { return b.pixels ? b.pixels[p] : b.pix0 + p; }
+#endif
 
 // Structure-of-arrays path state, capacity `cap` slots.  Rays / raw hits / skip ids / queue
 // entries are stored in QUEUE order (compacted, ping-pong [2]); throughput and accumulated

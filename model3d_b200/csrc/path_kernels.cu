@@ -73,7 +73,7 @@ path_raygen_kernel(DeviceCamera cam, DevicePathParams pp, PathBatch b, PathBuffe
   }
   if (slot >= n) return;
   const int p = (int)(slot % b.nP), s = (int)(slot / b.nP);
-  const int pix = b.pix0 + p;
+  const int pix = batch_pixel(b, p);
   const int x = pix % b.W, y = pix / b.W;
   double fx = (double)x, fy = (double)y;
   if (pp.antialias != 0.f) {  // ray_renderer.go:118-124
@@ -166,7 +166,7 @@ path_shade_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *_
         }
         if (depth < pp.max_depth) {
           Rng g;
-          g.init(pp.seed, (uint32_t)(b.pix0 + slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP), (uint32_t)depth);
+          g.init(pp.seed, (uint32_t)batch_pixel(b, slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP), (uint32_t)depth);
           // sampleNextSource (raytrace.go:183-199)
           V3f source;
           int tag = 0;
@@ -292,7 +292,7 @@ path_flush_kernel(PathBatch b, const float4 *__restrict__ accum, float *__restri
     qy += a.y * a.y;
     qz += a.z * a.z;
   }
-  const size_t o = (size_t)(b.pix0 + p) * 3;
+  const size_t o = (size_t)batch_pixel(b, p) * 3;
   rgb_sum[o] += sx;
   rgb_sum[o + 1] += sy;
   rgb_sum[o + 2] += sz;

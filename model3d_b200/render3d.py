@@ -485,9 +485,10 @@ def _samples_partition(partition):
 class RecursiveRayTracer:
     """render3d.RecursiveRayTracer (raytrace.go:14-119): same exported fields.
 
-    Render() runs the wavefront path tracer of libm3dgpu (m3d_render_path).  Adaptive early
-    stopping (MinSamples/MaxStddev/Convergence) is not available on the GPU path and raises
-    UnsupportedError: sample counts are fixed so that shards can be summed across GPUs."""
+    Render() runs the wavefront path tracer of libm3dgpu (m3d_render_path).  Early stopping
+    with MinSamples/MaxStddev/OversaturatedStddevs follows the reference's per-sample rule
+    (ray_renderer.go:128-148); a Convergence callback cannot cross the ABI and raises
+    UnsupportedError.  Adaptive renders cannot be sharded by sample index (shard by rows)."""
     Camera: Camera = None
     Lights: List[PointLight] = field(default_factory=list)
     FocusPoints: List[object] = field(default_factory=list)
@@ -509,14 +510,17 @@ class RecursiveRayTracer:
             raise ValueError("must set NumSamples to non-zero for rayRenderer")  # ray_renderer.go:26-28
         if len(self.FocusPoints) != len(self.FocusPointProbs):
             raise ValueError("FocusPoints and FocusPointProbs must match in length")  # raytrace.go:186-188
-        if (self.MinSamples != 0 and self.MaxStddev != 0) or self.Convergence is not None:
-            raise UnsupportedError("adaptive sampling (MinSamples/MaxStddev/Convergence) is not "
-                                   "supported on the GPU path")
+        if self.Convergence is not None:
+            raise UnsupportedError("Convergence callbacks cannot run on the GPU path (MinSamples/MaxStddev/"
+                                   "OversaturatedStddevs are supported)")
         if len(self.FocusPoints) > 4:
             raise UnsupportedError("at most 4 focus points are supported on the GPU path")
         p = N.PathParams()
         p.max_depth = int(self.MaxDepth)
         p.num_samples = int(num_samples or self.NumSamples)
+        p.min_samples = int(self.MinSamples)
+        p.max_stddev = float(self.MaxStddev)
+        p.oversaturated_stddevs = float(self.OversaturatedStddevs)
         p.cutoff = float(self.Cutoff)
         p.antialias = float(self.Antialias)
         p.epsilon = float(self.Epsilon)
@@ -536,6 +540,8 @@ class RecursiveRayTracer:
         p = self._params(sc, n)
         if antialias is not None:
             p.antialias = float(antialias)
+        if variance or sample_count is not None or partition is not None and partition[2] != 0:
+            p.min_samples = 0  # fixed-count shard / estimateVariance: no early stop
         cam = self.Camera._c()
         rgb = np.zeros((height, width, 3), np.float32)
         sq = np.zeros((height, width, 3), np.float32) if variance else None
@@ -665,14 +671,16 @@ class BidirPathTracer:
     def _params(self, num_samples):
         if self.NumSamples == 0 and num_samples == 0:
             raise ValueError("must set NumSamples to non-zero for rayRenderer")
-        if (self.MinSamples != 0 and self.MaxStddev != 0) or self.Convergence is not None:
-            raise UnsupportedError("adaptive sampling (MinSamples/MaxStddev/Convergence) is not "
-                                   "supported on the GPU path")
+        if self.Convergence is not None:
+            raise UnsupportedError("Convergence callbacks cannot run on the GPU path (MinSamples/MaxStddev/"
+                                   "OversaturatedStddevs are supported)")
         p = N.BidirParams()
         p.max_depth, p.max_light_depth, p.min_depth = int(self.MaxDepth), int(self.MaxLightDepth), int(self.MinDepth)
         p.num_samples = int(num_samples or self.NumSamples)
         p.roulette_delta, p.power_heuristic = float(self.RouletteDelta), float(self.PowerHeuristic)
         p.cutoff, p.antialias, p.epsilon = float(self.Cutoff), float(self.Antialias), float(self.Epsilon)
+        p.min_samples, p.max_stddev = int(self.MinSamples), float(self.MaxStddev)
+        p.oversaturated_stddevs = float(self.OversaturatedStddevs)
         p.seed = int(self.Seed)
         return p
 
@@ -682,6 +690,8 @@ class BidirPathTracer:
         p = self._params(n)
         if antialias is not None:
             p.antialias = float(antialias)
+        if variance or sample_count is not None or partition is not None and partition[2] != 0:
+            p.min_samples = 0  # fixed-count shard / estimateVariance: no early stop
         cam = self.Camera._c()
         lights, nl = _area_lights(sc, self.Light)
         rgb = np.zeros((height, width, 3), np.float32)

@@ -69,7 +69,8 @@ class BidirParams(C.Structure):
                 ("min_depth", C.c_int32), ("num_samples", C.c_int32),
                 ("roulette_delta", C.c_double), ("power_heuristic", C.c_double),
                 ("cutoff", C.c_double), ("antialias", C.c_double), ("epsilon", C.c_double),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("min_samples", C.c_int32), ("_pad", C.c_int32),
+                ("max_stddev", C.c_double), ("oversaturated_stddevs", C.c_double)]
 
 
 def build(force=False):

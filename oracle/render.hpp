@@ -568,7 +568,8 @@ inline void render_bidir(const Scene &sc, const m3d_camera &cam, const m3d_area_
   al.init(sc, lights, nl);
   std::vector<Bidir> bs;
   for (int i = 0; i < std::max(1, nthreads); i++) bs.push_back(Bidir{sc, al, p});
-  estimate_pixels(cam, W, H, p.num_samples, 0, 0, 0, p.antialias, p.seed, mean, var_of_mean, nthreads,
+  estimate_pixels(cam, W, H, p.num_samples, p.min_samples, p.max_stddev, p.oversaturated_stddevs, p.antialias,
+                  p.seed, mean, var_of_mean, nthreads,
                   [&](Rng &g, const Ray &ray, int tid) { return bs[tid].ray_color(g, ray); });
   if (rays_cast) {
     *rays_cast = 0;

@@ -108,3 +108,23 @@ def test_bidir_errors(built):
     tr.Light = R.NewSphereAreaLight(R.Sphere((0, 0, 0), 1.0), (1, 1, 1))
     with pytest.raises(ValueError):
         tr.RenderSums(4, 4, psc)  # the light is not part of the scene
+
+
+def test_bidir_adaptive_sampling(built, oracle):
+    """TestBidirPathTracer's own configuration (bidir_test.go:36-43): NumSamples 200000,
+    MinSamples 1000, MaxStddev 0.0015 -- early stop per pixel, image within 0.02 of the path
+    tracer's ground truth like the reference test demands."""
+    from model3d_b200 import render3d as R
+    spec = scenes.testing_scene()
+    osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
+    cam = spec["camera"]
+    ocam = oracle.camera_at(cam["src"], cam["dst"], cam["fov"])
+    pp = scenes.oracle_path_params(spec, osc, 10, 60000, seed=8)
+    truth = osc.render_path(ocam, [], pp, 4, 4, threads=4)["mean"]
+    tr = scenes.product_bidir(spec, psc, 10, 200000, seed=2)
+    tr.MinSamples, tr.MaxStddev = 1000, 0.0015
+    img = R.Image(4, 4)
+    stats = tr.Render(img, psc)
+    assert np.isfinite(img.Data).all()
+    assert np.linalg.norm(img.Data - truth, axis=2).max() < 0.02
+    assert 16 * 1000 < stats["samples"] < 16 * 200000

@@ -144,14 +144,36 @@ def test_path_partitions_add_up(built):
     assert np.allclose(top + bot, full, rtol=1e-4, atol=1e-4)
 
 
-def test_path_unsupported_adaptive(built):
+def test_path_adaptive_sampling_matches_reference_rule(built, oracle):
+    """MinSamples / MaxStddev early stop (ray_renderer.go:128-148) on testingScene as in
+    TestBidirPathTracer (bidir_test.go:16-35): pixels stop per the reference's per-sample test,
+    the image matches the oracle's adaptive render within the requested standard error, and far
+    fewer than NumSamples samples are taken."""
     from model3d_b200 import UnsupportedError
     spec = scenes.testing_scene()
-    psc = scenes.build_product(spec)
-    tr = scenes.product_tracer(spec, psc, 3, 100)
-    tr.MinSamples, tr.MaxStddev = 10, 0.01
+    osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
+    cam = spec["camera"]
+    ocam = oracle.camera_at(cam["src"], cam["dst"], cam["fov"])
+    W = H = 6
+    pp = scenes.oracle_path_params(spec, osc, 10, 100000, seed=3)
+    pp.min_samples, pp.max_stddev = 1000, 0.003
+    ref = osc.render_path(ocam, [], pp, W, H, threads=6)["mean"]
+    tr = scenes.product_tracer(spec, psc, 10, 100000, seed=9)
+    tr.MinSamples, tr.MaxStddev = 1000, 0.003
+    from model3d_b200 import render3d as R
+    img = R.Image(W, H)
+    stats = tr.Render(img, psc)
+    taken = stats["samples"] / (W * H)
+    assert 1000 < taken < 60000, taken          # stopped early, after MinSamples
+    # both images carry a standard error of about MaxStddev per channel
+    assert np.abs(img.Data - ref).max() < 6 * 0.003 * np.sqrt(2), np.abs(img.Data - ref).max()
+    # a looser target stops earlier; MaxStddev huge stops right at MinSamples (+1 sample, count-1 quirk)
+    tr.MaxStddev = 1e9
+    stats2 = tr.Render(R.Image(W, H), psc)
+    assert stats2["samples"] == W * H * 1001
+    tr.Convergence = lambda mean, stddev: True
     with pytest.raises(UnsupportedError):
-        tr.RenderSums(4, 4, psc)
+        tr.Render(R.Image(W, H), psc)
 
 
 def test_showcase_cast_and_path(built, oracle):
