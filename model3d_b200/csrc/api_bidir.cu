@@ -42,10 +42,12 @@ int32_t carve_bidir_buffers(m3d_ctx *ctx, int64_t cap, int De, int Dl, BidirBuff
     o_queue[i] = take(c * 4);
   }
   const size_t o_raw = take(c * 16), o_ef = take(c * 16), o_er = take(c * 16), o_acc = take(c * 16);
-  const size_t o_es = take(c * 32);
-  const size_t cc = c * (size_t)Dl;
+  const size_t o_ep = take(c * 32 * De), o_lp = take(c * 32 * Dl);
+  const size_t o_ma = take(c * 16 * (De + Dl)), o_mb = take(c * 16 * (De + Dl)), o_mc = take(c * 4 * (De + Dl));
+  const size_t cc = c * (size_t)De * (size_t)Dl;
   const size_t o_corg = take(cc * 16), o_cdir = take(cc * 16), o_craw = take(cc * 16), o_cpay = take(cc * 16),
                o_cskip = take(cc * 4);
+  const size_t o_work = take(c * (size_t)De * (size_t)(Dl + 1) * 4);
   const size_t o_counts = take(64);
   M3D_CUDA(ctx->scratch[6].reserve(total));
   char *p = ctx->scratch[6].as<char>();
@@ -66,12 +68,17 @@ int32_t carve_bidir_buffers(m3d_ctx *ctx, int64_t cap, int De, int Dl, BidirBuff
   b.ender_full = (float4 *)(p + o_ef);
   b.ender_roul = (float4 *)(p + o_er);
   b.accum = (float4 *)(p + o_acc);
-  b.eye_state = (double *)(p + o_es);
+  b.eyepre = (double *)(p + o_ep);
+  b.lightpre = (double *)(p + o_lp);
+  b.misA = (float4 *)(p + o_ma);
+  b.misB = (double2 *)(p + o_mb);
+  b.misC = (float *)(p + o_mc);
   b.corg = (float4 *)(p + o_corg);
   b.cdir = (float4 *)(p + o_cdir);
   b.craw = (float4 *)(p + o_craw);
   b.cpay = (float4 *)(p + o_cpay);
   b.cskip = (int32_t *)(p + o_cskip);
+  b.work = (uint32_t *)(p + o_work);
   b.counts = (int *)(p + o_counts);
   b.ray_total = (unsigned long long *)(p + o_counts + 32);
   return M3D_OK;
@@ -204,7 +211,8 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
     M3D_CUDA(cudaMemcpyAsync(d_tris, ht.data(), ht.size() * sizeof(DeviceLightTri), cudaMemcpyHostToDevice, s));
 
   // batch geometry: per-slot footprint is dominated by the stored path vertices
-  const size_t per_slot = (size_t)16 * kBidirVertexFields * (max_depth + max_ld) + (size_t)max_ld * 68 + 256;
+  const size_t per_slot = (size_t)(16 * kBidirVertexFields + 32 + 36) * (max_depth + max_ld) +
+                          (size_t)max_depth * (max_ld + 1) * 72 + 256;
   int64_t cap = (int64_t)std::min<size_t>((size_t)1 << 20, ((size_t)6 << 30) / per_slot);
   const int64_t total = npix * sample_count;
   cap = std::max<int64_t>(1, std::min(cap, total));
@@ -260,14 +268,13 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
       cur ^= 1;
       launches += 2;
     }
-    // connections
-    for (int i = 1; i <= max_depth; i++) {
-      M3D_CUDA(cudaMemsetAsync(buf.counts + 2, 0, sizeof(int), s));
-      launch_bidir_connect(sc, bp, b, buf, i, s);
-      if (int32_t rc = trace(buf.corg, buf.cdir, buf.cskip, buf.craw, n * max_ld, buf.counts + 2)) return rc;
-      launch_bidir_connect_resolve(sc, buf, s);
-      launches += 3;
-    }
+    // connections: all (eye prefix, light prefix) pairs at once
+    launch_bidir_prefix(bp, b, buf, s);
+    launch_bidir_connect(sc, bp, b, buf, s);
+    if (int32_t rc = trace(buf.corg, buf.cdir, buf.cskip, buf.craw, n * max_depth * max_ld, buf.counts + 2))
+      return rc;
+    launch_bidir_connect_resolve(sc, buf, s);
+    launches += 4;
     return M3D_OK;
   };
   int64_t samples_taken = npix * sample_count;

@@ -57,11 +57,18 @@ struct BidirBuffers {
   float4 *raw;
   float4 *ender_full, *ender_roul;  // PathEnder state: (fullMask, currentRoulette), rouletteMask
   float4 *accum;
-  double *eye_state;  // 4 doubles per slot: eyeDensity, eyeBSDF.xyz
-  // connection (visibility) rays of one round, compacted
+  // running products of allPathCombinations per sub-path prefix, 4 doubles each:
+  // eyepre[(i-1)*cap + slot] = eyeDensity, eyeBSDF.xyz; lightpre[(j-1)*cap + slot] likewise
+  double *eyepre, *lightpre;
+  // compact MIS records, depth-major: eye vertices at [0, De), light vertices at [De, De+Dl)
+  float4 *misA;
+  double2 *misB;
+  float *misC;
+  // connection (visibility) rays of all (i, j) pairs of the batch, compacted
   float4 *corg, *cdir, *craw, *cpay;
   int32_t *cskip;
-  int *counts;  // [0],[1] queue lengths, [2] connection rays
+  uint32_t *work;  // connection work items: slot | i << 20 | j << 25 (cap <= 2^20, depths <= 16)
+  int *counts;     // [0],[1] queue lengths, [2] connection rays, [3] work items
   unsigned long long *ray_total;
 };
 
@@ -74,9 +81,12 @@ void launch_bidir_light_raygen(const DeviceScene &sc, const DeviceBidirParams &b
                                cudaStream_t stream);
 void launch_bidir_light_shade(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
                               const BidirBuffers &buf, int cur, int depth, cudaStream_t stream);
-// connections of eye prefix length i (1-based) with every light prefix; emits visibility rays
+// running products + compact MIS records of both sub-paths (one thread per sample)
+void launch_bidir_prefix(const DeviceBidirParams &bp, const PathBatch &b, const BidirBuffers &buf,
+                         cudaStream_t stream);
+// every (eye prefix, light prefix) connection of the batch; emits compacted visibility rays
 void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
-                          const BidirBuffers &buf, int i, cudaStream_t stream);
+                          const BidirBuffers &buf, cudaStream_t stream);
 void launch_bidir_connect_resolve(const DeviceScene &sc, const BidirBuffers &buf, cudaStream_t stream);
 
 }  // namespace m3d

@@ -151,6 +151,7 @@ bidir_eye_raygen_kernel(DeviceCamera cam, DeviceBidirParams bp, PathBatch b, Bid
     buf.counts[0] = (int)n;
     buf.counts[1] = 0;
     buf.counts[2] = 0;
+    buf.counts[3] = 0;
   }
   if (slot >= n) return;
   const int p = (int)(slot % b.nP), s = (int)(slot / b.nP);
@@ -343,7 +344,12 @@ bidir_light_raygen_kernel(DeviceScene sc, DeviceBidirParams bp, const DeviceArea
   buf.ender_roul[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
 }
 
-// Per-vertex scalars of the MIS computation (bidir.go:421-471).
+// Per-vertex scalars of the MIS computation (bidir.go:421-471), written once per sub-path
+// vertex by bidir_prefix_kernel so that the connection threads load 36 bytes per vertex
+// instead of the 112-byte vertex record:
+//   misA = (point.xyz, sourceDot)   misB = (sourceDensity, destDensity) as float64 incl. the
+//   Dirac magnitudes                 misC = destDot
+// Eye vertices occupy depths [0, De), light vertices [De, De+Dl) of the mis arrays.
 struct Mis {
   double sd, dd;
   float sdot, ddot;
@@ -360,6 +366,26 @@ __device__ __forceinline__ Mis mis_of(const BVert &v) {
   m.pz = v.point.z;
   return m;
 }
+__device__ __forceinline__ void store_mis(const BidirBuffers &buf, int depth, int slot, const Mis &m) {
+  const size_t o = (size_t)depth * buf.cap + slot;
+  buf.misA[o] = make_float4(m.px, m.py, m.pz, m.sdot);
+  buf.misB[o] = make_double2(m.sd, m.dd);
+  buf.misC[o] = m.ddot;
+}
+__device__ __forceinline__ Mis load_mis(const BidirBuffers &buf, int depth, int slot) {
+  const size_t o = (size_t)depth * buf.cap + slot;
+  const float4 a = buf.misA[o];
+  const double2 b = buf.misB[o];
+  Mis m;
+  m.px = a.x;
+  m.py = a.y;
+  m.pz = a.z;
+  m.sdot = a.w;
+  m.sd = b.x;
+  m.dd = b.y;
+  m.ddot = buf.misC[o];
+  return m;
+}
 __device__ __forceinline__ double out_area(const Mis &a, const Mis &b) {
   const double dx = (double)a.px - b.px, dy = (double)a.py - b.py, dz = (double)a.pz - b.pz;
   return kFourPi * (dx * dx + dy * dy + dz * dz);
@@ -369,104 +395,45 @@ struct D3c {
   double x, y, z;
 };
 
-// allPathCombinations for one eye prefix length i (bidir.go:476-530) + rayColor's callback
-// (bidir.go:113-158).  One thread per sample.
-__global__ void __launch_bounds__(kBlock, 8)
-bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf, int i) {
+// The running products of allPathCombinations (bidir.go:482-483, 493-507, 527-528), which the
+// reference carries through its two nested loops, precomputed per sub-path so that every
+// (eye prefix i, light prefix j) pair becomes an independent work item:
+//   eyepre[i-1]   = (eyeDensity, eyeBSDF.xyz) as they stand when the outer loop reaches i
+//   lightpre[j-1] = (density / eyeDensity, lightBSDF.xyz) as they stand when the inner loop reaches j
+// One thread per sample; also writes the compact MIS records.
+__global__ void __launch_bounds__(256)
+bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
   const int n_slots = b.nP * b.S;
-  const int slot = blockIdx.x * kBlock + threadIdx.x;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
-  const int ne = buf.ne[slot];
-  if (i > ne) return;
-  const int nl = buf.nl[slot];
-
-  // eye prefix state: eyeDensity, eyeBSDF (bidir.go:482-483, 527-528)
+  const int ne = buf.ne[slot], nl = buf.nl[slot];
   double eye_density = 1.0;
   D3c eye_bsdf = {1.0, 1.0, 1.0};
-  if (i > 1) {
-    const double *st = buf.eye_state + (size_t)slot * 4;
-    eye_density = st[0];
-    eye_bsdf.x = st[1];
-    eye_bsdf.y = st[2];
-    eye_bsdf.z = st[3];
+  for (int i = 1; i <= ne; i++) {
+    const BVert v = load_vertex(buf.ev, buf.De, buf.cap, i - 1, slot);
+    double *st = buf.eyepre + ((size_t)(i - 1) * buf.cap + slot) * 4;
+    st[0] = eye_density;
+    st[1] = eye_bsdf.x;
+    st[2] = eye_bsdf.y;
+    st[3] = eye_bsdf.z;
+    store_mis(buf, i - 1, slot, mis_of(v));
+    const double sdv = (double)source_dot(v);
+    eye_density *= full_sd(v);
+    eye_bsdf.x *= ((double)v.bsdf_fin.x + (double)v.bsdf_del.x * kDeltaMag) * sdv;
+    eye_bsdf.y *= ((double)v.bsdf_fin.y + (double)v.bsdf_del.y * kDeltaMag) * sdv;
+    eye_bsdf.z *= ((double)v.bsdf_fin.z + (double)v.bsdf_del.z * kDeltaMag) * sdv;
   }
-
-  Mis E[kBidirMaxDepth], L[kBidirMaxDepth];
-  for (int k = 0; k < i; k++) E[k] = mis_of(load_vertex(buf.ev, buf.De, buf.cap, k, slot));
-  for (int k = 0; k < nl; k++) L[k] = mis_of(load_vertex(buf.lv, buf.Dl, buf.cap, k, slot));
-  const BVert ev = load_vertex(buf.ev, buf.De, buf.cap, i - 1, slot);
-  const BVert l0 = load_vertex(buf.lv, buf.Dl, buf.cap, 0, slot);
-  const double l0_sum = (double)l0.emission.x + l0.emission.y + l0.emission.z;
-  const int max_ld = bp.max_light_depth;  // already defaulted to max_depth by the host
-  const double ph = bp.power_heuristic;
-
-  float3 add = make_float3(0.f, 0.f, 0.f);
-
-  // MIS weight of the joined path made of light[0..j-2], JL, JE, eye[i-2..0] (j >= 1) or
-  // eye[i-1..0] (j == 0): sum over every way of splitting it into a light and an eye part.
-  auto mis_weight = [&](int j, const Mis &JL, const Mis &JE, double density, double emis0_sum) -> double {
-    const int n = i + j;
-    auto at = [&](int k) -> Mis {
-      if (j == 0) return E[i - 1 - k];
-      if (k < j - 1) return L[k];
-      if (k == j - 1) return JL;
-      if (k == j) return JE;
-      return E[i - 1 - (k - j)];
-    };
-    const double s = ph == 0.0 ? 1.0 : (ph == 2.0 ? rsqrt(density) : pow(density, -(ph - 1.0) / ph));
-    double weight = 0.0;
-    auto f = [&](double d) {
-      if (ph == 0.0) weight += d;
-      else if (ph == 2.0) weight += (d * s) * (d * s);
-      else weight += pow(d * s, ph);
-    };
-    double acc[2 * kBidirMaxDepth];
-    double sdp = 1.0;
-    for (int k = n - 1; k > 0; k--) {
-      acc[k] = sdp;
-      sdp *= at(k).sd;
-    }
-    if (n <= bp.max_depth) f(sdp);
-    if (n > 1) {
-      double ld = emis0_sum / bp.total_light;
-      Mis m0 = at(0), m1 = at(1);
-      if (n - 1 <= bp.max_depth) f(ld * acc[1] * out_area(m0, m1) / (double)m0.ddot);
-      for (int k = 0; k + 2 < n; k++) {
-        if (k + 1 >= max_ld) break;
-        const Mis m2 = at(k + 2);
-        ld *= m0.dd;
-        ld *= (double)m1.sdot / (double)m0.ddot;
-        if (n - (k + 2) <= bp.max_depth) f(acc[k + 2] * ld * out_area(m1, m2) / (double)m1.ddot);
-        m0 = m1;
-        m1 = m2;
-      }
-    }
-    return weight;
-  };
-
-  const Mis EV = mis_of(ev);
-  // ---- j == 0: the eye path itself reached an emitter (bidir.go:486-491)
-  if (!is_zero(ev.emission)) {
-    const double r = (double)ev.roulette;
-    const D3c cur = {ev.emission.x * eye_bsdf.x * r, ev.emission.y * eye_bsdf.y * r, ev.emission.z * eye_bsdf.z * r};
-    if (cur.x + cur.y + cur.z >= 1e-8) {
-      const double es = (double)ev.emission.x + ev.emission.y + ev.emission.z;
-      const double w = mis_weight(0, EV, EV, eye_density, es);
-      if (w > 0.0 && w < INFINITY) {
-        add.x += (float)(cur.x / w);
-        add.y += (float)(cur.y / w);
-        add.z += (float)(cur.z / w);
-      }
-    }
-  }
-  // ---- j >= 1 (bidir.go:493-525)
-  double density = eye_density * l0_sum / bp.total_light;
-  D3c light_bsdf = {l0.emission.x, l0.emission.y, l0.emission.z};
-  BVert prev = l0;  // light[j-2] inside the loop
-  BVert lj = l0;    // light[j-1]
+  double density = 0.0;
+  D3c light_bsdf = {0.0, 0.0, 0.0};
+  BVert prev;
   for (int j = 1; j <= nl; j++) {
-    if (j > 1) {
-      lj = load_vertex(buf.lv, buf.Dl, buf.cap, j - 1, slot);
+    const BVert lj = load_vertex(buf.lv, buf.Dl, buf.cap, j - 1, slot);
+    if (j == 1) {
+      density = ((double)lj.emission.x + lj.emission.y + lj.emission.z) / bp.total_light;
+      light_bsdf.x = lj.emission.x;
+      light_bsdf.y = lj.emission.y;
+      light_bsdf.z = lj.emission.z;
+    } else {
       density *= full_dd(prev);
       density *= (double)source_dot(lj) / (double)dest_dot(prev);
       if (j > 2) {
@@ -479,77 +446,167 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
       light_bsdf.y *= sdj;
       light_bsdf.z *= sdj;
     }
-    const V3f diff = lj.point - ev.point;
-    const float dist2 = dot(diff, diff);
-    // combinePaths (bidir.go:544-566): both junction vertices re-evaluated for the new edge
-    BVert jl = lj;
-    const float dist = sqrtf(dist2);
-    jl.dest = (ev.point - lj.point) * (1.f / dist);
-    eval_vertex(sc, jl, 0);
-    BVert je = ev;
-    je.source = jl.dest;
-    eval_vertex(sc, je, 0);
-    const float dd = dest_dot(jl);
-    const float sd = source_dot(je);
-    if (dd > 0.f && sd > 0.f && dist > 0.f) {
-      const double cur_density = density * (kFourPi * (double)dist2) / (double)dd;
-      const double scale = (double)sd * (double)lj.roulette * (double)ev.roulette;
-      D3c inten = {eye_bsdf.x * light_bsdf.x * scale * (double)je.bsdf_fin.x,
-                   eye_bsdf.y * light_bsdf.y * scale * (double)je.bsdf_fin.y,
-                   eye_bsdf.z * light_bsdf.z * scale * (double)je.bsdf_fin.z};
-      if (j > 1) {
-        inten.x *= (double)jl.bsdf_fin.x;
-        inten.y *= (double)jl.bsdf_fin.y;
-        inten.z *= (double)jl.bsdf_fin.z;
-      }
-      if (inten.x + inten.y + inten.z >= 1e-8) {
-        const double w = mis_weight(j, mis_of(jl), mis_of(je), cur_density, l0_sum);
-        if (w > 0.0 && w < INFINITY) {
-          D3c color = {inten.x / w, inten.y / w, inten.z / w};
-          bool keep_it = true;
-          const double brightness = fmax(fmax(color.x, color.y), color.z);
-          if (bp.roulette_delta > 0.0 && brightness < bp.roulette_delta) {  // bidir.go:133-142
-            const double keep = brightness / bp.roulette_delta;
-            Rng g;
-            g.init(bp.seed, (uint32_t)batch_pixel(b, slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP),
-                   0x1000u + (uint32_t)(i * 64 + j));
-            if ((double)g.f32() > keep) keep_it = false;
-            color.x /= keep;
-            color.y /= keep;
-            color.z /= keep;
-          }
-          if (keep_it && (color.x > 0.0 || color.y > 0.0 || color.z > 0.0)) {
-            // visibility ray eye vertex -> light vertex (bidir.go:144-152): blocked iff something
-            // lies strictly between the end points; both end surfaces are excluded (start: skip
-            // id, end: parameter interval) since float32 cannot express the 1e-8 offsets
-            const int pos = warp_aggregated_alloc(buf.counts + 2);
-            const V3f dirn = (lj.point - ev.point) * (1.f / dist);
-            buf.corg[pos] = make_float4(ev.point.x, ev.point.y, ev.point.z, 0.f);
-            buf.cdir[pos] = make_float4(dirn.x, dirn.y, dirn.z, dist * (1.f - 2e-4f));
-            buf.cskip[pos] = ev.surf;
-            buf.cpay[pos] = make_float4((float)color.x, (float)color.y, (float)color.z, __int_as_float(slot));
-          }
-        }
-      }
-    }
+    double *st = buf.lightpre + ((size_t)(j - 1) * buf.cap + slot) * 4;
+    st[0] = density;
+    st[1] = light_bsdf.x;
+    st[2] = light_bsdf.y;
+    st[3] = light_bsdf.z;
+    store_mis(buf, buf.De + j - 1, slot, mis_of(lj));
     prev = lj;
   }
-  if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {
-    float4 a = buf.accum[slot];
-    a.x += add.x;
-    a.y += add.y;
-    a.z += add.z;
-    buf.accum[slot] = a;
+  // work list of the connection stage: one item per (i, j) pair of this sample, packed
+  // slot | i << 20 | j << 25, items of one sample adjacent so that a warp re-uses its vertices
+  const int cnt = ne * (nl + 1);
+  if (cnt > 0) {
+    const int base = atomicAdd(buf.counts + 3, cnt);
+    int w = base;
+    for (int i = 1; i <= ne; i++)
+      for (int j = 0; j <= nl; j++) buf.work[w++] = (uint32_t)slot | ((uint32_t)i << 20) | ((uint32_t)j << 25);
   }
-  // bidir.go:527-528
-  {
-    double *st = buf.eye_state + (size_t)slot * 4;
-    const double sdv = (double)source_dot(ev);
-    st[0] = eye_density * full_sd(ev);
-    st[1] = eye_bsdf.x * ((double)ev.bsdf_fin.x + (double)ev.bsdf_del.x * kDeltaMag) * sdv;
-    st[2] = eye_bsdf.y * ((double)ev.bsdf_fin.y + (double)ev.bsdf_del.y * kDeltaMag) * sdv;
-    st[3] = eye_bsdf.z * ((double)ev.bsdf_fin.z + (double)ev.bsdf_del.z * kDeltaMag) * sdv;
+}
+
+// allPathCombinations (bidir.go:476-530) + rayColor's callback (bidir.go:113-158): one thread
+// per (eye prefix length i, light prefix length j, sample); threads of a warp share (i, j).
+__global__ void __launch_bounds__(kBlock, 4)
+bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
+  const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (tid >= (long long)buf.counts[3]) return;
+  const uint32_t item = buf.work[tid];
+  const int slot = (int)(item & 0xfffffu);
+  const int i = (int)((item >> 20) & 31u);
+  const int j = (int)(item >> 25);
+
+  const double *est = buf.eyepre + ((size_t)(i - 1) * buf.cap + slot) * 4;
+  const double eye_density = est[0];
+  const D3c eye_bsdf = {est[1], est[2], est[3]};
+  const BVert ev = load_vertex(buf.ev, buf.De, buf.cap, i - 1, slot);
+  const int max_ld = bp.max_light_depth;  // already defaulted to max_depth by the host
+  const double ph = bp.power_heuristic;
+  const int n = i + j;
+
+  // joined path (combinePaths bidir.go:532-572): light[0..j-2], JL, JE, eye[i-2..0] for j >= 1,
+  // eye[i-1..0] for j == 0
+  Mis JL, JE;
+  auto at = [&](int k) -> Mis {
+    if (j == 0) return load_mis(buf, i - 1 - k, slot);
+    if (k < j - 1) return load_mis(buf, buf.De + k, slot);
+    if (k == j - 1) return JL;
+    if (k == j) return JE;
+    return load_mis(buf, i - 1 - (k - j), slot);
+  };
+  // sum over every way of splitting the joined path into a light and an eye part
+  // (densities, bidir.go:421-471) under the power / balance heuristic (bidir.go:118-131)
+  auto mis_weight = [&](double density, double emis0_sum) -> double {
+    const double s = ph == 0.0 ? 1.0 : (ph == 2.0 ? rsqrt(density) : pow(density, -(ph - 1.0) / ph));
+    double weight = 0.0;
+    auto f = [&](double d) {
+      if (ph == 0.0) weight += d;
+      else if (ph == 2.0) weight += (d * s) * (d * s);
+      else weight += pow(d * s, ph);
+    };
+    // pass 1, from the light end: the light-side density of every split, times the geometry
+    // term of the connecting edge; term[t] belongs to the split with t light-sampled vertices
+    double term[2 * kBidirMaxDepth + 1];
+    if (n > 1) {
+      double ld = emis0_sum / bp.total_light;
+      Mis m0 = at(0), m1 = at(1);
+      term[1] = n - 1 <= bp.max_depth ? ld * out_area(m0, m1) / (double)m0.ddot : 0.0;
+      int t = 2;
+      for (int k = 0; k + 2 < n; k++, t++) {
+        if (k + 1 >= max_ld) break;
+        const Mis m2 = at(k + 2);
+        ld *= m0.dd;
+        ld *= (double)m1.sdot / (double)m0.ddot;
+        term[t] = n - (k + 2) <= bp.max_depth ? ld * out_area(m1, m2) / (double)m1.ddot : 0.0;
+        m0 = m1;
+        m1 = m2;
+      }
+      // pass 2, from the eye end: acc = product of the source densities beyond the split
+      double acc = 1.0;
+      for (int k = n - 1; k >= 1; k--) {
+        if (k < t && term[k] != 0.0) f(acc * term[k]);
+        acc *= at(k).sd;
+      }
+      if (n <= bp.max_depth) f(acc);
+    } else if (n <= bp.max_depth) {
+      f(1.0);
+    }
+    return weight;
+  };
+
+  if (j == 0) {
+    // the eye path itself reached an emitter (bidir.go:486-491)
+    if (is_zero(ev.emission)) return;
+    const double r = (double)ev.roulette;
+    const D3c cur = {ev.emission.x * eye_bsdf.x * r, ev.emission.y * eye_bsdf.y * r, ev.emission.z * eye_bsdf.z * r};
+    if (cur.x + cur.y + cur.z < 1e-8) return;
+    const double es = (double)ev.emission.x + ev.emission.y + ev.emission.z;
+    const double w = mis_weight(eye_density, es);
+    if (!(w > 0.0 && w < INFINITY)) return;
+    float *a = reinterpret_cast<float *>(buf.accum + slot);
+    atomicAdd(a, (float)(cur.x / w));
+    atomicAdd(a + 1, (float)(cur.y / w));
+    atomicAdd(a + 2, (float)(cur.z / w));
+    return;
   }
+  // j >= 1 (bidir.go:493-525)
+  const double *lst = buf.lightpre + ((size_t)(j - 1) * buf.cap + slot) * 4;
+  const double density = eye_density * lst[0];
+  const D3c light_bsdf = {lst[1], lst[2], lst[3]};
+  const BVert lj = load_vertex(buf.lv, buf.Dl, buf.cap, j - 1, slot);
+  const float4 l0e = buf.lv[vidx(6, buf.Dl, buf.cap, 0, slot)];
+  const double l0_sum = (double)l0e.x + l0e.y + l0e.z;
+  const V3f diff = lj.point - ev.point;
+  const float dist2 = dot(diff, diff);
+  const float dist = sqrtf(dist2);
+  if (!(dist > 0.f)) return;
+  // combinePaths (bidir.go:544-566): both junction vertices re-evaluated for the new edge
+  BVert jl = lj;
+  jl.dest = (ev.point - lj.point) * (1.f / dist);
+  eval_vertex(sc, jl, 0);
+  BVert je = ev;
+  je.source = jl.dest;
+  eval_vertex(sc, je, 0);
+  const float dd = dest_dot(jl);
+  const float sd = source_dot(je);
+  if (!(dd > 0.f && sd > 0.f)) return;
+  const double cur_density = density * (kFourPi * (double)dist2) / (double)dd;
+  const double scale = (double)sd * (double)lj.roulette * (double)ev.roulette;
+  D3c inten = {eye_bsdf.x * light_bsdf.x * scale * (double)je.bsdf_fin.x,
+               eye_bsdf.y * light_bsdf.y * scale * (double)je.bsdf_fin.y,
+               eye_bsdf.z * light_bsdf.z * scale * (double)je.bsdf_fin.z};
+  if (j > 1) {
+    inten.x *= (double)jl.bsdf_fin.x;
+    inten.y *= (double)jl.bsdf_fin.y;
+    inten.z *= (double)jl.bsdf_fin.z;
+  }
+  if (inten.x + inten.y + inten.z < 1e-8) return;
+  JL = mis_of(jl);
+  JE = mis_of(je);
+  const double w = mis_weight(cur_density, l0_sum);
+  if (!(w > 0.0 && w < INFINITY)) return;
+  D3c color = {inten.x / w, inten.y / w, inten.z / w};
+  const double brightness = fmax(fmax(color.x, color.y), color.z);
+  if (bp.roulette_delta > 0.0 && brightness < bp.roulette_delta) {  // bidir.go:133-142
+    const double keep = brightness / bp.roulette_delta;
+    Rng g;
+    g.init(bp.seed, (uint32_t)batch_pixel(b, slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP),
+           0x1000u + (uint32_t)(i * 64 + j));
+    if ((double)g.f32() > keep) return;
+    color.x /= keep;
+    color.y /= keep;
+    color.z /= keep;
+  }
+  if (!(color.x > 0.0 || color.y > 0.0 || color.z > 0.0)) return;
+  // visibility ray eye vertex -> light vertex (bidir.go:144-152): blocked iff something lies
+  // strictly between the end points; both end surfaces are excluded (start: skip id, end:
+  // parameter interval) since float32 cannot express the reference's 1e-8 offsets
+  const int pos = warp_aggregated_alloc(buf.counts + 2);
+  const V3f dirn = diff * (1.f / dist);
+  buf.corg[pos] = make_float4(ev.point.x, ev.point.y, ev.point.z, 0.f);
+  buf.cdir[pos] = make_float4(dirn.x, dirn.y, dirn.z, dist * (1.f - 2e-4f));
+  buf.cskip[pos] = ev.surf;
+  buf.cpay[pos] = make_float4((float)color.x, (float)color.y, (float)color.z, __int_as_float(slot));
 }
 
 __global__ void __launch_bounds__(256)
@@ -607,11 +664,18 @@ void launch_bidir_light_shade(const DeviceScene &sc, const DeviceBidirParams &bp
   bidir_shade_kernel<false><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf, cur, depth);
 }
 
-void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
-                          const BidirBuffers &buf, int i, cudaStream_t stream) {
+void launch_bidir_prefix(const DeviceBidirParams &bp, const PathBatch &b, const BidirBuffers &buf,
+                         cudaStream_t stream) {
   const int64_t n = (int64_t)b.nP * b.S;
   if (n <= 0) return;
-  bidir_connect_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, stream>>>(sc, bp, b, buf, i);
+  bidir_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bp, b, buf);
+}
+
+void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
+                          const BidirBuffers &buf, cudaStream_t stream) {
+  const int64_t n = (int64_t)b.nP * b.S * bp.max_depth * (bp.max_light_depth + 1);
+  if (n <= 0) return;
+  bidir_connect_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, stream>>>(sc, bp, b, buf);
 }
 
 void launch_bidir_connect_resolve(const DeviceScene &sc, const BidirBuffers &buf, cudaStream_t stream) {
