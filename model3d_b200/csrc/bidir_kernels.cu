@@ -467,7 +467,7 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
 
 // allPathCombinations (bidir.go:476-530) + rayColor's callback (bidir.go:113-158): one thread
 // per (eye prefix length i, light prefix length j, sample); threads of a warp share (i, j).
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, 8)
 bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
   const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (tid >= (long long)buf.counts[3]) return;
