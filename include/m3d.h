@@ -118,6 +118,19 @@ int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org,
                                       int32_t *prim, float *normal, float *bary,
                                       uint32_t flags, m3d_stats *stats);
 
+/* Batched Collider.RayCollisions(r, nil) (model3d/collisions.go:263-273, primitives.go:189-196):
+ * counts[i] = number of triangles the forward half-line of ray i crosses (no callback: the
+ * reference's func(RayCollision) cannot cross the ABI). */
+int32_t m3d_mesh_ray_collision_counts(m3d_mesh *mesh, const float *org, const float *dir,
+                                      int64_t n, int32_t *counts, m3d_stats *stats);
+
+/* Batched model3d.ColliderContains(c, p, margin) (collisions.go:113-134) and with it
+ * ColliderSolid.Contains (model3d/solid.go:256-300): inside[i] = 1 iff an odd number of
+ * triangles lies along the reference's fixed probe direction from points[i].  margin must
+ * be 0 (other margins need SphereCollision: M3D_ERR_UNSUPPORTED). */
+int32_t m3d_mesh_contains(m3d_mesh *mesh, const float *points, int64_t n, double margin,
+                          uint8_t *inside, m3d_stats *stats);
+
 /* Same query on device-resident SoA buffers (what the renderers use internally
  * and what bench.py times with inputs already in HBM).
  *   d_org_tmin : n float4  (ox, oy, oz, tmin)

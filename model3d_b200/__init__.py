@@ -5,9 +5,9 @@ this package is the thin host-side mirror of the reference's ``model3d`` collisi
 interface and ``render3d`` renderer interface for that path.
 """
 from . import _native  # noqa: F401
-from .model3d import (BatchCollisions, MeshCollider, MeshToCollider,  # noqa: F401
-                      MeshToInterpNormalCollider, Ray, RayCollision, TriangleCollision,
-                      UnsupportedError)
+from .model3d import (BatchCollisions, ColliderContains, ColliderSolid, MeshCollider,  # noqa: F401
+                      MeshToCollider, MeshToInterpNormalCollider, NewColliderSolid, Ray, RayCollision,
+                      TriangleCollision, UnsupportedError)
 
 from . import render3d  # noqa: F401,E402
 

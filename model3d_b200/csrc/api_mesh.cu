@@ -379,4 +379,73 @@ int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const fl
   return rc;
 }
 
+int32_t m3d_mesh_ray_collision_counts(m3d_mesh *mesh, const float *org, const float *dir, int64_t n,
+                                      int32_t *counts, m3d_stats *stats) {
+  if (!mesh || n < 0 || (n > 0 && (!org || !dir || !counts)))
+    return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_ray_collision_counts: bad arguments");
+  if (n > (int64_t)0x7ff00000) return fail(M3D_ERR_INVALID_ARG, "batch too large; split it");
+  m3d_ctx *ctx = mesh->ctx;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n == 0) return M3D_OK;
+  cudaStream_t s = ctx->stream;
+  const size_t per = (size_t)n;
+  M3D_CUDA(ctx->scratch[9].reserve(per * (6 * sizeof(float) + sizeof(int32_t))));
+  float *d_org = ctx->scratch[9].as<float>();
+  float *d_dir = d_org + 3 * per;
+  int32_t *d_counts = (int32_t *)(d_dir + 3 * per);
+  M3D_CUDA(cudaMemcpyAsync(d_org, org, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  M3D_CUDA(cudaMemcpyAsync(d_dir, dir, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  GpuTimer tm;
+  tm.start(s);
+  launch_count_hits(mesh->bvh, d_org, d_dir, n, d_counts, nullptr, s);
+  tm.stop(s);
+  M3D_CUDA(cudaMemcpyAsync(counts, d_counts, per * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  M3D_CUDA(cudaStreamSynchronize(s));
+  M3D_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->rays = n;
+    stats->kernel_ms = tm.ms();
+    stats->launches = 1;
+    stats->h2d_bytes = n * 24;
+    stats->d2h_bytes = n * 4;
+  }
+  return M3D_OK;
+}
+
+int32_t m3d_mesh_contains(m3d_mesh *mesh, const float *points, int64_t n, double margin, uint8_t *inside,
+                          m3d_stats *stats) {
+  if (!mesh || n < 0 || (n > 0 && (!points || !inside)))
+    return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_contains: bad arguments");
+  if (margin != 0)
+    return fail(M3D_ERR_UNSUPPORTED,
+                "ColliderContains with a non-zero margin needs SphereCollision, which is not on the GPU path");
+  if (n > (int64_t)0x7ff00000) return fail(M3D_ERR_INVALID_ARG, "batch too large; split it");
+  m3d_ctx *ctx = mesh->ctx;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n == 0) return M3D_OK;
+  cudaStream_t s = ctx->stream;
+  const size_t per = (size_t)n;
+  M3D_CUDA(ctx->scratch[9].reserve(per * (3 * sizeof(float) + 1) + 16));
+  float *d_pts = ctx->scratch[9].as<float>();
+  uint8_t *d_inside = (uint8_t *)(d_pts + 3 * per);
+  M3D_CUDA(cudaMemcpyAsync(d_pts, points, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  GpuTimer tm;
+  tm.start(s);
+  launch_count_hits(mesh->bvh, d_pts, nullptr, n, nullptr, d_inside, s);
+  tm.stop(s);
+  M3D_CUDA(cudaMemcpyAsync(inside, d_inside, per, cudaMemcpyDeviceToHost, s));
+  M3D_CUDA(cudaStreamSynchronize(s));
+  M3D_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->rays = n;
+    stats->kernel_ms = tm.ms();
+    stats->launches = 1;
+    stats->h2d_bytes = n * 12;
+    stats->d2h_bytes = n;
+  }
+  return M3D_OK;
+}
+
 }  // extern "C"

@@ -40,6 +40,11 @@ void launch_pack_rays(const float *org3, const float *dir3, int64_t n, float tmi
 void launch_unpack_hits(const float4 *hit0, const float4 *hit1, int64_t n, float *t, int32_t *prim,
                         int32_t *obj, float *normal3, float *bary3, cudaStream_t stream);
 
+// all-hits counts per ray (counts) and / or their parity (inside); dir3 == nullptr: the fixed
+// ColliderContains direction (collisions.go:119-134)
+void launch_count_hits(const DeviceBVH &bvh, const float *org3, const float *dir3, int64_t n, int32_t *counts,
+                       uint8_t *inside, cudaStream_t stream);
+
 int device_sm_count();
 
 }  // namespace m3d

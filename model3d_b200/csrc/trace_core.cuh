@@ -425,6 +425,39 @@ M3D_HD void trace_bvh(const uint4 *__restrict__ nodes, const float4 *__restrict_
   }
 }
 
+// All-hits traversal: the number of triangles the ray's forward half-line (t >= tmin) crosses ==
+// Collider.RayCollisions(r, nil) (model3d/collisions.go:263-273, primitives.go:189-196).  No
+// tmax pruning and no ordering: every child whose box the ray enters is visited, like the
+// reference.  Each triangle is decided by the same float32 test + float64 arbitration as the
+// first-hit query, so counts equal the float64 reference's except for exact ties.
+M3D_HD int count_bvh_hits(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
+                          const float *scene_min, const float *scene_max, const RayF &ray) {
+  const RayPre rp = precompute_ray(ray, scene_min, scene_max);
+  const float tmax = ray.tmax;
+  int count = 0;
+  uint2 stack[M3D_STACK_SIZE];
+  int sp = 0;
+  uint2 ngroup, tgroup;
+  uint32_t node_index = 0;
+  for (;;) {
+    intersect_node(nodes, node_index, rp, tmax, ngroup, tgroup);
+    while (tgroup.y) {
+      const int bit = bfind32(tgroup.y);
+      tgroup.y &= ~(1u << bit);
+      const int32_t ti = (int32_t)(tgroup.x + (uint32_t)bit);
+      float t, b1, b2;
+      if (intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) count++;
+    }
+    if ((ngroup.y & 0xff000000u) == 0) {
+      if (sp == 0) break;
+      ngroup = stack[--sp];
+    }
+    node_index = take_nearest_child(ngroup, rp.octinv4);
+    if ((ngroup.y & 0xff000000u) && sp < M3D_STACK_SIZE) stack[sp++] = ngroup;
+  }
+  return count;
+}
+
 // ---- float64 re-evaluation of the winning triangle ---------------------------------------
 // The reference's Moeller-Trumbore (primitives.go:207-249) and flat normal
 // (primitives.go:27-33) in double, on the float32 inputs widened exactly.

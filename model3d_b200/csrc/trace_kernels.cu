@@ -198,6 +198,48 @@ __global__ void unpack_hits_kernel(const float4 *__restrict__ hit0, const float4
   }
 }
 
+// Collider.RayCollisions counts / ColliderContains parity (collisions.go:119-134, 263-273):
+// one thread per ray, all-hits traversal (count_bvh_hits).  FIXED_DIR: the rays are the
+// containment probes of ColliderContains, origin = query point, the reference's fixed direction.
+template <bool FIXED_DIR>
+__global__ void __launch_bounds__(128)
+count_hits_kernel(DeviceBVH bvh, const float *__restrict__ org3, const float *__restrict__ dir3, int64_t n,
+                  int32_t *__restrict__ counts, uint8_t *__restrict__ inside) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RayF ray;
+  ray.ox = org3[3 * i];
+  ray.oy = org3[3 * i + 1];
+  ray.oz = org3[3 * i + 2];
+  if (FIXED_DIR) {
+    ray.dx = 0.5224892708603626f;  // collisions.go:126 (rounded to float32 like every direction)
+    ray.dy = 0.10494477243214506f;
+    ray.dz = 0.43558938446126527f;
+  } else {
+    ray.dx = dir3[3 * i];
+    ray.dy = dir3[3 * i + 1];
+    ray.dz = dir3[3 * i + 2];
+  }
+  ray.tmin = 0.f;
+  ray.tmax = INFINITY;
+  const int c = bvh.num_tris > 0 ? count_bvh_hits(bvh.nodes, bvh.tris, bvh.bmin, bvh.bmax, ray) : 0;
+  if (counts) counts[i] = c;
+  if (inside) inside[i] = (uint8_t)(c & 1);
+}
+
+}  // namespace
+
+void launch_count_hits(const DeviceBVH &bvh, const float *org3, const float *dir3, int64_t n, int32_t *counts,
+                       uint8_t *inside, cudaStream_t stream) {
+  if (n <= 0) return;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (dir3)
+    count_hits_kernel<false><<<blocks, 128, 0, stream>>>(bvh, org3, dir3, n, counts, inside);
+  else
+    count_hits_kernel<true><<<blocks, 128, 0, stream>>>(bvh, org3, nullptr, n, counts, inside);
+}
+
+namespace {
 }  // namespace
 
 template <bool COUNT, int MIN_BLOCKS>

@@ -157,8 +157,32 @@ class MeshCollider:
             C.byref(stats) if (counters or want_stats) else None))
         return {k: getattr(stats, k) for k, _ in stats._fields_} if (counters or want_stats) else {}
 
+    def RayCollisionCounts(self, origins, directions):
+        """Batched Collider.RayCollisions(r, nil) (collisions.go:263-273): the number of
+        triangles each ray's forward half-line crosses, int32 [n]."""
+        org = np.ascontiguousarray(np.asarray(origins, dtype=np.float32).reshape(-1, 3))
+        dr = np.ascontiguousarray(np.asarray(directions, dtype=np.float32).reshape(-1, 3))
+        if org.shape != dr.shape:
+            raise ValueError("origins and directions must have the same shape")
+        counts = np.zeros(org.shape[0], np.int32)
+        N.check(N.lib().m3d_mesh_ray_collision_counts(self.h, _p(org, f32p), _p(dr, f32p),
+                                                      C.c_int64(org.shape[0]), _p(counts, i32p), None))
+        return counts
+
     def RayCollisions(self, r, f=None):
-        raise UnsupportedError("RayCollisions (all hits) is not on the GPU path yet")
+        """Collider.RayCollisions: the count for one ray.  A per-hit callback cannot run on the
+        GPU path: f must be None (ColliderContains, the main caller, passes nil)."""
+        if f is not None:
+            raise UnsupportedError("RayCollisions with a callback is not on the GPU path")
+        return int(self.RayCollisionCounts([r.Origin], [r.Direction])[0])
+
+    def Contains(self, coords, margin=0.0):
+        """Batched model3d.ColliderContains(self, p, margin) (collisions.go:113-134), bool [n]."""
+        pts = np.ascontiguousarray(np.asarray(coords, dtype=np.float32).reshape(-1, 3))
+        inside = np.zeros(pts.shape[0], np.uint8)
+        N.check(N.lib().m3d_mesh_contains(self.h, _p(pts, f32p), C.c_int64(pts.shape[0]), C.c_double(margin),
+                                          inside.ctypes.data_as(C.POINTER(C.c_uint8)), None))
+        return inside.astype(bool)
 
     def SphereCollision(self, c, r):
         raise UnsupportedError("SphereCollision is not on the GPU path")
@@ -172,3 +196,37 @@ def MeshToCollider(triangles, ctx=None) -> MeshCollider:
 def MeshToInterpNormalCollider(triangles, vertex_normals, ctx=None) -> MeshCollider:
     """model3d.MeshToInterpNormalCollider (collisions.go:147-162)."""
     return MeshCollider(triangles, vertex_normals=vertex_normals, ctx=ctx)
+
+
+def ColliderContains(c: MeshCollider, coords, margin=0.0):
+    """model3d.ColliderContains (collisions.go:113-134), batched over coords [n,3]."""
+    return c.Contains(coords, margin)
+
+
+class ColliderSolid:
+    """model3d.ColliderSolid / NewColliderSolid (model3d/solid.go:243-300): a Solid whose
+    Contains is the collider's parity test, batched.  Inset / hollow variants need
+    SphereCollision and are not on the GPU path."""
+
+    def __init__(self, collider: MeshCollider):
+        self.collider = collider
+        self.min, self.max = collider.Min(), collider.Max()
+
+    def Min(self):
+        return self.min
+
+    def Max(self):
+        return self.max
+
+    def Contains(self, coords):
+        pts = np.asarray(coords, dtype=np.float32).reshape(-1, 3)
+        mn, mx = np.asarray(self.min, np.float32), np.asarray(self.max, np.float32)
+        inb = np.all((pts >= mn) & (pts <= mx), axis=1)  # InBounds (solid.go:293-295)
+        out = np.zeros(pts.shape[0], bool)
+        if inb.any():
+            out[inb] = self.collider.Contains(pts[inb])
+        return out
+
+
+def NewColliderSolid(c: MeshCollider) -> ColliderSolid:
+    return ColliderSolid(c)

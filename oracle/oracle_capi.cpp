@@ -176,6 +176,37 @@ int64_t orc_collider_all_hits(void *h, const double org[3], const double dir[3],
   return (int64_t)hits.size();
 }
 
+// Batched Collider.RayCollisions(r, nil) counts (collisions.go:263-273, primitives.go:189-196).
+void orc_collider_hit_counts(void *h, const float *org, const float *dir, int64_t n, int32_t *counts,
+                             int nthreads) {
+  auto *m = (MeshCollider *)h;
+  parallel_for(n, nthreads, [&](int64_t b, int64_t e, int) {
+    std::vector<Hit> hits;
+    for (int64_t i = b; i < e; i++) {
+      Ray r{V3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2])};
+      hits.clear();
+      m->ray_collisions(r, hits);
+      counts[i] = (int32_t)hits.size();
+    }
+  });
+}
+
+// ColliderContains with margin 0 (collisions.go:119-134): odd number of collisions along the
+// reference's fixed direction.
+void orc_collider_contains(void *h, const float *pts, int64_t n, uint8_t *inside, int nthreads) {
+  auto *m = (MeshCollider *)h;
+  parallel_for(n, nthreads, [&](int64_t b, int64_t e, int) {
+    std::vector<Hit> hits;
+    for (int64_t i = b; i < e; i++) {
+      Ray r{V3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]),
+            V3(0.5224892708603626, 0.10494477243214506, 0.43558938446126527)};
+      hits.clear();
+      m->ray_collisions(r, hits);
+      inside[i] = (uint8_t)(hits.size() % 2);
+    }
+  });
+}
+
 // Single-triangle test exposed for edge-case tests (primitives.go:181-249).
 int orc_triangle_first_hit(const double tri[9], const double org[3], const double dir[3], double *t,
                            double normal[3], double bary[3]) {

@@ -202,6 +202,20 @@ class Collider:
             res["nodes"], res["tris"] = int(cnt[0]), int(cnt[1])
         return res
 
+    def hit_counts(self, org, dir, threads=1):
+        org = np.ascontiguousarray(org, np.float32)
+        dir = np.ascontiguousarray(dir, np.float32)
+        out = np.zeros(org.shape[0], np.int32)
+        lib().orc_collider_hit_counts(self.h, _p(org, f32p), _p(dir, f32p), C.c_int64(org.shape[0]),
+                                      _p(out, i32p), C.c_int(threads))
+        return out
+
+    def contains(self, pts, threads=1):
+        pts = np.ascontiguousarray(pts, np.float32)
+        out = np.zeros(pts.shape[0], np.uint8)
+        lib().orc_collider_contains(self.h, _p(pts, f32p), C.c_int64(pts.shape[0]), _p(out, u8p), C.c_int(threads))
+        return out.astype(bool)
+
     def all_hits(self, org, dir, brute=False, cap=4096):
         t = np.zeros(cap, np.float64)
         prim = np.zeros(cap, np.int32)

@@ -225,3 +225,41 @@ def test_full_size_c2_properties(built, oracle):
     sub = type(got)(Collides=got.Collides[idx], Scale=got.Scale[idx], Normal=got.Normal[idx],
                     Triangle=got.Triangle[idx], Barycentric=got.Barycentric[idx])
     check_parity(oracle, tris, org[idx], d[idx], sub)
+
+
+def test_ray_collision_counts_and_contains(built, oracle):
+    """Section 8f-2: Collider.RayCollisions counts (collisions.go:263-273) and ColliderContains
+    (collisions.go:113-134) on a closed mesh, bit-for-bit against the oracle's all-hits walk
+    except rays within float32 rounding of an edge."""
+    from model3d_b200 import MeshCollider, NewColliderSolid, Ray, UnsupportedError
+    from model3d_b200 import meshes
+    tris = meshes.NewMeshIcosphere((0.1, -0.2, 0.05), 1.0, 24).astype(np.float32)
+    col = MeshCollider(tris)
+    ocol = oracle.Collider(tris)
+    rng = np.random.default_rng(11)
+    n = 200000
+    org = (rng.normal(size=(n, 3)) * 0.8).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    got = col.RayCollisionCounts(org, d)
+    ref = ocol.hit_counts(org, d, threads=8)
+    assert (got != ref).sum() <= 2, (got != ref).sum()
+    assert set(np.unique(ref).tolist()) >= {0, 1, 2}
+    # closed surface: rays from inside cross once, from outside an even number of times
+    r = np.linalg.norm(org - np.array([0.1, -0.2, 0.05], np.float32), axis=1)
+    assert (got[r < 0.98] == 1).all() and (got[r > 1.02] % 2 == 0).all()
+    pts = (rng.normal(size=(n, 3)) * 0.7).astype(np.float32)
+    inside = col.Contains(pts)
+    ref_in = ocol.contains(pts, threads=8)
+    assert (inside != ref_in).sum() <= 2
+    rp = np.linalg.norm(pts - np.array([0.1, -0.2, 0.05], np.float32), axis=1)
+    assert inside[rp < 0.98].all() and not inside[rp > 1.02].any()
+    solid = NewColliderSolid(col)
+    far = np.array([[5.0, 0, 0], [0.1, -0.2, 0.05]], np.float32)
+    assert solid.Contains(far).tolist() == [False, True]
+    assert col.RayCollisions(Ray((0.1, -0.2, 0.05), (0.3, 0.2, 1))) == 1  # generic direction (no vertex tie)
+    with pytest.raises(UnsupportedError):
+        col.RayCollisions(Ray((0, 0, 0), (0, 0, 1)), f=lambda c: None)
+    from model3d_b200 import _native as N
+    with pytest.raises(N.M3DError) as ei:
+        col.Contains(pts[:4], margin=0.1)
+    assert ei.value.code == 2
