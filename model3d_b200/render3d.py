@@ -361,6 +361,32 @@ class Camera:
         return c
 
 
+def _camera_axes(cam, w, h):
+    """Camera.axes (camera.go:100-113)."""
+    plane = 1.0 / math.tan(cam.FieldOfView / 2)
+    x, y = np.asarray(cam.ScreenX, np.float64), np.asarray(cam.ScreenY, np.float64)
+    z = np.cross(x, y)
+    z = z * (1 / math.sqrt(float(z @ z)))
+    if w > h:
+        y = y * (h / w)
+    else:
+        x = x * (w / h)
+    return x, y, z * plane
+
+
+def Uncaster(cam, imageWidth, imageHeight):
+    """Camera.Uncaster (camera.go:84-98): spatial -> screen coordinates."""
+    x, y, z = _camera_axes(cam, imageWidth, imageHeight)
+    inv = np.linalg.inv(np.stack([x, y, z], axis=1))
+    cx, cy = imageWidth / 2, imageHeight / 2
+    org = np.asarray(cam.Origin, np.float64)
+
+    def f(coord):
+        v = inv @ (np.asarray(coord, np.float64) - org)
+        return v[0] / v[2] * cx + cx, v[1] / v[2] * cy + cy
+    return f
+
+
 def NewCameraAt(source, dest, fov=0.0):
     """render3d.NewCameraAt (camera.go:48-66), float64 host arithmetic."""
     if fov == 0:
@@ -403,6 +429,52 @@ class Image:
         c = np.clip(self.Data.astype(np.float64), 0.0, 1.0)
         s = np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055)
         return (s * (256.0 - 0.001)).astype(np.uint8)
+
+    def SetAll(self, c):
+        """Image.SetAll (image.go:48-53)."""
+        self.Data[...] = np.asarray(c, np.float32)
+
+    def CopyFrom(self, i1, x, y):
+        """Image.CopyFrom (image.go:55-69): copy i1 into this image at (x, y), clipped."""
+        w = min(i1.Width, self.Width - x)
+        h = min(i1.Height, self.Height - y)
+        if w > 0 and h > 0:
+            self.Data[y:y + h, x:x + w] = i1.Data[:h, :w]
+
+    def FillRange(self):
+        """Image.FillRange (image.go:71-86)."""
+        m = float(self.Data.max()) if self.Data.size else 0.0
+        if m > 0:
+            self.Data *= np.float32(1.0 / m)
+
+    def Scale(self, s):
+        self.Data *= np.float32(s)
+
+    def Downsample(self, factor):
+        """Image.Downsample (image.go:95-120): box filter in linear RGB."""
+        if self.Width % factor or self.Height % factor:
+            raise ValueError("image size %d x %d cannot be divided evenly by factor %d"
+                             % (self.Width, self.Height, factor))
+        out = Image(self.Width // factor, self.Height // factor)
+        d = self.Data.astype(np.float64).reshape(out.Height, factor, out.Width, factor, 3)
+        out.Data = (d.sum(axis=(1, 3)) * (1.0 / (factor * factor))).astype(np.float32)
+        return out
+
+    def Gray8(self):
+        """Image.Gray (image.go:147-172): 8-bit sRGB, then Go's color.GrayModel luma
+        (19595 R + 38470 G + 7471 B + 2^15) >> 24 on 16-bit channels."""
+        rgb = self.RGBA8().astype(np.uint32) * 0x101
+        y = (19595 * rgb[..., 0] + 38470 * rgb[..., 1] + 7471 * rgb[..., 2] + (1 << 15)) >> 24
+        return y.astype(np.uint8)
+
+    def Save(self, path):
+        """Image.Save (image.go:174-199): PNG only here (the extension decides; JPEG is not
+        implemented on this side)."""
+        ext = path.lower().rsplit(".", 1)[-1] if "." in path else ""
+        if ext != "png":
+            raise ValueError("save image: unknown extension '.%s' (only .png is supported here)" % ext)
+        from .helpers import write_png
+        write_png(path, self.RGBA8())
 
 
 def _lights(lights):
