@@ -78,7 +78,8 @@ typedef struct {
  * MeshToInterpNormalCollider (collisions.go:147-162) when vnormals != NULL.
  */
 #define M3D_MESH_BUILD_HOST_SAH 0u   /* host binned-SAH build, collapsed to 8-wide */
-#define M3D_MESH_BUILD_DEVICE_LBVH 1u /* device Morton/radix/Karras build         */
+#define M3D_MESH_BUILD_DEVICE_LBVH 1u /* device Morton / radix sort / Karras / refit binary
+                                         tree, then the same 8-wide collapse            */
 
 typedef struct {
   int64_t num_triangles;

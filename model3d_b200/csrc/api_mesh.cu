@@ -83,6 +83,21 @@ int32_t upload_bvh(m3d_ctx *ctx, const WideBVH &bvh, const float *vnormals_by_pr
   return M3D_OK;
 }
 
+int32_t build_bvh_with_flags(m3d_ctx *ctx, const BuildInput &in, uint32_t build_flags, WideBVH &out) {
+  if ((build_flags & M3D_MESH_BUILD_DEVICE_LBVH) && in.n > 0) {
+    std::vector<BinaryNode> bn;
+    std::vector<int32_t> order;
+    int32_t root = 0;
+    double device_ms = 0;
+    if (int32_t rc = lbvh_build_binary(ctx, in.tris, in.n, bn, order, &root, &device_ms)) return rc;
+    build_wide_bvh_from_binary(in, bn.data(), (int64_t)bn.size(), root, order.data(), out);
+    out.build_ms += device_ms;
+    return M3D_OK;
+  }
+  build_wide_bvh(in, out);
+  return M3D_OK;
+}
+
 }  // namespace m3d
 
 using namespace m3d;
@@ -143,8 +158,6 @@ int32_t m3d_mesh_create(m3d_ctx *ctx, const float *tris, int64_t n, const float 
     return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_create: bad arguments");
   if (n > (int64_t)0x7fffff00) return fail(M3D_ERR_INVALID_ARG, "too many triangles (%lld)", (long long)n);
   *out = nullptr;
-  if (build_flags & M3D_MESH_BUILD_DEVICE_LBVH)
-    return fail(M3D_ERR_UNSUPPORTED, "device LBVH build is not available in this build");
   M3D_CUDA(cudaSetDevice(ctx->device));
   for (int64_t i = 0; i < n * 9; i++)
     if (!(tris[i] == tris[i]) || tris[i] > 3e38f || tris[i] < -3e38f)
@@ -153,7 +166,7 @@ int32_t m3d_mesh_create(m3d_ctx *ctx, const float *tris, int64_t n, const float 
   BuildInput in;
   in.tris = tris;
   in.n = n;
-  build_wide_bvh(in, bvh);
+  if (int32_t rc = build_bvh_with_flags(ctx, in, build_flags, bvh)) return rc;
   auto *m = new m3d_mesh();
   m->ctx = ctx;
   int32_t rc = upload_bvh(ctx, bvh, vnormals, m->nodes, m->tris, m->vnormals, m->bvh);

@@ -288,8 +288,6 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
   if (!b || !out) return fail(M3D_ERR_INVALID_ARG, "m3d_scene_build: NULL argument");
   *out = nullptr;
   if (b->objects.empty()) return fail(M3D_ERR_INVALID_ARG, "scene has no objects");
-  if (build_flags & M3D_MESH_BUILD_DEVICE_LBVH)
-    return fail(M3D_ERR_UNSUPPORTED, "device LBVH build is not available in this build");
   if (b->objects.size() > 0x7fffff) return fail(M3D_ERR_INVALID_ARG, "too many objects");
   m3d_ctx *ctx = b->ctx;
   M3D_CUDA(cudaSetDevice(ctx->device));
@@ -346,7 +344,7 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
   in.n = ntri;
   in.prim_ids = prim_ids.data();
   in.obj_ids = obj_ids.data();
-  build_wide_bvh(in, bvh);
+  if (int32_t rc = build_bvh_with_flags(ctx, in, build_flags, bvh)) return rc;
   sc->leaf_of_merged.assign((size_t)ntri, -1);
   for (size_t li = 0; li < bvh.tris.size(); li++)
     sc->leaf_of_merged[(size_t)(sc->object_tri_begin[bvh.tris[li].object] + bvh.tris[li].prim)] = (int32_t)li;

@@ -43,11 +43,13 @@ struct Box {
   }
 };
 
+// binary-tree node shared with the device LBVH builder (wide_bvh.h BinaryNode has this layout)
 struct B2Node {
   Box box;
   int32_t left = -1, right = -1;  // children (internal)
   int32_t first = 0, count = 0;   // range in idx; leaf iff left < 0
 };
+static_assert(sizeof(B2Node) == sizeof(BinaryNode), "B2Node must match BinaryNode");
 
 struct Builder2 {
   const float *tris;
@@ -276,6 +278,8 @@ inline uint8_t exp_byte_for(double extent) {
   return (uint8_t)byte;
 }
 
+void finish_wide_bvh(const BuildInput &in, Builder2 &b2, int32_t root2, WideBVH &out);
+
 }  // namespace
 
 void build_wide_bvh(const BuildInput &in, WideBVH &out, int num_threads) {
@@ -317,6 +321,14 @@ void build_wide_bvh(const BuildInput &in, WideBVH &out, int num_threads) {
   int32_t root2 = b2.alloc();
   b2.build_range(root2, 0, (int32_t)in.n, 0);
 
+  finish_wide_bvh(in, b2, root2, out);
+  out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+namespace {
+// binary tree -> cost-optimal 8-wide collapse -> octant slots -> quantised nodes + leaf-ordered
+// triangle records
+void finish_wide_bvh(const BuildInput &in, Builder2 &b2, int32_t root2, WideBVH &out) {
   Collapse col(b2);
   col.run(root2);
   out.sah_cost = col.cost[(size_t)root2 * 7] / std::max(1e-300, b2.nodes[root2].box.area());
@@ -450,6 +462,24 @@ void build_wide_bvh(const BuildInput &in, WideBVH &out, int num_threads) {
       }
     out.nodes[w.wide] = nd;
   }
+}
+}  // namespace
+
+void build_wide_bvh_from_binary(const BuildInput &in, const BinaryNode *nodes, int64_t num_nodes, int32_t root,
+                                const int32_t *order, WideBVH &out) {
+  auto t0 = std::chrono::steady_clock::now();
+  out.nodes.clear();
+  out.tris.clear();
+  out.max_depth = 0;
+  out.sah_cost = 0;
+  Builder2 b2;
+  b2.tris = in.tris;
+  b2.n = in.n;
+  b2.idx.assign(order, order + in.n);
+  b2.nodes.resize((size_t)num_nodes);
+  std::memcpy((void *)b2.nodes.data(), nodes, (size_t)num_nodes * sizeof(BinaryNode));
+  b2.next_node.store((int32_t)num_nodes);
+  finish_wide_bvh(in, b2, root, out);
   out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 

@@ -56,6 +56,19 @@ struct WideBVH {
   double build_ms = 0;
 };
 
+// Binary BVH node as produced by the device LBVH builder (lbvh.cu): leaf iff left < 0; a leaf
+// owns order[first .. first+count), an internal node's range is the union of its children's.
+struct BinaryNode {
+  float mn[3], mx[3];
+  int32_t left, right;
+  int32_t first, count;
+};
+
+// Collapse a binary BVH (any builder) into the compressed 8-wide layout: cost-optimal collapse
+// -> octant slot assignment -> quantisation -> leaf-ordered triangle records.
+void build_wide_bvh_from_binary(const BuildInput &in, const BinaryNode *nodes, int64_t num_nodes, int32_t root,
+                                const int32_t *order, WideBVH &out);
+
 // Host build: binned SAH binary tree -> cost-optimal 8-wide collapse -> octant slot
 // assignment -> quantisation.  n == 0 yields a single empty node.
 void build_wide_bvh(const BuildInput &in, WideBVH &out, int num_threads = 0);

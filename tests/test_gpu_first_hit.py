@@ -263,3 +263,50 @@ def test_ray_collision_counts_and_contains(built, oracle):
     with pytest.raises(N.M3DError) as ei:
         col.Contains(pts[:4], margin=0.1)
     assert ei.value.code == 2
+
+
+@pytest.mark.parametrize("n_sub", [1, 7, 40])
+def test_device_lbvh_build_same_hits(built, oracle, n_sub):
+    """M3D_MESH_BUILD_DEVICE_LBVH: Morton / radix sort / Karras / refit on the device, then the
+    shared 8-wide collapse.  First hits are hierarchy independent: identical to the oracle and
+    to the host-SAH build."""
+    from model3d_b200 import MeshCollider
+    from model3d_b200 import meshes
+    tris = np.concatenate([meshes.NewMeshIcosphere((0, 0, 0), 1.0, n_sub),
+                           meshes.NewMeshRect((-2.5, -0.2, -0.3), (-1.5, 0.4, 0.2)),
+                           meshes.NewMeshIcosphere((0.4, 0.3, 0.2), 0.5, max(1, n_sub // 2))]).astype(np.float32)
+    lb = MeshCollider(tris, device_lbvh=True)
+    sah = MeshCollider(tris)
+    info_l, info_s = lb.Info(), sah.Info()
+    assert info_l["num_triangles"] == info_s["num_triangles"] == tris.shape[0]
+    rng = np.random.default_rng(3 + n_sub)
+    n = 100000
+    org = (rng.normal(size=(n, 3)) * 1.2).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    a = lb.FirstRayCollisions(org, d, counters=True)
+    b = sah.FirstRayCollisions(org, d, counters=True)
+    ref = oracle.Collider(tris).first_hits(org, d, threads=8)
+    hit = ref["prim"] >= 0
+    assert np.array_equal(a.Collides, hit)
+    same = hit & (a.Triangle == ref["prim"])
+    assert same.sum() >= hit.sum() - 3
+    assert (a.Triangle != b.Triangle).sum() <= 3
+    rel = np.abs(a.Scale[same] - ref["t"][same]) / np.maximum(np.abs(ref["t"][same]), 1e-30)
+    assert rel.max() < 1e-5
+    # all-hits counts agree as well
+    assert (lb.RayCollisionCounts(org[:20000], d[:20000]) != sah.RayCollisionCounts(org[:20000], d[:20000])).sum() <= 2
+    print("lbvh nodes/ray %.2f vs sah %.2f; build %.1f ms vs %.1f ms" % (
+        a.Stats["nodes_visited"] / n, b.Stats["nodes_visited"] / n, info_l["build_ms"], info_s["build_ms"]))
+
+
+def test_device_lbvh_edge_cases(built):
+    from model3d_b200 import MeshCollider
+    one = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], np.float32)
+    c = MeshCollider(one, device_lbvh=True)
+    r = c.FirstRayCollisions([[0.2, 0.2, 1.0]], [[0, 0, -1.0]])
+    assert r.Collides[0] and r.Triangle[0] == 0 and r.Scale[0] == pytest.approx(1.0)
+    # many identical triangles: equal Morton keys are split by position
+    same = np.repeat(one, 50, axis=0)
+    c = MeshCollider(same, device_lbvh=True)
+    assert c.RayCollisionCounts([[0.2, 0.2, 1.0]], [[0, 0, -1.0]])[0] == 50
+    assert MeshCollider(np.zeros((0, 3, 3), np.float32), device_lbvh=True).Info()["num_triangles"] == 0
