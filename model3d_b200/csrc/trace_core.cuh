@@ -267,6 +267,9 @@ M3D_HD RayPre precompute_ray(const RayF &ray, const float *scene_min, const floa
 // for exact ties.  tri[2].w carries the triangle's longest edge (infinity norm) for the
 // bound.  Accepts t in [tmin, tmax], barycentrics inclusive, no back-face culling
 // (primitives.go:183,232,238).
+M3D_HD bool intersect_tri_loaded(const float4 *__restrict__ tri, const float4 q0, const float4 q1, const float4 q2,
+                                 const RayPre &rp, float tmax, float &t_out, float &b1, float &b2);
+
 M3D_HD bool intersect_tri(const float4 *__restrict__ tri, const RayPre &rp, float tmax, float &t_out,
                           float &b1, float &b2) {
 #if defined(__CUDA_ARCH__)
@@ -274,6 +277,13 @@ M3D_HD bool intersect_tri(const float4 *__restrict__ tri, const RayPre &rp, floa
 #else
   const float4 q0 = tri[0], q1 = tri[1], q2 = tri[2];
 #endif
+  return intersect_tri_loaded(tri, q0, q1, q2, rp, tmax, t_out, b1, b2);
+}
+
+// Same test on a triangle record that is already in registers (the traversal kernel issues the
+// three loads one node visit ahead of the test to hide their latency).
+M3D_HD bool intersect_tri_loaded(const float4 *__restrict__ tri, const float4 q0, const float4 q1, const float4 q2,
+                                 const RayPre &rp, float tmax, float &t_out, float &b1, float &b2) {
   const float e1x = q1.x - q0.x, e1y = q1.y - q0.y, e1z = q1.z - q0.z;
   const float e2x = q2.x - q0.x, e2y = q2.y - q0.y, e2z = q2.z - q0.z;
   const float c1x = rp.d.y * e2z - rp.d.z * e2y, c1y = rp.d.z * e2x - rp.d.x * e2z,

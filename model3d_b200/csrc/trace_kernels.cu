@@ -20,6 +20,7 @@ constexpr int kWarpsPerBlock = kTraceBlock / 32;
 constexpr int kSmemStack = 10;    // stack entries per thread kept in shared memory
 constexpr int kLocalStack = 54;   // overflow entries (local memory; untouched for sane trees)
 constexpr int kRayBatch = 32 * 6; // rays a warp claims per global atomic
+constexpr bool kPrefetchL1 = false;  // measured: no gain on B200 (rays are already L2-prefetched per batch)
 
 // Persistent-warp traversal with dynamic ray fetch.
 //
@@ -97,6 +98,15 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
         }
       }
       batch_next += __popc(need);
+      // the rays the warp will pick up during its next few iterations: L2 -> L1 now, so that
+      // their first use does not stall a 6-lane divergent section for an L2 round trip
+      if (kPrefetchL1) {
+        const int r = batch_next + (int)lane;
+        if (r < batch_end) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.org_tmin + r));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.dir_tmax + r));
+        }
+      }
       if (batch_end < 0 && __ballot_sync(0xffffffffu, ray_idx >= 0) == 0u) break;
     }
 
@@ -266,11 +276,13 @@ void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p, cudaStrea
   if (!minb) {
     const char *e = getenv("M3D_TRACE_MINB");
     minb = e ? atoi(e) : 6;
-    if (minb < 6 || minb > 8) minb = 6;
+    if (minb < 5 || minb > 8) minb = 6;
   }
   cudaMemsetAsync(p.ray_counter, 0, sizeof(unsigned long long), stream);
   if (p.counters) {
     launch_trace_variant<true, 6>(bvh, p, stream);
+  } else if (minb == 5) {
+    launch_trace_variant<false, 5>(bvh, p, stream);
   } else if (minb == 8) {
     launch_trace_variant<false, 8>(bvh, p, stream);
   } else if (minb == 7) {

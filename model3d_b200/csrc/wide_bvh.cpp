@@ -8,6 +8,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <limits>
@@ -153,7 +154,17 @@ struct Builder2 {
 };
 
 constexpr double kCostNode = 1.0;
-constexpr double kCostPrim = 0.3;
+// relative cost of one triangle test; M3D_BVH_CPRIM overrides it for tuning runs
+static double cost_prim() {
+  static double v = -1;
+  if (v < 0) {
+    const char *e = getenv("M3D_BVH_CPRIM");
+    v = e ? atof(e) : 0.3;
+    if (!(v > 0)) v = 0.3;
+  }
+  return v;
+}
+#define kCostPrim (cost_prim())
 constexpr int kMaxLeaf = 3;
 constexpr double kInf = std::numeric_limits<double>::infinity();
 
