@@ -42,6 +42,9 @@ int32_t carve_path_buffers(m3d_ctx *ctx, int64_t cap, int num_lights, PathBuffer
     o_queue[i] = take(c * 4);
   }
   const size_t o_raw = take(c * 16), o_thr = take(c * 16), o_acc = take(c * 16);
+  const size_t o_hra = take(c * 16), o_hrb = take(c * 16), o_hrc = take(c * 16);
+  size_t o_kl[4];
+  for (int i = 0; i < 4; i++) o_kl[i] = take(c * 4);
   const size_t o_sorg = take(c * nl * 16), o_sdir = take(c * nl * 16), o_sraw = take(c * nl * 16),
                o_spay = take(c * nl * 16), o_sskip = take(c * nl * 4);
   const size_t o_counts = take(64);
@@ -57,6 +60,10 @@ int32_t carve_path_buffers(m3d_ctx *ctx, int64_t cap, int num_lights, PathBuffer
   b.raw = (float4 *)(p + o_raw);
   b.thr = (float4 *)(p + o_thr);
   b.accum = (float4 *)(p + o_acc);
+  b.hrA = (float4 *)(p + o_hra);
+  b.hrB = (float4 *)(p + o_hrb);
+  b.hrC = (float4 *)(p + o_hrc);
+  for (int i = 0; i < 4; i++) b.klist[i] = (int32_t *)(p + o_kl[i]);
   b.sorg = (float4 *)(p + o_sorg);
   b.sdir = (float4 *)(p + o_sdir);
   b.sraw = (float4 *)(p + o_sraw);
@@ -154,6 +161,9 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   M3D_CUDA(cudaMemsetAsync(buf.ray_total, 0, sizeof(unsigned long long), s));
   const DeviceCamera dc = device_camera(*cam, width, height);
 
+  // material kinds that occur in the scene: one sampling kernel per kind and bounce
+  unsigned kinds_present = 0;
+  for (const m3d_material_desc &m : scene_materials(scene)) kinds_present |= 1u << (unsigned)m.kind;
   GpuTimer tm;
   tm.start(s);
   int64_t launches = 0;
@@ -178,8 +188,14 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
       t.ray_counter = next_work_counter(ctx);
       if (!t.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
       launch_trace_bvh_only(sc.bvh, t, s);
-      launch_path_shade(sc, pp, d_lights, b, buf, cur, depth, s);
+      launch_path_resolve(sc, pp, d_lights, b, buf, cur, depth, s);
       launches += 2;
+      if (depth < pp.max_depth)
+        for (int k = 0; k < 4; k++)
+          if (kinds_present & (1u << k)) {
+            launch_path_sample(k, sc, pp, b, buf, cur, depth, s);
+            launches++;
+          }
       if (num_lights > 0) {
         TraceLaunch ts;
         ts.org_tmin = buf.sorg;
@@ -197,8 +213,9 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
         launch_path_shadow_resolve(sc, pp, buf, cur, s);
         launches += 2;
       }
-      // the consumed queue becomes the next output queue
+      // the consumed queue becomes the next output queue; the work lists start empty again
       M3D_CUDA(cudaMemsetAsync(buf.counts + cur, 0, sizeof(int), s));
+      M3D_CUDA(cudaMemsetAsync(buf.counts + 4, 0, 4 * sizeof(int), s));
       cur ^= 1;
     }
     return M3D_OK;

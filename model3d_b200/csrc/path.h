@@ -49,18 +49,27 @@ struct PathBuffers {
   int32_t *skip[2], *queue[2];
   float4 *raw;
   float4 *thr, *accum;
+  // hit records of the current bounce, in queue order: (point, surface id), (normal, object),
+  // (direction to the viewer, slot); and the per-material-kind work lists of queue positions
+  float4 *hrA, *hrB, *hrC;
+  int32_t *klist[4];
   // shadow rays towards point lights (num_lights per queue entry, fixed positions)
   float4 *sorg, *sdir, *sraw, *spay;
   int32_t *sskip;
-  int *counts;                    // [0],[1]: queue lengths (ping-pong); [2]: shadow rays
+  int *counts;                    // [0],[1]: queue lengths (ping-pong); [2]: shadow rays;
+                                  // [4..7]: work-list lengths per material kind
   unsigned long long *ray_total;  // rays cast (statistics)
 };
 
 void launch_path_raygen(const DeviceCamera &cam, const DevicePathParams &pp, const PathBatch &b,
                         const PathBuffers &buf, cudaStream_t stream);
-// one bounce: resolve hits of queue `cur`, shade, emit shadow rays, sample and enqueue into 1-cur
-void launch_path_shade(const DeviceScene &sc, const DevicePathParams &pp, const DevicePointLight *lights,
-                       const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream);
+// bounce stage 1: resolve hits of queue `cur`, emission / ambient, shadow rays, hit records and
+// per-material-kind work lists
+void launch_path_resolve(const DeviceScene &sc, const DevicePathParams &pp, const DevicePointLight *lights,
+                         const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream);
+// bounce stage 2 for one material kind (m3d_material_kind): sample, weight, compact into queue 1-cur
+void launch_path_sample(int kind, const DeviceScene &sc, const DevicePathParams &pp, const PathBatch &b,
+                        const PathBuffers &buf, int cur, int depth, cudaStream_t stream);
 void launch_path_shadow_resolve(const DeviceScene &sc, const DevicePathParams &pp, const PathBuffers &buf,
                                 int cur, cudaStream_t stream);
 // per pixel: add the S per-sample colours (and their squares) into the frame accumulators

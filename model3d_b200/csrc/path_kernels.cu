@@ -10,6 +10,8 @@
 //   path_shadow_resolve_kernel  shadow test `hit && Scale < 1` (raytrace.go:157-163)
 //   path_flush_kernel           colorSum (+ squares) per pixel (ray_renderer.go:125-127,150)
 // Traversal between the stages is trace_first_hit_kernel (trace_kernels.cu).
+#include <algorithm>
+
 #include "materials.cuh"
 #include "path.h"
 #include "scene_hit.cuh"
@@ -70,6 +72,7 @@ path_raygen_kernel(DeviceCamera cam, DevicePathParams pp, PathBatch b, PathBuffe
     buf.counts[0] = (int)n;
     buf.counts[1] = 0;
     buf.counts[2] = 0;
+    buf.counts[4] = buf.counts[5] = buf.counts[6] = buf.counts[7] = 0;
   }
   if (slot >= n) return;
   const int p = (int)(slot % b.nP), s = (int)(slot / b.nP);
@@ -94,9 +97,16 @@ path_raygen_kernel(DeviceCamera cam, DevicePathParams pp, PathBatch b, PathBuffe
   buf.accum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Stage 1 of a bounce: resolve the hits of queue `cur` (closest of BVH hit and analytic shapes),
+// add emission / ambient, emit the shadow rays, and -- unless the path ends here -- write a hit
+// record and append the queue position to the work list of the hit material's KIND.  The
+// sampling stage then runs one kernel per material kind over its own list, so that warps are
+// coherent in material code and every kernel's instruction footprint fits the instruction
+// cache (the fused shade kernel of the first version stalled on instruction fetch 2/3 of the
+// time, profiles/ncu_path_r1.md).
 __global__ void __launch_bounds__(kShadeBlock, 8)
-path_shade_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *__restrict__ lights, PathBatch b,
-                  PathBuffers buf, int cur, int depth) {
+path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *__restrict__ lights, PathBatch b,
+                    PathBuffers buf, int cur, int depth) {
   const int n = buf.counts[cur];
   const unsigned lane = threadIdx.x & 31u;
   const int warps_total = (gridDim.x * kShadeBlock) >> 5;
@@ -105,7 +115,6 @@ path_shade_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *_
   const float4 *__restrict__ dir_in = buf.dir[cur];
   const int32_t *__restrict__ skip_in = buf.skip[cur];
   const int32_t *__restrict__ queue_in = buf.queue[cur];
-  const int nxt = cur ^ 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(buf.ray_total, (unsigned long long)n);
     buf.counts[2] = n * pp.num_lights;
@@ -113,14 +122,13 @@ path_shade_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *_
 
   for (int base = warp_id * 32; base < n; base += warps_total * 32) {
     const int q = base + (int)lane;
-    bool alive = false;
-    int slot = 0, surf = -1;
-    V3f point = v3f(0.f, 0.f, 0.f), next_dir = v3f(0.f, 0.f, 1.f);
-    float4 thr = make_float4(0.f, 0.f, 0.f, 0.f);
+    int kind = -1;  // material kind whose sampler continues this path, -1: the path ends
     if (q < n) {
-      slot = queue_in[q];
+      const int slot = queue_in[q];
       const float4 o = __ldcs(org_in + q), d = __ldcs(dir_in + q), raw = __ldcs(buf.raw + q);
-      const SceneHit h = resolve_scene_hit(sc, o, d, raw, skip_in[q], true);
+      // float32 hit evaluation: Monte-Carlo parity is statistical, the float64 refinement of the
+      // first-hit API (1e-5 on t and normals) is not needed here; shapes stay float64
+      const SceneHit h = resolve_scene_hit(sc, o, d, raw, skip_in[q], false);
       if (pp.num_lights > 0 && h.obj < 0) {
         // no shadow rays for a miss: give the slots an empty parameter interval
         for (int l = 0; l < pp.num_lights; l++) {
@@ -133,11 +141,10 @@ path_shade_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *_
       }
       if (h.obj >= 0) {
         const V3f org = v3f(o.x, o.y, o.z), dir = v3f(d.x, d.y, d.z), nrm = v3f(h.nx, h.ny, h.nz);
-        point = org + dir * h.t;
-        surf = h.surf;
+        const V3f point = org + dir * h.t;
         const MatAt m = material_at(sc, h.obj, point);
         const V3f dest = normalize(dir) * -1.f;
-        thr = buf.thr[slot];
+        const float4 thr = buf.thr[slot];
         const V3f tv = v3f(thr.x, thr.y, thr.z);
         // raytrace.go:150-155
         V3f color = mat_emission(sc, m);
@@ -161,73 +168,161 @@ path_shade_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *_
           const bool useful = !is_zero(c);
           buf.sorg[si] = make_float4(point.x, point.y, point.z, useful ? 0.f : 1.f);
           buf.sdir[si] = make_float4(light_dir.x, light_dir.y, light_dir.z, useful ? 1.f : -1.f);
-          buf.sskip[si] = surf;
+          buf.sskip[si] = h.surf;
           buf.spay[si] = make_float4(c.x, c.y, c.z, __int_as_float(slot));
         }
         if (depth < pp.max_depth) {
-          Rng g;
-          g.init(pp.seed, (uint32_t)batch_pixel(b, slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP), (uint32_t)depth);
-          // sampleNextSource (raytrace.go:183-199)
-          V3f source;
-          int tag = 0;
-          int chosen = -1;
-          if (pp.num_focus > 0) {
-            float u = g.f32();
-            for (int i = 0; i < pp.num_focus; i++) {
-              u -= pp.focus[i].prob;
-              if (u < 0.f) {
-                chosen = i;
-                break;
-              }
-            }
-          }
-          bool from_focus = false;
-          if (chosen >= 0) {
-            V3f fdir;
-            float min_cos;
-            if (focus_active(pp.focus[chosen], m.index, point, fdir, min_cos)) {
-              from_focus = true;
-              source = pp.focus[chosen].kind == M3D_FOCUS_PHONG
-                           ? sample_around_direction(g, pp.focus[chosen].alpha, fdir)
-                           : sample_around_uniform(g, min_cos, fdir);
-            }
-          }
-          if (!from_focus) source = mat_sample_source(sc, m, g, nrm, dest, tag);
-          // sourceDensity (raytrace.go:201-215): mixture of focus densities and the material's
-          const Density md = mat_source_density(sc, m, nrm, source, dest, tag);
-          float dens_fin = md.fin, dens_del = md.del;
-          if (pp.num_focus > 0) {
-            float mat_prob = 1.f, fin = 0.f;
-            for (int i = 0; i < pp.num_focus; i++) {
-              V3f fdir;
-              float min_cos;
-              if (focus_active(pp.focus[i], m.index, point, fdir, min_cos)) {
-                fin += pp.focus[i].prob * focus_density(pp.focus[i], fdir, min_cos, source);
-                mat_prob -= pp.focus[i].prob;
-              }
-            }
-            dens_fin = fin + mat_prob * md.fin;
-            dens_del = mat_prob * md.del;
-          }
-          // weight = |cos| / density; mask = BSDF * weight (raytrace.go:170-176).  A direction
-          // drawn from a Dirac lobe carries bsdf and density proportional to 2/cosineEpsilon:
-          // their ratio is taken analytically (the finite parts are 1e-8 relative).
-          const float cosv = fabsf(dot(source, nrm));
-          V3f mask;
-          if (dens_del > 0.f)
-            mask = mat_bsdf_delta(sc, m, nrm, source, dest, tag) * (cosv / dens_del);
-          else
-            mask = mat_bsdf(sc, m, nrm, source, dest) * (dens_fin > 0.f ? cosv / dens_fin : 0.f);
-          const V3f nt = tv * mask;
-          const float mean = (nt.x + nt.y + nt.z) * (1.f / 3.f);
-          // recurse() entry test (raytrace.go:139-142); a zero / non-finite throughput can
-          // never contribute again
-          if (mean >= pp.cutoff && mean > 0.f && mean < INFINITY) {
-            alive = true;
-            thr = make_float4(nt.x, nt.y, nt.z, 0.f);
-            next_dir = source * -1.f;
+          kind = sc.materials[m.index].kind;
+          buf.hrA[q] = make_float4(point.x, point.y, point.z, __int_as_float(h.surf));
+          buf.hrB[q] = make_float4(nrm.x, nrm.y, nrm.z, __int_as_float(h.obj));
+          buf.hrC[q] = make_float4(dest.x, dest.y, dest.z, __int_as_float(slot));
+        }
+      }
+    }
+    // append to the per-kind work lists (one atomic per warp and kind present in the warp)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned m = __ballot_sync(0xffffffffu, kind == k);
+      if (m) {
+        int pos0 = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) pos0 = atomicAdd(buf.counts + 4 + k, __popc(m));
+        pos0 = __shfl_sync(0xffffffffu, pos0, __ffs(m) - 1);
+        if (kind == k) buf.klist[k][pos0 + __popc(m & ((1u << lane) - 1u))] = q;
+      }
+    }
+  }
+}
+
+// Material sampling specialised by kind: the direction, its density (finite, Dirac
+// coefficient) and BSDF * |cos| / density.
+template <int KIND>
+__device__ __forceinline__ V3f kind_sample_source(const DeviceScene &sc, const MatAt &m, Rng &g, V3f nrm, V3f dest,
+                                                  int &tag) {
+  if (KIND == M3D_MAT_LAMBERT) {
+    tag = 0;
+    return lambert_sample(g, nrm);
+  }
+  if (KIND == M3D_MAT_JOINED) return mat_sample_source(sc, m, g, nrm, dest, tag);
+  return simple_sample_source(sc.materials[m.index], m.diffuse, g, nrm, dest, tag);
+}
+template <int KIND>
+__device__ __forceinline__ Density kind_source_density(const DeviceScene &sc, const MatAt &m, V3f nrm, V3f source,
+                                                       V3f dest, int tag) {
+  if (KIND == M3D_MAT_LAMBERT) {
+    Density r;
+    r.fin = lambert_density(nrm, source);
+    r.del = 0.f;
+    return r;
+  }
+  if (KIND == M3D_MAT_JOINED) return mat_source_density(sc, m, nrm, source, dest, tag);
+  return simple_source_density(sc.materials[m.index], m.diffuse, nrm, source, dest, tag & 3);
+}
+template <int KIND>
+__device__ __forceinline__ V3f kind_bsdf(const DeviceScene &sc, const MatAt &m, V3f nrm, V3f source, V3f dest) {
+  if (KIND == M3D_MAT_LAMBERT) {  // material.go:125-134
+    if (dot(dest, nrm) < 0.f || dot(source, nrm) > 0.f) return v3f(0.f, 0.f, 0.f);
+    return m.diffuse * 4.f;
+  }
+  if (KIND == M3D_MAT_REFRACT) return v3f(0.f, 0.f, 0.f);  // Dirac lobes only
+  if (KIND == M3D_MAT_JOINED) return mat_bsdf(sc, m, nrm, source, dest);
+  return simple_bsdf(sc.materials[m.index], m.diffuse, nrm, source, dest);
+}
+template <int KIND>
+__device__ __forceinline__ V3f kind_bsdf_delta(const DeviceScene &sc, const MatAt &m, V3f nrm, V3f source, V3f dest,
+                                               int tag) {
+  if (KIND == M3D_MAT_LAMBERT || KIND == M3D_MAT_PHONG) return v3f(0.f, 0.f, 0.f);
+  return mat_bsdf_delta(sc, m, nrm, source, dest, tag);
+}
+
+// Stage 2 of a bounce, one launch per material kind present in the scene: sampleNextSource /
+// sourceDensity with focus points (raytrace.go:183-215), throughput update and cutoff
+// (raytrace.go:139-142, 170-180), ballot/popc compaction of the survivors into the next queue.
+template <int KIND>
+__global__ void __launch_bounds__(kShadeBlock, 8)
+path_sample_kernel(DeviceScene sc, DevicePathParams pp, PathBatch b, PathBuffers buf, int cur, int depth) {
+  const int n = buf.counts[4 + KIND];
+  const unsigned lane = threadIdx.x & 31u;
+  const int warps_total = (gridDim.x * kShadeBlock) >> 5;
+  const int warp_id = (blockIdx.x * kShadeBlock + threadIdx.x) >> 5;
+  const int nxt = cur ^ 1;
+  const int32_t *__restrict__ list = buf.klist[KIND];
+
+  for (int base = warp_id * 32; base < n; base += warps_total * 32) {
+    const int li = base + (int)lane;
+    bool alive = false;
+    int slot = 0, surf = -1;
+    V3f point = v3f(0.f, 0.f, 0.f), next_dir = v3f(0.f, 0.f, 1.f);
+    float4 thr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (li < n) {
+      const int q = list[li];
+      const float4 ra = buf.hrA[q], rb = buf.hrB[q], rc = buf.hrC[q];
+      point = v3f(ra.x, ra.y, ra.z);
+      surf = __float_as_int(ra.w);
+      const V3f nrm = v3f(rb.x, rb.y, rb.z), dest = v3f(rc.x, rc.y, rc.z);
+      slot = __float_as_int(rc.w);
+      const MatAt m = material_at(sc, __float_as_int(rb.w), point);
+      thr = buf.thr[slot];
+      const V3f tv = v3f(thr.x, thr.y, thr.z);
+      Rng g;
+      g.init(pp.seed, (uint32_t)batch_pixel(b, slot % b.nP), b.sample0 + (uint32_t)(slot / b.nP), (uint32_t)depth);
+      // sampleNextSource (raytrace.go:183-199)
+      V3f source;
+      int tag = 0;
+      int chosen = -1;
+      if (pp.num_focus > 0) {
+        float u = g.f32();
+        for (int i = 0; i < pp.num_focus; i++) {
+          u -= pp.focus[i].prob;
+          if (u < 0.f) {
+            chosen = i;
+            break;
           }
         }
+      }
+      bool from_focus = false;
+      if (chosen >= 0) {
+        V3f fdir;
+        float min_cos;
+        if (focus_active(pp.focus[chosen], m.index, point, fdir, min_cos)) {
+          from_focus = true;
+          source = pp.focus[chosen].kind == M3D_FOCUS_PHONG ? sample_around_direction(g, pp.focus[chosen].alpha, fdir)
+                                                            : sample_around_uniform(g, min_cos, fdir);
+        }
+      }
+      if (!from_focus) source = kind_sample_source<KIND>(sc, m, g, nrm, dest, tag);
+      // sourceDensity (raytrace.go:201-215): mixture of focus densities and the material's
+      const Density md = kind_source_density<KIND>(sc, m, nrm, source, dest, tag);
+      float dens_fin = md.fin, dens_del = md.del;
+      if (pp.num_focus > 0) {
+        float mat_prob = 1.f, fin = 0.f;
+        for (int i = 0; i < pp.num_focus; i++) {
+          V3f fdir;
+          float min_cos;
+          if (focus_active(pp.focus[i], m.index, point, fdir, min_cos)) {
+            fin += pp.focus[i].prob * focus_density(pp.focus[i], fdir, min_cos, source);
+            mat_prob -= pp.focus[i].prob;
+          }
+        }
+        dens_fin = fin + mat_prob * md.fin;
+        dens_del = mat_prob * md.del;
+      }
+      // weight = |cos| / density; mask = BSDF * weight (raytrace.go:170-176).  A direction drawn
+      // from a Dirac lobe carries bsdf and density proportional to 2/cosineEpsilon: their ratio
+      // is taken analytically (the finite parts are 1e-8 relative).
+      const float cosv = fabsf(dot(source, nrm));
+      V3f mask;
+      if (dens_del > 0.f)
+        mask = kind_bsdf_delta<KIND>(sc, m, nrm, source, dest, tag) * (cosv / dens_del);
+      else
+        mask = kind_bsdf<KIND>(sc, m, nrm, source, dest) * (dens_fin > 0.f ? cosv / dens_fin : 0.f);
+      const V3f nt = tv * mask;
+      const float mean = (nt.x + nt.y + nt.z) * (1.f / 3.f);
+      // recurse() entry test (raytrace.go:139-142); a zero / non-finite throughput can never
+      // contribute again
+      if (mean >= pp.cutoff && mean > 0.f && mean < INFINITY) {
+        alive = true;
+        thr = make_float4(nt.x, nt.y, nt.z, 0.f);
+        next_dir = source * -1.f;
       }
     }
     // compaction: surviving lanes take consecutive positions of the next queue
@@ -312,20 +407,44 @@ void launch_path_raygen(const DeviceCamera &cam, const DevicePathParams &pp, con
   path_raygen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cam, pp, b, buf);
 }
 
-void launch_path_shade(const DeviceScene &sc, const DevicePathParams &pp, const DevicePointLight *lights,
-                       const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream) {
-  static int blocks_per_sm = 0;
-  if (!blocks_per_sm) {
-    int x = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&x, path_shade_kernel, kShadeBlock, 0);
-    blocks_per_sm = x > 0 ? x : 1;
-  }
-  const int64_t n = (int64_t)b.nP * b.S;
-  int64_t grid = (int64_t)device_sm_count() * blocks_per_sm;
+template <class K>
+static int shade_grid(K kernel, int64_t n) {
+  int x = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&x, kernel, kShadeBlock, 0);
+  int64_t grid = (int64_t)device_sm_count() * (x > 0 ? x : 1);
   const int64_t want = (n + kShadeBlock - 1) / kShadeBlock;
   if (grid > want) grid = want;
-  if (grid < 1) grid = 1;
-  path_shade_kernel<<<(unsigned)grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth);
+  return (int)(grid < 1 ? 1 : grid);
+}
+
+void launch_path_resolve(const DeviceScene &sc, const DevicePathParams &pp, const DevicePointLight *lights,
+                         const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream) {
+  static int grid_full = 0;
+  const int64_t n = (int64_t)b.nP * b.S;
+  if (!grid_full) grid_full = shade_grid(path_resolve_kernel, (int64_t)1 << 40);
+  const int64_t want = (n + kShadeBlock - 1) / kShadeBlock;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_full, want));
+  path_resolve_kernel<<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth);
+}
+
+void launch_path_sample(int kind, const DeviceScene &sc, const DevicePathParams &pp, const PathBatch &b,
+                        const PathBuffers &buf, int cur, int depth, cudaStream_t stream) {
+  const int64_t n = (int64_t)b.nP * b.S;
+  static int grids[4] = {0, 0, 0, 0};
+  if (!grids[0]) {
+    grids[0] = shade_grid(path_sample_kernel<0>, (int64_t)1 << 40);
+    grids[1] = shade_grid(path_sample_kernel<1>, (int64_t)1 << 40);
+    grids[2] = shade_grid(path_sample_kernel<2>, (int64_t)1 << 40);
+    grids[3] = shade_grid(path_sample_kernel<3>, (int64_t)1 << 40);
+  }
+  const int64_t want = (n + kShadeBlock - 1) / kShadeBlock;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grids[kind], want));
+  switch (kind) {
+    case 0: path_sample_kernel<0><<<grid, kShadeBlock, 0, stream>>>(sc, pp, b, buf, cur, depth); break;
+    case 1: path_sample_kernel<1><<<grid, kShadeBlock, 0, stream>>>(sc, pp, b, buf, cur, depth); break;
+    case 2: path_sample_kernel<2><<<grid, kShadeBlock, 0, stream>>>(sc, pp, b, buf, cur, depth); break;
+    default: path_sample_kernel<3><<<grid, kShadeBlock, 0, stream>>>(sc, pp, b, buf, cur, depth); break;
+  }
 }
 
 void launch_path_shadow_resolve(const DeviceScene &sc, const DevicePathParams &pp, const PathBuffers &buf,
