@@ -11,6 +11,7 @@
 #include "api_common.h"
 #include "path.h"
 #include "scene.h"
+#include "scene_host.h"
 
 using namespace m3d;
 
@@ -162,8 +163,9 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   const DeviceCamera dc = device_camera(*cam, width, height);
 
   // material kinds that occur in the scene: one sampling kernel per kind and bounce
+  // (kinds of the objects' own materials; parts of a JoinedMaterial are sampled by the joined kernel)
   unsigned kinds_present = 0;
-  for (const m3d_material_desc &m : scene_materials(scene)) kinds_present |= 1u << (unsigned)m.kind;
+  for (int32_t mi : scene->object_material) kinds_present |= 1u << (unsigned)scene->host_materials[(size_t)mi].kind;
   GpuTimer tm;
   tm.start(s);
   int64_t launches = 0;
