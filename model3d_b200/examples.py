@@ -3,7 +3,7 @@ spec into product objects (model3d_b200.render3d).  bench.py renders them; tests
 builds the same specs a second time for the CPU oracle.
 
 Scenes restate the reference's examples:
-  c1_scene       SaveRendering setup (render3d/helpers.go:105-123, Objectify :71-99)
+  c1_scene       marching-cubes sphere in the SaveRendering setup (render3d/helpers.go:105-123, Objectify :71-99)
   cornell_box    examples/renderings/cornell_box/main.go:15-121
   testing_scene  render3d/bidir_test.go:85-111
 """
@@ -137,15 +137,22 @@ def mixed_scene():
     return dict(objects=objs)
 
 
-def c1_scene(n=137):
-    """BASELINE config 1 with an icosphere standing in for the marching-cubes sphere
-    (NewMeshIcosphere(0,1,137) = 375,380 triangles vs ~376,832)."""
+def c1_scene(n=None, delta=0.01, iters=8):
+    """BASELINE config 1: model3d.Sphere{radius 1} -> MarchingCubesSearch(0.01, 8) (376,832
+    triangles) set up the way SaveRendering does (helpers.go:101-128: camera at `origin`
+    looking at the bounding-box centre, one far point light behind the camera, Objectify's
+    default yellow Phong material).  `n` selects an icosphere NewMeshIcosphere(0,1,n) instead
+    (small test meshes)."""
     yellow = NewColorRGB(224.0 / 255, 209.0 / 255, 0.0)
     mat = phong(10.0, specular=gray(0.2), diffuse=tuple(0.8 * c for c in yellow),
                 ambient=tuple(0.1 * c for c in yellow))
-    tris = meshes.NewMeshIcosphere((0, 0, 0), 1.0, n).astype(np.float32)
+    if n is None:
+        tris = meshes.MarchingCubesSearch(meshes.SphereSolid((0, 0, 0), 1.0), delta, iters).astype(np.float32)
+    else:
+        tris = meshes.NewMeshIcosphere((0, 0, 0), 1.0, n).astype(np.float32)
     origin = np.array([2.0, -3.0, 1.5])
-    center = np.zeros(3)
+    v = tris.reshape(-1, 3).astype(np.float64)
+    center = (v.min(0) + v.max(0)) * 0.5  # Mesh.Min().Mid(Mesh.Max()) (helpers.go:107-108)
     return dict(objects=[dict(kind="mesh", tris=tris, material=mat)],
                 camera=dict(src=tuple(origin), dst=tuple(center), fov=math.pi / 3.6),
                 lights=[dict(origin=tuple(center + (origin - center) * 1000), color=gray(1.0))])

@@ -108,3 +108,190 @@ def NewMeshRect(mn, mx):
         tris.append([p1, p2, p4])
         tris.append([p2, p3, p4])
     return np.array(tris, np.float64)
+
+
+# ---------------------------------------------------------------------------------------
+# Marching cubes (model3d/mc.go), vectorised over grid layers.  BASELINE config C1 is
+# "model3d.Sphere -> MarchingCubesSearch(0.01, 8)".
+
+_MC_BASE = [  # baseTriangleTable (mc.go:460-586): (corners inside, triangles as 3 cube edges)
+    ((), ()),
+    ((0,), ((0, 1, 0, 2, 0, 4),)),
+    ((0, 1), ((0, 4, 1, 5, 0, 2), (1, 5, 1, 3, 0, 2))),
+    ((0, 5), ((0, 1, 0, 2, 0, 4), (5, 7, 1, 5, 4, 5))),
+    ((0, 7), ((0, 1, 0, 2, 0, 4), (6, 7, 3, 7, 5, 7))),
+    ((1, 2, 3), ((0, 1, 1, 5, 0, 2), (0, 2, 1, 5, 2, 6), (2, 6, 1, 5, 3, 7))),
+    ((0, 1, 7), ((0, 4, 1, 5, 0, 2), (1, 5, 1, 3, 0, 2), (6, 7, 3, 7, 5, 7))),
+    ((1, 4, 7), ((4, 6, 4, 5, 0, 4), (1, 5, 1, 3, 0, 1), (6, 7, 3, 7, 5, 7))),
+    ((0, 1, 2, 3), ((0, 4, 1, 5, 3, 7), (0, 4, 3, 7, 2, 6))),
+    ((0, 2, 3, 6), ((0, 1, 4, 6, 0, 4), (0, 1, 6, 7, 4, 6), (0, 1, 1, 3, 6, 7), (1, 3, 3, 7, 6, 7))),
+    ((1, 2, 5, 6), ((0, 2, 2, 3, 6, 7), (0, 2, 6, 7, 4, 6), (0, 1, 4, 5, 5, 7), (5, 7, 1, 3, 0, 1))),
+    ((0, 2, 3, 7), ((0, 4, 0, 1, 2, 6), (0, 1, 5, 7, 2, 6), (2, 6, 5, 7, 6, 7), (0, 1, 1, 3, 5, 7))),
+    ((1, 2, 3, 4), ((0, 1, 1, 5, 0, 2), (0, 2, 1, 5, 2, 6), (2, 6, 1, 5, 3, 7), (4, 5, 0, 4, 4, 6))),
+    ((1, 2, 4, 7), ((0, 1, 1, 5, 1, 3), (0, 2, 2, 3, 2, 6), (4, 5, 0, 4, 4, 6), (5, 7, 6, 7, 3, 7))),
+    ((1, 2, 3, 6), ((0, 2, 0, 1, 4, 6), (0, 1, 3, 7, 4, 6), (0, 1, 1, 5, 3, 7), (4, 6, 3, 7, 6, 7))),
+    ((0, 2, 3, 5, 6), ((0, 1, 4, 6, 0, 4), (0, 1, 6, 7, 4, 6), (0, 1, 1, 3, 6, 7), (1, 3, 3, 7, 6, 7),
+                       (5, 7, 1, 5, 4, 5))),
+    ((2, 3, 4, 5, 6), ((5, 7, 1, 5, 0, 4), (0, 4, 6, 7, 5, 7), (0, 2, 6, 7, 0, 4), (0, 2, 3, 7, 6, 7),
+                       (0, 2, 1, 3, 3, 7))),
+    ((0, 4, 5, 6, 7), ((1, 5, 0, 1, 0, 2), (0, 2, 2, 6, 1, 5), (1, 5, 2, 6, 3, 7))),
+    ((1, 2, 3, 4, 5, 6), ((0, 2, 0, 1, 0, 4), (3, 7, 6, 7, 5, 7))),
+    ((1, 2, 3, 4, 6, 7), ((0, 2, 4, 5, 0, 4), (0, 2, 5, 7, 4, 5), (0, 2, 1, 5, 5, 7), (0, 1, 1, 5, 0, 2))),
+    ((2, 3, 4, 5, 6, 7), ((1, 5, 0, 4, 0, 2), (1, 3, 1, 5, 0, 2))),
+    ((1, 2, 3, 4, 5, 6, 7), ((0, 2, 0, 1, 0, 4),)),
+    ((0, 1, 2, 3, 4, 5, 6, 7), ()),
+]
+_MC_TABLE = None
+
+
+def _mc_lookup_table():
+    """mcLookupTable (mc.go:431-454): the 24 cube rotations (closure of a z and an x quarter
+    turn, sorted lexicographically, mc.go:312-352) applied to the base cases; the first
+    rotation that produces a corner mask defines its triangles.  Returns (counts[256],
+    corners[256, 5, 6])."""
+    global _MC_TABLE
+    if _MC_TABLE is not None:
+        return _MC_TABLE
+    zr, xr = (2, 0, 3, 1, 6, 4, 7, 5), (2, 3, 6, 7, 0, 1, 4, 5)
+    queue, seen = [tuple(range(8))], {tuple(range(8))}
+    while queue:
+        nxt = queue.pop(0)
+        for op in (zr, xr):
+            rot = tuple(op[nxt[i]] for i in range(8))  # Compose (mc.go:355-361)
+            if rot not in seen:
+                seen.add(rot)
+                queue.append(rot)
+    rots = sorted(seen)
+    assert len(rots) == 24
+    counts = np.zeros(256, np.int32)
+    corners = np.zeros((256, 5, 6), np.uint8)
+    done = np.zeros(256, bool)
+    for inside, tris in _MC_BASE:
+        for rot in rots:
+            bits = 0
+            for c in inside:
+                bits |= 1 << rot[c]
+            if done[bits]:
+                continue
+            done[bits] = True
+            counts[bits] = len(tris)
+            for k, t in enumerate(tris):
+                corners[bits, k] = [rot[c] for c in t]
+    assert done.all()
+    _MC_TABLE = (counts, corners)
+    return _MC_TABLE
+
+
+class SphereSolid:
+    """model3d.Sphere as a Solid (shapes.go:17-31), Contains vectorised over [n, 3] points."""
+
+    def __init__(self, center, radius):
+        self.Center = np.asarray(center, np.float64)
+        self.Radius = float(radius)
+
+    def Min(self):
+        return self.Center - self.Radius
+
+    def Max(self):
+        return self.Center + self.Radius
+
+    def Contains(self, pts):
+        d = pts - self.Center
+        return np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]) <= self.Radius
+
+
+def _mc_spacer(solid, delta):
+    """newSquareSpacer (mc.go:594-612): the same running sums as the reference's loops."""
+    out = []
+    mn, mx = solid.Min(), solid.Max()
+    for a in range(3):
+        vals, v = [], float(mn[a]) - delta
+        while v <= float(mx[a]) + delta:
+            vals.append(v)
+            v += delta
+        out.append(np.array(vals, np.float64))
+    return out
+
+
+def MarchingCubes(solid, delta):
+    """model3d.MarchingCubes (mc.go:14-37).  Triangles in scan order (z, y, x, table order);
+    the reference's Mesh is an unordered set."""
+    counts, tcorn = _mc_lookup_table()
+    xs, ys, zs = _mc_spacer(solid, float(delta))
+    nx, ny, nz = len(xs), len(ys), len(zs)
+    gx, gy = np.meshgrid(xs, ys)  # [ny, nx]
+
+    def layer(z):
+        pts = np.stack([gx.ravel(), gy.ravel(), np.full(nx * ny, zs[z])], axis=1)
+        v = np.asarray(solid.Contains(pts), bool).reshape(ny, nx)
+        if v.any() and (z == 0 or z == nz - 1 or v[0].any() or v[-1].any() or v[:, 0].any() or v[:, -1].any()):
+            raise ValueError("solid is true outside of bounds")  # mc.go:686-688
+        return v
+
+    def square(v):  # GetSquare (mc.go:697-710): bit = x + 2*y
+        v = v.astype(np.uint8)
+        return v[:-1, :-1] | (v[:-1, 1:] << 1) | (v[1:, :-1] << 2) | (v[1:, 1:] << 3)
+
+    # corner c of a cell = (x + (c&1), y + ((c>>1)&1), z-1 + (c>>2)) (mc.go:289-301)
+    out = []
+    bottom = layer(0)
+    for z in range(1, nz):
+        top = layer(z)
+        bits = square(bottom) | (square(top) << 4)
+        cy, cx = np.nonzero(counts[bits])
+        if cy.size:
+            b = bits[cy, cx]
+            cnt = counts[b]
+            cell = np.repeat(np.arange(cy.size), cnt)
+            first = np.cumsum(cnt) - cnt
+            k = np.arange(cell.size) - np.repeat(first, cnt)
+            tc = tcorn[b[cell], k]  # [m, 6] corner ids
+            px = xs[cx[cell][:, None] + (tc & 1)]
+            py = ys[cy[cell][:, None] + ((tc >> 1) & 1)]
+            pz = zs[(z - 1) + (tc >> 2)]
+            p = np.stack([px, py, pz], axis=-1)  # [m, 6, 3]
+            out.append((p[:, 0::2] + p[:, 1::2]) * 0.5)  # Coord3D.Mid (coords.go:196-198)
+        bottom = top
+    if not out:
+        return np.zeros((0, 3, 3), np.float64)
+    return np.concatenate(out, axis=0)
+
+
+def MarchingCubesSearch(solid, delta, iters):
+    """model3d.MarchingCubesSearch (mc.go:45-51): every vertex is moved along its cube edge by
+    `iters` bisection steps of solid.Contains (mcSearch / mcSearchPoint mc.go:182-260,
+    LookupEdgePoint :647-660).  The result depends on the vertex alone, so all triangle
+    corners are processed independently."""
+    mesh = MarchingCubes(solid, delta)
+    if iters == 0 or mesh.shape[0] == 0:
+        return mesh
+    sp = _mc_spacer(solid, float(delta))
+    d = sp[0][1] - sp[0][0]
+    pts = mesh.reshape(-1, 3).copy()
+    n = pts.shape[0]
+    axis = np.full(n, -1)
+    fp = np.zeros(n)
+    tp = np.zeros(n)
+    for a in range(3):
+        rel = pts[:, a] - sp[a][0]
+        modulus = np.abs(np.fmod(rel, d))
+        sel = (axis < 0) & (modulus > d / 4) & (modulus < 3 * d / 4)
+        idx = (rel[sel] / d).astype(np.int64)
+        fp[sel] = sp[a][idx]
+        tp[sel] = sp[a][idx + 1]
+        axis[sel] = a
+    if (axis < 0).any():
+        raise ValueError("vertex not on edge")
+    rows = np.arange(n)
+    probe = pts.copy()
+    probe[rows, axis] = tp
+    swap = ~np.asarray(solid.Contains(probe), bool)
+    fp[swap], tp[swap] = tp[swap], fp[swap].copy()
+    for _ in range(int(iters)):
+        mid = (fp + tp) / 2
+        probe[rows, axis] = mid
+        inside = np.asarray(solid.Contains(probe), bool)
+        tp = np.where(inside, mid, tp)
+        fp = np.where(inside, fp, mid)
+    pts[rows, axis] = (fp + tp) / 2
+    return pts.reshape(-1, 3, 3)

@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "collide.hpp"
+#include "mcubes.hpp"
 #include "meshgen.hpp"
 #include "render.hpp"
 #include "scene.hpp"
@@ -64,6 +65,31 @@ void orc_mesh_icosphere(double cx, double cy, double cz, double radius, int n, d
 }
 void orc_mesh_rect(const double mn[3], const double mx[3], double *out /*12*9*/) {
   tris_to_f64(mesh_rect(v3(mn), v3(mx)), out);
+}
+// marching-cubes sphere (C1): two calls, count then fill (the mesh is cached between them)
+static std::vector<Triangle> g_mc_cache;
+int64_t orc_mesh_mc_sphere_build(double cx, double cy, double cz, double radius, double delta, int iters) {
+  try {
+    g_mc_cache = marching_cubes_sphere(V3(cx, cy, cz), radius, delta, iters);
+  } catch (const std::exception &e) {
+    g_mc_cache.clear();
+    return -1;
+  }
+  return (int64_t)g_mc_cache.size();
+}
+void orc_mesh_mc_sphere_fetch(double *out) {
+  tris_to_f64(g_mc_cache, out);
+  g_mc_cache.clear();
+  g_mc_cache.shrink_to_fit();
+}
+// the 256-entry case table, flattened: counts[256], corners[256][5][6] (0-padded)
+void orc_mc_table(int32_t *counts, uint8_t *corners) {
+  const auto &t = mc_lookup_table();
+  for (int i = 0; i < 256; i++) {
+    counts[i] = (int32_t)t[i].size();
+    for (size_t k = 0; k < 5; k++)
+      for (int c = 0; c < 6; c++) corners[(i * 5 + k) * 6 + c] = k < t[i].size() ? t[i][k][c] : 0;
+  }
 }
 int64_t orc_mesh_polar_count(int stops) { return 2LL * stops * (stops - 1); }
 void orc_mesh_polar(double ra, double rb, int stops, double *out) {

@@ -93,6 +93,7 @@ def lib():
         L.orc_scene_create.restype = C.c_void_p
         L.orc_mesh_icosphere_count.restype = C.c_int64
         L.orc_mesh_polar_count.restype = C.c_int64
+        L.orc_mesh_mc_sphere_build.restype = C.c_int64
         L.orc_collider_num_nodes.restype = C.c_int64
         L.orc_collider_all_hits.restype = C.c_int64
         L.orc_gamma_expand.restype = C.c_double
@@ -134,6 +135,25 @@ def mesh_rect(mn, mx):
     out = np.empty((12, 3, 3), np.float64)
     lib().orc_mesh_rect(_d3(mn), _d3(mx), _p(out, f64p))
     return out
+
+
+def mesh_mc_sphere(center, radius, delta, iters):
+    """MarchingCubesSearch(&Sphere{center, radius}, delta, iters) (mc.go:45-51), scan order."""
+    cnt = lib().orc_mesh_mc_sphere_build(C.c_double(center[0]), C.c_double(center[1]), C.c_double(center[2]),
+                                         C.c_double(radius), C.c_double(delta), C.c_int(iters))
+    if cnt < 0:
+        raise RuntimeError("oracle marching cubes failed")
+    out = np.empty((cnt, 3, 3), np.float64)
+    lib().orc_mesh_mc_sphere_fetch(_p(out, f64p))
+    return out
+
+
+def mc_table():
+    """mcLookupTable (mc.go:431-454): (counts[256], corners[256,5,6])."""
+    counts = np.zeros(256, np.int32)
+    corners = np.zeros((256, 5, 6), np.uint8)
+    lib().orc_mc_table(_p(counts, C.POINTER(C.c_int32)), _p(corners, C.POINTER(C.c_uint8)))
+    return counts, corners
 
 
 def mesh_polar(ra, rb, stops):

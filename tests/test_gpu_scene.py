@@ -96,10 +96,13 @@ def test_raycaster_mixed_scene_image(built, oracle, size):
 
 
 def test_raycaster_c1_config(built, oracle):
-    """BASELINE config 1: sphere mesh (375,380-triangle icosphere standing in for the
-    marching-cubes sphere), RayCaster 512x512, one frame; per-pixel id / t / image parity."""
+    """BASELINE config 1: Sphere -> MarchingCubesSearch(0.01, 8) mesh (376,832 triangles, the
+    product-side mesh is bit-identical to the oracle's restatement of mc.go), RayCaster 512x512,
+    one frame; per-pixel id / t / image parity."""
     from model3d_b200 import render3d as R
     spec = scenes.c1_scene()
+    assert spec["objects"][0]["tris"].shape[0] == 376832
+    assert np.array_equal(spec["objects"][0]["tris"], oracle.mesh_mc_sphere((0, 0, 0), 1.0, 0.01, 8).astype(np.float32))
     osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
     W = H = 512
     cam = spec["camera"]
