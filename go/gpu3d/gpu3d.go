@@ -150,14 +150,7 @@ func (m *MeshCollider) FirstRayCollision(r *model3d.Ray) (model3d.RayCollision, 
 	return out[0], hit[0]
 }
 
-// RayCollisions and SphereCollision are outside the GPU path (SURVEY 8f-2).
-func (m *MeshCollider) RayCollisions(r *model3d.Ray, f func(model3d.RayCollision)) int {
-	panic("gpu3d: RayCollisions is not supported on the GPU path")
-}
-
-func (m *MeshCollider) SphereCollision(c model3d.Coord3D, r float64) bool {
-	panic("gpu3d: SphereCollision is not supported on the GPU path")
-}
+// RayCollisions, SphereCollision, Contains and the SDF queries live in queries.go.
 
 func cvec(v model3d.Coord3D) [3]C.double {
 	return [3]C.double{C.double(v.X), C.double(v.Y), C.double(v.Z)}

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define M3D_ABI_VERSION 2
+#define M3D_ABI_VERSION 3
 
 typedef enum {
   M3D_OK = 0,
@@ -126,11 +126,28 @@ int32_t m3d_mesh_ray_collision_counts(m3d_mesh *mesh, const float *org, const fl
                                       int64_t n, int32_t *counts, m3d_stats *stats);
 
 /* Batched model3d.ColliderContains(c, p, margin) (collisions.go:113-134) and with it
- * ColliderSolid.Contains (model3d/solid.go:256-300): inside[i] = 1 iff an odd number of
- * triangles lies along the reference's fixed probe direction from points[i].  margin must
- * be 0 (other margins need SphereCollision: M3D_ERR_UNSUPPORTED). */
+ * ColliderSolid.Contains (model3d/solid.go:256-300): odd number of triangles along the
+ * reference's fixed probe direction from points[i]; margin > 0 additionally requires that no
+ * triangle is closer than margin, margin < 0 also accepts outside points closer than -margin
+ * (both through the nearest-triangle query below, == Collider.SphereCollision). */
 int32_t m3d_mesh_contains(m3d_mesh *mesh, const float *points, int64_t n, double margin,
                           uint8_t *inside, m3d_stats *stats);
+
+/* Batched MeshToSDF(mesh).FaceSDF / PointSDF / NormalSDF / SDF (model3d/sdf.go:186-311,
+ * Triangle.Closest primitives.go:153-175).  Any output may be NULL.
+ *   sdf     : n floats, distance to the nearest triangle, positive inside
+ *             (ColliderSolid.Contains, solid.go:292-300), negative outside
+ *   closest : n*3 floats, nearest point on the surface
+ *   face    : n int32, triangle id of the nearest face (ties: any of the equidistant faces)
+ *   normal  : n*3 floats, flat normal of that face (meshSDF.NormalSDF)
+ * An empty mesh is M3D_ERR_INVALID_ARG (the reference panics, sdf.go:198-200). */
+int32_t m3d_mesh_sdf(m3d_mesh *mesh, const float *points, int64_t n, float *sdf, float *closest,
+                     int32_t *face, float *normal, m3d_stats *stats);
+
+/* Batched Collider.SphereCollision(centers[i], radii[i]) (model3d/collisions.go:292-303,
+ * primitives.go:253-279): collides[i] = 1 iff some triangle is closer than radii[i]. */
+int32_t m3d_mesh_sphere_collisions(m3d_mesh *mesh, const float *centers, const float *radii,
+                                   int64_t n, uint8_t *collides, m3d_stats *stats);
 
 /* Same query on device-resident SoA buffers (what the renderers use internally
  * and what bench.py times with inputs already in HBM).

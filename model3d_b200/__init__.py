@@ -6,10 +6,12 @@ interface and ``render3d`` renderer interface for that path.
 """
 from . import _native  # noqa: F401
 from .model3d import (BatchCollisions, ColliderContains, ColliderSolid, MeshCollider,  # noqa: F401
-                      MeshToCollider, MeshToInterpNormalCollider, NewColliderSolid, Ray, RayCollision,
+                      MeshSDF, MeshToCollider, MeshToInterpNormalCollider, MeshToSDF, NewColliderSolid,
+                      NewColliderSolidHollow, NewColliderSolidInset, Ray, RayCollision,
                       TriangleCollision, UnsupportedError)
 
 from . import render3d  # noqa: F401,E402
 
 __all__ = ["render3d", "MeshCollider", "MeshToCollider", "MeshToInterpNormalCollider", "Ray", "RayCollision",
-           "TriangleCollision", "BatchCollisions", "UnsupportedError"]
+           "TriangleCollision", "BatchCollisions", "UnsupportedError", "MeshToSDF", "MeshSDF", "ColliderContains",
+           "ColliderSolid", "NewColliderSolid", "NewColliderSolidInset", "NewColliderSolidHollow"]

@@ -2,6 +2,7 @@
 // Replaces model3d.MeshToCollider + Collider.FirstRayCollision
 // (model3d/collisions.go:138-142, 275-290) with a device-resident wide BVH and a
 // batched query.  No CPU fallback: every compute call needs a CUDA device.
+#include <cmath>
 #include <cstring>
 
 #include "api_common.h"
@@ -426,27 +427,45 @@ int32_t m3d_mesh_ray_collision_counts(m3d_mesh *mesh, const float *org, const fl
   return M3D_OK;
 }
 
+static int32_t check_sdf_depth(const m3d_mesh *mesh, const char *who) {
+  if (7 * (int64_t)mesh->info.max_depth + 1 > sdf_stack_capacity())
+    return fail(M3D_ERR_UNSUPPORTED, "%s: BVH depth %d exceeds the nearest-triangle traversal stack", who,
+                mesh->info.max_depth);
+  return M3D_OK;
+}
+
 int32_t m3d_mesh_contains(m3d_mesh *mesh, const float *points, int64_t n, double margin, uint8_t *inside,
                           m3d_stats *stats) {
-  if (!mesh || n < 0 || (n > 0 && (!points || !inside)))
+  if (!mesh || n < 0 || (n > 0 && (!points || !inside)) || margin != margin)
     return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_contains: bad arguments");
-  if (margin != 0)
-    return fail(M3D_ERR_UNSUPPORTED,
-                "ColliderContains with a non-zero margin needs SphereCollision, which is not on the GPU path");
   if (n > (int64_t)0x7ff00000) return fail(M3D_ERR_INVALID_ARG, "batch too large; split it");
+  if (margin != 0) {
+    int32_t rc = check_sdf_depth(mesh, "m3d_mesh_contains");
+    if (rc != M3D_OK) return rc;
+  }
   m3d_ctx *ctx = mesh->ctx;
   M3D_CUDA(cudaSetDevice(ctx->device));
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return M3D_OK;
   cudaStream_t s = ctx->stream;
   const size_t per = (size_t)n;
-  M3D_CUDA(ctx->scratch[9].reserve(per * (3 * sizeof(float) + 1) + 16));
+  M3D_CUDA(ctx->scratch[9].reserve(per * (3 * sizeof(float) + 3) + 64));
   float *d_pts = ctx->scratch[9].as<float>();
   uint8_t *d_inside = (uint8_t *)(d_pts + 3 * per);
+  uint8_t *d_parity = d_inside + per, *d_near = d_parity + per;
   M3D_CUDA(cudaMemcpyAsync(d_pts, points, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
   GpuTimer tm;
   tm.start(s);
-  launch_count_hits(mesh->bvh, d_pts, nullptr, n, nullptr, d_inside, s);
+  int launches = 1;
+  if (margin == 0) {
+    launch_count_hits(mesh->bvh, d_pts, nullptr, n, nullptr, d_inside, s);
+  } else {
+    // collisions.go:127-133: the parity decides which way the sphere test is read
+    launch_count_hits(mesh->bvh, d_pts, nullptr, n, nullptr, d_parity, s);
+    launch_sphere_collisions(mesh->bvh, d_pts, nullptr, (float)std::fabs(margin), n, d_near, s);
+    launch_contains_margin(d_parity, d_near, n, margin < 0, d_inside, s);
+    launches = 3;
+  }
   tm.stop(s);
   M3D_CUDA(cudaMemcpyAsync(inside, d_inside, per, cudaMemcpyDeviceToHost, s));
   M3D_CUDA(cudaStreamSynchronize(s));
@@ -454,8 +473,99 @@ int32_t m3d_mesh_contains(m3d_mesh *mesh, const float *points, int64_t n, double
   if (stats) {
     stats->rays = n;
     stats->kernel_ms = tm.ms();
+    stats->launches = launches;
+    stats->h2d_bytes = n * 12;
+    stats->d2h_bytes = n;
+  }
+  return M3D_OK;
+}
+
+int32_t m3d_mesh_sdf(m3d_mesh *mesh, const float *points, int64_t n, float *sdf, float *closest, int32_t *face,
+                     float *normal, m3d_stats *stats) {
+  if (!mesh || n < 0 || (n > 0 && !points))
+    return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_sdf: bad arguments");
+  if (mesh->info.num_triangles == 0)
+    return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_sdf: cannot create empty SDF");  // sdf.go:198-200 panics
+  if (n > (int64_t)0x7ff00000) return fail(M3D_ERR_INVALID_ARG, "batch too large; split it");
+  int32_t rc = check_sdf_depth(mesh, "m3d_mesh_sdf");
+  if (rc != M3D_OK) return rc;
+  m3d_ctx *ctx = mesh->ctx;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n == 0) return M3D_OK;
+  cudaStream_t s = ctx->stream;
+  const size_t per = (size_t)n;
+  // points | sdf | closest | normal | face
+  M3D_CUDA(ctx->scratch[9].reserve(per * (3 + 1 + 3 + 3 + 1) * sizeof(float) + 64));
+  float *d_pts = ctx->scratch[9].as<float>();
+  float *d_sdf = d_pts + 3 * per, *d_cp = d_sdf + per, *d_nrm = d_cp + 3 * per;
+  int32_t *d_face = (int32_t *)(d_nrm + 3 * per);
+  M3D_CUDA(cudaMemcpyAsync(d_pts, points, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  GpuTimer tm;
+  tm.start(s);
+  launch_mesh_sdf(mesh->bvh, d_pts, n, sdf ? d_sdf : nullptr, closest ? d_cp : nullptr, face ? d_face : nullptr,
+                  normal ? d_nrm : nullptr, s);
+  tm.stop(s);
+  int64_t out_bytes = 0;
+  if (sdf) {
+    M3D_CUDA(cudaMemcpyAsync(sdf, d_sdf, per * 4, cudaMemcpyDeviceToHost, s));
+    out_bytes += n * 4;
+  }
+  if (closest) {
+    M3D_CUDA(cudaMemcpyAsync(closest, d_cp, per * 12, cudaMemcpyDeviceToHost, s));
+    out_bytes += n * 12;
+  }
+  if (normal) {
+    M3D_CUDA(cudaMemcpyAsync(normal, d_nrm, per * 12, cudaMemcpyDeviceToHost, s));
+    out_bytes += n * 12;
+  }
+  if (face) {
+    M3D_CUDA(cudaMemcpyAsync(face, d_face, per * 4, cudaMemcpyDeviceToHost, s));
+    out_bytes += n * 4;
+  }
+  M3D_CUDA(cudaStreamSynchronize(s));
+  M3D_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->rays = n;
+    stats->kernel_ms = tm.ms();
     stats->launches = 1;
     stats->h2d_bytes = n * 12;
+    stats->d2h_bytes = out_bytes;
+  }
+  return M3D_OK;
+}
+
+int32_t m3d_mesh_sphere_collisions(m3d_mesh *mesh, const float *centers, const float *radii, int64_t n,
+                                   uint8_t *collides, m3d_stats *stats) {
+  if (!mesh || n < 0 || (n > 0 && (!centers || !radii || !collides)))
+    return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_sphere_collisions: bad arguments");
+  if (n > (int64_t)0x7ff00000) return fail(M3D_ERR_INVALID_ARG, "batch too large; split it");
+  int32_t rc = check_sdf_depth(mesh, "m3d_mesh_sphere_collisions");
+  if (rc != M3D_OK) return rc;
+  m3d_ctx *ctx = mesh->ctx;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n == 0) return M3D_OK;
+  cudaStream_t s = ctx->stream;
+  const size_t per = (size_t)n;
+  M3D_CUDA(ctx->scratch[9].reserve(per * (4 * sizeof(float) + 1) + 64));
+  float *d_pts = ctx->scratch[9].as<float>();
+  float *d_rad = d_pts + 3 * per;
+  uint8_t *d_out = (uint8_t *)(d_rad + per);
+  M3D_CUDA(cudaMemcpyAsync(d_pts, centers, per * 12, cudaMemcpyHostToDevice, s));
+  M3D_CUDA(cudaMemcpyAsync(d_rad, radii, per * 4, cudaMemcpyHostToDevice, s));
+  GpuTimer tm;
+  tm.start(s);
+  launch_sphere_collisions(mesh->bvh, d_pts, d_rad, 0.f, n, d_out, s);
+  tm.stop(s);
+  M3D_CUDA(cudaMemcpyAsync(collides, d_out, per, cudaMemcpyDeviceToHost, s));
+  M3D_CUDA(cudaStreamSynchronize(s));
+  M3D_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->rays = n;
+    stats->kernel_ms = tm.ms();
+    stats->launches = 1;
+    stats->h2d_bytes = n * 16;
     stats->d2h_bytes = n;
   }
   return M3D_OK;

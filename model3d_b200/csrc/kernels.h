@@ -45,6 +45,18 @@ void launch_unpack_hits(const float4 *hit0, const float4 *hit1, int64_t n, float
 void launch_count_hits(const DeviceBVH &bvh, const float *org3, const float *dir3, int64_t n, int32_t *counts,
                        uint8_t *inside, cudaStream_t stream);
 
+// nearest-triangle queries (sdf_kernels.cu): meshSDF.FaceSDF per point (any output may be null) ...
+void launch_mesh_sdf(const DeviceBVH &bvh, const float *pts3, int64_t n, float *sdf, float *closest3,
+                     int32_t *face, float *normal3, cudaStream_t stream);
+// ... Collider.SphereCollision per (centre, radius); radii == nullptr: one radius for all ...
+void launch_sphere_collisions(const DeviceBVH &bvh, const float *centers3, const float *radii, float radius,
+                              int64_t n, uint8_t *out, cudaStream_t stream);
+// ... and ColliderContains' margin rule from the crossing parity and the sphere test
+void launch_contains_margin(const uint8_t *parity, const uint8_t *near, int64_t n, bool margin_negative,
+                            uint8_t *inside, cudaStream_t stream);
+// deepest wide-BVH the nearest-triangle traversal stack covers (7 entries per level + 1)
+int sdf_stack_capacity();
+
 int device_sm_count();
 
 }  // namespace m3d

@@ -188,8 +188,35 @@ class MeshCollider:
                                           inside.ctypes.data_as(C.POINTER(C.c_uint8)), None))
         return inside.astype(bool)
 
+    def SphereCollisions(self, centers, radii):
+        """Batched Collider.SphereCollision (collisions.go:292-303, primitives.go:253-279):
+        bool [n], some triangle is closer than radii[i] to centers[i]."""
+        pts = np.ascontiguousarray(np.asarray(centers, dtype=np.float32).reshape(-1, 3))
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, dtype=np.float32), pts.shape[:1]))
+        out = np.zeros(pts.shape[0], np.uint8)
+        N.check(N.lib().m3d_mesh_sphere_collisions(self.h, _p(pts, f32p), _p(rad, f32p), C.c_int64(pts.shape[0]),
+                                                   out.ctypes.data_as(C.POINTER(C.c_uint8)), None))
+        return out.astype(bool)
+
     def SphereCollision(self, c, r):
-        raise UnsupportedError("SphereCollision is not on the GPU path")
+        """Collider.SphereCollision: a batch of one."""
+        return bool(self.SphereCollisions([c], [r])[0])
+
+    def FaceSDF(self, coords, want_stats=False):
+        """Batched meshSDF.FaceSDF (sdf.go:229-240) on this collider's hierarchy: (face ids [n],
+        nearest points [n,3], signed distances [n], flat normals [n,3])."""
+        pts = np.ascontiguousarray(np.asarray(coords, dtype=np.float32).reshape(-1, 3))
+        n = pts.shape[0]
+        sdf = np.zeros(n, np.float32)
+        cp = np.zeros((n, 3), np.float32)
+        nrm = np.zeros((n, 3), np.float32)
+        face = np.full(n, -1, np.int32)
+        stats = N.Stats()
+        N.check(N.lib().m3d_mesh_sdf(self.h, _p(pts, f32p), C.c_int64(n), _p(sdf, f32p), _p(cp, f32p),
+                                     _p(face, i32p), _p(nrm, f32p), C.byref(stats) if want_stats else None))
+        if want_stats:
+            return face, cp, sdf, nrm, {k: getattr(stats, k) for k, _ in stats._fields_}
+        return face, cp, sdf, nrm
 
 
 def MeshToCollider(triangles, ctx=None) -> MeshCollider:
@@ -208,29 +235,89 @@ def ColliderContains(c: MeshCollider, coords, margin=0.0):
 
 
 class ColliderSolid:
-    """model3d.ColliderSolid / NewColliderSolid (model3d/solid.go:243-300): a Solid whose
-    Contains is the collider's parity test, batched.  Inset / hollow variants need
-    SphereCollision and are not on the GPU path."""
+    """model3d.ColliderSolid (model3d/solid.go:236-300): a Solid whose Contains is the collider's
+    parity test, batched; NewColliderSolidInset / NewColliderSolidHollow add the margin / shell
+    variants through the nearest-triangle query."""
 
-    def __init__(self, collider: MeshCollider):
+    def __init__(self, collider: MeshCollider, inset=0.0, radius=0.0):
         self.collider = collider
-        self.min, self.max = collider.Min(), collider.Max()
+        cmin, cmax = np.asarray(collider.Min(), np.float64), np.asarray(collider.Max(), np.float64)
+        self.inset, self.radius = float(inset), float(radius)
+        if radius != 0:  # solid.go:274-279
+            self.min, self.max = cmin - radius, cmax + radius
+        elif inset != 0:  # solid.go:265-270
+            self.min = cmin + inset
+            self.max = np.maximum(self.min, cmax - inset)
+        else:
+            self.min, self.max = cmin, cmax
 
     def Min(self):
-        return self.min
+        return tuple(self.min)
 
     def Max(self):
-        return self.max
+        return tuple(self.max)
 
     def Contains(self, coords):
         pts = np.asarray(coords, dtype=np.float32).reshape(-1, 3)
-        mn, mx = np.asarray(self.min, np.float32), np.asarray(self.max, np.float32)
-        inb = np.all((pts >= mn) & (pts <= mx), axis=1)  # InBounds (solid.go:293-295)
+        p64 = pts.astype(np.float64)
+        inb = np.all((p64 >= np.asarray(self.min)) & (p64 <= np.asarray(self.max)), axis=1)  # InBounds (solid.go:293-295)
         out = np.zeros(pts.shape[0], bool)
         if inb.any():
-            out[inb] = self.collider.Contains(pts[inb])
+            if self.radius != 0:
+                out[inb] = self.collider.SphereCollisions(pts[inb], self.radius)
+            else:
+                out[inb] = self.collider.Contains(pts[inb], self.inset)
         return out
 
 
 def NewColliderSolid(c: MeshCollider) -> ColliderSolid:
     return ColliderSolid(c)
+
+
+def NewColliderSolidInset(c: MeshCollider, inset) -> ColliderSolid:
+    """model3d.NewColliderSolidInset (solid.go:260-270)."""
+    return ColliderSolid(c, inset=inset)
+
+
+def NewColliderSolidHollow(c: MeshCollider, r) -> ColliderSolid:
+    """model3d.NewColliderSolidHollow (solid.go:272-279)."""
+    return ColliderSolid(c, radius=r)
+
+
+class MeshSDF:
+    """model3d.MeshToSDF (sdf.go:186-240): a FaceSDF over a triangle mesh, batched.  Every method
+    takes coords [n,3]; distances are positive inside the mesh, negative outside."""
+
+    def __init__(self, collider: MeshCollider):
+        if collider.Info()["num_triangles"] == 0:
+            raise ValueError("cannot create empty SDF")  # sdf.go:198-200
+        self.collider = collider
+
+    def Min(self):
+        return self.collider.Min()
+
+    def Max(self):
+        return self.collider.Max()
+
+    def SDF(self, coords):
+        return self.collider.FaceSDF(coords)[2]
+
+    def PointSDF(self, coords):
+        _, cp, sdf, _ = self.collider.FaceSDF(coords)
+        return cp, sdf
+
+    def NormalSDF(self, coords):
+        _, _, sdf, nrm = self.collider.FaceSDF(coords)
+        return nrm, sdf
+
+    def FaceSDF(self, coords):
+        face, cp, sdf, _ = self.collider.FaceSDF(coords)
+        return face, cp, sdf
+
+
+def MeshToSDF(triangles, ctx=None) -> MeshSDF:
+    """model3d.MeshToSDF (sdf.go:186-191); `triangles` may be an existing MeshCollider (the SDF
+    and the collider share one device hierarchy)."""
+    if isinstance(triangles, MeshCollider):
+        return MeshSDF(triangles)
+    return MeshSDF(MeshCollider(triangles, ctx=ctx))

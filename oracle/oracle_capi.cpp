@@ -11,6 +11,7 @@
 #include "meshgen.hpp"
 #include "render.hpp"
 #include "scene.hpp"
+#include "sdf.hpp"
 
 using namespace orc;
 
@@ -231,6 +232,64 @@ void orc_collider_contains(void *h, const float *pts, int64_t n, uint8_t *inside
       inside[i] = (uint8_t)(hits.size() % 2);
     }
   });
+}
+
+// ---- nearest-triangle queries (sdf.hpp) ---------------------------------------------------
+// MeshToSDF(...).FaceSDF (sdf.go:186-240): signed distance (positive inside), nearest point
+// (n*3 or NULL), face id (n or NULL).
+void orc_collider_sdf(void *h, const float *pts, int64_t n, double *sdf, double *point, int32_t *face,
+                      int nthreads) {
+  auto *m = (MeshCollider *)h;
+  MeshDistFunc mdf(*m);
+  parallel_for(n, nthreads, [&](int64_t b, int64_t e, int) {
+    for (int64_t i = b; i < e; i++) {
+      V3 p;
+      int32_t f;
+      sdf[i] = mdf.face_sdf(V3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), p, f);
+      if (point) point[3 * i] = p.x, point[3 * i + 1] = p.y, point[3 * i + 2] = p.z;
+      if (face) face[i] = f;
+    }
+  });
+}
+// Collider.SphereCollision (collisions.go:292-303, primitives.go:253-279), batched.
+void orc_collider_sphere_collisions(void *h, const float *centers, const double *radii, int64_t n,
+                                    uint8_t *out, int nthreads) {
+  auto *m = (MeshCollider *)h;
+  parallel_for(n, nthreads, [&](int64_t b, int64_t e, int) {
+    for (int64_t i = b; i < e; i++)
+      out[i] = sphere_collision(*m, V3(centers[3 * i], centers[3 * i + 1], centers[3 * i + 2]), radii[i]);
+  });
+}
+// ColliderContains(c, p, margin) (collisions.go:119-134); solid != 0: ColliderSolid.Contains
+// (solid.go:292-300, bounds check first, margin = inset).
+void orc_collider_contains_margin(void *h, const float *pts, int64_t n, double margin, int solid,
+                                  uint8_t *inside, int nthreads) {
+  auto *m = (MeshCollider *)h;
+  parallel_for(n, nthreads, [&](int64_t b, int64_t e, int) {
+    for (int64_t i = b; i < e; i++) {
+      V3 p(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+      bool in = true;
+      if (solid) {
+        V3 mn = m->mn(), mx = m->mx();
+        if (solid == 2) {  // NewColliderSolidInset bounds (solid.go:265-270)
+          V3 iv(margin, margin, margin);
+          mn = add(mn, iv);
+          mx = vmax(mn, sub(m->mx(), iv));
+        }
+        in = !m->empty && vmin(p, mn) == mn && vmax(p, mx) == mx;
+      }
+      inside[i] = in && collider_contains(*m, p, margin);
+    }
+  });
+}
+void orc_triangle_closest(const double tri[9], const double p[3], double out[3]) {
+  Triangle tr = mk_tri(v3(tri), v3(tri + 3), v3(tri + 6));
+  V3 c = tri_closest(tr, v3(p));
+  out[0] = c.x, out[1] = c.y, out[2] = c.z;
+}
+int orc_triangle_sphere_collision(const double tri[9], const double c[3], double r) {
+  Triangle tr = mk_tri(v3(tri), v3(tri + 3), v3(tri + 6));
+  return tri_sphere_collision(tr, v3(c), r);
 }
 
 // Single-triangle test exposed for edge-case tests (primitives.go:181-249).

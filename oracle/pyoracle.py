@@ -156,6 +156,20 @@ def mc_table():
     return counts, corners
 
 
+def triangle_closest(tri, p):
+    """Triangle.Closest (primitives.go:153-175)."""
+    tri = np.ascontiguousarray(tri, np.float64).reshape(9)
+    out = np.empty(3, np.float64)
+    lib().orc_triangle_closest(_p(tri, f64p), _d3(p), _p(out, f64p))
+    return out
+
+
+def triangle_sphere_collision(tri, c, r):
+    """Triangle.SphereCollision (primitives.go:253-279)."""
+    tri = np.ascontiguousarray(tri, np.float64).reshape(9)
+    return bool(lib().orc_triangle_sphere_collision(_p(tri, f64p), _d3(c), C.c_double(r)))
+
+
 def mesh_polar(ra, rb, stops):
     cnt = lib().orc_mesh_polar_count(C.c_int(stops))
     out = np.empty((cnt, 3, 3), np.float64)
@@ -229,6 +243,35 @@ class Collider:
         lib().orc_collider_hit_counts(self.h, _p(org, f32p), _p(dir, f32p), C.c_int64(org.shape[0]),
                                       _p(out, i32p), C.c_int(threads))
         return out
+
+    def sdf(self, pts, threads=1):
+        """MeshToSDF(mesh).FaceSDF per point (sdf.go:229-240): (sdf, nearest point, face id)."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        n = pts.shape[0]
+        sdf = np.empty(n, np.float64)
+        point = np.empty((n, 3), np.float64)
+        face = np.empty(n, np.int32)
+        lib().orc_collider_sdf(self.h, _p(pts, f32p), C.c_int64(n), _p(sdf, f64p), _p(point, f64p),
+                               _p(face, i32p), C.c_int(threads))
+        return sdf, point, face
+
+    def sphere_collisions(self, centers, radii, threads=1):
+        """Collider.SphereCollision per (center, radius) (collisions.go:292-303)."""
+        centers = np.ascontiguousarray(centers, np.float32)
+        radii = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, np.float64), centers.shape[:1]))
+        out = np.empty(centers.shape[0], np.uint8)
+        lib().orc_collider_sphere_collisions(self.h, _p(centers, f32p), _p(radii, f64p),
+                                             C.c_int64(centers.shape[0]), _p(out, u8p), C.c_int(threads))
+        return out.astype(bool)
+
+    def contains_margin(self, pts, margin, solid=0, threads=1):
+        """ColliderContains(c, p, margin) (collisions.go:119-134); solid=1: ColliderSolid.Contains of
+        NewColliderSolid, solid=2: of NewColliderSolidInset(c, margin) (solid.go:256-300)."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        out = np.empty(pts.shape[0], np.uint8)
+        lib().orc_collider_contains_margin(self.h, _p(pts, f32p), C.c_int64(pts.shape[0]), C.c_double(margin),
+                                           C.c_int(solid), _p(out, u8p), C.c_int(threads))
+        return out.astype(bool)
 
     def contains(self, pts, threads=1):
         pts = np.ascontiguousarray(pts, np.float32)

@@ -259,10 +259,8 @@ def test_ray_collision_counts_and_contains(built, oracle):
     assert col.RayCollisions(Ray((0.1, -0.2, 0.05), (0.3, 0.2, 1))) == 1  # generic direction (no vertex tie)
     with pytest.raises(UnsupportedError):
         col.RayCollisions(Ray((0, 0, 0), (0, 0, 1)), f=lambda c: None)
-    from model3d_b200 import _native as N
-    with pytest.raises(N.M3DError) as ei:
-        col.Contains(pts[:4], margin=0.1)
-    assert ei.value.code == 2
+    # margins go through the nearest-triangle query (tests/test_gpu_sdf.py)
+    assert np.array_equal(col.Contains(pts[:1000], margin=0.1), ocol.contains_margin(pts[:1000], 0.1, threads=8))
 
 
 @pytest.mark.parametrize("n_sub", [1, 7, 40])
