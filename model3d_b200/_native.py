@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm3dgpu.so")
+# M3D_LIB: another build of the same library (kernel tuning runs, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("M3D_LIB") or os.path.join(_HERE, "libm3dgpu.so")
 
 M3D_OK = 0
 ERR_NAMES = {1: "INVALID_ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "OOM"}

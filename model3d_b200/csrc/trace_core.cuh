@@ -234,6 +234,12 @@ struct RayPre {
   uint32_t octinv4;     // (7 - octant) replicated in four bytes; bit 2/1/0 clear <=> dx/dy/dz < 0
 };
 
+// (7 - octant) of a direction replicated in four bytes
+M3D_HD uint32_t ray_octinv4(float dx, float dy, float dz) {
+  const uint32_t octinv = ((dx < 0.f ? 0u : 4u) | (dy < 0.f ? 0u : 2u) | (dz < 0.f ? 0u : 1u));
+  return octinv * 0x01010101u;
+}
+
 // scene_min/max: bounds of all triangle vertices (for the error bound: no vertex is
 // farther than Dmax from the origin in the infinity norm).
 M3D_HD RayPre precompute_ray(const RayF &ray, const float *scene_min, const float *scene_max) {
@@ -254,8 +260,7 @@ M3D_HD RayPre precompute_ray(const RayF &ray, const float *scene_min, const floa
                            fmaxf(fabsf(ray.oy - scene_min[1]), fabsf(ray.oy - scene_max[1])),
                            fmaxf(fabsf(ray.oz - scene_min[2]), fabsf(ray.oz - scene_max[2])));
   rp.err = 3e-6f * dmax * sqrtf(ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz);
-  const uint32_t octinv = ((ray.dx < 0.f ? 0u : 4u) | (ray.dy < 0.f ? 0u : 2u) | (ray.dz < 0.f ? 0u : 1u));
-  rp.octinv4 = octinv * 0x01010101u;
+  rp.octinv4 = ray_octinv4(ray.dx, ray.dy, ray.dz);
   return rp;
 }
 

@@ -20,7 +20,14 @@ constexpr int kWarpsPerBlock = kTraceBlock / 32;
 constexpr int kSmemStack = 10;    // stack entries per thread kept in shared memory
 constexpr int kLocalStack = 54;   // overflow entries (local memory; untouched for sane trees)
 constexpr int kRayBatch = 32 * 6; // rays a warp claims per global atomic
-constexpr bool kPrefetchL1 = false;  // measured: no gain on B200 (rays are already L2-prefetched per batch)
+#ifndef M3D_PREFETCH_NEXT_NODE
+#define M3D_PREFETCH_NEXT_NODE 0  // measured on B200: 2.58 -> 3.98 ms per 2^24 rays (L1 prefetches throttle the LSU)
+#endif
+constexpr bool kPrefetchNextNode = M3D_PREFETCH_NEXT_NODE != 0;
+#ifndef M3D_PREFETCH_QUEUED_TRI
+#define M3D_PREFETCH_QUEUED_TRI 0
+#endif
+constexpr bool kPrefetchQueuedTri = M3D_PREFETCH_QUEUED_TRI != 0;
 
 // Persistent-warp traversal with dynamic ray fetch.
 //
@@ -36,6 +43,7 @@ template <bool COUNT, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kTraceBlock, MIN_BLOCKS)
 trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ ray_counter) {
   __shared__ uint2 s_stack[kSmemStack][kTraceBlock];
+  __shared__ float4 s_stage[3][kTraceBlock];  // per warp: 32 prepared rays (origin|tmin, dir|tmax, 1/dir|err)
   uint2 l_stack[kLocalStack];
   const unsigned lane = threadIdx.x & 31u;
   const uint4 *__restrict__ nodes = bvh.nodes;
@@ -43,6 +51,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
   const int n = p.n_ptr ? min(__ldg(p.n_ptr), (int)p.n) : (int)p.n;
 
   int batch_next = 0, batch_end = 0;  // warp-uniform; batch_end < 0: the global counter ran past n
+  int stage_base = 0, stage_cnt = 0, stage_pos = 0;  // warp-uniform: staged rays [stage_pos, stage_cnt)
   int ray_idx = -1;                   // < 0: the lane has no ray
   RayPre rp;
   float tmax = 0.f;
@@ -57,33 +66,62 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
 
   for (;;) {
     // ---- refill idle lanes ----------------------------------------------------------
+    // Rays are prepared 32 at a time by the whole warp (coalesced loads, precompute_ray at full
+    // lane utilisation) into a shared-memory stage; a lane that finishes its ray only pops the
+    // next staged entry.  Per-lane refills ran the same ~140 instructions on ~5 of 32 lanes in
+    // almost every trip of the loop (ncu source view: 27 % of all issued instructions).
     const unsigned need = __ballot_sync(0xffffffffu, ray_idx < 0);
     if (need) {
-      if (batch_next >= batch_end && batch_end >= 0) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(ray_counter, (unsigned)kRayBatch);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= (unsigned)n) {
-          batch_end = -1;
-        } else {
-          batch_next = (int)base;
-          batch_end = (int)base + kRayBatch < n ? (int)base + kRayBatch : n;
-          // pull the batch's rays towards the SM now; lanes pick them up one by one later
-          for (int r = batch_next + 4 * (int)lane; r < batch_end; r += 128) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.org_tmin + r));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dir_tmax + r));
+      if (stage_pos >= stage_cnt && batch_end >= 0) {
+        if (batch_next >= batch_end) {
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(ray_counter, (unsigned)kRayBatch);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (base >= (unsigned)n) {
+            batch_end = -1;
+          } else {
+            batch_next = (int)base;
+            batch_end = (int)base + kRayBatch < n ? (int)base + kRayBatch : n;
+            // pull the batch's rays towards the SM now; they are staged 32 at a time later
+            for (int r = batch_next + 4 * (int)lane; r < batch_end; r += 128) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.org_tmin + r));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dir_tmax + r));
+            }
           }
         }
+        if (batch_end >= 0) {
+          const int cnt = batch_end - batch_next < 32 ? batch_end - batch_next : 32;
+          __syncwarp();  // every lane has consumed its entry of the previous stage
+          if ((int)lane < cnt) {
+            const int idx = batch_next + (int)lane;
+            const float4 o = __ldcs(p.org_tmin + idx);  // streaming: keep the BVH in L2
+            const float4 d = __ldcs(p.dir_tmax + idx);
+            RayF ray;
+            ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmin = o.w;
+            ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.tmax = d.w;
+            const RayPre r = precompute_ray(ray, bvh.bmin, bvh.bmax);
+            s_stage[0][threadIdx.x] = o;
+            s_stage[1][threadIdx.x] = d;
+            s_stage[2][threadIdx.x] = make_float4(r.idx, r.idy, r.idz, r.err);
+          }
+          __syncwarp();
+          stage_base = batch_next;
+          stage_cnt = cnt;
+          stage_pos = 0;
+          batch_next += cnt;
+        }
       }
+      const int avail = stage_cnt - stage_pos;
       if (ray_idx < 0) {
-        const int idx = batch_next + __popc(need & ((1u << lane) - 1u));
-        if (idx < batch_end) {
-          const float4 o = __ldcs(p.org_tmin + idx);  // streaming: keep the BVH in L2
-          const float4 d = __ldcs(p.dir_tmax + idx);
-          RayF ray;
-          ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmin = o.w;
-          ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.tmax = d.w;
-          rp = precompute_ray(ray, bvh.bmin, bvh.bmax);
+        const int rank = __popc(need & ((1u << lane) - 1u));
+        if (rank < avail) {
+          const int e = (int)(threadIdx.x & ~31u) + stage_pos + rank;
+          const float4 o = s_stage[0][e], d = s_stage[1][e], c = s_stage[2][e];
+          const int idx = stage_base + stage_pos + rank;
+          rp.ox = o.x; rp.oy = o.y; rp.oz = o.z; rp.tmin = o.w;
+          rp.d = mk3(d.x, d.y, d.z);
+          rp.idx = c.x; rp.idy = c.y; rp.idz = c.z; rp.err = c.w;
+          rp.octinv4 = ray_octinv4(d.x, d.y, d.z);
           tmax = d.w;
           hit_tri = -1;
           skip_tri = p.skip_tris ? __ldg(p.skip_tris + idx) : -1;
@@ -97,17 +135,9 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
           ray_idx = idx;
         }
       }
-      batch_next += __popc(need);
-      // the rays the warp will pick up during its next few iterations: L2 -> L1 now, so that
-      // their first use does not stall a 6-lane divergent section for an L2 round trip
-      if (kPrefetchL1) {
-        const int r = batch_next + (int)lane;
-        if (r < batch_end) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.org_tmin + r));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.dir_tmax + r));
-        }
-      }
-      if (batch_end < 0 && __ballot_sync(0xffffffffu, ray_idx >= 0) == 0u) break;
+      const int want = __popc(need);
+      stage_pos += want < avail ? want : avail;
+      if (batch_end < 0 && stage_pos >= stage_cnt && __ballot_sync(0xffffffffu, ray_idx >= 0) == 0u) break;
     }
 
     if (ray_idx >= 0) {
@@ -130,10 +160,24 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
         if (COUNT) cnt.nodes++;
         uint2 tnew;
         intersect_node(nodes, node_index, rp, tmax, ngroup, tnew);
-        if (tq.y == 0u)
+        if (tq.y == 0u) {
           tq = tnew;
-        else
+        } else {
           tq2 = tnew;
+          if (kPrefetchQueuedTri && tnew.y) {
+            // this leaf waits behind another one for at least a trip: pull its first triangle in
+            const float4 *tp = tris + (size_t)(tnew.x + (uint32_t)bfind32(tnew.y)) * 3;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(tp));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + 2));
+          }
+        }
+        if (kPrefetchNextNode && (ngroup.y & 0xff000000u)) {
+          // the child the next trip descends into: L2 -> L1 while the triangle phase runs
+          uint2 g = ngroup;
+          const uint4 *nn = nodes + (size_t)take_nearest_child(g, rp.octinv4) * 5;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(nn));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(nn + 4));
+        }
       }
       // ---- phase B: one triangle test for every lane that has one pending --------------
       // (a per-lane "while" here ran at 2.2 of 32 lanes; one test per trip of the common
