@@ -3,6 +3,7 @@
 // (model3d/collisions.go:138-142, 275-290) with a device-resident wide BVH and a
 // batched query.  No CPU fallback: every compute call needs a CUDA device.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "api_common.h"
@@ -261,6 +262,8 @@ int32_t m3d_mesh_first_ray_collisions_device(m3d_mesh *mesh, const void *d_org_t
   return M3D_OK;
 }
 
+static constexpr int kMaxPipeBuf = 8;
+
 int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const float *dir, int64_t n,
                                       float *t, int32_t *prim, float *normal, float *bary,
                                       uint32_t flags, m3d_stats *stats) {
@@ -272,8 +275,21 @@ int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const fl
   if (n == 0) return M3D_OK;
 
   // Chunked 3-stage pipeline: H2D (copy_in) -> pack + trace + unpack (stream) -> D2H (copy_out).
-  const int64_t kChunk = 1 << 21;
-  const int nbuf = 2;
+  // Three stages need three buffers in flight to overlap fully (a fourth absorbs jitter); small
+  // chunks keep the exposed pipeline fill (first H2D) and drain (last kernels + D2H) short.
+  // M3D_PIPE_CHUNK_LOG2 / M3D_PIPE_NBUF override both for tuning runs.
+  static int64_t kChunk = 0;
+  static int nbuf = 0;
+  if (!kChunk) {
+    const char *e = getenv("M3D_PIPE_CHUNK_LOG2");
+    int lg = e ? atoi(e) : 20;
+    if (lg < 14 || lg > 24) lg = 20;
+    const char *f = getenv("M3D_PIPE_NBUF");
+    int nb = f ? atoi(f) : 4;
+    if (nb < 2 || nb > kMaxPipeBuf) nb = 4;
+    nbuf = nb;
+    kChunk = (int64_t)1 << lg;
+  }
   // per buffer: org3, dir3, org4, dir4, hit0, hit1, out_t, out_prim, out_normal, out_bary
   const size_t per = (size_t)kChunk;
   const size_t sz_in3 = per * 3 * sizeof(float), sz_f4 = per * sizeof(float4);
@@ -282,7 +298,7 @@ int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const fl
   const int64_t chunk = n < kChunk ? n : kChunk;
   (void)chunk;
   M3D_CUDA(ctx->scratch[0].reserve(per_buf * nbuf));
-  cudaEvent_t ev_in[nbuf], ev_k[nbuf], ev_out[nbuf];
+  cudaEvent_t ev_in[kMaxPipeBuf], ev_k[kMaxPipeBuf], ev_out[kMaxPipeBuf];
   for (int b = 0; b < nbuf; b++) {
     cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming);

@@ -15,11 +15,17 @@ namespace m3d {
 
 namespace {
 
-constexpr int kTraceBlock = 128;
+#ifndef M3D_TRACE_BLOCK
+#define M3D_TRACE_BLOCK 128
+#endif
+#ifndef M3D_RAY_BATCH
+#define M3D_RAY_BATCH (32 * 6)
+#endif
+constexpr int kTraceBlock = M3D_TRACE_BLOCK;
 constexpr int kWarpsPerBlock = kTraceBlock / 32;
 constexpr int kSmemStack = 10;    // stack entries per thread kept in shared memory
 constexpr int kLocalStack = 54;   // overflow entries (local memory; untouched for sane trees)
-constexpr int kRayBatch = 32 * 6; // rays a warp claims per global atomic
+constexpr int kRayBatch = M3D_RAY_BATCH;  // rays a warp claims per global atomic
 #ifndef M3D_PREFETCH_NEXT_NODE
 #define M3D_PREFETCH_NEXT_NODE 0  // measured on B200: 2.58 -> 3.98 ms per 2^24 rays (L1 prefetches throttle the LSU)
 #endif
@@ -40,7 +46,7 @@ constexpr bool kPrefetchQueuedTri = M3D_PREFETCH_QUEUED_TRI != 0;
 // The trace kernel only writes the raw float32 hit (t, b1, b2, triangle index);
 // finish_hits_kernel re-evaluates hits in float64 in a separate, fully coherent pass.
 template <bool COUNT, int MIN_BLOCKS>
-__global__ void __launch_bounds__(kTraceBlock, MIN_BLOCKS)
+__global__ void __launch_bounds__(kTraceBlock, (MIN_BLOCKS * 128) / kTraceBlock)
 trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ ray_counter) {
   __shared__ uint2 s_stack[kSmemStack][kTraceBlock];
   __shared__ float4 s_stage[3][kTraceBlock];  // per warp: 32 prepared rays (origin|tmin, dir|tmax, 1/dir|err)
@@ -49,6 +55,15 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
   const uint4 *__restrict__ nodes = bvh.nodes;
   const float4 *__restrict__ tris = bvh.tris;
   const int n = p.n_ptr ? min(__ldg(p.n_ptr), (int)p.n) : (int)p.n;
+  // Rays a warp claims per global atomic: kRayBatch for big launches; small launches (pipeline
+  // chunks, late bounces of the wavefront renderers) use smaller batches so that every resident
+  // warp gets work instead of a few warps walking 192 rays each.
+  int ray_batch = kRayBatch;
+  {
+    const int warps = (int)gridDim.x * kWarpsPerBlock;
+    const int fair = (n / (2 * warps) + 31) & ~31;
+    ray_batch = fair < 32 ? 32 : (fair < kRayBatch ? fair : kRayBatch);
+  }
 
   int batch_next = 0, batch_end = 0;  // warp-uniform; batch_end < 0: the global counter ran past n
   int stage_base = 0, stage_cnt = 0, stage_pos = 0;  // warp-uniform: staged rays [stage_pos, stage_cnt)
@@ -75,13 +90,13 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
       if (stage_pos >= stage_cnt && batch_end >= 0) {
         if (batch_next >= batch_end) {
           unsigned base = 0;
-          if (lane == 0) base = atomicAdd(ray_counter, (unsigned)kRayBatch);
+          if (lane == 0) base = atomicAdd(ray_counter, (unsigned)ray_batch);
           base = __shfl_sync(0xffffffffu, base, 0);
           if (base >= (unsigned)n) {
             batch_end = -1;
           } else {
             batch_next = (int)base;
-            batch_end = (int)base + kRayBatch < n ? (int)base + kRayBatch : n;
+            batch_end = (int)base + ray_batch < n ? (int)base + ray_batch : n;
             // pull the batch's rays towards the SM now; they are staged 32 at a time later
             for (int r = batch_next + 4 * (int)lane; r < batch_end; r += 128) {
               asm volatile("prefetch.global.L2 [%0];" ::"l"(p.org_tmin + r));
