@@ -263,6 +263,127 @@ def run_path(args):
         dist.destroy_process_group()
 
 
+C1_WORKLOAD = ("C1 model3d.Sphere -> MarchingCubesSearch(0.01, 8) mesh (376,832 triangles) rendered by "
+               "render3d.RayCaster 512x512 in the SaveRendering setup, one frame per step")
+
+
+def run_c1(args):
+    """BASELINE configs[0]: one RayCaster frame per step (raygen + first-hit traversal + float64
+    finish + Phong shading).  N GPUs: row bands, one frame each per step, gathered by summing the
+    zero-initialised band images (NCCL reduce), inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    from model3d_b200 import _native as N, distributed as D, examples, render3d as R
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    N.default_context(local_rank)
+    spec = examples.c1_scene()
+    psc = examples.build_product(spec)
+    W = H = 512
+    cam = spec["camera"]
+    lt = spec["lights"][0]
+    rc = R.RayCaster(Camera=R.NewCameraAt(cam["src"], cam["dst"], cam["fov"]),
+                     Lights=[R.PointLight(lt["origin"], lt["color"])])
+    band = (rank * H // world, (rank + 1) * H // world)
+    acc = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    ts = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(ts)
+    launches = [0]
+
+    def step():
+        acc.zero_()
+        st = rc.RenderDevice(W, H, psc, acc.data_ptr(), partition=band, stream=ts.cuda_stream)
+        launches[0] = st["launches"]
+        D.reduce_sums(acc, dst=0)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    if rank == 0:
+        e2e = None
+        if world == 1 and not args.no_e2e:
+            img = R.Image(W, H)
+            rc.Render(img, psc)
+            t0 = time.perf_counter()
+            k = max(3, args.steps // 4)
+            for _ in range(k):
+                rc.Render(img, psc)
+            dt = (time.perf_counter() - t0) / k
+            e2e = {"value": W * H / dt / 1e6, "unit": "Mrays/s", "ms_per_step": dt * 1e3,
+                   "h2d_bytes_per_step": W * H * 12, "d2h_bytes_per_step": W * H * 12,
+                   "api": "m3d_render_raycast (host image buffer in and out)"}
+        line = {"metric": "first_hit_Mrays_per_s", "value": W * H / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": C1_WORKLOAD, "width": W, "height": H, "triangles": 376832,
+                           "frames_per_s": 1e3 / ms_step, "sharding": "row bands, NCCL reduce of the band images",
+                           "l2": "the 262,144-ray frame and the 21 MB BVH fit in L2; a launch-latency-bound case"},
+                "clocks": clocks, "gpu_launches": int(launches[0]) * args.steps}
+        if e2e:
+            line["e2e"] = e2e
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_c1(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenes
+    from oracle import pyoracle as O
+    threads = O.hardware_threads()
+    spec = scenes.c1_scene()
+    osc = scenes.build_oracle(spec)
+    cam = spec["camera"]
+    ocam = O.camera_at(cam["src"], cam["dst"], cam["fov"])
+    lt = spec["lights"][0]
+    ol = O.PointLight()
+    ol.origin[:], ol.color[:], ol.quad_dropoff = lt["origin"], lt["color"], 0
+    W = H = 512
+    k = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(k):
+        osc.render_raycast(ocam, [ol], W, H, threads=threads)
+    dt = (time.perf_counter() - t0) / k
+    rate = W * H / dt / 1e6
+    line = {"impl": "reference", "metric": "first_hit_Mrays_per_s", "value": rate, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": C1_WORKLOAD},
+            "cpu_baseline": {"value": rate, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                             "sample": "the full 512x512 frame per step"},
+            "e2e": {"value": rate, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference_path(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -367,8 +488,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the short path-tracing measurements appended to the headline line")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
-                    help="c2: raw first-hit ray batch (headline); c3: cornell_box RecursiveRayTracer 1024x1024; "
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="c2: raw first-hit ray batch (headline); c1: marching-cubes sphere, RayCaster 512x512; "
+                         "c3: cornell_box RecursiveRayTracer 1024x1024; c4: showcase HD; "
                          "c5: cornell_box BidirPathTracer 1024x1024")
     ap.add_argument("--spp", type=int, default=256, help="samples per pixel per step (c3)")
     ap.add_argument("--size", type=int, default=1024, help="frame width == height (c3)")
@@ -376,11 +498,16 @@ def main():
     if args.impl == "reference":
         if args.workload in ("c3", "c4", "c5"):
             run_reference_path(args)
+        elif args.workload == "c1":
+            run_reference_c1(args)
         else:
             run_reference(args)
         return
     if args.workload in ("c3", "c4", "c5"):
         run_path(args)
+        return
+    if args.workload == "c1":
+        run_c1(args)
         return
 
     import torch

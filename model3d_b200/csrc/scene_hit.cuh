@@ -212,6 +212,8 @@ struct SceneHit {
 
 // o = (origin, tmin), d = (direction, tmax); raw = trace_first_hit_kernel's output
 // (t_f32, -, -, bits(leaf-order triangle | -1)); skip = surface the ray starts on.
+// SHAPES = false compiles the analytic-shape part out (mesh colliders: a third of the registers).
+template <bool SHAPES = true>
 __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, float4 d, float4 raw, int skip,
                                              bool refine) {
   SceneHit h;
@@ -285,7 +287,7 @@ __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, fl
     }
     best_obj = obj;
   }
-  if (sc.num_shapes > 0) {
+  if (SHAPES && sc.num_shapes > 0) {
     const D3 od = d3(o.x, o.y, o.z), dd = d3(d.x, d.y, d.z);
     const double t_hi = (double)d.w;  // ray tmax (shadow / visibility rays)
     const double inv_len = 1.0 / dnorm(dd);

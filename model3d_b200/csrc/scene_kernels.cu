@@ -17,20 +17,23 @@ namespace m3d {
 
 namespace {
 
-__global__ void __launch_bounds__(256)
+// SHAPES = false: the scene is one triangle BVH (MeshCollider batches, the C2 headline): misses
+// need no ray, and the kernel stays at half the registers of the general one.
+template <bool SHAPES>
+__global__ void __launch_bounds__(256, SHAPES ? 1 : 4)
 finish_scene_hits_kernel(DeviceScene sc, SceneTraceLaunch sp) {
   const TraceLaunch &p = sp.t;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= p.n) return;
-  const float4 raw = p.hit0[i];
-  const bool need_ray = __float_as_int(raw.w) >= 0 || sc.num_shapes > 0;
+  const float4 raw = __ldcs(p.hit0 + i);
+  const bool need_ray = __float_as_int(raw.w) >= 0 || (SHAPES && sc.num_shapes > 0);
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 1.f, 0.f);
   if (need_ray) {
     o = __ldcs(p.org_tmin + i);
     d = __ldcs(p.dir_tmax + i);
   }
-  const int skip = sp.skip_ids ? sp.skip_ids[i] : -1;
-  const SceneHit h = resolve_scene_hit(sc, o, d, raw, skip, p.refine);
+  const int skip = (SHAPES && sp.skip_ids) ? sp.skip_ids[i] : -1;
+  const SceneHit h = resolve_scene_hit<SHAPES>(sc, o, d, raw, skip, p.refine);
   __stcs(p.hit0 + i, make_float4(h.t, h.b1, h.b2, __int_as_float(h.prim)));
   __stcs(p.hit1 + i, make_float4(h.nx, h.ny, h.nz, __int_as_float(h.obj)));
   if (sp.surf_ids) sp.surf_ids[i] = h.surf;
@@ -96,7 +99,11 @@ __global__ void finalize_image_kernel(const float *__restrict__ sum, int64_t n, 
 
 void launch_finish_scene_hits(const DeviceScene &scene, const SceneTraceLaunch &p, cudaStream_t stream) {
   if (p.t.n <= 0) return;
-  finish_scene_hits_kernel<<<(unsigned)((p.t.n + 255) / 256), 256, 0, stream>>>(scene, p);
+  const unsigned blocks = (unsigned)((p.t.n + 255) / 256);
+  if (scene.num_shapes > 0)
+    finish_scene_hits_kernel<true><<<blocks, 256, 0, stream>>>(scene, p);
+  else
+    finish_scene_hits_kernel<false><<<blocks, 256, 0, stream>>>(scene, p);
 }
 
 void launch_raygen_camera(const DeviceCamera &cam, int W, int row_begin, int row_end, float4 *org_tmin,

@@ -503,6 +503,21 @@ class RayCaster:
         img.Data = data
         return {k: getattr(stats, k) for k, _ in stats._fields_}
 
+    def RenderDevice(self, width, height, obj, d_rgb, partition=None, stream=0):
+        """Render into a device buffer (pointer to W*H*3 float32; pixels whose ray misses keep
+        their value, raycast.go:26-28): what a multi-GPU driver gathers by row band."""
+        sc = _as_scene(obj)
+        cam = self.Camera._c()
+        stats = N.Stats()
+        part = None
+        if partition is not None:
+            part = N.Partition(int(partition[0]), int(partition[1]), 0)
+        N.check(N.lib().m3d_render_raycast_device(
+            sc.h, C.byref(cam), _lights(self.Lights), C.c_int32(len(self.Lights)), C.c_int32(width),
+            C.c_int32(height), C.byref(part) if part is not None else None, C.c_void_p(d_rgb),
+            C.c_void_p(stream or None), C.byref(stats)))
+        return {k: getattr(stats, k) for k, _ in stats._fields_}
+
 
 # ---- focus points (focus_point.go) ----------------------------------------------------------
 @dataclass(eq=False)
