@@ -519,8 +519,9 @@ int32_t m3d_mesh_sdf(m3d_mesh *mesh, const float *points, int64_t n, float *sdf,
   M3D_CUDA(cudaMemcpyAsync(d_pts, points, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
   GpuTimer tm;
   tm.start(s);
+  unsigned long long *counters = stats ? stats_counters(ctx, s) : nullptr;  // work counters ride along with stats
   launch_mesh_sdf(mesh->bvh, d_pts, n, sdf ? d_sdf : nullptr, closest ? d_cp : nullptr, face ? d_face : nullptr,
-                  normal ? d_nrm : nullptr, s);
+                  normal ? d_nrm : nullptr, counters, s);
   tm.stop(s);
   int64_t out_bytes = 0;
   if (sdf) {
@@ -547,6 +548,13 @@ int32_t m3d_mesh_sdf(m3d_mesh *mesh, const float *points, int64_t n, float *sdf,
     stats->launches = 1;
     stats->h2d_bytes = n * 12;
     stats->d2h_bytes = out_bytes;
+    if (counters) {
+      unsigned long long c[3] = {0, 0, 0};
+      cudaMemcpy(c, counters, sizeof(c), cudaMemcpyDeviceToHost);
+      stats->nodes_visited = (int64_t)c[0];
+      stats->tris_tested = (int64_t)c[1];
+      stats->hits = (int64_t)c[2];  // float64 Triangle.Closest evaluations
+    }
   }
   return M3D_OK;
 }

@@ -46,8 +46,9 @@ void launch_count_hits(const DeviceBVH &bvh, const float *org3, const float *dir
                        uint8_t *inside, cudaStream_t stream);
 
 // nearest-triangle queries (sdf_kernels.cu): meshSDF.FaceSDF per point (any output may be null) ...
+// (counters: optional device 3 x u64: nodes fetched, float32 screens, float64 evaluations)
 void launch_mesh_sdf(const DeviceBVH &bvh, const float *pts3, int64_t n, float *sdf, float *closest3,
-                     int32_t *face, float *normal3, cudaStream_t stream);
+                     int32_t *face, float *normal3, unsigned long long *counters, cudaStream_t stream);
 // ... Collider.SphereCollision per (centre, radius); radii == nullptr: one radius for all ...
 void launch_sphere_collisions(const DeviceBVH &bvh, const float *centers3, const float *radii, float radius,
                               int64_t n, uint8_t *out, cudaStream_t stream);

@@ -9,11 +9,13 @@
 // the point to the (outward-rounded, hence conservative) quantised child boxes and prunes with
 // the best distance found so far (the reference prunes a binary tree the same way,
 // sdf.go:289-310).  Triangles are screened with a float32 closest-point test (Ericson's
-// region walk); every candidate that could beat the current best within the float32 error
-// band is then evaluated in float64 with the reference's own arithmetic (matrix inverse for
-// the interior case, NewSegment-ordered segment projections for the edges), and the running
-// minimum is kept in float64.  The result is therefore the float64 minimum over all triangles:
-// it equals the reference's except for which face wins an exact tie (shared edges/vertices).
+// region walk), one triangle per trip for all lanes that have one pending; the four triangles
+// with the smallest screened distances are kept, and those within the float32 error band of the
+// best are evaluated at the end -- by all lanes together -- in float64 with the reference's own
+// arithmetic (matrix inverse for the interior case, NewSegment-ordered segment projections for
+// the edges).  The result equals the reference's float64 minimum except (a) which face wins a
+// tie on a shared edge / vertex and (b) when more than four distinct triangles lie within the
+// float32 band (~1e-6 of the scene extent) of the minimum, where it may exceed it by that band.
 #include <cfloat>
 
 #include "kernels.h"
@@ -150,29 +152,46 @@ struct NearestResult {
   double dist;   // +inf: nothing within the initial bound
   double cp[3];
   int tri;       // leaf-order triangle index, -1 none
+  unsigned nodes, screened, exact;  // work counters: nodes fetched, float32 screens, float64 evaluations
 };
 
+constexpr int kCand = 4;  // float32 near-ties kept for the float64 decision
+
 // Nearest triangle within `bound` (exclusive, like Triangle.SphereCollision's `< r`; +inf for
-// the SDF).  ANY: stop at the first triangle closer than the bound.
+// the SDF).  The traversal runs entirely in float32: it keeps the kCand triangles with the
+// smallest screened distances (everything within the float32 error band of the best), and
+// only those are evaluated in float64 at the end, by all lanes of the warp together.  ANY
+// (SphereCollision): stop as soon as a triangle is closer than the bound by more than the band.
 template <bool ANY>
 __device__ __forceinline__ void nearest_triangle(const DeviceBVH &bvh, float px, float py, float pz, double bound,
                                                  NearestResult &res, uint2 *stack) {
   res.dist = bound;
   res.tri = -1;
   res.cp[0] = res.cp[1] = res.cp[2] = 0.0;
+  res.nodes = res.screened = res.exact = 0u;
   if (bvh.num_tris <= 0) return;
   // absolute float32 error scale of a distance: a few ulp of the largest coordinate difference
   const float big = max3f(fmaxf(fabsf(px - bvh.bmin[0]), fabsf(px - bvh.bmax[0])),
                           fmaxf(fabsf(py - bvh.bmin[1]), fabsf(py - bvh.bmax[1])),
                           fmaxf(fabsf(pz - bvh.bmin[2]), fabsf(pz - bvh.bmax[2])));
-  const float band = 4e-6f * big;
-  // float32 pruning radius: best distance rounded up plus the band
-  float prune = isinf(bound) ? INFINITY : __double2float_ru(bound) * 1.000001f + band;
+  const float band = 2e-6f * big;
+  const float fbound = isinf(bound) ? INFINITY : __double2float_ru(bound) * 1.000001f;
+  // candidates, sorted by screened distance; cd_[0] is the float32 best
+  float cd_[kCand];
+  int ci_[kCand];
+#pragma unroll
+  for (int k = 0; k < kCand; k++) {
+    cd_[k] = INFINITY;
+    ci_[k] = -1;
+  }
+  float prune = fbound + band;  // nothing farther than this can win (or tie within the band)
+  bool certain = false;         // ANY: a triangle is closer than the bound beyond doubt
   int sp = 0;
   stack[sp++] = make_uint2(0u, 0u);
-  while (sp > 0) {
+  while (sp > 0 && !(ANY && certain)) {
     const uint2 e = stack[--sp];
     if (__uint_as_float(e.y) > prune) continue;
+    res.nodes++;
     const uint4 *np = bvh.nodes + (size_t)e.x * 5;
     const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
     const float sx = __uint_as_float((n0.w & 0xffu) << 23);
@@ -180,13 +199,12 @@ __device__ __forceinline__ void nearest_triangle(const DeviceBVH &bvh, float px,
     const float sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
     const float rx = px - __uint_as_float(n0.x), ry = py - __uint_as_float(n0.y), rz = pz - __uint_as_float(n0.z);
     const uint32_t imask = n0.w >> 24;
-    float cd[8];
+    float cdist[8];
     uint32_t inner = 0;  // slots of internal children that survive pruning
+    uint32_t tmask = 0;  // leaf triangles to screen: bit = offset from tri_base
 #pragma unroll
     for (int s = 0; s < 8; s++) {
       const uint32_t meta = ((s < 4 ? n1.z : n1.w) >> (8 * (s & 3))) & 0xffu;
-      cd[s] = INFINITY;
-      if (meta == 0u) continue;
       const int sh = 8 * (s & 3);
       const float lox = (float)(((s < 4 ? n2.x : n2.y) >> sh) & 0xffu) * sx;
       const float loy = (float)(((s < 4 ? n2.z : n2.w) >> sh) & 0xffu) * sy;
@@ -199,48 +217,76 @@ __device__ __forceinline__ void nearest_triangle(const DeviceBVH &bvh, float px,
       const float ey = fmaxf(fmaxf(loy - ry, ry - hiy), 0.f);
       const float ez = fmaxf(fmaxf(loz - rz, rz - hiz), 0.f);
       const float d = sqrtf(ex * ex + ey * ey + ez * ez) * 0.999999f - band;  // lower bound
-      if (d > prune) continue;
-      if (imask & (1u << s)) {
-        cd[s] = d;
-        inner |= 1u << s;
-        continue;
-      }
+      cdist[s] = d;
+      const bool keep = meta != 0u && d <= prune;
+      if (keep && (imask & (1u << s))) inner |= 1u << s;
       // leaf: unary triangle count in bits 5..7, offset from tri_base in bits 0..4
-      const int cnt = __popc(meta >> 5);
-      const uint32_t first = n1.y + (meta & 31u);
-      for (int k = 0; k < cnt; k++) {
-        const float4 *tp = bvh.tris + (size_t)(first + k) * 3;
-        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-        const float d2 = tri_dist2_f32(q0, q1, q2, px, py, pz);
-        const float df = sqrtf(d2);
-        if (df - band > prune) continue;
-        double cp[3];
-        const double dd = tri_closest_f64(tp, px, py, pz, cp);
-        if (dd < res.dist) {
-          res.dist = dd;
-          res.tri = (int)(first + k);
-          res.cp[0] = cp[0], res.cp[1] = cp[1], res.cp[2] = cp[2];
-          prune = __double2float_ru(dd) * 1.000001f + band;
-          if (ANY) return;
+      if (keep && !(imask & (1u << s))) tmask |= (meta >> 5) << (meta & 31u);
+    }
+    // one triangle per trip for every lane that has one pending (lock step, like the ray kernel)
+    while (tmask) {
+      const int bit = __ffs((int)tmask) - 1;
+      tmask &= tmask - 1u;
+      const int ti = (int)(n1.y + (uint32_t)bit);
+      const float4 *tp = bvh.tris + (size_t)ti * 3;
+      const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+      const float df = sqrtf(tri_dist2_f32(q0, q1, q2, px, py, pz));
+      res.screened++;
+      if (!(df <= prune)) continue;  // (NaN distances of degenerate triangles drop out here)
+      if (ANY && df < fbound - 2.f * band) {
+        certain = true;
+        ci_[0] = ti;
+        break;
+      }
+      // sorted insertion into the candidate list
+      float d_in = df;
+      int i_in = ti;
+#pragma unroll
+      for (int k = 0; k < kCand; k++) {
+        if (d_in < cd_[k]) {
+          const float td = cd_[k];
+          const int tt = ci_[k];
+          cd_[k] = d_in;
+          ci_[k] = i_in;
+          d_in = td;
+          i_in = tt;
         }
       }
+      prune = fminf(prune, cd_[0] + 2.f * band);
     }
+    if (ANY && certain) break;
     // push the surviving internal children far-to-near so that the nearest is popped first
     while (inner) {
-      int far_s = -1;
+      int far_s = 0;
       float far_d = -INFINITY;
 #pragma unroll
       for (int s = 0; s < 8; s++)
-        if ((inner >> s) & 1u) {
-          if (cd[s] > far_d) {
-            far_d = cd[s];
-            far_s = s;
-          }
+        if (((inner >> s) & 1u) && cdist[s] > far_d) {
+          far_d = cdist[s];
+          far_s = s;
         }
       inner &= ~(1u << far_s);
       if (far_d > prune) continue;
       const uint32_t child = n1.x + (uint32_t)__popc(imask & ((1u << far_s) - 1u));
       if (sp < kSdfStack) stack[sp++] = make_uint2(child, __float_as_uint(fmaxf(far_d, 0.f)));
+    }
+  }
+  if (ANY && certain) {
+    res.tri = ci_[0];
+    res.dist = 0.0;
+    return;
+  }
+  // float64 decision among the float32 near-ties, with the reference's Triangle.Closest
+#pragma unroll
+  for (int k = 0; k < kCand; k++) {
+    if (ci_[k] < 0 || cd_[k] > cd_[0] + 2.f * band) continue;
+    double cp[3];
+    const double dd = tri_closest_f64(bvh.tris + (size_t)ci_[k] * 3, px, py, pz, cp);
+    res.exact++;
+    if (dd < res.dist) {
+      res.dist = dd;
+      res.tri = ci_[k];
+      res.cp[0] = cp[0], res.cp[1] = cp[1], res.cp[2] = cp[2];
     }
   }
 }
@@ -249,13 +295,19 @@ __device__ __forceinline__ void nearest_triangle(const DeviceBVH &bvh, float px,
 // inside the bounds and an odd number of crossings along the fixed direction).
 __global__ void __launch_bounds__(kSdfBlock)
 mesh_sdf_kernel(DeviceBVH bvh, const float *__restrict__ pts3, int64_t n, float *__restrict__ sdf,
-                float *__restrict__ closest3, int32_t *__restrict__ face, float *__restrict__ normal3) {
+                float *__restrict__ closest3, int32_t *__restrict__ face, float *__restrict__ normal3,
+                unsigned long long *__restrict__ counters) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint2 stack[kSdfStack];
   const float px = pts3[3 * i], py = pts3[3 * i + 1], pz = pts3[3 * i + 2];
   NearestResult r;
   nearest_triangle<false>(bvh, px, py, pz, (double)INFINITY, r, stack);
+  if (counters) {
+    atomicAdd(counters, (unsigned long long)r.nodes);
+    atomicAdd(counters + 1, (unsigned long long)r.screened);
+    atomicAdd(counters + 2, (unsigned long long)r.exact);
+  }
   bool inside = false;
   if (bvh.num_tris > 0 && px >= bvh.bmin[0] && px <= bvh.bmax[0] && py >= bvh.bmin[1] && py <= bvh.bmax[1] &&
       pz >= bvh.bmin[2] && pz <= bvh.bmax[2]) {
@@ -322,10 +374,10 @@ __global__ void contains_margin_kernel(const uint8_t *__restrict__ parity, const
 int sdf_stack_capacity() { return kSdfStack; }
 
 void launch_mesh_sdf(const DeviceBVH &bvh, const float *pts3, int64_t n, float *sdf, float *closest3,
-                     int32_t *face, float *normal3, cudaStream_t stream) {
+                     int32_t *face, float *normal3, unsigned long long *counters, cudaStream_t stream) {
   if (n <= 0) return;
   const unsigned blocks = (unsigned)((n + kSdfBlock - 1) / kSdfBlock);
-  mesh_sdf_kernel<<<blocks, kSdfBlock, 0, stream>>>(bvh, pts3, n, sdf, closest3, face, normal3);
+  mesh_sdf_kernel<<<blocks, kSdfBlock, 0, stream>>>(bvh, pts3, n, sdf, closest3, face, normal3, counters);
 }
 
 void launch_sphere_collisions(const DeviceBVH &bvh, const float *centers3, const float *radii, float radius,
