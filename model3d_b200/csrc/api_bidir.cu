@@ -49,6 +49,7 @@ int32_t carve_bidir_buffers(m3d_ctx *ctx, int64_t cap, int De, int Dl, BidirBuff
                o_cskip = take(cc * 4);
   const size_t o_work = take(c * (size_t)De * (size_t)(Dl + 1) * 4);
   const size_t o_counts = take(64);
+  const size_t o_class = take((size_t)De * (size_t)(Dl + 1) * 4);
   M3D_CUDA(ctx->scratch[6].reserve(total));
   char *p = ctx->scratch[6].as<char>();
   b.cap = cap;
@@ -80,6 +81,7 @@ int32_t carve_bidir_buffers(m3d_ctx *ctx, int64_t cap, int De, int Dl, BidirBuff
   b.cskip = (int32_t *)(p + o_cskip);
   b.work = (uint32_t *)(p + o_work);
   b.counts = (int *)(p + o_counts);
+  b.class_counts = (int *)(p + o_class);
   b.ray_total = (unsigned long long *)(p + o_counts + 32);
   return M3D_OK;
 }

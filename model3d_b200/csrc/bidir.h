@@ -67,8 +67,11 @@ struct BidirBuffers {
   // connection (visibility) rays of all (i, j) pairs of the batch, compacted
   float4 *corg, *cdir, *craw, *cpay;
   int32_t *cskip;
-  uint32_t *work;  // connection work items: slot | i << 20 | j << 25 (cap <= 2^20, depths <= 16)
-  int *counts;     // [0],[1] queue lengths, [2] connection rays, [3] work items
+  // connection work items slot | i << 20 | j << 25 (cap <= 2^20, depths <= 16), grouped by
+  // (i, j) class: class c = (i-1) * (max_light_depth+1) + j owns work[c*cap, c*cap + class_counts[c])
+  uint32_t *work;
+  int *class_counts;
+  int *counts;     // [0],[1] queue lengths, [2] connection rays
   unsigned long long *ray_total;
 };
 

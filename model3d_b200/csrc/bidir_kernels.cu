@@ -151,8 +151,8 @@ bidir_eye_raygen_kernel(DeviceCamera cam, DeviceBidirParams bp, PathBatch b, Bid
     buf.counts[0] = (int)n;
     buf.counts[1] = 0;
     buf.counts[2] = 0;
-    buf.counts[3] = 0;
   }
+  if (slot < (int64_t)buf.De * (buf.Dl + 1)) buf.class_counts[slot] = 0;
   if (slot >= n) return;
   const int p = (int)(slot % b.nP), s = (int)(slot / b.nP);
   const int pix = batch_pixel(b, p);
@@ -403,66 +403,84 @@ struct D3c {
 // One thread per sample; also writes the compact MIS records.
 __global__ void __launch_bounds__(256)
 bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
+  __shared__ int s_cnt[kBidirMaxDepth * (kBidirMaxDepth + 1)], s_base[kBidirMaxDepth * (kBidirMaxDepth + 1)];
   const int n_slots = b.nP * b.S;
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n_slots) return;
-  const int ne = buf.ne[slot], nl = buf.nl[slot];
-  double eye_density = 1.0;
-  D3c eye_bsdf = {1.0, 1.0, 1.0};
-  for (int i = 1; i <= ne; i++) {
-    const BVert v = load_vertex(buf.ev, buf.De, buf.cap, i - 1, slot);
-    double *st = buf.eyepre + ((size_t)(i - 1) * buf.cap + slot) * 4;
-    st[0] = eye_density;
-    st[1] = eye_bsdf.x;
-    st[2] = eye_bsdf.y;
-    st[3] = eye_bsdf.z;
-    store_mis(buf, i - 1, slot, mis_of(v));
-    const double sdv = (double)source_dot(v);
-    eye_density *= full_sd(v);
-    eye_bsdf.x *= ((double)v.bsdf_fin.x + (double)v.bsdf_del.x * kDeltaMag) * sdv;
-    eye_bsdf.y *= ((double)v.bsdf_fin.y + (double)v.bsdf_del.y * kDeltaMag) * sdv;
-    eye_bsdf.z *= ((double)v.bsdf_fin.z + (double)v.bsdf_del.z * kDeltaMag) * sdv;
-  }
-  double density = 0.0;
-  D3c light_bsdf = {0.0, 0.0, 0.0};
-  BVert prev;
-  for (int j = 1; j <= nl; j++) {
-    const BVert lj = load_vertex(buf.lv, buf.Dl, buf.cap, j - 1, slot);
-    if (j == 1) {
-      density = ((double)lj.emission.x + lj.emission.y + lj.emission.z) / bp.total_light;
-      light_bsdf.x = lj.emission.x;
-      light_bsdf.y = lj.emission.y;
-      light_bsdf.z = lj.emission.z;
-    } else {
-      density *= full_dd(prev);
-      density *= (double)source_dot(lj) / (double)dest_dot(prev);
-      if (j > 2) {
-        light_bsdf.x *= (double)prev.bsdf_fin.x + (double)prev.bsdf_del.x * kDeltaMag;
-        light_bsdf.y *= (double)prev.bsdf_fin.y + (double)prev.bsdf_del.y * kDeltaMag;
-        light_bsdf.z *= (double)prev.bsdf_fin.z + (double)prev.bsdf_del.z * kDeltaMag;
-      }
-      const double sdj = (double)source_dot(lj);
-      light_bsdf.x *= sdj;
-      light_bsdf.y *= sdj;
-      light_bsdf.z *= sdj;
+  const int row = bp.max_light_depth + 1;
+  const int n_classes = bp.max_depth * row;
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) s_cnt[c] = 0;
+  int ne = 0, nl = 0;
+  if (slot < n_slots) {
+    ne = buf.ne[slot];
+    nl = buf.nl[slot];
+    double eye_density = 1.0;
+    D3c eye_bsdf = {1.0, 1.0, 1.0};
+    for (int i = 1; i <= ne; i++) {
+      const BVert v = load_vertex(buf.ev, buf.De, buf.cap, i - 1, slot);
+      double *st = buf.eyepre + ((size_t)(i - 1) * buf.cap + slot) * 4;
+      st[0] = eye_density;
+      st[1] = eye_bsdf.x;
+      st[2] = eye_bsdf.y;
+      st[3] = eye_bsdf.z;
+      store_mis(buf, i - 1, slot, mis_of(v));
+      const double sdv = (double)source_dot(v);
+      eye_density *= full_sd(v);
+      eye_bsdf.x *= ((double)v.bsdf_fin.x + (double)v.bsdf_del.x * kDeltaMag) * sdv;
+      eye_bsdf.y *= ((double)v.bsdf_fin.y + (double)v.bsdf_del.y * kDeltaMag) * sdv;
+      eye_bsdf.z *= ((double)v.bsdf_fin.z + (double)v.bsdf_del.z * kDeltaMag) * sdv;
     }
-    double *st = buf.lightpre + ((size_t)(j - 1) * buf.cap + slot) * 4;
-    st[0] = density;
-    st[1] = light_bsdf.x;
-    st[2] = light_bsdf.y;
-    st[3] = light_bsdf.z;
-    store_mis(buf, buf.De + j - 1, slot, mis_of(lj));
-    prev = lj;
+    double density = 0.0;
+    D3c light_bsdf = {0.0, 0.0, 0.0};
+    BVert prev;
+    for (int j = 1; j <= nl; j++) {
+      const BVert lj = load_vertex(buf.lv, buf.Dl, buf.cap, j - 1, slot);
+      if (j == 1) {
+        density = ((double)lj.emission.x + lj.emission.y + lj.emission.z) / bp.total_light;
+        light_bsdf.x = lj.emission.x;
+        light_bsdf.y = lj.emission.y;
+        light_bsdf.z = lj.emission.z;
+      } else {
+        density *= full_dd(prev);
+        density *= (double)source_dot(lj) / (double)dest_dot(prev);
+        if (j > 2) {
+          light_bsdf.x *= (double)prev.bsdf_fin.x + (double)prev.bsdf_del.x * kDeltaMag;
+          light_bsdf.y *= (double)prev.bsdf_fin.y + (double)prev.bsdf_del.y * kDeltaMag;
+          light_bsdf.z *= (double)prev.bsdf_fin.z + (double)prev.bsdf_del.z * kDeltaMag;
+        }
+        const double sdj = (double)source_dot(lj);
+        light_bsdf.x *= sdj;
+        light_bsdf.y *= sdj;
+        light_bsdf.z *= sdj;
+      }
+      double *st = buf.lightpre + ((size_t)(j - 1) * buf.cap + slot) * 4;
+      st[0] = density;
+      st[1] = light_bsdf.x;
+      st[2] = light_bsdf.y;
+      st[3] = light_bsdf.z;
+      store_mis(buf, buf.De + j - 1, slot, mis_of(lj));
+      prev = lj;
+    }
   }
-  // work list of the connection stage: one item per (i, j) pair of this sample, packed
-  // slot | i << 20 | j << 25, items of one sample adjacent so that a warp re-uses its vertices
-  const int cnt = ne * (nl + 1);
-  if (cnt > 0) {
-    const int base = atomicAdd(buf.counts + 3, cnt);
-    int w = base;
-    for (int i = 1; i <= ne; i++)
-      for (int j = 0; j <= nl; j++) buf.work[w++] = (uint32_t)slot | ((uint32_t)i << 20) | ((uint32_t)j << 25);
+  // Work list of the connection stage: one item per (i, j) pair of this sample, packed
+  // slot | i << 20 | j << 25 and grouped by (i, j) class, so that the threads of a warp of the
+  // connection kernel walk joined paths of the same length (uniform loops) and read their
+  // vertices from consecutive slots (coalesced).  Block-level counting sort: count per class in
+  // shared memory, reserve the block's range of every class with one global atomic, scatter.
+  __syncthreads();
+  for (int i = 1; i <= ne; i++)
+    for (int j = 0; j <= nl; j++) atomicAdd(&s_cnt[(i - 1) * row + j], 1);
+  __syncthreads();
+  for (int c = threadIdx.x; c < n_classes; c += blockDim.x) {
+    s_base[c] = s_cnt[c] > 0 ? atomicAdd(buf.class_counts + c, s_cnt[c]) : 0;
+    s_cnt[c] = 0;
   }
+  __syncthreads();
+  for (int i = 1; i <= ne; i++)
+    for (int j = 0; j <= nl; j++) {
+      const int c = (i - 1) * row + j;
+      const int r = atomicAdd(&s_cnt[c], 1);
+      buf.work[(size_t)c * buf.cap + s_base[c] + r] = (uint32_t)slot | ((uint32_t)i << 20) | ((uint32_t)j << 25);
+    }
 }
 
 // allPathCombinations (bidir.go:476-530) + rayColor's callback (bidir.go:113-158): one thread
@@ -470,8 +488,10 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
 __global__ void __launch_bounds__(kBlock, 8)
 bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
   const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (tid >= (long long)buf.counts[3]) return;
-  const uint32_t item = buf.work[tid];
+  const int n_slots = b.nP * b.S;
+  const int cls = (int)(tid / n_slots), rank = (int)(tid % n_slots);
+  if (cls >= bp.max_depth * (bp.max_light_depth + 1) || rank >= buf.class_counts[cls]) return;
+  const uint32_t item = buf.work[(size_t)cls * buf.cap + rank];
   const int slot = (int)(item & 0xfffffu);
   const int i = (int)((item >> 20) & 31u);
   const int j = (int)(item >> 25);
