@@ -487,10 +487,9 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
 // per (eye prefix length i, light prefix length j, sample); threads of a warp share (i, j).
 __global__ void __launch_bounds__(kBlock, 8)
 bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
-  const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x;
-  const int n_slots = b.nP * b.S;
-  const int cls = (int)(tid / n_slots), rank = (int)(tid % n_slots);
-  if (cls >= bp.max_depth * (bp.max_light_depth + 1) || rank >= buf.class_counts[cls]) return;
+  // grid: x over the items of a class, y = class; most blocks of a sparsely filled class exit here
+  const int cls = (int)blockIdx.y, rank = (int)(blockIdx.x * kBlock + threadIdx.x);
+  if (rank >= buf.class_counts[cls]) return;
   const uint32_t item = buf.work[(size_t)cls * buf.cap + rank];
   const int slot = (int)(item & 0xfffffu);
   const int i = (int)((item >> 20) & 31u);
@@ -693,9 +692,10 @@ void launch_bidir_prefix(const DeviceBidirParams &bp, const PathBatch &b, const 
 
 void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
                           const BidirBuffers &buf, cudaStream_t stream) {
-  const int64_t n = (int64_t)b.nP * b.S * bp.max_depth * (bp.max_light_depth + 1);
+  const int64_t n = (int64_t)b.nP * b.S;
   if (n <= 0) return;
-  bidir_connect_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, stream>>>(sc, bp, b, buf);
+  const dim3 grid((unsigned)((n + kBlock - 1) / kBlock), (unsigned)(bp.max_depth * (bp.max_light_depth + 1)));
+  bidir_connect_kernel<<<grid, kBlock, 0, stream>>>(sc, bp, b, buf);
 }
 
 void launch_bidir_connect_resolve(const DeviceScene &sc, const BidirBuffers &buf, cudaStream_t stream) {
