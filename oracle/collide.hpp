@@ -1,6 +1,7 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see vec.hpp header).  "parity unpinned"
-// against reference outputs (no Go toolchain); pinned by the reference's own
-// property tests restated in tests/test_oracle_collide.py.
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see vec.hpp header for the parity status: pinned
+// statistically by the reference's committed cornell_box renderings and by the reference's
+// own property tests restated in tests/test_oracle_collide.py; per-ray outputs otherwise
+// "parity unpinned" -- no Go toolchain).
 //
 // float64 CPU restatement of the reference's collision path:
 //   Ray / RayCollision               model3d/collisions.go:12-46

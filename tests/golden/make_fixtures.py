@@ -10,8 +10,17 @@ The GPU box has no /root/reference; tests only read the .npy files written here.
                      (BASELINE config 4; vase.stl.gz is missing from the reference checkout),
                      each stored indexed: <name>_v float32 [V,3] unique vertices in first-use
                      order, <name>_f int32 [n,3]; triangles = v[f] in file order.
+  ref_cornell_box_output.png / ref_cornell_box_output_hd.png
+                     byte copies of examples/renderings/cornell_box/output.png (200x200; the
+                     configuration of cornell_box/main.go: MaxDepth 5, NumSamples 400, Antialias 1,
+                     Cutoff 1e-4, PhongFocusPoint 0.3) and output_hd.png (500x500; README.md:
+                     "MaxDepth to maybe 15, NumSamples to 20000"): renderings produced by the Go
+                     reference itself and committed upstream -- the only reference OUTPUTS for
+                     this path, used to pin the oracle and the GPU path statistically
+                     (tests/test_reference_golden.py).
 """
 import os
+import shutil
 import struct
 
 import numpy as np
@@ -63,3 +72,7 @@ if __name__ == "__main__":
     assert tris.shape == (46, 3, 3), tris.shape
     np.save(os.path.join(HERE, "diamond_tris.npy"), tris)
     print("diamond:", tris.shape, tris.min(axis=(0, 1)), tris.max(axis=(0, 1)))
+
+    for src, dst in (("output.png", "ref_cornell_box_output.png"), ("output_hd.png", "ref_cornell_box_output_hd.png")):
+        shutil.copyfile(os.path.join(REF, "examples/renderings/cornell_box", src), os.path.join(HERE, dst))
+        print("copied", src, "->", dst)
