@@ -18,6 +18,11 @@ The GPU box has no /root/reference; tests only read the .npy files written here.
                      reference itself and committed upstream -- the only reference OUTPUTS for
                      this path, used to pin the oracle and the GPU path statistically
                      (tests/test_reference_golden.py).
+  ref_rose_rendering.png
+                     byte copy of examples/decoration/rose/rendering.png: render3d.SaveRendering of
+                     the rose mesh from (0,-2,4) at 500x500 (rose/main.go:31), a deterministic
+                     RayCaster image produced by the Go reference.  showcase/models/rose.stl.gz is a
+                     later export of the same model (same silhouette, slightly different facets).
 """
 import os
 import shutil
@@ -73,6 +78,7 @@ if __name__ == "__main__":
     np.save(os.path.join(HERE, "diamond_tris.npy"), tris)
     print("diamond:", tris.shape, tris.min(axis=(0, 1)), tris.max(axis=(0, 1)))
 
+    shutil.copyfile(os.path.join(REF, "examples/decoration/rose/rendering.png"), os.path.join(HERE, "ref_rose_rendering.png"))
     for src, dst in (("output.png", "ref_cornell_box_output.png"), ("output_hd.png", "ref_cornell_box_output_hd.png")):
         shutil.copyfile(os.path.join(REF, "examples/renderings/cornell_box", src), os.path.join(HERE, dst))
         print("copied", src, "->", dst)
