@@ -619,6 +619,35 @@ def main():
                "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 20,
                "api": "m3d_mesh_first_ray_collisions (host buffers, pinned)"}
 
+    # mix B: coherent primary rays of a 4096x4096 pinhole camera at (0,-3,0) looking at
+    # the origin, fov pi/3.6 -- same mesh, same kernels, reported beside the incoherent headline
+    mix_b = None
+    if not args.no_secondary and n == N_RAYS:
+        from model3d_b200 import render3d as R
+        cam = R.NewCameraAt((0.0, -3.0, 0.0), (0.0, 0.0, 0.0), np.pi / 3.6)
+        db = torch.from_numpy(R.CasterRays(cam, 4096, 4096).astype(np.float32))
+        o4.zero_()
+        o4[:, 1] = -3.0
+        d4[:, :3] = db.to(dev)
+        del db
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kb = max(5, min(args.steps, 20))
+        eb0.record()
+        for _ in range(kb):
+            step()
+        eb1.record()
+        torch.cuda.synchronize()
+        tb = torch.tensor([eb0.elapsed_time(eb1) / kb], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        hit_b = float((h0[:, 3].contiguous().view(torch.int32) >= 0).float().mean().item())
+        mix_b = {"ray_mix": "B: 4096x4096 pinhole camera at (0,-3,0) looking at the origin, fov pi/3.6",
+                 "Mrays_per_s": world * n / (float(tb.item()) * 1e-3) / 1e6, "ms_per_step": float(tb.item()),
+                 "hit_fraction": hit_b}
+
     secondary = None
     if not args.no_secondary:
         try:
@@ -662,6 +691,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if mix_b:
+            line["coherent_rays"] = mix_b
         if secondary:
             line["path_tracing"] = secondary
         if not args.no_cpu_baseline and world == 1:

@@ -374,6 +374,19 @@ def _camera_axes(cam, w, h):
     return x, y, z * plane
 
 
+def CasterRays(cam, imageWidth, imageHeight):
+    """Camera.Caster (camera.go:68-82) for every pixel: float64 directions [H*W, 3], row-major
+    (idx = x + y*W), built from imageWidth-1 / imageHeight-1 like the renderers' callers do
+    (raycast.go:16-18)."""
+    w, h = float(imageWidth - 1), float(imageHeight - 1)
+    x, y, z = _camera_axes(cam, w, h)
+    cx, cy = w / 2, h / 2
+    fx = (np.arange(imageWidth, dtype=np.float64) - cx) / cx
+    fy = (np.arange(imageHeight, dtype=np.float64) - cy) / cy
+    d = fx[None, :, None] * x[None, None, :] + fy[:, None, None] * y[None, None, :] + z[None, None, :]
+    return d.reshape(-1, 3)
+
+
 def Uncaster(cam, imageWidth, imageHeight):
     """Camera.Uncaster (camera.go:84-98): spatial -> screen coordinates."""
     x, y, z = _camera_axes(cam, imageWidth, imageHeight)

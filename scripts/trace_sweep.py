@@ -19,7 +19,7 @@ if mix == "A":
 else:
     from model3d_b200 import render3d as R
     cam = R.NewCameraAt((0.0, -3.0, 0.0), (0.0, 0.0, 0.0), np.pi / 3.6)
-    d = cam.Rays(4096, 4096).astype(np.float32).reshape(-1, 3) if hasattr(cam, "Rays") else None
+    d = R.CasterRays(cam, 4096, 4096).astype(np.float32)
     org = np.tile(np.array([[0.0, -3.0, 0.0]], np.float32), (n, 1))
 o4 = torch.zeros((n, 4), dtype=torch.float32)
 d4 = torch.full((n, 4), float("inf"), dtype=torch.float32)
