@@ -630,6 +630,8 @@ def main():
         o4[:, 1] = -3.0
         d4[:, :3] = db.to(dev)
         del db
+        stb = col.FirstRayCollisionsDevice(o4.data_ptr(), d4.data_ptr(), n, h0.data_ptr(), h1.data_ptr(),
+                                           stream=stream, counters=True)
         for _ in range(3):
             step()
         torch.cuda.synchronize()
@@ -646,7 +648,9 @@ def main():
         hit_b = float((h0[:, 3].contiguous().view(torch.int32) >= 0).float().mean().item())
         mix_b = {"ray_mix": "B: 4096x4096 pinhole camera at (0,-3,0) looking at the origin, fov pi/3.6",
                  "Mrays_per_s": world * n / (float(tb.item()) * 1e-3) / 1e6, "ms_per_step": float(tb.item()),
-                 "hit_fraction": hit_b}
+                 "hit_fraction": hit_b, "nodes_per_ray": stb["nodes_visited"] / n, "tris_per_ray": stb["tris_tested"] / n}
+        mix_b["bytes_per_ray"] = RAY_IO_BYTES + mix_b["nodes_per_ray"] * NODE_BYTES + mix_b["tris_per_ray"] * TRI_BYTES
+        mix_b["achieved_GBps"] = n * mix_b["bytes_per_ray"] / (mix_b["ms_per_step"] * 1e-3) / 1e9
 
     secondary = None
     if not args.no_secondary:
