@@ -201,6 +201,42 @@ __device__ __forceinline__ bool shape_certainly_missed(const DeviceShape &sh, fl
   return false;
 }
 
+// Sphere.FirstRayCollision (shapes.go:35-93) in float32 for the Monte-Carlo renderers (their
+// parity contract is statistical).  The discriminant is formed as a*(r^2 - |oc - (b/a) d|^2),
+// which does not cancel for distant origins.  Returns 0 miss, 1 hit, 2 undecided (grazing ray or
+// a root next to t_floor): the caller falls back to the float64 test.
+__device__ __forceinline__ int sphere_hit_f32(const DeviceShape &sh, float4 o, float4 d, float t_floor, float &t,
+                                              float &nx, float &ny, float &nz) {
+  const float cx = (float)sh.p0[0], cy = (float)sh.p0[1], cz = (float)sh.p0[2], r = (float)sh.radius;
+  const float ox = o.x - cx, oy = o.y - cy, oz = o.z - cz;
+  const float a = d.x * d.x + d.y * d.y + d.z * d.z;
+  const float b = ox * d.x + oy * d.y + oz * d.z;
+  const float ba = b / a;
+  const float lx = ox - ba * d.x, ly = oy - ba * d.y, lz = oz - ba * d.z;
+  const float r2 = r * r;
+  const float q = r2 - (lx * lx + ly * ly + lz * lz);  // discriminant / (4 a)
+  if (fabsf(q) < 1e-4f * r2) return 2;
+  if (q < 0.f) return 0;
+  const float sq = sqrtf(q / a);
+  const float t1 = -ba - sq, t2 = -ba + sq;
+  const float slack = 1e-5f * (fabsf(ba) + sq) + 1e-5f * t_floor;
+  float tt;
+  if (fabsf(t1 - t_floor) < slack || fabsf(t2 - t_floor) < slack) return 2;
+  if (t1 >= t_floor)
+    tt = t1;
+  else if (t2 >= t_floor)
+    tt = t2;
+  else
+    return 0;
+  t = tt;
+  const float px = ox + d.x * tt, py = oy + d.y * tt, pz = oz + d.z * tt;
+  const float inv = rsqrtf(px * px + py * py + pz * pz);
+  nx = px * inv;
+  ny = py * inv;
+  nz = pz * inv;
+  return 1;
+}
+
 // Result of resolving one scene ray: the closest of the BVH's raw triangle hit and the
 // analytic shapes.  surf: leaf-order triangle index, or -2-shape index, or -1 (miss).
 struct SceneHit {
@@ -306,7 +342,19 @@ __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, fl
       double t;
       D3 n;
       bool ok = false;
-      if (sh.kind == SHAPE_SPHERE) ok = sphere_hit(sh, od, dd, t_floor, t, n);
+      int fast = 2;
+      if (!refine && sh.kind == SHAPE_SPHERE) {
+        float tf, fx, fy, fz;
+        fast = sphere_hit_f32(sh, o, d, (float)t_floor, tf, fx, fy, fz);
+        if (fast == 0) continue;
+        if (fast == 1) {
+          ok = true;
+          t = (double)tf;
+          n = d3(fx, fy, fz);
+        }
+      }
+      if (fast != 2) {
+      } else if (sh.kind == SHAPE_SPHERE) ok = sphere_hit(sh, od, dd, t_floor, t, n);
       else if (sh.kind == SHAPE_RECT) ok = rect_hit(sh, od, dd, t_floor, t, n);
       else if (sh.kind == SHAPE_CYLINDER) ok = cylinder_hit(sh, od, dd, t_floor, t, n);
       if (!ok || t > t_hi) continue;

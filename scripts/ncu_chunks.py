@@ -4,13 +4,17 @@ share of issued instructions, share of stall samples, average active threads.
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 step = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-hdr, data, k = None, [], 0
+want = sys.argv[3] if len(sys.argv) > 3 else ""  # substring of the kernel name (default: first kernel)
+hdr, data, k, on = None, [], 0, False
 for r in rows:
     if r and r[0] == "Kernel Name":
-        k += 1
-        if k > 1:
+        if on:
             break
-        print(r[1][:100])
+        on = want in r[1]
+        if on:
+            print(r[1][:100])
+        continue
+    if not on:
         continue
     if r and r[0] == "Address":
         hdr = r
