@@ -79,7 +79,9 @@ typedef struct {
  */
 #define M3D_MESH_BUILD_HOST_SAH 0u   /* host binned-SAH build, collapsed to 8-wide */
 #define M3D_MESH_BUILD_DEVICE_LBVH 1u /* device Morton / radix sort / Karras / refit binary
-                                         tree, then the same 8-wide collapse            */
+                                         tree, then the same 8-wide collapse on the host */
+#define M3D_MESH_BUILD_DEVICE_COLLAPSE 2u /* whole build on the device: LBVH, cost-optimal
+                                             8-wide collapse and node emission            */
 
 typedef struct {
   int64_t num_triangles;

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("M3D_LIB") or os.path.join(_HERE, "libm3dgpu.so")
 M3D_OK = 0
 ERR_NAMES = {1: "INVALID_ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "OOM"}
 
-MESH_BUILD_HOST_SAH, MESH_BUILD_DEVICE_LBVH = 0, 1
+MESH_BUILD_HOST_SAH, MESH_BUILD_DEVICE_LBVH, MESH_BUILD_DEVICE_COLLAPSE = 0, 1, 2
 TRACE_COUNTERS = 1
 TRACE_NO_REFINE = 2
 

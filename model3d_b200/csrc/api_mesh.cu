@@ -86,6 +86,11 @@ int32_t upload_bvh(m3d_ctx *ctx, const WideBVH &bvh, const float *vnormals_by_pr
 }
 
 int32_t build_bvh_with_flags(m3d_ctx *ctx, const BuildInput &in, uint32_t build_flags, WideBVH &out) {
+  if ((build_flags & M3D_MESH_BUILD_DEVICE_COLLAPSE) && in.n > 0) {
+    out.nodes.clear();
+    out.tris.clear();
+    return lbvh_build_wide(ctx, in, bvh_cost_prim(), out);
+  }
   if ((build_flags & M3D_MESH_BUILD_DEVICE_LBVH) && in.n > 0) {
     std::vector<BinaryNode> bn;
     std::vector<int32_t> order;

@@ -476,6 +476,8 @@ void finish_wide_bvh(const BuildInput &in, Builder2 &b2, int32_t root2, WideBVH 
 }
 }  // namespace
 
+double bvh_cost_prim() { return cost_prim(); }
+
 void build_wide_bvh_from_binary(const BuildInput &in, const BinaryNode *nodes, int64_t num_nodes, int32_t root,
                                 const int32_t *order, WideBVH &out) {
   auto t0 = std::chrono::steady_clock::now();

@@ -69,6 +69,9 @@ struct BinaryNode {
 void build_wide_bvh_from_binary(const BuildInput &in, const BinaryNode *nodes, int64_t num_nodes, int32_t root,
                                 const int32_t *order, WideBVH &out);
 
+// Relative cost of one triangle test in the collapse (0.3; M3D_BVH_CPRIM overrides it for tuning).
+double bvh_cost_prim();
+
 // Host build: binned SAH binary tree -> cost-optimal 8-wide collapse -> octant slot
 // assignment -> quantisation.  n == 0 yields a single empty node.
 void build_wide_bvh(const BuildInput &in, WideBVH &out, int num_threads = 0);

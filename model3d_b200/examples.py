@@ -65,7 +65,7 @@ def rotation(axis, angle):
 
 
 # ---- builders -------------------------------------------------------------------------------
-def build_product(spec):
+def build_product(spec, **scene_kw):
     from . import render3d as R
     cache = {}
 
@@ -110,7 +110,7 @@ def build_product(spec):
         if xf is not None:
             obj = R.Translate(R.MatrixMultiply(obj, xf[0]), xf[1])
         objs.append(obj)
-    scene = R.Scene(objs)
+    scene = R.Scene(objs, **scene_kw)
     scene.material_of = lambda m: cache[id(m)]
     scene.area_light = R.JoinAreaLights(*[objs[l["object"]] for l in spec.get("area_lights", [])]) \
         if spec.get("area_lights") else None

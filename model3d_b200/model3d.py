@@ -68,10 +68,12 @@ class MeshCollider:
     MeshToInterpNormalCollider semantics (collisions.go:147-162).
     """
 
-    def __init__(self, triangles, vertex_normals=None, ctx=None, device_lbvh=False):
+    def __init__(self, triangles, vertex_normals=None, ctx=None, device_lbvh=False, device_build=False):
         """device_lbvh: build the binary hierarchy on the GPU (Morton codes + radix sort + Karras,
         M3D_MESH_BUILD_DEVICE_LBVH) instead of the host binned-SAH build: much faster to build,
-        somewhat more nodes visited per ray; query results are identical."""
+        somewhat more nodes visited per ray; query results are identical.  device_build: the whole
+        build on the GPU (M3D_MESH_BUILD_DEVICE_COLLAPSE: LBVH + cost-optimal 8-wide collapse + node
+        emission)."""
         self.ctx = ctx or N.default_context()
         tris = np.ascontiguousarray(np.asarray(triangles, dtype=np.float32).reshape(-1, 9))
         vn = None
@@ -85,7 +87,7 @@ class MeshCollider:
         self.vertex_normals = None if vn is None else vn.reshape(-1, 3, 3)
         self.h = C.c_void_p()
         N.check(N.lib().m3d_mesh_create(self.ctx.h, _p(tris, f32p), C.c_int64(self.num_triangles),
-                                        _p(vn, f32p), C.c_uint32(N.MESH_BUILD_DEVICE_LBVH if device_lbvh else 0),
+                                        _p(vn, f32p), C.c_uint32(N.MESH_BUILD_DEVICE_COLLAPSE if device_build else (N.MESH_BUILD_DEVICE_LBVH if device_lbvh else 0)),
                                         C.byref(self.h)))
 
     def close(self):

@@ -221,7 +221,7 @@ def _compose(outer, inner):
 class Scene:
     """A render3d.Object compiled to a device scene (m3d_scene)."""
 
-    def __init__(self, obj, ctx=None, device_lbvh=False):
+    def __init__(self, obj, ctx=None, device_lbvh=False, device_build=False):
         self.ctx = ctx or N.default_context()
         L = N.lib()
         b = C.c_void_p()
@@ -232,7 +232,7 @@ class Scene:
         try:
             self._add(b, obj, None)
             self.h = C.c_void_p()
-            N.check(L.m3d_scene_build(b, C.c_uint32(N.MESH_BUILD_DEVICE_LBVH if device_lbvh else 0), C.byref(self.h)))
+            N.check(L.m3d_scene_build(b, C.c_uint32(N.MESH_BUILD_DEVICE_COLLAPSE if device_build else (N.MESH_BUILD_DEVICE_LBVH if device_lbvh else 0)), C.byref(self.h)))
         finally:
             L.m3d_scene_builder_destroy(b)
 

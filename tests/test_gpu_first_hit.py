@@ -295,6 +295,22 @@ def test_device_lbvh_build_same_hits(built, oracle, n_sub):
     assert (lb.RayCollisionCounts(org[:20000], d[:20000]) != sah.RayCollisionCounts(org[:20000], d[:20000])).sum() <= 2
     print("lbvh nodes/ray %.2f vs sah %.2f; build %.1f ms vs %.1f ms" % (
         a.Stats["nodes_visited"] / n, b.Stats["nodes_visited"] / n, info_l["build_ms"], info_s["build_ms"]))
+    # whole build on the device (collapse + emission too): same decisions as the host collapse of
+    # the same binary tree up to float-vs-double cost ties, hence (nearly) the same node count and
+    # the same hits
+    full = MeshCollider(tris, device_build=True)
+    info_f = full.Info()
+    assert info_f["num_triangles"] == tris.shape[0]
+    assert abs(info_f["num_nodes"] - info_l["num_nodes"]) <= max(2, info_l["num_nodes"] // 50)
+    c = full.FirstRayCollisions(org, d, counters=True)
+    assert np.array_equal(c.Collides, hit)
+    assert (c.Triangle != a.Triangle).sum() <= 3
+    same_c = hit & (c.Triangle == ref["prim"])
+    assert (np.abs(c.Scale[same_c] - ref["t"][same_c]) / np.maximum(np.abs(ref["t"][same_c]), 1e-30)).max() < 1e-5
+    assert abs(c.Stats["nodes_visited"] - a.Stats["nodes_visited"]) <= 0.03 * a.Stats["nodes_visited"]
+    assert (full.RayCollisionCounts(org[:20000], d[:20000]) != sah.RayCollisionCounts(org[:20000], d[:20000])).sum() <= 2
+    print("device collapse: %d nodes (host collapse %d), build %.1f ms" % (
+        info_f["num_nodes"], info_l["num_nodes"], info_f["build_ms"]))
 
 
 def test_device_lbvh_edge_cases(built):
@@ -308,3 +324,13 @@ def test_device_lbvh_edge_cases(built):
     c = MeshCollider(same, device_lbvh=True)
     assert c.RayCollisionCounts([[0.2, 0.2, 1.0]], [[0, 0, -1.0]])[0] == 50
     assert MeshCollider(np.zeros((0, 3, 3), np.float32), device_lbvh=True).Info()["num_triangles"] == 0
+    # the same edge cases through the full device build
+    c = MeshCollider(one, device_build=True)
+    r = c.FirstRayCollisions([[0.2, 0.2, 1.0]], [[0, 0, -1.0]])
+    assert r.Collides[0] and r.Triangle[0] == 0 and r.Scale[0] == pytest.approx(1.0)
+    c = MeshCollider(same, device_build=True)
+    assert c.RayCollisionCounts([[0.2, 0.2, 1.0]], [[0, 0, -1.0]])[0] == 50
+    two = np.concatenate([one, one + 2.0])
+    c = MeshCollider(two, device_build=True)
+    assert c.RayCollisionCounts([[0.2, 0.2, 1.0], [2.2, 2.2, 5.0]], [[0, 0, -1.0], [0, 0, -1.0]]).tolist() == [1, 1]
+    assert MeshCollider(np.zeros((0, 3, 3), np.float32), device_build=True).Info()["num_triangles"] == 0

@@ -146,3 +146,21 @@ def test_raycaster_row_partition(built, oracle):
     for band in [(0, 13), (13, 40), (40, 80)]:
         rc.Render(parts, psc, partition=band)
     assert np.array_equal(whole.Data, parts.Data)
+
+
+def test_scene_device_build_same_casts(built, oracle):
+    """m3d_scene_build with M3D_MESH_BUILD_DEVICE_COLLAPSE (object / triangle ids travel through
+    the device build): the showcase scene casts identically to the host-SAH scene."""
+    spec = scenes.showcase(hd=False)
+    a = scenes.build_product(spec)
+    b = scenes.build_product(spec, device_build=True)
+    rng = np.random.default_rng(12)
+    n = 200000
+    org = (rng.normal(size=(n, 3)) * 2.0 + np.array([0.0, 0.0, 2.0])).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    ra, rb = a.Cast(org, d), b.Cast(org, d)
+    assert (ra["obj"] != rb["obj"]).sum() <= 3
+    same = (ra["obj"] == rb["obj"]) & (ra["prim"] == rb["prim"])
+    assert same.sum() >= n - 6
+    assert np.array_equal(ra["t"][same], rb["t"][same])
+    assert np.array_equal(ra["normal"][same], rb["normal"][same])
