@@ -62,8 +62,20 @@ type MeshCollider struct {
 	min, max  model3d.Coord3D
 }
 
+// BVH builders (m3d_mesh_create build_flags).
+const (
+	BuildHostSAH        uint32 = C.M3D_MESH_BUILD_HOST_SAH        // best tree, ~0.75 s per million triangles
+	BuildDeviceLBVH     uint32 = C.M3D_MESH_BUILD_DEVICE_LBVH     // device binary tree, host collapse
+	BuildDeviceCollapse uint32 = C.M3D_MESH_BUILD_DEVICE_COLLAPSE // whole build on the device, ~46 ms per million
+)
+
 // MeshToCollider replaces model3d.MeshToCollider (collisions.go:138-142).
 func MeshToCollider(ctx *Context, m *model3d.Mesh) (*MeshCollider, error) {
+	return MeshToColliderBuild(ctx, m, BuildHostSAH)
+}
+
+// MeshToColliderBuild is MeshToCollider with an explicit BVH builder.
+func MeshToColliderBuild(ctx *Context, m *model3d.Mesh, buildFlags uint32) (*MeshCollider, error) {
 	tris := m.TriangleSlice()
 	flat := make([]float32, 0, len(tris)*9)
 	for _, t := range tris {
@@ -76,7 +88,7 @@ func MeshToCollider(ctx *Context, m *model3d.Mesh) (*MeshCollider, error) {
 	if len(flat) > 0 {
 		ptr = (*C.float)(unsafe.Pointer(&flat[0]))
 	}
-	if err := status(C.m3d_mesh_create(ctx.h, ptr, C.int64_t(len(tris)), nil, 0, &res.h)); err != nil {
+	if err := status(C.m3d_mesh_create(ctx.h, ptr, C.int64_t(len(tris)), nil, C.uint32_t(buildFlags), &res.h)); err != nil {
 		return nil, err
 	}
 	var mn, mx [3]C.double
