@@ -18,6 +18,13 @@
 #include "materials.cuh"
 #include "scene_hit.cuh"
 
+#ifndef M3D_BSHADE_MINB
+#define M3D_BSHADE_MINB 8
+#endif
+#ifndef M3D_BCONNECT_MINB
+#define M3D_BCONNECT_MINB 8
+#endif
+
 namespace m3d {
 
 namespace {
@@ -182,7 +189,7 @@ bidir_eye_raygen_kernel(DeviceCamera cam, DeviceBidirParams bp, PathBatch b, Bid
 // One step of sampleEyePath (EYE) or sampleLightPath's loop (!EYE): resolve the hit, build and
 // store the vertex, sample the continuation, apply pathEnder, compact survivors.
 template <bool EYE>
-__global__ void __launch_bounds__(kBlock, 8)
+__global__ void __launch_bounds__(kBlock, M3D_BSHADE_MINB)
 bidir_shade_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf, int cur, int depth) {
   const int n = buf.counts[cur];
   const unsigned lane = threadIdx.x & 31u;
@@ -485,7 +492,7 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
 
 // allPathCombinations (bidir.go:476-530) + rayColor's callback (bidir.go:113-158): one thread
 // per (eye prefix length i, light prefix length j, sample); threads of a warp share (i, j).
-__global__ void __launch_bounds__(kBlock, 8)
+__global__ void __launch_bounds__(kBlock, M3D_BCONNECT_MINB)
 bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
   // grid: x over the items of a class, y = class; most blocks of a sparsely filled class exit here
   const int cls = (int)blockIdx.y, rank = (int)(blockIdx.x * kBlock + threadIdx.x);

@@ -104,7 +104,15 @@ path_raygen_kernel(DeviceCamera cam, DevicePathParams pp, PathBatch b, PathBuffe
 // coherent in material code and every kernel's instruction footprint fits the instruction
 // cache (the fused shade kernel of the first version stalled on instruction fetch 2/3 of the
 // time, profiles/ncu_path_r1.md).
-__global__ void __launch_bounds__(kShadeBlock, 8)
+// LIGHTS = false (no point lights: C3 / C4 / C5) compiles the shadow-ray and BSDF evaluation out.
+#ifndef M3D_RESOLVE_MINB
+#define M3D_RESOLVE_MINB 4
+#endif
+#ifndef M3D_SAMPLE_MINB
+#define M3D_SAMPLE_MINB 8
+#endif
+template <bool LIGHTS>
+__global__ void __launch_bounds__(kShadeBlock, M3D_RESOLVE_MINB)
 path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *__restrict__ lights, PathBatch b,
                     PathBuffers buf, int cur, int depth) {
   const int n = buf.counts[cur];
@@ -129,7 +137,7 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
       // float32 hit evaluation: Monte-Carlo parity is statistical, the float64 refinement of the
       // first-hit API (1e-5 on t and normals) is not needed here; shapes stay float64
       const SceneHit h = resolve_scene_hit(sc, o, d, raw, skip_in[q], false);
-      if (pp.num_lights > 0 && h.obj < 0) {
+      if (LIGHTS && pp.num_lights > 0 && h.obj < 0) {
         // no shadow rays for a miss: give the slots an empty parameter interval
         for (int l = 0; l < pp.num_lights; l++) {
           const size_t si = (size_t)q * pp.num_lights + l;
@@ -158,7 +166,7 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
         }
         // raytrace.go:156-168: one shadow ray per point light, un-normalised direction,
         // occluded iff a hit has Scale < 1
-        for (int l = 0; l < pp.num_lights; l++) {
+        for (int l = 0; LIGHTS && l < pp.num_lights; l++) {
           const DevicePointLight lt = lights[l];
           const V3f lo = v3f(lt.origin);
           const V3f light_dir = lo - point;
@@ -238,7 +246,7 @@ __device__ __forceinline__ V3f kind_bsdf_delta(const DeviceScene &sc, const MatA
 // sourceDensity with focus points (raytrace.go:183-215), throughput update and cutoff
 // (raytrace.go:139-142, 170-180), ballot/popc compaction of the survivors into the next queue.
 template <int KIND>
-__global__ void __launch_bounds__(kShadeBlock, 8)
+__global__ void __launch_bounds__(kShadeBlock, M3D_SAMPLE_MINB)
 path_sample_kernel(DeviceScene sc, DevicePathParams pp, PathBatch b, PathBuffers buf, int cur, int depth) {
   const int n = buf.counts[4 + KIND];
   const unsigned lane = threadIdx.x & 31u;
@@ -419,12 +427,18 @@ static int shade_grid(K kernel, int64_t n) {
 
 void launch_path_resolve(const DeviceScene &sc, const DevicePathParams &pp, const DevicePointLight *lights,
                          const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream) {
-  static int grid_full = 0;
+  static int grid_full[2] = {0, 0};
   const int64_t n = (int64_t)b.nP * b.S;
-  if (!grid_full) grid_full = shade_grid(path_resolve_kernel, (int64_t)1 << 40);
+  const int li = pp.num_lights > 0 ? 1 : 0;
+  if (!grid_full[li])
+    grid_full[li] = li ? shade_grid(path_resolve_kernel<true>, (int64_t)1 << 40)
+                       : shade_grid(path_resolve_kernel<false>, (int64_t)1 << 40);
   const int64_t want = (n + kShadeBlock - 1) / kShadeBlock;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_full, want));
-  path_resolve_kernel<<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_full[li], want));
+  if (li)
+    path_resolve_kernel<true><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth);
+  else
+    path_resolve_kernel<false><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth);
 }
 
 void launch_path_sample(int kind, const DeviceScene &sc, const DevicePathParams &pp, const PathBatch &b,
