@@ -26,6 +26,7 @@ constexpr int kWarpsPerBlock = kTraceBlock / 32;
 constexpr int kSmemStack = 10;    // stack entries per thread kept in shared memory
 constexpr int kLocalStack = 54;   // overflow entries (local memory; untouched for sane trees)
 constexpr int kRayBatch = M3D_RAY_BATCH;  // rays a warp claims per global atomic
+constexpr int kTinySceneNodes = 32;       // at most this many wide nodes: two triangle rounds per trip
 #ifndef M3D_PREFETCH_NEXT_NODE
 #define M3D_PREFETCH_NEXT_NODE 0  // measured on B200: 2.58 -> 3.98 ms per 2^24 rays (L1 prefetches throttle the LSU)
 #endif
@@ -45,7 +46,7 @@ constexpr bool kPrefetchQueuedTri = M3D_PREFETCH_QUEUED_TRI != 0;
 // body is "one node visit, then that node's triangles" for all lanes together.
 // The trace kernel only writes the raw float32 hit (t, b1, b2, triangle index);
 // finish_hits_kernel re-evaluates hits in float64 in a separate, fully coherent pass.
-template <bool COUNT, int MIN_BLOCKS>
+template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS>
 __global__ void __launch_bounds__(kTraceBlock, (MIN_BLOCKS * 128) / kTraceBlock)
 trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ ray_counter) {
   __shared__ uint2 s_stack[kSmemStack][kTraceBlock];
@@ -198,19 +199,24 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
       // (a per-lane "while" here ran at 2.2 of 32 lanes; one test per trip of the common
       // loop keeps the lanes of a warp in lock step, and the second slot lets the lane
       // keep traversing while a multi-triangle leaf drains)
-      if (tq.y == 0u) {
-        tq = tq2;
-        tq2.y = 0u;
-      }
-      if (tq.y) {
-        const int bit = bfind32(tq.y);
-        tq.y &= ~(1u << bit);
-        const int ti = (int)(tq.x + (uint32_t)bit);
-        if (COUNT) cnt.tris++;
-        float t, b1, b2;
-        if (ti != skip_tri && intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
-          tmax = t;
-          hit_tri = ti;
+      // TRI_ROUNDS = 2 (tiny scenes: a handful of nodes, several large triangles per ray) repeats
+      // the phase so that the node phase is not paid once per triangle
+#pragma unroll
+      for (int round = 0; round < TRI_ROUNDS; round++) {
+        if (tq.y == 0u) {
+          tq = tq2;
+          tq2.y = 0u;
+        }
+        if (tq.y) {
+          const int bit = bfind32(tq.y);
+          tq.y &= ~(1u << bit);
+          const int ti = (int)(tq.x + (uint32_t)bit);
+          if (COUNT) cnt.tris++;
+          float t, b1, b2;
+          if (ti != skip_tri && intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
+            tmax = t;
+            hit_tri = ti;
+          }
         }
       }
       // ---- ray finished? (checked here so that the lane is refilled before the next A) --
@@ -311,24 +317,24 @@ void launch_count_hits(const DeviceBVH &bvh, const float *org3, const float *dir
 namespace {
 }  // namespace
 
-template <bool COUNT, int MIN_BLOCKS>
+template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS = 1>
 static void launch_trace_variant(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
   // persistent grid: as many blocks as stay resident
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) {
     int b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_first_hit_kernel<COUNT, MIN_BLOCKS>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS>, kTraceBlock, 0);
     blocks_per_sm = b > 0 ? b : 1;
   }
   long long want = (p.n + kTraceBlock - 1) / kTraceBlock;
   long long grid = (long long)device_sm_count() * blocks_per_sm;
   if (grid > want) grid = want;
   unsigned int *rc32 = reinterpret_cast<unsigned int *>(p.ray_counter);
-  trace_first_hit_kernel<COUNT, MIN_BLOCKS><<<(unsigned)grid, kTraceBlock, 0, stream>>>(bvh, p, rc32);
+  trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS><<<(unsigned)grid, kTraceBlock, 0, stream>>>(bvh, p, rc32);
 }
 
-void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
-  if (p.n <= 0) return;
+void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p_in, cudaStream_t stream) {
+  if (p_in.n <= 0) return;
   // register budget of the traversal kernel: 6 resident blocks/SM (80 registers, no spills)
   // measured best on B200; M3D_TRACE_MINB=7|8 selects the tighter variants for tuning runs
   static int minb = 0;
@@ -337,9 +343,19 @@ void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p, cudaStrea
     minb = e ? atoi(e) : 6;
     if (minb < 5 || minb > 8) minb = 6;
   }
+  static int tri_rounds_env = -1;
+  if (tri_rounds_env < 0) {
+    const char *e = getenv("M3D_TRACE_TRI_ROUNDS");
+    tri_rounds_env = e ? atoi(e) : 0;
+  }
+  const TraceLaunch &p = p_in;
+  // tiny hierarchies (cornell_box: 72 triangles in 4 nodes) spend their time in the triangle phase
+  const int tri_rounds = tri_rounds_env > 0 ? tri_rounds_env : (bvh.num_nodes <= kTinySceneNodes ? 2 : 1);
   cudaMemsetAsync(p.ray_counter, 0, sizeof(unsigned long long), stream);
   if (p.counters) {
     launch_trace_variant<true, 6>(bvh, p, stream);
+  } else if (tri_rounds >= 2) {
+    launch_trace_variant<false, 6, 2>(bvh, p, stream);
   } else if (minb == 5) {
     launch_trace_variant<false, 5>(bvh, p, stream);
   } else if (minb == 8) {
