@@ -338,7 +338,8 @@ __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, fl
       }
       // cheap float32 rejection with a generous error margin: most rays miss most shapes, and
       // the float64 tests (sqrt / divisions) are an order of magnitude more instructions
-      if (shape_certainly_missed(sh, o, d)) continue;
+      // (Monte-Carlo spheres go straight to their float32 test, which all lanes run together)
+      if ((refine || sh.kind != SHAPE_SPHERE) && shape_certainly_missed(sh, o, d)) continue;
       double t;
       D3 n;
       bool ok = false;
