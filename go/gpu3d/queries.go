@@ -52,17 +52,70 @@ func (m *MeshCollider) RayCollisionCounts(rays []model3d.Ray) ([]int, error) {
 	return res, nil
 }
 
-// RayCollisions implements model3d.Collider for f == nil (what ColliderContains passes);
-// a per-hit Go callback cannot run on the GPU path.
-func (m *MeshCollider) RayCollisions(r *model3d.Ray, f func(model3d.RayCollision)) int {
-	if f != nil {
-		panic("gpu3d: RayCollisions with a callback is not supported on the GPU path")
+// AllRayCollisions is the batched Collider.RayCollisions(r, f) with the collisions delivered
+// (model3d/collisions.go:263-273, primitives.go:189-196): res[i] holds the collisions of rays[i]
+// in order of Scale; Extra is a *model3d.TriangleCollision into the collider's own triangles.
+func (m *MeshCollider) AllRayCollisions(rays []model3d.Ray) ([][]model3d.RayCollision, error) {
+	n := len(rays)
+	org := make([]float32, 0, n*3)
+	dir := make([]float32, 0, n*3)
+	for _, r := range rays {
+		org = append(org, float32(r.Origin.X), float32(r.Origin.Y), float32(r.Origin.Z))
+		dir = append(dir, float32(r.Direction.X), float32(r.Direction.Y), float32(r.Direction.Z))
 	}
-	c, err := m.RayCollisionCounts([]model3d.Ray{*r})
+	offsets := make([]int64, n+1)
+	op := (*C.int64_t)(unsafe.Pointer(&offsets[0]))
+	// first call sizes the outputs (capacity 0), second call fills them
+	if err := status(C.m3d_mesh_ray_collisions(m.h, fptr(org), fptr(dir), C.int64_t(n), 0, op,
+		nil, nil, nil, nil, nil)); err != nil {
+		return nil, err
+	}
+	total := int(offsets[n])
+	res := make([][]model3d.RayCollision, n)
+	if total == 0 {
+		return res, nil
+	}
+	ts := make([]float32, total)
+	prim := make([]int32, total)
+	normal := make([]float32, total*3)
+	bary := make([]float32, total*3)
+	if err := status(C.m3d_mesh_ray_collisions(m.h, fptr(org), fptr(dir), C.int64_t(n), C.int64_t(total), op,
+		fptr(ts), (*C.int32_t)(unsafe.Pointer(&prim[0])), fptr(normal), fptr(bary), nil)); err != nil {
+		return nil, err
+	}
+	for i := 0; i < n; i++ {
+		for k := offsets[i]; k < offsets[i+1]; k++ {
+			res[i] = append(res[i], model3d.RayCollision{
+				Scale:  float64(ts[k]),
+				Normal: model3d.XYZ(float64(normal[3*k]), float64(normal[3*k+1]), float64(normal[3*k+2])),
+				Extra: &model3d.TriangleCollision{
+					Triangle:    m.Triangles[prim[k]],
+					Barycentric: [3]float64{float64(bary[3*k]), float64(bary[3*k+1]), float64(bary[3*k+2])},
+				},
+			})
+		}
+	}
+	return res, nil
+}
+
+// RayCollisions implements model3d.Collider (model3d/collisions.go:263-273): f, if not nil, is
+// called on the calling goroutine for every triangle the ray crosses (batch of one).
+func (m *MeshCollider) RayCollisions(r *model3d.Ray, f func(model3d.RayCollision)) int {
+	if f == nil {
+		c, err := m.RayCollisionCounts([]model3d.Ray{*r})
+		if err != nil {
+			panic(err)
+		}
+		return c[0]
+	}
+	res, err := m.AllRayCollisions([]model3d.Ray{*r})
 	if err != nil {
 		panic(err)
 	}
-	return c[0]
+	for _, c := range res[0] {
+		f(c)
+	}
+	return len(res[0])
 }
 
 // SphereCollisions is the batched Collider.SphereCollision (model3d/collisions.go:292-303).

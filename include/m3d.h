@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define M3D_ABI_VERSION 3
+#define M3D_ABI_VERSION 4
 
 typedef enum {
   M3D_OK = 0,
@@ -122,10 +122,27 @@ int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org,
                                       uint32_t flags, m3d_stats *stats);
 
 /* Batched Collider.RayCollisions(r, nil) (model3d/collisions.go:263-273, primitives.go:189-196):
- * counts[i] = number of triangles the forward half-line of ray i crosses (no callback: the
- * reference's func(RayCollision) cannot cross the ABI). */
+ * counts[i] = number of triangles the forward half-line of ray i crosses
+ * (m3d_mesh_ray_collisions below also delivers them). */
 int32_t m3d_mesh_ray_collision_counts(m3d_mesh *mesh, const float *org, const float *dir,
                                       int64_t n, int32_t *counts, m3d_stats *stats);
+
+/* Batched Collider.RayCollisions(r, f) with the collisions delivered (model3d/collisions.go:263-273,
+ * primitives.go:189-196; the reference calls f once per crossed triangle).  Two-call idiom:
+ *   offsets : n+1 int64, always written: exclusive prefix sum of the per-ray counts,
+ *             offsets[n] == total number of collisions
+ *   capacity: number of collisions the output arrays can hold.  If offsets[n] <= capacity the
+ *             collisions of ray i are written at indices [offsets[i], offsets[i+1]) in order of
+ *             increasing t (the reference's order is its BVH's traversal order, i.e. unspecified);
+ *             otherwise only offsets is written (call with capacity 0 to size the arrays).
+ *   t       : capacity floats   (RayCollision.Scale)
+ *   prim    : capacity int32    (triangle id of TriangleCollision.Triangle)
+ *   normal  : capacity*3 floats or NULL (RayCollision.Normal; interpolated with vnormals)
+ *   bary    : capacity*3 floats or NULL (TriangleCollision.Barycentric)
+ * Each collision is re-evaluated in float64 like the first-hit query. */
+int32_t m3d_mesh_ray_collisions(m3d_mesh *mesh, const float *org, const float *dir, int64_t n,
+                                int64_t capacity, int64_t *offsets, float *t, int32_t *prim,
+                                float *normal, float *bary, m3d_stats *stats);
 
 /* Batched model3d.ColliderContains(c, p, margin) (collisions.go:113-134) and with it
  * ColliderSolid.Contains (model3d/solid.go:256-300): odd number of triangles along the

@@ -103,7 +103,7 @@ SYMBOLS = [
     "m3d_abi_version", "m3d_last_error", "m3d_ctx_create", "m3d_ctx_destroy", "m3d_ctx_device",
     "m3d_ctx_synchronize", "m3d_mesh_create", "m3d_mesh_destroy", "m3d_mesh_get_info",
     "m3d_mesh_bounds", "m3d_mesh_first_ray_collisions", "m3d_mesh_first_ray_collisions_device",
-    "m3d_mesh_ray_collision_counts", "m3d_mesh_contains", "m3d_mesh_sdf", "m3d_mesh_sphere_collisions",
+    "m3d_mesh_ray_collision_counts", "m3d_mesh_ray_collisions", "m3d_mesh_contains", "m3d_mesh_sdf", "m3d_mesh_sphere_collisions",
     "m3d_scene_builder_create", "m3d_scene_builder_destroy", "m3d_scene_add_material",
     "m3d_scene_add_mesh", "m3d_scene_add_sphere", "m3d_scene_add_rect", "m3d_scene_add_cylinder",
     "m3d_scene_build", "m3d_scene_destroy", "m3d_scene_bounds", "m3d_scene_cast",

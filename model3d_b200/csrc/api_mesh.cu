@@ -448,6 +448,79 @@ int32_t m3d_mesh_ray_collision_counts(m3d_mesh *mesh, const float *org, const fl
   return M3D_OK;
 }
 
+int32_t m3d_mesh_ray_collisions(m3d_mesh *mesh, const float *org, const float *dir, int64_t n,
+                                int64_t capacity, int64_t *offsets, float *t, int32_t *prim, float *normal,
+                                float *bary, m3d_stats *stats) {
+  if (!mesh || n < 0 || capacity < 0 || !offsets || (n > 0 && (!org || !dir)) ||
+      (capacity > 0 && (!t || !prim)))
+    return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_ray_collisions: bad arguments");
+  if (n > (int64_t)0x7ff00000) return fail(M3D_ERR_INVALID_ARG, "batch too large; split it");
+  m3d_ctx *ctx = mesh->ctx;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  offsets[0] = 0;
+  if (n == 0) return M3D_OK;
+  cudaStream_t s = ctx->stream;
+  const size_t per = (size_t)n;
+  // rays + counts, then (n + 1) offsets; 8-byte aligned
+  const size_t ray_bytes = per * (6 * sizeof(float) + sizeof(int32_t));
+  const size_t off_at = (ray_bytes + 7) & ~(size_t)7;
+  M3D_CUDA(ctx->scratch[9].reserve(off_at + (per + 1) * sizeof(int64_t)));
+  float *d_org = ctx->scratch[9].as<float>();
+  float *d_dir = d_org + 3 * per;
+  int32_t *d_counts = (int32_t *)(d_dir + 3 * per);
+  int64_t *d_off = (int64_t *)(ctx->scratch[9].as<char>() + off_at);
+  M3D_CUDA(cudaMemcpyAsync(d_org, org, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  M3D_CUDA(cudaMemcpyAsync(d_dir, dir, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  GpuTimer tm, tm2;
+  tm.start(s);
+  launch_count_hits(mesh->bvh, d_org, d_dir, n, d_counts, nullptr, s);
+  tm.stop(s);
+  std::vector<int32_t> counts(per);
+  M3D_CUDA(cudaMemcpyAsync(counts.data(), d_counts, per * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  M3D_CUDA(cudaStreamSynchronize(s));
+  int64_t total = 0;
+  for (size_t i = 0; i < per; i++) {
+    offsets[i] = total;
+    total += counts[i];
+  }
+  offsets[per] = total;
+  double ms = tm.ms();
+  int launches = 1;
+  int64_t d2h = n * 4;
+  if (total > 0 && total <= capacity) {
+    const size_t tot = (size_t)total;
+    const size_t out_bytes = tot * (sizeof(float) + sizeof(int32_t) + (normal ? 12 : 0) + (bary ? 12 : 0));
+    M3D_CUDA(ctx->scratch[10].reserve(out_bytes));
+    float *d_t = ctx->scratch[10].as<float>();
+    int32_t *d_prim = (int32_t *)(d_t + tot);
+    float *d_normal = normal ? (float *)(d_prim + tot) : nullptr;
+    float *d_bary = bary ? (float *)(d_prim + tot) + (normal ? 3 * tot : 0) : nullptr;
+    M3D_CUDA(cudaMemcpyAsync(d_off, offsets, (per + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    tm2.start(s);
+    launch_collect_hits(mesh->bvh, d_org, d_dir, n, d_off, d_t, d_prim, d_normal, d_bary, s);
+    tm2.stop(s);
+    M3D_CUDA(cudaMemcpyAsync(t, d_t, tot * sizeof(float), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaMemcpyAsync(prim, d_prim, tot * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (normal) M3D_CUDA(cudaMemcpyAsync(normal, d_normal, tot * 12, cudaMemcpyDeviceToHost, s));
+    if (bary) M3D_CUDA(cudaMemcpyAsync(bary, d_bary, tot * 12, cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaStreamSynchronize(s));
+    ms += tm2.ms();
+    launches++;
+    d2h += (int64_t)out_bytes;
+  }
+  M3D_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->rays = n;
+    stats->hits = total;
+    stats->kernel_ms = ms;
+    stats->launches = launches;
+    stats->h2d_bytes = n * 24 + (launches > 1 ? (n + 1) * 8 : 0);
+    stats->d2h_bytes = d2h;
+  }
+  return M3D_OK;
+}
+
 static int32_t check_sdf_depth(const m3d_mesh *mesh, const char *who) {
   if (7 * (int64_t)mesh->info.max_depth + 1 > sdf_stack_capacity())
     return fail(M3D_ERR_UNSUPPORTED, "%s: BVH depth %d exceeds the nearest-triangle traversal stack", who,

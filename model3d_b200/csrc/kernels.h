@@ -26,6 +26,7 @@ struct TraceLaunch {
   const int32_t *skip_tris = nullptr;  // optional per ray: leaf-order triangle index to ignore
   const int *n_ptr = nullptr;          // optional device count (<= n): wavefront queues whose
                                        // length is only known on the device
+  uint32_t one_bits = 0x3f800000u;     // bits of 1.0f, kept opaque to ptxas (see unit_plus_byte)
 };
 
 // BVH traversal only: hit0 = (t_f32, 0, 0, bits(leaf-order triangle index | -1))
@@ -44,6 +45,12 @@ void launch_unpack_hits(const float4 *hit0, const float4 *hit1, int64_t n, float
 // ColliderContains direction (collisions.go:119-134)
 void launch_count_hits(const DeviceBVH &bvh, const float *org3, const float *dir3, int64_t n, int32_t *counts,
                        uint8_t *inside, cudaStream_t stream);
+
+// all hits delivered: hit k of ray i goes to index offsets[i] + k of t / prim (caller triangle id) /
+// normal3 / bary3 (the last two optional), ordered by t; offsets = exclusive prefix sum of the counts
+void launch_collect_hits(const DeviceBVH &bvh, const float *org3, const float *dir3, int64_t n,
+                         const int64_t *offsets, float *t, int32_t *prim, float *normal3, float *bary3,
+                         cudaStream_t stream);
 
 // nearest-triangle queries (sdf_kernels.cu): meshSDF.FaceSDF per point (any output may be null) ...
 // (counters: optional device 3 x u64: nodes fetched, float32 screens, float64 evaluations)

@@ -176,11 +176,22 @@ M3D_HD float min3f(float a, float b, float c) {
 }
 // byte j of q placed in mantissa bits 8..15 of 1.0f: value == 1 + q_j * 2^-15 exactly.
 // One PRMT on the device instead of a byte extract + integer->float conversion.
-M3D_HD float unit_plus_byte(uint32_t q, int j) {
+// `one` is the bit pattern of 1.0f.  The traversal kernel passes it as a kernel parameter so that
+// ptxas cannot fold it: PRMT takes only one non-register operand, and with both the selector and
+// 0x3f800000 known it keeps re-materialising the four selectors in registers (one IMAD.U32 per
+// two PRMTs in the node test); with `one` opaque the selector is the immediate.
+M3D_HD float unit_plus_byte(uint32_t q, int j, uint32_t one) {
 #if defined(__CUDA_ARCH__)
-  return __uint_as_float(__byte_perm(q, 0x3f800000u, 0x7604u | ((uint32_t)j << 4)));
+  uint32_t r;
+  switch (j) {
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(q), "r"(one)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(q), "r"(one)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7624;" : "=r"(r) : "r"(q), "r"(one)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(q), "r"(one)); break;
+  }
+  return __uint_as_float(r);
 #else
-  return f_from_bits(0x3f800000u | (((q >> (8 * j)) & 0xffu) << 8));
+  return f_from_bits(one | (((q >> (8 * j)) & 0xffu) << 8));
 #endif
 }
 
@@ -326,7 +337,7 @@ M3D_HD bool intersect_tri_loaded(const float4 *__restrict__ tri, const float4 q0
 // b absorbs a rounding error of at most ulp(S)/2, so near planes are moved back and far
 // planes forward by |S| * 2^-22 (0.8 % of a grid step) to stay conservative.
 M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index, const RayPre &rp,
-                           float tmax, uint2 &ngroup, uint2 &tgroup) {
+                           float tmax, uint2 &ngroup, uint2 &tgroup, uint32_t one = 0x3f800000u) {
   const uint4 *np = nodes + (size_t)node_index * 5;
 #if defined(__CUDA_ARCH__)
   const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
@@ -362,12 +373,12 @@ M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index,
     const uint32_t zn = (rp.octinv4 & 1u) ? qloz : qhiz, zf = (rp.octinv4 & 1u) ? qhiz : qloz;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const float t0x = fmaf(unit_plus_byte(xn, j), Sx, bnx);
-      const float t0y = fmaf(unit_plus_byte(yn, j), Sy, bny);
-      const float t0z = fmaf(unit_plus_byte(zn, j), Sz, bnz);
-      const float t1x = fmaf(unit_plus_byte(xf, j), Sx, bfx);
-      const float t1y = fmaf(unit_plus_byte(yf, j), Sy, bfy);
-      const float t1z = fmaf(unit_plus_byte(zf, j), Sz, bfz);
+      const float t0x = fmaf(unit_plus_byte(xn, j, one), Sx, bnx);
+      const float t0y = fmaf(unit_plus_byte(yn, j, one), Sy, bny);
+      const float t0z = fmaf(unit_plus_byte(zn, j, one), Sz, bnz);
+      const float t1x = fmaf(unit_plus_byte(xf, j, one), Sx, bfx);
+      const float t1y = fmaf(unit_plus_byte(yf, j, one), Sy, bfy);
+      const float t1z = fmaf(unit_plus_byte(zf, j, one), Sz, bfz);
       const float cmin = fmaxf(max3f(t0x, t0y, t0z), rp.tmin);
       const float cmax = fminf(min3f(t1x, t1y, t1z), tmax_w);
       if (cmin <= cmax) {
@@ -462,6 +473,45 @@ M3D_HD int count_bvh_hits(const uint4 *__restrict__ nodes, const float4 *__restr
       const int32_t ti = (int32_t)(tgroup.x + (uint32_t)bit);
       float t, b1, b2;
       if (intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) count++;
+    }
+    if ((ngroup.y & 0xff000000u) == 0) {
+      if (sp == 0) break;
+      ngroup = stack[--sp];
+    }
+    node_index = take_nearest_child(ngroup, rp.octinv4);
+    if ((ngroup.y & 0xff000000u) && sp < M3D_STACK_SIZE) stack[sp++] = ngroup;
+  }
+  return count;
+}
+
+// All-hits traversal that also delivers the hits (Collider.RayCollisions(r, f) with f != nil,
+// model3d/collisions.go:263-273): same walk and same per-triangle decision as count_bvh_hits,
+// so the two agree hit for hit; the first `cap` hits are written as (float32 t, leaf-order
+// triangle index).  Returns the number of hits found (may exceed cap).
+M3D_HD int collect_bvh_hits(const uint4 *__restrict__ nodes, const float4 *__restrict__ tris,
+                            const float *scene_min, const float *scene_max, const RayF &ray, int cap,
+                            float *t_out, int32_t *tri_out) {
+  const RayPre rp = precompute_ray(ray, scene_min, scene_max);
+  const float tmax = ray.tmax;
+  int count = 0;
+  uint2 stack[M3D_STACK_SIZE];
+  int sp = 0;
+  uint2 ngroup, tgroup;
+  uint32_t node_index = 0;
+  for (;;) {
+    intersect_node(nodes, node_index, rp, tmax, ngroup, tgroup);
+    while (tgroup.y) {
+      const int bit = bfind32(tgroup.y);
+      tgroup.y &= ~(1u << bit);
+      const int32_t ti = (int32_t)(tgroup.x + (uint32_t)bit);
+      float t, b1, b2;
+      if (intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
+        if (count < cap) {
+          t_out[count] = t;
+          tri_out[count] = ti;
+        }
+        count++;
+      }
     }
     if ((ngroup.y & 0xff000000u) == 0) {
       if (sp == 0) break;

@@ -23,8 +23,14 @@ namespace {
 #endif
 constexpr int kTraceBlock = M3D_TRACE_BLOCK;
 constexpr int kWarpsPerBlock = kTraceBlock / 32;
-constexpr int kSmemStack = 10;    // stack entries per thread kept in shared memory
-constexpr int kLocalStack = 54;   // overflow entries (local memory; untouched for sane trees)
+#ifndef M3D_SMEM_STACK
+#define M3D_SMEM_STACK 10
+#endif
+#ifndef M3D_OPAQUE_ONE
+#define M3D_OPAQUE_ONE 1  // bits of 1.0f from the kernel parameters: PRMT selectors become immediates
+#endif
+constexpr int kSmemStack = M3D_SMEM_STACK;  // stack entries per thread kept in shared memory
+constexpr int kLocalStack = 64 - kSmemStack;  // overflow entries (local memory; untouched for sane trees)
 constexpr int kRayBatch = M3D_RAY_BATCH;  // rays a warp claims per global atomic
 constexpr int kTinySceneNodes = 32;       // at most this many wide nodes: two triangle rounds per trip
 #ifndef M3D_PREFETCH_NEXT_NODE
@@ -175,7 +181,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
         }
         if (COUNT) cnt.nodes++;
         uint2 tnew;
-        intersect_node(nodes, node_index, rp, tmax, ngroup, tnew);
+        intersect_node(nodes, node_index, rp, tmax, ngroup, tnew, M3D_OPAQUE_ONE ? p.one_bits : 0x3f800000u);
         if (tq.y == 0u) {
           tq = tnew;
         } else {
@@ -302,7 +308,92 @@ count_hits_kernel(DeviceBVH bvh, const float *__restrict__ org3, const float *__
   if (inside) inside[i] = (uint8_t)(c & 1);
 }
 
+
+// Collider.RayCollisions(r, f) with the collisions delivered (collisions.go:263-273,
+// primitives.go:189-196): one thread per ray re-walks the hierarchy exactly like the counting
+// pass, writes its hits into the ray's segment [offsets[i], offsets[i+1]) of the outputs, orders
+// the segment by t (the reference's callback order is its own BVH's traversal order) and
+// re-evaluates every hit in float64 with the reference's arithmetic like the first-hit finish pass.
+__global__ void __launch_bounds__(128)
+collect_hits_kernel(DeviceBVH bvh, const float *__restrict__ org3, const float *__restrict__ dir3, int64_t n,
+                    const int64_t *__restrict__ offsets, float *__restrict__ t_out, int32_t *__restrict__ prim_out,
+                    float *__restrict__ normal3, float *__restrict__ bary3) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t begin = offsets[i];
+  const int cap = (int)(offsets[i + 1] - begin);
+  if (cap <= 0 || bvh.num_tris <= 0) return;
+  RayF ray;
+  ray.ox = org3[3 * i];
+  ray.oy = org3[3 * i + 1];
+  ray.oz = org3[3 * i + 2];
+  ray.dx = dir3[3 * i];
+  ray.dy = dir3[3 * i + 1];
+  ray.dz = dir3[3 * i + 2];
+  ray.tmin = 0.f;
+  ray.tmax = INFINITY;
+  float *ts = t_out + begin;
+  int32_t *ids = prim_out + begin;  // leaf-order indices until the last loop
+  int found = collect_bvh_hits(bvh.nodes, bvh.tris, bvh.bmin, bvh.bmax, ray, cap, ts, ids);
+  if (found > cap) found = cap;
+  for (int a = 1; a < found; a++) {  // insertion sort by (t, leaf index): segments are short
+    const float ta = ts[a];
+    const int32_t ia = ids[a];
+    int b = a - 1;
+    while (b >= 0 && (ts[b] > ta || (ts[b] == ta && ids[b] > ia))) {
+      ts[b + 1] = ts[b];
+      ids[b + 1] = ids[b];
+      b--;
+    }
+    ts[b + 1] = ta;
+    ids[b + 1] = ia;
+  }
+  for (int k = 0; k < cap; k++) {
+    const int64_t o = begin + k;
+    if (k >= found) {  // cannot happen for offsets made from the counting pass; keep the output defined
+      ts[k] = 0.f;
+      ids[k] = -1;
+      continue;
+    }
+    const int32_t ti = ids[k];
+    const float4 *tri = bvh.tris + (size_t)ti * 3;
+    const HitD r = refine_hit_f64(tri, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz);
+    if (r.t >= 0.0) ts[k] = (float)r.t;
+    ids[k] = __float_as_int(__ldg(&tri[0].w));
+    if (normal3) {
+      double nx = r.nx, ny = r.ny, nz = r.nz;
+      if (bvh.vnormals) {  // InterpNormalTriangle.InterpNormal (primitives.go:508-516)
+        const float4 *vn = bvh.vnormals + (size_t)ti * 3;
+        const float4 a = __ldg(vn), b = __ldg(vn + 1), c = __ldg(vn + 2);
+        nx = r.b0 * a.x + r.b1 * b.x + r.b2 * c.x;
+        ny = r.b0 * a.y + r.b1 * b.y + r.b2 * c.y;
+        nz = r.b0 * a.z + r.b1 * b.z + r.b2 * c.z;
+        const double s = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+        nx *= s;
+        ny *= s;
+        nz *= s;
+      }
+      normal3[3 * o] = (float)nx;
+      normal3[3 * o + 1] = (float)ny;
+      normal3[3 * o + 2] = (float)nz;
+    }
+    if (bary3) {
+      bary3[3 * o] = (float)r.b0;
+      bary3[3 * o + 1] = (float)r.b1;
+      bary3[3 * o + 2] = (float)r.b2;
+    }
+  }
+}
+
 }  // namespace
+
+void launch_collect_hits(const DeviceBVH &bvh, const float *org3, const float *dir3, int64_t n,
+                         const int64_t *offsets, float *t, int32_t *prim, float *normal3, float *bary3,
+                         cudaStream_t stream) {
+  if (n <= 0) return;
+  collect_hits_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(bvh, org3, dir3, n, offsets, t, prim,
+                                                                        normal3, bary3);
+}
 
 void launch_count_hits(const DeviceBVH &bvh, const float *org3, const float *dir3, int64_t n, int32_t *counts,
                        uint8_t *inside, cudaStream_t stream) {

@@ -175,12 +175,43 @@ class MeshCollider:
                                                       C.c_int64(org.shape[0]), _p(counts, i32p), None))
         return counts
 
+    def RayCollisionsBatch(self, origins, directions, normals=True, barycentric=True):
+        """Batched Collider.RayCollisions(r, f) with the collisions delivered (collisions.go:263-273,
+        primitives.go:189-196).  Returns a dict: offsets int64 [n+1] (the collisions of ray i are
+        rows offsets[i]:offsets[i+1], ordered by Scale), Scale float32 [total], Triangle int32
+        [total], Normal float32 [total,3], Barycentric float32 [total,3] (None when not asked for)."""
+        org = np.ascontiguousarray(np.asarray(origins, dtype=np.float32).reshape(-1, 3))
+        dr = np.ascontiguousarray(np.asarray(directions, dtype=np.float32).reshape(-1, 3))
+        if org.shape != dr.shape:
+            raise ValueError("origins and directions must have the same shape")
+        n = org.shape[0]
+        offsets = np.zeros(n + 1, np.int64)
+        i64p = C.POINTER(C.c_int64)
+        fn = N.lib().m3d_mesh_ray_collisions
+        N.check(fn(self.h, _p(org, f32p), _p(dr, f32p), C.c_int64(n), C.c_int64(0), _p(offsets, i64p),
+                   None, None, None, None, None))
+        total = int(offsets[n])
+        t = np.zeros(total, np.float32)
+        prim = np.zeros(total, np.int32)
+        nrm = np.zeros((total, 3), np.float32) if normals else None
+        bary = np.zeros((total, 3), np.float32) if barycentric else None
+        if total > 0:
+            N.check(fn(self.h, _p(org, f32p), _p(dr, f32p), C.c_int64(n), C.c_int64(total),
+                       _p(offsets, i64p), _p(t, f32p), _p(prim, i32p),
+                       _p(nrm, f32p) if normals else None, _p(bary, f32p) if barycentric else None, None))
+        return dict(offsets=offsets, Scale=t, Triangle=prim, Normal=nrm, Barycentric=bary)
+
     def RayCollisions(self, r, f=None):
-        """Collider.RayCollisions: the count for one ray.  A per-hit callback cannot run on the
-        GPU path: f must be None (ColliderContains, the main caller, passes nil)."""
-        if f is not None:
-            raise UnsupportedError("RayCollisions with a callback is not on the GPU path")
-        return int(self.RayCollisionCounts([r.Origin], [r.Direction])[0])
+        """Collider.RayCollisions (collisions.go:263-273): calls f(RayCollision) for every triangle
+        the ray crosses (in order of Scale) and returns their number."""
+        if f is None:
+            return int(self.RayCollisionCounts([r.Origin], [r.Direction])[0])
+        b = self.RayCollisionsBatch([r.Origin], [r.Direction])
+        for k in range(int(b["offsets"][1])):
+            f(RayCollision(
+                Scale=float(b["Scale"][k]), Normal=tuple(float(x) for x in b["Normal"][k]),
+                Extra=TriangleCollision(int(b["Triangle"][k]), tuple(float(x) for x in b["Barycentric"][k]))))
+        return int(b["offsets"][1])
 
     def Contains(self, coords, margin=0.0):
         """Batched model3d.ColliderContains(self, p, margin) (collisions.go:113-134), bool [n]."""

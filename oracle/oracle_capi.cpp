@@ -218,6 +218,39 @@ void orc_collider_hit_counts(void *h, const float *org, const float *dir, int64_
   });
 }
 
+// Batched Collider.RayCollisions(r, f) with the collisions delivered (collisions.go:263-273): the
+// hits of ray i go to rows [offsets[i], offsets[i+1]) ordered by scale (stable: ties keep the
+// reference traversal order); offsets must come from orc_collider_hit_counts.
+void orc_collider_all_hits_batch(void *h, const float *org, const float *dir, int64_t n, const int64_t *offsets,
+                                 double *t, int32_t *prim, double *normal, double *bary, int nthreads) {
+  auto *m = (MeshCollider *)h;
+  parallel_for(n, nthreads, [&](int64_t b, int64_t e, int) {
+    std::vector<Hit> hits;
+    for (int64_t i = b; i < e; i++) {
+      Ray r{V3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2])};
+      hits.clear();
+      m->ray_collisions(r, hits);
+      std::stable_sort(hits.begin(), hits.end(), [](const Hit &a, const Hit &b) { return a.scale < b.scale; });
+      const int64_t cap = offsets[i + 1] - offsets[i];
+      for (int64_t k = 0; k < (int64_t)hits.size() && k < cap; k++) {
+        const int64_t o = offsets[i] + k;
+        t[o] = hits[k].scale;
+        prim[o] = hits[k].prim;
+        if (normal) {
+          normal[3 * o] = hits[k].normal.x;
+          normal[3 * o + 1] = hits[k].normal.y;
+          normal[3 * o + 2] = hits[k].normal.z;
+        }
+        if (bary) {
+          bary[3 * o] = hits[k].bary[0];
+          bary[3 * o + 1] = hits[k].bary[1];
+          bary[3 * o + 2] = hits[k].bary[2];
+        }
+      }
+    }
+  });
+}
+
 // ColliderContains with margin 0 (collisions.go:119-134): odd number of collisions along the
 // reference's fixed direction.
 void orc_collider_contains(void *h, const float *pts, int64_t n, uint8_t *inside, int nthreads) {

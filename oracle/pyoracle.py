@@ -244,6 +244,25 @@ class Collider:
                                       _p(out, i32p), C.c_int(threads))
         return out
 
+    def all_hits_batch(self, org, dir, threads=1):
+        """Collider.RayCollisions(r, f) per ray (collisions.go:263-273): dict(offsets, t, prim,
+        normal, bary), the hits of ray i in rows offsets[i]:offsets[i+1] ordered by t."""
+        org = np.ascontiguousarray(org, np.float32)
+        dir = np.ascontiguousarray(dir, np.float32)
+        n = org.shape[0]
+        counts = self.hit_counts(org, dir, threads)
+        offsets = np.zeros(n + 1, np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        total = int(offsets[n])
+        t = np.zeros(total, np.float64)
+        prim = np.zeros(total, np.int32)
+        normal = np.zeros((total, 3), np.float64)
+        bary = np.zeros((total, 3), np.float64)
+        lib().orc_collider_all_hits_batch(self.h, _p(org, f32p), _p(dir, f32p), C.c_int64(n),
+                                          _p(offsets, i64p), _p(t, f64p), _p(prim, i32p),
+                                          _p(normal, f64p), _p(bary, f64p), C.c_int(threads))
+        return dict(offsets=offsets, t=t, prim=prim, normal=normal, bary=bary)
+
     def sdf(self, pts, threads=1):
         """MeshToSDF(mesh).FaceSDF per point (sdf.go:229-240): (sdf, nearest point, face id)."""
         pts = np.ascontiguousarray(pts, np.float32)

@@ -64,4 +64,24 @@ void emul_trace(void *h, const float *org, const float *dir, int64_t n, float *t
   }
   if (counters) { counters[0] = cn; counters[1] = ct; }
 }
+// collect_bvh_hits + count_bvh_hits per ray: counts[n], and the first cap hits of every ray as
+// (t, caller triangle id) rows at i * cap
+void emul_collect(void *h, const float *org, const float *dir, int64_t n, int cap, int32_t *counts,
+                  int32_t *counts2, float *t, int32_t *prim) {
+  auto *e = (Emul *)h;
+  const uint4 *nodes = (const uint4 *)e->bvh.nodes.data();
+  const float4 *tris = (const float4 *)e->bvh.tris.data();
+  std::vector<int32_t> ids(cap);
+  for (int64_t i = 0; i < n; i++) {
+    RayF r;
+    r.ox = org[3 * i]; r.oy = org[3 * i + 1]; r.oz = org[3 * i + 2]; r.tmin = 0.f;
+    r.dx = dir[3 * i]; r.dy = dir[3 * i + 1]; r.dz = dir[3 * i + 2]; r.tmax = __builtin_inff();
+    counts[i] = collect_bvh_hits(nodes, tris, e->bvh.bounds_min, e->bvh.bounds_max, r, cap, t + i * cap, ids.data());
+    counts2[i] = count_bvh_hits(nodes, tris, e->bvh.bounds_min, e->bvh.bounds_max, r);
+    for (int k = 0; k < counts[i] && k < cap; k++) {
+      int32_t p; memcpy(&p, &tris[(size_t)ids[k] * 3].w, 4);
+      prim[i * cap + k] = p;
+    }
+  }
+}
 }

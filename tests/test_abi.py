@@ -28,7 +28,7 @@ def test_python_symbol_list_matches_header():
 
 
 def test_abi_version(built):
-    assert built.m3d_abi_version() == 3
+    assert built.m3d_abi_version() == 4
 
 
 def test_struct_sizes_match_header(built):

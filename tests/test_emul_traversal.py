@@ -94,3 +94,30 @@ def test_emulated_no_refine_within_tolerance(emul, oracle):
     same = (ref["prim"] >= 0) & (ref["prim"] == got["prim"])
     rel = np.abs(got["t"] - ref["t"])[same] / np.abs(ref["t"][same])
     assert np.quantile(rel, 0.999) < 1e-5
+
+
+def test_emulated_collect_hits_matches_oracle(emul, oracle):
+    """collect_bvh_hits (Collider.RayCollisions with the hits delivered, collisions.go:263-273) on
+    the product's wide BVH == the oracle's all-hits walk: same triangles per ray, t within 1e-5."""
+    rng = np.random.default_rng(9)
+    tris = (rng.normal(size=(2000, 1, 3)) + rng.normal(size=(2000, 3, 3)) * 0.3).astype(np.float32).reshape(-1, 9)
+    org, d = rays(rng, 4000)
+    h = C.c_void_p(emul.emul_build(P(tris, C.c_float), C.c_int64(tris.shape[0])))
+    n, cap = org.shape[0], 64
+    counts, counts2 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    t = np.zeros((n, cap), np.float32)
+    prim = np.zeros((n, cap), np.int32)
+    emul.emul_collect(h, P(org, C.c_float), P(d, C.c_float), C.c_int64(n), C.c_int(cap), P(counts, C.c_int32),
+                      P(counts2, C.c_int32), P(t, C.c_float), P(prim, C.c_int32))
+    emul.emul_destroy(h)
+    assert np.array_equal(counts, counts2) and counts.max() < cap and counts.max() > 4
+    ref = oracle.Collider(tris.reshape(-1, 3, 3)).all_hits_batch(org, d, threads=4)
+    rc = np.diff(ref["offsets"])
+    assert (rc != counts).sum() <= 1
+    for i in np.nonzero(rc == counts)[0]:
+        a0 = ref["offsets"][i]
+        go, ro = np.argsort(prim[i, :counts[i]]), np.argsort(ref["prim"][a0:a0 + rc[i]])
+        assert np.array_equal(prim[i, :counts[i]][go], ref["prim"][a0:a0 + rc[i]][ro])
+        rt = ref["t"][a0:a0 + rc[i]][ro]
+        # raw float32 t of the traversal (the kernel re-evaluates every hit in float64 afterwards)
+        assert np.all(np.abs(t[i, :counts[i]][go] - rt) <= 1e-4 * np.maximum(np.abs(rt), 1.0))  # glancing hits are ill-conditioned in float32

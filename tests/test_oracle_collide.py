@@ -164,3 +164,24 @@ def test_scene_cast_closest_wins(oracle):
     r = sc.cast(np.array([[0, 0, -3.0], [0, 0, 20.0], [5, 5, 5]]), np.array([[0, 0, 1.0], [0, 0, -1.0], [1, 0, 0]]))
     assert r["obj"].tolist() == [1, 2, -1]
     assert np.allclose(r["t"][:2], [4.0, 11.0])
+
+
+def test_all_hits_batch_matches_single_ray_walk(oracle):
+    """The batched all-hits helper the GPU RayCollisions test compares with == the per-ray
+    BVH walk == brute force over every triangle (collisions_test.go:22-76)."""
+    rng = np.random.default_rng(5)
+    tris = (rng.normal(size=(400, 1, 3)) + rng.normal(size=(400, 3, 3)) * 0.4).astype(np.float32)
+    col = oracle.Collider(tris)
+    org = rng.normal(size=(300, 3)).astype(np.float32)
+    d = rng.normal(size=(300, 3)).astype(np.float32)
+    b = col.all_hits_batch(org, d, threads=2)
+    assert b["offsets"][-1] > 300
+    for i in range(300):
+        n, t, prim = col.all_hits(org[i].astype(np.float64), d[i].astype(np.float64), brute=True)
+        a0, a1 = b["offsets"][i], b["offsets"][i + 1]
+        assert n == a1 - a0
+        assert np.array_equal(np.sort(prim), np.sort(b["prim"][a0:a1]))
+        assert np.allclose(np.sort(t), b["t"][a0:a1], rtol=0, atol=1e-12)
+        p = org[i] + d[i] * b["t"][a0:a1, None]
+        q = np.einsum("nk,nkc->nc", b["bary"][a0:a1], tris[b["prim"][a0:a1]].astype(np.float64))
+        assert np.abs(p - q).max() < 1e-8 if n else True
