@@ -247,8 +247,10 @@ struct RayPre {
 
 // (7 - octant) of a direction replicated in four bytes
 M3D_HD uint32_t ray_octinv4(float dx, float dy, float dz) {
-  const uint32_t octinv = ((dx < 0.f ? 0u : 4u) | (dy < 0.f ? 0u : 2u) | (dz < 0.f ? 0u : 1u));
-  return octinv * 0x01010101u;
+  // by SIGN BIT, like the copysignf() of precompute_ray: a -0.0 component gets a negative
+  // reciprocal there, so it must also count as negative here (near / far planes swap with it)
+  const uint32_t neg = ((bits_from_f(dx) >> 31) << 2) | ((bits_from_f(dy) >> 31) << 1) | (bits_from_f(dz) >> 31);
+  return (neg ^ 7u) * 0x01010101u;
 }
 
 // scene_min/max: bounds of all triangle vertices (for the error bound: no vertex is

@@ -83,6 +83,11 @@ def test_emulated_axis_aligned_rays(emul, oracle):
     d[np.arange(n), rng.integers(0, 3, n)] = rng.choice([-1.0, 1.0, 2.5], n)
     got = emul_trace(emul, tris, org, d)
     compare(oracle, tris, org, d, got)
+    # negative zeros: the reciprocal's sign and the near / far plane choice must agree
+    d[::2] = np.where(d[::2] == 0, np.float32(-0.0), d[::2])
+    got = emul_trace(emul, tris, org, d)
+    ref = compare(oracle, tris, org, d, got)
+    assert (ref["prim"] >= 0).sum() > n // 10
 
 
 def test_emulated_no_refine_within_tolerance(emul, oracle):

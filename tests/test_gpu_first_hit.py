@@ -83,8 +83,15 @@ def test_axis_aligned_rays(built, oracle):
     org = rng.uniform(-1.5, 1.5, size=(n, 3)).astype(np.float32)
     d = np.zeros((n, 3), np.float32)
     d[np.arange(n), rng.integers(0, 3, n)] = rng.choice([-1.0, 1.0, 2.5], n)
-    got = MeshCollider(tris).FirstRayCollisions(org, d)
+    col = MeshCollider(tris)
+    got = col.FirstRayCollisions(org, d)
     check_parity(oracle, tris, org, d, got)
+    # negative zeros are zeros too (rate == 0 in the reference): same hits
+    d2 = d.copy()
+    d2[::2] = np.where(d2[::2] == 0, np.float32(-0.0), d2[::2])
+    got2 = col.FirstRayCollisions(org, d2)
+    check_parity(oracle, tris, org, d2, got2)
+    assert np.array_equal(got.Triangle, got2.Triangle) and (got2.Triangle >= 0).sum() > n // 10
 
 
 def test_empty_single_and_degenerate(built, oracle):
