@@ -338,8 +338,13 @@ M3D_HD bool intersect_tri_loaded(const float4 *__restrict__ tri, const float4 q0
 // S = 2^(e_a+15) / d_a and b = (origin_a - o_a) / d_a - S: one PRMT and one FMA per plane.
 // b absorbs a rounding error of at most ulp(S)/2, so near planes are moved back and far
 // planes forward by |S| * 2^-22 (0.8 % of a grid step) to stay conservative.
+// lut (optional, 256 entries 12 bytes apart in shared memory): lut[m] = ((m >> 5) & 7) << (m & 31), the hit bits of a
+// child with meta byte m.  The shift-and-mask sequence it replaces is ~3 ALU-pipe instructions per
+// child, and the ALU pipe (PRMT / FMNMX / LOP3 / SHF, half rate) is the busiest unit of the kernel.
+template <bool USE_LUT = false>
 M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index, const RayPre &rp,
-                           float tmax, uint2 &ngroup, uint2 &tgroup, uint32_t one = 0x3f800000u) {
+                           float tmax, uint2 &ngroup, uint2 &tgroup, uint32_t one = 0x3f800000u,
+                           uint32_t lut_saddr = 0u /* shared-window address of the table */) {
   const uint4 *np = nodes + (size_t)node_index * 5;
 #if defined(__CUDA_ARCH__)
   const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
@@ -365,7 +370,8 @@ M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index,
     const uint32_t meta4 = half == 0 ? n1.z : n1.w;
     const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
     const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-    const uint32_t bit_index4 = (meta4 ^ (rp.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t lut_index4 = meta4 ^ (rp.octinv4 & inner_mask4);
+    const uint32_t bit_index4 = lut_index4 & 0x1f1f1f1fu;
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     const uint32_t qlox = half == 0 ? n2.x : n2.y, qloy = half == 0 ? n2.z : n2.w;
     const uint32_t qloz = half == 0 ? n3.x : n3.y, qhix = half == 0 ? n3.z : n3.w;
@@ -383,7 +389,19 @@ M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index,
       const float t1z = fmaf(unit_plus_byte(zf, j, one), Sz, bfz);
       const float cmin = fmaxf(max3f(t0x, t0y, t0z), rp.tmin);
       const float cmax = fminf(min3f(t1x, t1y, t1z), tmax_w);
-      if (cmin <= cmax) {
+      if (USE_LUT) {
+#if defined(__CUDA_ARCH__)
+        // PRMT (byte j) + IMAD (address, FMA pipe) + LDS, issued for all lanes: no dependence on the
+        // slab test, so the eight loads are in flight while the min / max chains run
+        const uint32_t m = __byte_perm(lut_index4, 0u, 0x4440u + (uint32_t)j);
+        uint32_t bits;
+        uint32_t addr;
+        // stride 12 bytes, not 4: a power-of-two scale becomes LEA (ALU pipe), this one IMAD (FMA pipe)
+        asm("mad.lo.u32 %0, %1, 12, %2;" : "=r"(addr) : "r"(m), "r"(lut_saddr));
+        asm("ld.shared.u32 %0, [%1];" : "=r"(bits) : "r"(addr));
+        if (cmin <= cmax) hitmask |= bits;
+#endif
+      } else if (cmin <= cmax) {
         const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu;
         const uint32_t bi = (bit_index4 >> (8 * j)) & 0xffu;
         hitmask |= cb << bi;
