@@ -55,7 +55,9 @@ constexpr bool kPrefetchQueuedTri = M3D_PREFETCH_QUEUED_TRI != 0;
 // body is "one node visit, then that node's triangles" for all lanes together.
 // The trace kernel only writes the raw float32 hit (t, b1, b2, triangle index);
 // finish_hits_kernel re-evaluates hits in float64 in a separate, fully coherent pass.
-template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS>
+// HAS_SKIP = false (plain mesh batches: no per-ray surface to ignore) drops the skip-id load and
+// compare and frees a register of the 80.
+template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS, bool HAS_SKIP>
 __global__ void __launch_bounds__(kTraceBlock, (MIN_BLOCKS * 128) / kTraceBlock)
 trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ ray_counter) {
   __shared__ uint2 s_stack[kSmemStack][kTraceBlock];
@@ -155,7 +157,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
           rp.octinv4 = ray_octinv4(d.x, d.y, d.z);
           tmax = d.w;
           hit_tri = -1;
-          skip_tri = p.skip_tris ? __ldg(p.skip_tris + idx) : -1;
+          if (HAS_SKIP) skip_tri = __ldg(p.skip_tris + idx);
           // virtual parent whose only child is the root: child base 0, slot (7 ^ octinv)
           // of an all-internal imask so that take_nearest_child() yields node 0
           ngroup.x = 0u;
@@ -232,7 +234,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
           const int ti = (int)(tq.x + (uint32_t)bit);
           if (COUNT) cnt.tris++;
           float t, b1, b2;
-          if (ti != skip_tri && intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
+          if ((!HAS_SKIP || ti != skip_tri) && intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
             tmax = t;
             hit_tri = ti;
           }
@@ -421,20 +423,30 @@ void launch_count_hits(const DeviceBVH &bvh, const float *org3, const float *dir
 namespace {
 }  // namespace
 
-template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS = 1>
-static void launch_trace_variant(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
+template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS, bool HAS_SKIP>
+static void launch_trace_instance(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
   // persistent grid: as many blocks as stay resident
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) {
     int b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &b, trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS, HAS_SKIP>, kTraceBlock, 0);
     blocks_per_sm = b > 0 ? b : 1;
   }
   long long want = (p.n + kTraceBlock - 1) / kTraceBlock;
   long long grid = (long long)device_sm_count() * blocks_per_sm;
   if (grid > want) grid = want;
   unsigned int *rc32 = reinterpret_cast<unsigned int *>(p.ray_counter);
-  trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS><<<(unsigned)grid, kTraceBlock, 0, stream>>>(bvh, p, rc32);
+  trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS, HAS_SKIP>
+      <<<(unsigned)grid, kTraceBlock, 0, stream>>>(bvh, p, rc32);
+}
+
+template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS = 1>
+static void launch_trace_variant(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
+  if (p.skip_tris)
+    launch_trace_instance<COUNT, MIN_BLOCKS, TRI_ROUNDS, true>(bvh, p, stream);
+  else
+    launch_trace_instance<COUNT, MIN_BLOCKS, TRI_ROUNDS, false>(bvh, p, stream);
 }
 
 void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p_in, cudaStream_t stream) {
