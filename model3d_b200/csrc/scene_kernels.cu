@@ -39,6 +39,64 @@ finish_scene_hits_kernel(DeviceScene sc, SceneTraceLaunch sp) {
   if (sp.surf_ids) sp.surf_ids[i] = h.surf;
 }
 
+// Mesh-only finish pass with K rays per thread.  One ray per thread keeps only ~16 KB (raw hits),
+// then ~24 KB (rays + triangles of the 30 % hits) in flight per SM, short of what HBM latency x
+// bandwidth needs (~35 KB per SM): the K raw hits are loaded together, the rays and triangle
+// records of the hits are pulled towards L1 with non-blocking prefetches, and only then does the
+// thread run the float64 re-evaluation ray by ray.
+#ifndef M3D_FINISH_MINB
+#define M3D_FINISH_MINB 4
+#endif
+template <int K>
+__global__ void __launch_bounds__(256, M3D_FINISH_MINB)
+finish_mesh_hits_kernel(DeviceScene sc, SceneTraceLaunch sp) {
+  const TraceLaunch &p = sp.t;
+  const int64_t base = (int64_t)blockIdx.x * (256 * K) + threadIdx.x;
+  float raw_t[K];
+  int raw_tri[K];  // the raw record is (t, 0, 0, triangle)
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int64_t i = base + 256 * k;
+    const float4 r = i < p.n ? __ldcs(p.hit0 + i) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    raw_t[k] = r.x;
+    raw_tri[k] = __float_as_int(r.w);
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int tri_idx = raw_tri[k];
+    if (tri_idx >= 0) {
+      const int64_t i = base + 256 * k;
+      const float4 *tri = sc.bvh.tris + (size_t)tri_idx * 3;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.org_tmin + i));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.dir_tmax + i));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(tri));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(tri + 2));
+    }
+  }
+#pragma unroll 1
+  for (int k = 0; k < K; k++) {
+    const int64_t i = base + 256 * k;
+    if (i >= p.n) break;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(0.f, 0.f, 1.f, 0.f);
+    float rt = raw_t[0];
+    int rtri = raw_tri[0];
+#pragma unroll
+    for (int q = 1; q < K; q++) {  // no dynamic register indexing
+      rt = k == q ? raw_t[q] : rt;
+      rtri = k == q ? raw_tri[q] : rtri;
+    }
+    const float4 r = make_float4(rt, 0.f, 0.f, __int_as_float(rtri));
+    if (rtri >= 0) {
+      o = __ldcs(p.org_tmin + i);
+      d = __ldcs(p.dir_tmax + i);
+    }
+    const SceneHit h = resolve_scene_hit<false>(sc, o, d, r, -1, p.refine);
+    __stcs(p.hit0 + i, make_float4(h.t, h.b1, h.b2, __int_as_float(h.prim)));
+    __stcs(p.hit1 + i, make_float4(h.nx, h.ny, h.nz, __int_as_float(h.obj)));
+    if (sp.surf_ids) sp.surf_ids[i] = h.surf;
+  }
+}
+
 __global__ void raygen_camera_kernel(DeviceCamera cam, int W, int row_begin, int row_end,
                                      float4 *__restrict__ org_tmin, float4 *__restrict__ dir_tmax) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,8 +158,13 @@ __global__ void finalize_image_kernel(const float *__restrict__ sum, int64_t n, 
 void launch_finish_scene_hits(const DeviceScene &scene, const SceneTraceLaunch &p, cudaStream_t stream) {
   if (p.t.n <= 0) return;
   const unsigned blocks = (unsigned)((p.t.n + 255) / 256);
+#ifndef M3D_FINISH_K
+#define M3D_FINISH_K 2
+#endif
   if (scene.num_shapes > 0)
     finish_scene_hits_kernel<true><<<blocks, 256, 0, stream>>>(scene, p);
+  else if (M3D_FINISH_K > 1 && p.t.n >= (int64_t)256 * M3D_FINISH_K * 148)
+    finish_mesh_hits_kernel<M3D_FINISH_K><<<(unsigned)((p.t.n + 256 * M3D_FINISH_K - 1) / (256 * M3D_FINISH_K)), 256, 0, stream>>>(scene, p);
   else
     finish_scene_hits_kernel<false><<<blocks, 256, 0, stream>>>(scene, p);
 }

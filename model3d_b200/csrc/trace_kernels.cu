@@ -29,6 +29,12 @@ constexpr int kWarpsPerBlock = kTraceBlock / 32;
 #ifndef M3D_OPAQUE_ONE
 #define M3D_OPAQUE_ONE 1  // bits of 1.0f from the kernel parameters: PRMT selectors become immediates
 #endif
+#ifndef M3D_RELOAD_SKIP
+#define M3D_RELOAD_SKIP 1
+#endif
+#ifndef M3D_TINY_MINB
+#define M3D_TINY_MINB 6  // resident blocks per SM of the tiny-scene instantiation (two triangle rounds)
+#endif
 #ifndef M3D_MASK_LUT
 #define M3D_MASK_LUT 1  // child hit bits from a shared-memory table (ALU-pipe relief): C2 2.405 -> 2.347 ms
 #endif
@@ -157,7 +163,9 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
           rp.octinv4 = ray_octinv4(d.x, d.y, d.z);
           tmax = d.w;
           hit_tri = -1;
+#if !M3D_RELOAD_SKIP
           if (HAS_SKIP) skip_tri = __ldg(p.skip_tris + idx);
+#endif
           // virtual parent whose only child is the root: child base 0, slot (7 ^ octinv)
           // of an all-internal imask so that take_nearest_child() yields node 0
           ngroup.x = 0u;
@@ -234,6 +242,11 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
           const int ti = (int)(tq.x + (uint32_t)bit);
           if (COUNT) cnt.tris++;
           float t, b1, b2;
+#if M3D_RELOAD_SKIP
+          // the skip id is only needed here: re-read it (4 bytes, L1 / L2 hit) instead of holding a
+          // register across the node phase, where the kernel sits exactly at its 80-register budget
+          if (HAS_SKIP) skip_tri = __ldg(p.skip_tris + ray_idx);
+#endif
           if ((!HAS_SKIP || ti != skip_tri) && intersect_tri(tris + (size_t)ti * 3, rp, tmax, t, b1, b2)) {
             tmax = t;
             hit_tri = ti;
@@ -471,7 +484,7 @@ void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p_in, cudaSt
   if (p.counters) {
     launch_trace_variant<true, 6>(bvh, p, stream);
   } else if (tri_rounds >= 2) {
-    launch_trace_variant<false, 6, 2>(bvh, p, stream);
+    launch_trace_variant<false, M3D_TINY_MINB, 2>(bvh, p, stream);
   } else if (minb == 5) {
     launch_trace_variant<false, 5>(bvh, p, stream);
   } else if (minb == 8) {
