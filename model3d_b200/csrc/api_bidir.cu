@@ -5,6 +5,7 @@
 //   for every eye prefix length: connect (MIS in float64) -> trace visibility rays -> resolve
 //   flush
 // all on one stream with device-side queue lengths.
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -215,7 +216,16 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
   // batch geometry: per-slot footprint is dominated by the stored path vertices
   const size_t per_slot = (size_t)(16 * kBidirVertexFields + 32 + 36) * (max_depth + max_ld) +
                           (size_t)max_depth * (max_ld + 1) * 72 + 256;
-  int64_t cap = (int64_t)std::min<size_t>((size_t)1 << 20, ((size_t)6 << 30) / per_slot);
+#ifndef M3D_BIDIR_BUDGET_GB
+#define M3D_BIDIR_BUDGET_GB 64  // device memory for one batch's path vertices / work lists (of 180 GB)
+#endif
+  static int batch_log2 = 0;  // M3D_BIDIR_BATCH_LOG2: samples per batch (tuning runs)
+  if (!batch_log2) {
+    const char *e = getenv("M3D_BIDIR_BATCH_LOG2");
+    batch_log2 = e ? atoi(e) : 22;
+    if (batch_log2 < 10 || batch_log2 > 22) batch_log2 = 22;
+  }
+  int64_t cap = (int64_t)std::min<size_t>((size_t)1 << batch_log2, ((size_t)M3D_BIDIR_BUDGET_GB << 30) / per_slot);
   const int64_t total = npix * sample_count;
   cap = std::max<int64_t>(1, std::min(cap, total));
   const int64_t nP_max = std::min(npix, cap);

@@ -469,7 +469,7 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
     }
   }
   // Work list of the connection stage: one item per (i, j) pair of this sample, packed
-  // slot | i << 20 | j << 25 and grouped by (i, j) class, so that the threads of a warp of the
+  // slot | i << 22 | j << 27 (slots < 2^22, depths <= 16) and grouped by (i, j) class, so that the threads of a warp of the
   // connection kernel walk joined paths of the same length (uniform loops) and read their
   // vertices from consecutive slots (coalesced).  Block-level counting sort: count per class in
   // shared memory, reserve the block's range of every class with one global atomic, scatter.
@@ -486,7 +486,7 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
     for (int j = 0; j <= nl; j++) {
       const int c = (i - 1) * row + j;
       const int r = atomicAdd(&s_cnt[c], 1);
-      buf.work[(size_t)c * buf.cap + s_base[c] + r] = (uint32_t)slot | ((uint32_t)i << 20) | ((uint32_t)j << 25);
+      buf.work[(size_t)c * buf.cap + s_base[c] + r] = (uint32_t)slot | ((uint32_t)i << 22) | ((uint32_t)j << 27);
     }
 }
 
@@ -498,9 +498,9 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
   const int cls = (int)blockIdx.y, rank = (int)(blockIdx.x * kBlock + threadIdx.x);
   if (rank >= buf.class_counts[cls]) return;
   const uint32_t item = buf.work[(size_t)cls * buf.cap + rank];
-  const int slot = (int)(item & 0xfffffu);
-  const int i = (int)((item >> 20) & 31u);
-  const int j = (int)(item >> 25);
+  const int slot = (int)(item & 0x3fffffu);
+  const int i = (int)((item >> 22) & 31u);
+  const int j = (int)(item >> 27);
 
   const double *est = buf.eyepre + ((size_t)(i - 1) * buf.cap + slot) * 4;
   const double eye_density = est[0];
