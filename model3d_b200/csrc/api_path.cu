@@ -3,6 +3,7 @@
 // pipeline: raygen -> [trace -> shade/compact (-> shadow trace -> shadow resolve)] x depth
 // -> flush, batch by batch, all enqueued on one stream with device-side queue lengths
 // (no host round trip between bounces).
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -139,7 +140,17 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   if (pp.cutoff > 1.f) return M3D_OK;  // recurse() returns black at depth 0 (raytrace.go:139-142)
 
   // batch geometry: nP pixels x S samples <= cap slots
-  const int64_t kMaxSlots = (int64_t)1 << 22;
+  static int batch_log2 = 0;  // M3D_PATH_BATCH_LOG2: path slots per batch (tuning runs)
+  if (!batch_log2) {
+    const char *e = getenv("M3D_PATH_BATCH_LOG2");
+    batch_log2 = e ? atoi(e) : 26;
+    if (batch_log2 < 10 || batch_log2 > 28) batch_log2 = 26;
+  }
+  // <= 48 GB of the 180 GB for the path state (192 B per slot + 68 B per point light), and queue
+  // positions / shadow-ray counts stay below 2^31
+  const int64_t per_slot = 192 + 68 * (int64_t)num_lights;
+  const int64_t kMaxSlots = std::min<int64_t>(std::min<int64_t>((int64_t)1 << batch_log2, ((int64_t)48 << 30) / per_slot),
+                                              ((int64_t)1 << 30) / std::max<int64_t>(1, num_lights));
   const int64_t total = npix * sample_count;
   const int64_t cap = std::min(total, std::max<int64_t>(kMaxSlots, 1));
   const int64_t nP_max = std::min(npix, cap);
