@@ -258,6 +258,20 @@ def run_path(args):
         }
         if e2e:
             line["e2e"] = e2e
+        # Path state that crosses HBM per traced ray: queue entry 40 B written and
+        # read, raw hit 16 + 16, hit record 48 + 48, throughput 16 + 16 = 256 B.  The path tracers
+        # are bound by issue rate and dependent-load latency, not by this stream; the fraction says so.
+        peak, peak_src = hbm_peak()
+        achieved = total_rays * 256.0 / (ms_step * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "bytes_per_ray": 256.0, "kernel": "trace_first_hit_kernel + path_resolve / path_sample"
+                            if args.workload != "c5" else "bidir_connect_kernel + trace_first_hit_kernel"}
+        if world == 1 and not args.no_cpu_baseline:
+            rate, _, threads, sample = path_cpu_rate(args.workload, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                                    "sample": sample,
+                                    "note": "C++ float64 restatement of the Go renderer on all host threads"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -384,44 +398,62 @@ def run_reference_c1(args):
     print(json.dumps(line), flush=True)
 
 
-def run_reference_path(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def hbm_peak():
+    """(GB/s, source): the driver-measured copy bandwidth of this pool's B200s, else the profiling
+    recipe's fallback."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    return (float(peaks.get("hbm_gbs", 6650.0)),
+            "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s")
+
+
+def path_cpu_rate(workload, steps):
+    """The oracle's float64 restatement of the reference renderer for this workload on all host
+    threads, on a bounded sample (a small frame at a few spp): (Msamples/s, s per step, threads, sample)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import scenes
     from oracle import pyoracle as O
     threads = O.hardware_threads()
-    spec = scenes.showcase(hd=True) if args.workload == "c4" else scenes.cornell_box()
+    spec = scenes.showcase(hd=True) if workload == "c4" else scenes.cornell_box()
     osc = scenes.build_oracle(spec)
     cam = spec["camera"]
     ocam = O.camera_at(cam["src"], cam["dst"], cam["fov"])
     W = H = 256
     spp = 8
-    if args.workload == "c4":
+    if workload == "c4":
         W, H, spp = 240, 160, 4
-    if args.workload == "c5":
+    if workload == "c5":
         W = H = 128
         bp, lights = scenes.oracle_bidir_params(spec, num_samples=spp, seed=3, **C5_KW)
-    elif args.workload == "c4":
+    elif workload == "c4":
         pp = scenes.oracle_path_params(spec, osc, 10, spp, cutoff=1e-4, antialias=1.0, seed=3)
     else:
         pp = scenes.oracle_path_params(spec, osc, 5, spp, cutoff=1e-4, antialias=1.0, seed=3)
     t0 = time.perf_counter()
-    k = max(1, args.steps)
+    k = max(1, steps)
     for _ in range(k):
-        if args.workload == "c5":
+        if workload == "c5":
             osc.render_bidir(ocam, lights, bp, W, H, threads=threads)
         else:
             osc.render_path(ocam, [], pp, W, H, threads=threads)
     dt = (time.perf_counter() - t0) / k
-    rate = W * H * spp / dt / 1e6
+    return W * H * spp / dt / 1e6, dt, threads, "%dx%d at %d spp per step" % (W, H, spp)
+
+
+def run_reference_path(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, dt, threads, sample = path_cpu_rate(args.workload, args.steps)
     line = {"impl": "reference", "metric": "path_traced_Msamples_per_s", "value": rate, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME[args.workload]},
             "cpu_baseline": {"value": rate, "unit": "Msamples/s", "cores": threads, "kind": "port",
-                             "sample": "%dx%d at %d spp per step" % (W, H, spp)},
+                             "sample": sample},
             "e2e": {"value": rate, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -659,13 +691,7 @@ def main():
         except Exception as e:  # the headline must still be reported
             secondary = {"error": str(e)[:200]}
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        peak, peak_src = hbm_peak()
         bytes_per_ray = RAY_IO_BYTES + nodes_per_ray * NODE_BYTES + tris_per_ray * TRI_BYTES
         achieved = n * bytes_per_ray / (ms_step * 1e-3) / 1e9
         traffic = None
