@@ -53,6 +53,12 @@ func (c *Context) Close() {
 	}
 }
 
+// Trim releases the scratch buffers the renderers keep between calls (path state of up to
+// 48-64 GB for the largest batches); later calls allocate again on demand.
+func (c *Context) Trim() error {
+	return status(C.m3d_ctx_trim(c.h))
+}
+
 // MeshCollider implements model3d.Collider on the GPU for a triangle mesh.
 // Triangle ids are indices into Triangles (the reference identifies triangles by
 // pointer, model3d/collisions.go:39-46).

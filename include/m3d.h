@@ -54,6 +54,10 @@ int32_t m3d_ctx_create(int32_t device, m3d_ctx **out);
 void m3d_ctx_destroy(m3d_ctx *ctx);
 int32_t m3d_ctx_device(const m3d_ctx *ctx);
 int32_t m3d_ctx_synchronize(m3d_ctx *ctx);
+/* Releases the context's scratch buffers (ray batches, path state: the renderers size their
+ * batches for up to 48-64 GB of a 180 GB device and keep the allocation for the next call).
+ * Waits for the context's streams first; later calls allocate again on demand. */
+int32_t m3d_ctx_trim(m3d_ctx *ctx);
 
 /* ---- statistics ---------------------------------------------------------- */
 

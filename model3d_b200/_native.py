@@ -101,7 +101,7 @@ class BidirParams(C.Structure):
 # every symbol include/m3d.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "m3d_abi_version", "m3d_last_error", "m3d_ctx_create", "m3d_ctx_destroy", "m3d_ctx_device",
-    "m3d_ctx_synchronize", "m3d_mesh_create", "m3d_mesh_destroy", "m3d_mesh_get_info",
+    "m3d_ctx_synchronize", "m3d_ctx_trim", "m3d_mesh_create", "m3d_mesh_destroy", "m3d_mesh_get_info",
     "m3d_mesh_bounds", "m3d_mesh_first_ray_collisions", "m3d_mesh_first_ray_collisions_device",
     "m3d_mesh_ray_collision_counts", "m3d_mesh_ray_collisions", "m3d_mesh_contains", "m3d_mesh_sdf", "m3d_mesh_sphere_collisions",
     "m3d_scene_builder_create", "m3d_scene_builder_destroy", "m3d_scene_add_material",
@@ -155,6 +155,10 @@ class Context:
 
     def synchronize(self):
         check(lib().m3d_ctx_synchronize(self.h))
+
+    def trim(self):
+        """Release the scratch buffers the renderers keep between calls (m3d_ctx_trim)."""
+        check(lib().m3d_ctx_trim(self.h))
 
     def __del__(self):
         try:

@@ -225,7 +225,11 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
     batch_log2 = e ? atoi(e) : 22;
     if (batch_log2 < 10 || batch_log2 > 22) batch_log2 = 22;
   }
-  int64_t cap = (int64_t)std::min<size_t>((size_t)1 << batch_log2, ((size_t)M3D_BIDIR_BUDGET_GB << 30) / per_slot);
+  // at most half of what is free on the device right now (beyond what this context already holds)
+  size_t free_b = 0, total_b = 0;
+  M3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = std::min<size_t>((size_t)M3D_BIDIR_BUDGET_GB << 30, (free_b + ctx->scratch[6].bytes) / 2);
+  int64_t cap = (int64_t)std::min<size_t>((size_t)1 << batch_log2, budget / per_slot);
   const int64_t total = npix * sample_count;
   cap = std::max<int64_t>(1, std::min(cap, total));
   const int64_t nP_max = std::min(npix, cap);

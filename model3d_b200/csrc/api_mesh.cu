@@ -159,6 +159,14 @@ int32_t m3d_ctx_synchronize(m3d_ctx *ctx) {
   return M3D_OK;
 }
 
+int32_t m3d_ctx_trim(m3d_ctx *ctx) {
+  if (!ctx) return fail(M3D_ERR_INVALID_ARG, "ctx is NULL");
+  int32_t rc = m3d_ctx_synchronize(ctx);
+  if (rc != M3D_OK) return rc;
+  for (auto &b : ctx->scratch) b.release();
+  return M3D_OK;
+}
+
 int32_t m3d_mesh_create(m3d_ctx *ctx, const float *tris, int64_t n, const float *vnormals,
                         uint32_t build_flags, m3d_mesh **out) {
   if (!ctx || !out || n < 0 || (n > 0 && !tris))

@@ -149,7 +149,11 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   // <= 48 GB of the 180 GB for the path state (192 B per slot + 68 B per point light), and queue
   // positions / shadow-ray counts stay below 2^31
   const int64_t per_slot = 192 + 68 * (int64_t)num_lights;
-  const int64_t kMaxSlots = std::min<int64_t>(std::min<int64_t>((int64_t)1 << batch_log2, ((int64_t)48 << 30) / per_slot),
+  // ... and at most half of what is free on the device right now (beyond what this context already holds)
+  size_t free_b = 0, total_b = 0;
+  M3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const int64_t budget = std::min<int64_t>((int64_t)48 << 30, (int64_t)((free_b + ctx->scratch[4].bytes) / 2));
+  const int64_t kMaxSlots = std::min<int64_t>(std::min<int64_t>((int64_t)1 << batch_log2, budget / per_slot),
                                               ((int64_t)1 << 30) / std::max<int64_t>(1, num_lights));
   const int64_t total = npix * sample_count;
   const int64_t cap = std::min(total, std::max<int64_t>(kMaxSlots, 1));

@@ -152,11 +152,16 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
         const V3f point = org + dir * h.t;
         const MatAt m = material_at(sc, h.obj, point);
         const V3f dest = normalize(dir) * -1.f;
-        const float4 thr = buf.thr[slot];
-        const V3f tv = v3f(thr.x, thr.y, thr.z);
         // raytrace.go:150-155
         V3f color = mat_emission(sc, m);
         if (depth == 0) color = color + mat_ambient(sc, m);
+        // the throughput is a random 16-byte gather: only paths that add light (or cast shadow
+        // rays) need it here
+        V3f tv = v3f(0.f, 0.f, 0.f);
+        if ((LIGHTS && pp.num_lights > 0) || !is_zero(color)) {
+          const float4 thr = buf.thr[slot];
+          tv = v3f(thr.x, thr.y, thr.z);
+        }
         if (!is_zero(color)) {
           float4 a = buf.accum[slot];
           a.x += tv.x * color.x;
