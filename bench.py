@@ -650,6 +650,33 @@ def main():
         e2e = {"value": world * n / dt / 1e6, "unit": "Mrays/s", "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 20,
                "api": "m3d_mesh_first_ray_collisions (host buffers, pinned)"}
+        # what the link allows: the same bytes copied both ways at once with no compute at all
+        # (two streams, pinned memory); e2e / this bound says how well the chunked pipeline hides
+        # the kernels behind the copies
+        if world == 1:
+            d_in = torch.empty(n * 24, dtype=torch.uint8, device=dev)
+            d_out = torch.empty(n * 20, dtype=torch.uint8, device=dev)
+            h_in = org_p.view(torch.uint8).reshape(-1), d_p.view(torch.uint8).reshape(-1)
+            h_out = torch.empty(n * 20, dtype=torch.uint8).pin_memory()
+            s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+            def copies(reps):
+                torch.cuda.synchronize()
+                t0c = time.perf_counter()
+                for _ in range(reps):
+                    with torch.cuda.stream(s_in):
+                        d_in[:n * 12].copy_(h_in[0], non_blocking=True)
+                        d_in[n * 12:].copy_(h_in[1], non_blocking=True)
+                    with torch.cuda.stream(s_out):
+                        h_out.copy_(d_out, non_blocking=True)
+                s_in.synchronize()
+                s_out.synchronize()
+                return (time.perf_counter() - t0c) / reps
+            copies(2)
+            cb = copies(5)
+            e2e["copy_bound_ms"] = cb * 1e3
+            e2e["frac_of_copy_bound"] = cb / dt
+            del d_in, d_out, h_out
 
     # mix B: coherent primary rays of a 4096x4096 pinhole camera at (0,-3,0) looking at
     # the origin, fov pi/3.6 -- same mesh, same kernels, reported beside the incoherent headline
