@@ -6,7 +6,7 @@
 namespace m3d {
 
 struct DeviceBVH {
-  const uint4 *nodes = nullptr;    // 5 x uint4 per WideNode
+  const uint4 *nodes = nullptr;    // M3D_NODE_QUADS x uint4 per WideNode (node_layout.h)
   const float4 *tris = nullptr;    // 3 x float4 per TriRecord
   const float4 *vnormals = nullptr; // optional, 3 x float4 per triangle (leaf order)
   int64_t num_nodes = 0, num_tris = 0;

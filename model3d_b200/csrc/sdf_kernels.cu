@@ -192,7 +192,7 @@ __device__ __forceinline__ void nearest_triangle(const DeviceBVH &bvh, float px,
     const uint2 e = stack[--sp];
     if (__uint_as_float(e.y) > prune) continue;
     res.nodes++;
-    const uint4 *np = bvh.nodes + (size_t)e.x * 5;
+    const uint4 *np = bvh.nodes + (size_t)e.x * M3D_NODE_QUADS;
     const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
     const float sx = __uint_as_float((n0.w & 0xffu) << 23);
     const float sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23);

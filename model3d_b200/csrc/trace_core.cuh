@@ -20,6 +20,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "node_layout.h"
+
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
 #define M3D_HD __host__ __device__ __forceinline__
@@ -345,8 +347,18 @@ template <bool USE_LUT = false>
 M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index, const RayPre &rp,
                            float tmax, uint2 &ngroup, uint2 &tgroup, uint32_t one = 0x3f800000u,
                            uint32_t lut_saddr = 0u /* shared-window address of the table */) {
-  const uint4 *np = nodes + (size_t)node_index * 5;
-#if defined(__CUDA_ARCH__)
+  const uint4 *np = nodes + (size_t)node_index * M3D_NODE_QUADS;
+#if defined(__CUDA_ARCH__) && M3D_NODE_QUADS == 6
+  // 32-byte aligned nodes: two 256-bit loads + one 128-bit load, one sector each
+  uint4 n0, n1, n2, n3;
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(n0.x), "=r"(n0.y), "=r"(n0.z), "=r"(n0.w), "=r"(n1.x), "=r"(n1.y), "=r"(n1.z), "=r"(n1.w)
+      : "l"(np));
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(n2.x), "=r"(n2.y), "=r"(n2.z), "=r"(n2.w), "=r"(n3.x), "=r"(n3.y), "=r"(n3.z), "=r"(n3.w)
+      : "l"(np + 2));
+  const uint4 n4 = __ldg(np + 4);
+#elif defined(__CUDA_ARCH__)
   const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 #else
   const uint4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];

@@ -219,7 +219,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
         if (kPrefetchNextNode && (ngroup.y & 0xff000000u)) {
           // the child the next trip descends into: L2 -> L1 while the triangle phase runs
           uint2 g = ngroup;
-          const uint4 *nn = nodes + (size_t)take_nearest_child(g, rp.octinv4) * 5;
+          const uint4 *nn = nodes + (size_t)take_nearest_child(g, rp.octinv4) * M3D_NODE_QUADS;
           asm volatile("prefetch.global.L1 [%0];" ::"l"(nn));
           asm volatile("prefetch.global.L1 [%0];" ::"l"(nn + 4));
         }

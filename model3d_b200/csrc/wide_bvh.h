@@ -7,14 +7,16 @@
 // binned-SAH binary tree is collapsed into 8-wide nodes whose child boxes are
 // quantised to 8 bits on a per-node power-of-two grid (layout after Ylitie, Karras,
 // Laine, "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs",
-// HPG 2017).  80 bytes per node, five 16-byte loads.
+// HPG 2017).  80 bytes per node at a stride of M3D_NODE_BYTES (node_layout.h).
 #pragma once
 #include <cstdint>
 #include <vector>
 
+#include "node_layout.h"
+
 namespace m3d {
 
-struct alignas(16) WideNode {
+struct alignas(M3D_NODE_BYTES == 96 ? 32 : 16) WideNode {
   float origin[3];     // node AABB min: quantisation origin
   uint8_t exp[3];      // per-axis biased float exponent of the grid step (2^(e-127))
   uint8_t imask;       // bit s set <=> slot s holds an internal child
@@ -23,8 +25,11 @@ struct alignas(16) WideNode {
   uint8_t meta[8];     // 0 empty | internal: 0b001sssss (sssss = 24+slot) | leaf: unary count<<5 | tri offset
   uint8_t qlo[3][8];   // quantised child box mins  [axis][slot]
   uint8_t qhi[3][8];   // quantised child box maxes [axis][slot]
+#if M3D_NODE_BYTES == 96
+  uint8_t pad[16];     // keeps every node on a 32-byte sector boundary (node_layout.h)
+#endif
 };
-static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+static_assert(sizeof(WideNode) == M3D_NODE_BYTES, "WideNode stride");
 
 // One triangle record: three float4.  The w lanes carry ids so that the winning hit
 // needs no second lookup: v0.w = bits(prim id in the caller's array),
