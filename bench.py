@@ -461,16 +461,19 @@ def run_reference_path(args):
 
 def secondary_path_metrics(rank, world, dev):
     """Short path-tracing measurements appended to the headline line (BASELINE metric: 'Mrays/s
-    first-hit AND path-traced samples/s'): cornell_box 1024x1024, RecursiveRayTracer (C3) at
-    64 spp and BidirPathTracer (C5) at 8 spp, samples sharded over the ranks, sums reduced to
-    rank 0 inside the timed region.  CUDA-event timed, max over ranks."""
+    first-hit AND path-traced samples/s'): cornell_box 1024x1024 with the RecursiveRayTracer (C3,
+    64 spp) and the BidirPathTracer (C5, 16 spp), the showcase scene 960x640 (C4, 64 spp); samples
+    sharded over the ranks, sums reduced to rank 0 inside the timed region.  CUDA-event timed, max
+    over ranks."""
     import torch
     import torch.distributed as dist
     from model3d_b200 import distributed as D
     out = {}
-    W = H = 1024
-    for wl, spp in (("c3", 64), ("c5", 8)):
+    for wl, spp in (("c3", 64), ("c4", 64), ("c5", 16)):
+        W = H = 1024
         spec, psc, tr = cornell_tracer(spp, wl)
+        if wl == "c4":
+            W, H = spec["size"]  # "HD" 960x640 (showcase/main.go:61-69)
         part, my_spp = D.sample_shard(spp, rank, world)
         acc = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
         stream = torch.cuda.current_stream().cuda_stream
