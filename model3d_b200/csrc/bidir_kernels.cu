@@ -352,11 +352,14 @@ bidir_light_raygen_kernel(DeviceScene sc, DeviceBidirParams bp, const DeviceArea
 }
 
 // Per-vertex scalars of the MIS computation (bidir.go:421-471), written once per sub-path
-// vertex by bidir_prefix_kernel so that the connection threads load 36 bytes per vertex
-// instead of the 112-byte vertex record:
-//   misA = (point.xyz, sourceDot)   misB = (sourceDensity, destDensity) as float64 incl. the
-//   Dirac magnitudes                 misC = destDot
+// vertex by bidir_prefix_kernel so that the connection threads load 32 bytes per vertex (two
+// 16-byte loads) instead of the 112-byte vertex record:
+//   misA = (point.xyz, sourceDot)   misB = (sourceDensity, destDensity, destDot, -) as float32,
+//   densities incl. the Dirac magnitudes (M3D_MIS_F32=0: float64 pairs + misC = destDot, 36 bytes)
 // Eye vertices occupy depths [0, De), light vertices [De, De+Dl) of the mis arrays.
+#ifndef M3D_MIS_F32
+#define M3D_MIS_F32 1
+#endif
 struct Mis {
   double sd, dd;
   float sdot, ddot;
@@ -376,13 +379,24 @@ __device__ __forceinline__ Mis mis_of(const BVert &v) {
 __device__ __forceinline__ void store_mis(const BidirBuffers &buf, int depth, int slot, const Mis &m) {
   const size_t o = (size_t)depth * buf.cap + slot;
   buf.misA[o] = make_float4(m.px, m.py, m.pz, m.sdot);
+#if M3D_MIS_F32
+  // single densities (<= a few times the 2e8 Dirac magnitude) fit float32 at 6e-8 relative; only
+  // their products along a path need float64, and those are formed in the connection kernel
+  reinterpret_cast<float4 *>(buf.misB)[o] = make_float4((float)m.sd, (float)m.dd, m.ddot, 0.f);
+#else
   buf.misB[o] = make_double2(m.sd, m.dd);
   buf.misC[o] = m.ddot;
+#endif
 }
 __device__ __forceinline__ Mis load_mis(const BidirBuffers &buf, int depth, int slot) {
   const size_t o = (size_t)depth * buf.cap + slot;
   const float4 a = buf.misA[o];
+#if M3D_MIS_F32
+  const float4 bf = reinterpret_cast<const float4 *>(buf.misB)[o];
+  const double2 b = make_double2((double)bf.x, (double)bf.y);
+#else
   const double2 b = buf.misB[o];
+#endif
   Mis m;
   m.px = a.x;
   m.py = a.y;
@@ -390,7 +404,11 @@ __device__ __forceinline__ Mis load_mis(const BidirBuffers &buf, int depth, int 
   m.sdot = a.w;
   m.sd = b.x;
   m.dd = b.y;
+#if M3D_MIS_F32
+  m.ddot = bf.z;
+#else
   m.ddot = buf.misC[o];
+#endif
   return m;
 }
 __device__ __forceinline__ double out_area(const Mis &a, const Mis &b) {
