@@ -18,6 +18,12 @@ The GPU box has no /root/reference; tests only read the .npy files written here.
                      reference itself and committed upstream -- the only reference OUTPUTS for
                      this path, used to pin the oracle and the GPU path statistically
                      (tests/test_reference_golden.py).
+  ref_showcase_output.png
+                     byte copy of examples/renderings/showcase/output.png (480x320; the configuration of
+                     showcase/main.go: MaxDepth 10, NumSamples 50, Antialias 1, Cutoff 1e-4,
+                     SphereFocusPoint 0.3), produced by the Go reference and committed upstream as a
+                     244-colour palette PNG.  It shows the vase whose mesh is missing from the checkout;
+                     tests mask that region (tests/test_reference_golden.py).
   ref_rose_rendering.png
                      byte copy of examples/decoration/rose/rendering.png: render3d.SaveRendering of
                      the rose mesh from (0,-2,4) at 500x500 (rose/main.go:31), a deterministic
@@ -79,6 +85,7 @@ if __name__ == "__main__":
     print("diamond:", tris.shape, tris.min(axis=(0, 1)), tris.max(axis=(0, 1)))
 
     shutil.copyfile(os.path.join(REF, "examples/decoration/rose/rendering.png"), os.path.join(HERE, "ref_rose_rendering.png"))
+    shutil.copyfile(os.path.join(REF, "examples/renderings/showcase/output.png"), os.path.join(HERE, "ref_showcase_output.png"))
     for src, dst in (("output.png", "ref_cornell_box_output.png"), ("output_hd.png", "ref_cornell_box_output_hd.png")):
         shutil.copyfile(os.path.join(REF, "examples/renderings/cornell_box", src), os.path.join(HERE, dst))
         print("copied", src, "->", dst)

@@ -25,20 +25,22 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def read_png_rgb8(path):
-    """Minimal 8-bit RGB(A) PNG decoder (all five filter types)."""
+    """Minimal 8-bit RGB(A) / palette PNG decoder (all five filter types)."""
     d = open(path, "rb").read()
     assert d[:8] == b"\x89PNG\r\n\x1a\n"
-    pos, idat = 8, b""
+    pos, idat, plte = 8, b"", None
     while pos < len(d):
         n, typ = struct.unpack(">I4s", d[pos:pos + 8])
         body = d[pos + 8:pos + 8 + n]
         pos += 12 + n
         if typ == b"IHDR":
             W, H, depth, ctype = struct.unpack(">IIBB", body[:10])
-            assert depth == 8 and ctype in (2, 6)
+            assert depth == 8 and ctype in (2, 3, 6)
+        elif typ == b"PLTE":
+            plte = np.frombuffer(body, np.uint8).reshape(-1, 3)
         elif typ == b"IDAT":
             idat += body
-    bpp = 3 if ctype == 2 else 4
+    bpp = {2: 3, 3: 1, 6: 4}[ctype]
     raw = zlib.decompress(idat)
     stride = W * bpp
     out = np.zeros((H, stride), np.int64)
@@ -66,6 +68,8 @@ def read_png_rgb8(path):
                 cur[x] = (line[x] + p) & 255
         out[y] = cur
         prev = cur
+    if ctype == 3:
+        return plte[out.reshape(H, W)]
     return out.reshape(H, W, bpp)[:, :, :3].astype(np.uint8)
 
 
@@ -150,6 +154,67 @@ def test_gpu_matches_the_references_hd_rendering(built):
     d8 = np.abs(ours8.astype(np.int64) - ref8.astype(np.int64)).max(axis=2)
     ok = (ref8 < 250).all(axis=2)
     assert (d8[ok] <= 3).mean() > 0.85 and (d8[ok] <= 5).mean() > 0.94, ((d8[ok] <= 3).mean(), (d8[ok] <= 5).mean())
+
+
+# ---- showcase (BASELINE config C4): examples/renderings/showcase/output.png -----------------------
+def _check_showcase(mean):
+    """mean: linear 320x480x3 estimate of showcase/main.go's frame (480x320, MaxDepth 10, Antialias 1,
+    Cutoff 1e-4, SphereFocusPoint 0.3).  The reference image was committed as a 244-colour palette
+    PNG at 50 spp, so single pixels carry several 8-bit levels of quantisation on top of the noise:
+    16x16 block means in linear light are compared.  The vase (mesh missing from the checkout) and
+    the floor / base it shades are masked."""
+    ref8 = read_png_rgb8(os.path.join(GOLD, "ref_showcase_output.png"))
+    assert ref8.shape == (320, 480, 3)
+    lin, ours = srgb_expand(ref8), np.clip(mean, 0, 1)
+    B = 16
+    lb = lin.reshape(320 // B, B, 480 // B, B, 3).mean(axis=(1, 3))
+    mb = ours.reshape(320 // B, B, 480 // B, B, 3).mean(axis=(1, 3))
+    mask = np.ones(lb.shape[:2], bool)
+    mask[6:, 21:] = False    # the vase and its shadow (x >= 336, y >= 96)
+    mask[14:19, 16:] = False  # the base of the curvy thing, shaded by the vase in the reference
+    rel_map = np.abs((mb - lb) / np.maximum(lb, 0.02)).max(axis=2)
+    rel = rel_map[mask]
+    assert mask.sum() >= 400
+    # measured: oracle at 64 spp median 1.2 %, 90th percentile 3.5 %; GPU at 1024 spp 1.3 % / 4.4 %
+    assert np.median(rel) < 0.02, np.median(rel)
+    assert np.percentile(rel, 90) < 0.06, np.percentile(rel, 90)
+    # The only blocks far off are caustics in, under and beside the wine glass (x < 192): single
+    # 50-sample frames are fireflies there (the reference is one such frame); everywhere else every
+    # block agrees within 20 %.
+    far = (rel_map > 0.2) & mask
+    assert far[:, 12:].sum() == 0, np.argwhere(far[:, 12:])
+    assert far.sum() <= 10, far.sum()
+    g_ref, g_ours = lin[:, :336].mean(axis=(0, 1)), ours[:, :336].mean(axis=(0, 1))
+    assert np.abs(g_ours / g_ref - 1).max() < 0.025, (g_ref, g_ours)  # measured +1.3 % (no vase)
+
+
+# The reference clamps each pixel's 50-sample mean to [0, 1] (image.go:125-145); under the glass and
+# on the specular highlights those means are heavy tailed, so E[clip(mean_50)] < clip(E[mean]).  Both
+# tests therefore average frames rendered at exactly 50 spp and clamped one by one -- the
+# reference's own estimator -- instead of clamping one converged frame (which reads 3 % brighter).
+def test_oracle_matches_the_references_showcase_rendering(oracle):
+    spec = scenes.showcase()
+    osc = scenes.build_oracle(spec)
+    cam = spec["camera"]
+    ocam = oracle.camera_at(cam["src"], cam["dst"], cam["fov"])
+    acc = np.zeros((320, 480, 3))
+    for seed in (7, 8):
+        pp = scenes.oracle_path_params(spec, osc, 10, 50, cutoff=1e-4, antialias=1.0, seed=seed)
+        acc += np.clip(osc.render_path(ocam, [], pp, 480, 320, threads=8)["mean"], 0, 1)
+    _check_showcase(acc / 2)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_the_references_showcase_rendering(built):
+    spec = scenes.showcase()
+    psc = scenes.build_product(spec)
+    acc = np.zeros((320, 480, 3))
+    frames = 24
+    for k in range(frames):
+        tr = scenes.product_tracer(spec, psc, 10, 50, cutoff=1e-4, antialias=1.0, seed=100 + k)
+        rgb, _, _ = tr.RenderSums(480, 320, psc, sample_count=50)
+        acc += np.clip(rgb.astype(np.float64) / 50, 0, 1)
+    _check_showcase(acc / frames)
 
 
 # ---- RayCaster: examples/decoration/rose/rendering.png ---------------------------------------
