@@ -23,7 +23,9 @@ The GPU box has no /root/reference; tests only read the .npy files written here.
                      showcase/main.go: MaxDepth 10, NumSamples 50, Antialias 1, Cutoff 1e-4,
                      SphereFocusPoint 0.3), produced by the Go reference and committed upstream as a
                      244-colour palette PNG.  It shows the vase whose mesh is missing from the checkout;
-                     tests mask that region (tests/test_reference_golden.py).
+                     tests mask that region (tests/test_reference_golden.py).  ref_showcase_output_hd.png
+                     is output_hd.png of the same directory (960x640, main.go's HighRes mode: adaptive
+                     1000...100000 spp until MaxStddev 0.02).
   ref_rose_rendering.png
                      byte copy of examples/decoration/rose/rendering.png: render3d.SaveRendering of
                      the rose mesh from (0,-2,4) at 500x500 (rose/main.go:31), a deterministic
@@ -86,6 +88,7 @@ if __name__ == "__main__":
 
     shutil.copyfile(os.path.join(REF, "examples/decoration/rose/rendering.png"), os.path.join(HERE, "ref_rose_rendering.png"))
     shutil.copyfile(os.path.join(REF, "examples/renderings/showcase/output.png"), os.path.join(HERE, "ref_showcase_output.png"))
+    shutil.copyfile(os.path.join(REF, "examples/renderings/showcase/output_hd.png"), os.path.join(HERE, "ref_showcase_output_hd.png"))
     for src, dst in (("output.png", "ref_cornell_box_output.png"), ("output_hd.png", "ref_cornell_box_output_hd.png")):
         shutil.copyfile(os.path.join(REF, "examples/renderings/cornell_box", src), os.path.join(HERE, dst))
         print("copied", src, "->", dst)
