@@ -304,8 +304,10 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
       any_vn |= !o.vnormals.empty();
       all_vn &= !o.vnormals.empty();
     }
-  if (any_vn && !all_vn)
-    return fail(M3D_ERR_UNSUPPORTED, "mixing flat and interpolated-normal meshes in one scene is not supported");
+  // A scene that mixes MeshToCollider and MeshToInterpNormalCollider objects (smooth_shading/main.go)
+  // keeps one per-corner normal array for the merged BVH: flat meshes get their face normal at all
+  // three corners, which the interpolation (primitives.go:508-516) returns unchanged.
+  (void)all_vn;
   std::vector<DeviceObject> dobjs;
   for (size_t oi = 0; oi < b->objects.size(); oi++) {
     const BuilderObject &o = b->objects[oi];
@@ -324,7 +326,23 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
     if (o.kind == 0) {
       const int64_t n = (int64_t)o.tris.size() / 9;
       sc->merged_tris.insert(sc->merged_tris.end(), o.tris.begin(), o.tris.end());
-      if (any_vn) vnormals.insert(vnormals.end(), o.vnormals.begin(), o.vnormals.end());
+      if (any_vn && !o.vnormals.empty()) {
+        vnormals.insert(vnormals.end(), o.vnormals.begin(), o.vnormals.end());
+      } else if (any_vn) {
+        for (int64_t i = 0; i < n; i++) {
+          const float *t = o.tris.data() + 9 * i;
+          const double ax = (double)t[3] - t[0], ay = (double)t[4] - t[1], az = (double)t[5] - t[2];
+          const double bx = (double)t[6] - t[0], by = (double)t[7] - t[1], bz = (double)t[8] - t[2];
+          double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+          const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+          const double inv = len > 0.0 ? 1.0 / len : 0.0;  // degenerate triangles are never hit
+          for (int k = 0; k < 3; k++) {
+            vnormals.push_back((float)(nx * inv));
+            vnormals.push_back((float)(ny * inv));
+            vnormals.push_back((float)(nz * inv));
+          }
+        }
+      }
       for (int64_t i = 0; i < n; i++) {
         prim_ids.push_back((int32_t)i);
         obj_ids.push_back((int32_t)oi);

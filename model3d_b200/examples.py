@@ -95,6 +95,9 @@ def build_product(spec, **scene_kw):
         m = mat(o["material"])
         if o["kind"] == "mesh":
             c = np.asarray(o["tris"], np.float32)
+            if o.get("vnormals") is not None:  # MeshToInterpNormalCollider (collisions.go:147-162)
+                from .model3d import MeshToInterpNormalCollider
+                c = MeshToInterpNormalCollider(c, np.asarray(o["vnormals"], np.float32))
         elif o["kind"] == "sphere":
             c = R.Sphere(tuple(o["center"]), o["radius"])
         elif o["kind"] == "rect":

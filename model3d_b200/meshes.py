@@ -295,3 +295,29 @@ def MarchingCubesSearch(solid, delta, iters):
         fp = np.where(inside, fp, mid)
     pts[rows, axis] = (fp + tp) / 2
     return pts.reshape(-1, 3, 3)
+
+
+def VertexNormals(tris):
+    """Mesh.VertexNormals (model3d/mesh_ops.go:146-169) as per-corner normals [n,3,3]: for every
+    vertex the sum of the flat normals of its triangles, each weighted by the triangle's interior
+    angle at that vertex, normalised.  Vertices are identified by exact coordinates like the
+    reference's CoordMap.  This is what MeshToInterpNormalCollider (collisions.go:147-162) feeds to
+    its InterpNormalTriangles."""
+    t = np.asarray(tris, np.float64).reshape(-1, 3, 3)
+    n = t.shape[0]
+
+    def unit(v):
+        return v * (1.0 / np.sqrt((v * v).sum(axis=-1, keepdims=True)))
+
+    edges = np.stack([unit(t[:, 0] - t[:, 1]), unit(t[:, 1] - t[:, 2]), unit(t[:, 2] - t[:, 0])], axis=1)
+    normal = unit(np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]))
+    weighted = np.zeros((n, 3, 3))
+    for i in range(3):
+        e1, e2 = edges[:, (i + 2) % 3], edges[:, i]
+        theta = np.arccos(np.clip(-(e1 * e2).sum(axis=1), -1.0, 1.0))
+        weighted[:, i] = normal * theta[:, None]
+    keys = np.ascontiguousarray(t.reshape(-1, 3) + 0.0).view(np.dtype((np.void, 24))).ravel()  # -0.0 == 0.0
+    _, inv = np.unique(keys, return_inverse=True)
+    sums = np.zeros((inv.max() + 1, 3))
+    np.add.at(sums, inv, weighted.reshape(-1, 3))
+    return unit(sums)[inv].reshape(n, 3, 3)

@@ -257,8 +257,12 @@ def MeshToCollider(triangles, ctx=None) -> MeshCollider:
     return MeshCollider(triangles, ctx=ctx)
 
 
-def MeshToInterpNormalCollider(triangles, vertex_normals, ctx=None) -> MeshCollider:
-    """model3d.MeshToInterpNormalCollider (collisions.go:147-162)."""
+def MeshToInterpNormalCollider(triangles, vertex_normals=None, ctx=None) -> MeshCollider:
+    """model3d.MeshToInterpNormalCollider (collisions.go:147-162): like the reference, computes
+    the vertex normals itself (Mesh.VertexNormals, mesh_ops.go:146-169) unless they are given."""
+    if vertex_normals is None:
+        from . import meshes
+        vertex_normals = meshes.VertexNormals(triangles)
     return MeshCollider(triangles, vertex_normals=vertex_normals, ctx=ctx)
 
 

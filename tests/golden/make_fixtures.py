@@ -26,6 +26,12 @@ The GPU box has no /root/reference; tests only read the .npy files written here.
                      tests mask that region (tests/test_reference_golden.py).  ref_showcase_output_hd.png
                      is output_hd.png of the same directory (960x640, main.go's HighRes mode: adaptive
                      1000...100000 spp until MaxStddev 0.02).
+  ref_smooth_shading_rendering.png
+                     byte copy of examples/renderings/smooth_shading/rendering.png (768x432): the
+                     deterministic RayCaster image of smooth_shading/main.go -- NewMeshIcosphere(0,1,4)
+                     twice, flat (MeshToCollider) and smooth (MeshToInterpNormalCollider), Phong
+                     material, one point light, rendered at 4x and box-filtered.  The text labels under
+                     the spheres need model2d and are masked.
   ref_rose_rendering.png
                      byte copy of examples/decoration/rose/rendering.png: render3d.SaveRendering of
                      the rose mesh from (0,-2,4) at 500x500 (rose/main.go:31), a deterministic
@@ -87,6 +93,8 @@ if __name__ == "__main__":
     print("diamond:", tris.shape, tris.min(axis=(0, 1)), tris.max(axis=(0, 1)))
 
     shutil.copyfile(os.path.join(REF, "examples/decoration/rose/rendering.png"), os.path.join(HERE, "ref_rose_rendering.png"))
+    shutil.copyfile(os.path.join(REF, "examples/renderings/smooth_shading/rendering.png"),
+                    os.path.join(HERE, "ref_smooth_shading_rendering.png"))
     shutil.copyfile(os.path.join(REF, "examples/renderings/showcase/output.png"), os.path.join(HERE, "ref_showcase_output.png"))
     shutil.copyfile(os.path.join(REF, "examples/renderings/showcase/output_hd.png"), os.path.join(HERE, "ref_showcase_output_hd.png"))
     for src, dst in (("output.png", "ref_cornell_box_output.png"), ("output_hd.png", "ref_cornell_box_output_hd.png")):

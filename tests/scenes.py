@@ -51,7 +51,9 @@ def build_oracle(spec):
         flags = 1 if o.get("flip") else 0
         xf = o.get("xf")
         if o["kind"] == "mesh":
-            sc.add_mesh(np.asarray(o["tris"], np.float32), mi, flags=flags, xf=xf)
+            vn = o.get("vnormals")
+            sc.add_mesh(np.asarray(o["tris"], np.float32), mi, vnormals=None if vn is None else np.asarray(vn, np.float32),
+                        flags=flags, xf=xf)
         elif o["kind"] == "sphere":
             sc.add_sphere(o["center"], o["radius"], mi, flags=flags, xf=xf)
         elif o["kind"] == "rect":

@@ -281,3 +281,88 @@ def test_gpu_matches_the_references_showcase_hd_rendering(built):
     tr = scenes.product_tracer(spec, psc, 10, n, cutoff=1e-4, antialias=1.0, seed=31)
     rgb, _, _ = tr.RenderSums(960, 640, psc, sample_count=n)
     _check_showcase(rgb.astype(np.float64) / n, hd=True)
+
+
+# ---- flat vs interpolated normals: examples/renderings/smooth_shading/rendering.png -----------------
+def _smooth_shading_spec():
+    """smooth_shading/main.go:13-55 without the two text labels (they need model2d)."""
+    from model3d_b200 import meshes
+    ico = meshes.NewMeshIcosphere((0, 0, 0), 1.0, 4)
+    assert ico.shape[0] == 320
+    mat = scenes.phong(10.0, specular=scenes.gray(0.15), diffuse=scenes.gray(0.75), ambient=scenes.gray(0.1))
+    flat = (ico + np.array([-1.3, 0.0, 0.0])).astype(np.float32)
+    smooth = (ico + np.array([1.3, 0.0, 0.0])).astype(np.float32)
+    return dict(objects=[dict(kind="mesh", tris=flat, material=mat),
+                         dict(kind="mesh", tris=smooth, material=mat, vnormals=meshes.VertexNormals(smooth))],
+                camera=dict(src=(0.0, -8.0, -0.6), dst=(0.0, 0.0, -0.6), fov=0.8),
+                lights=[dict(origin=(2.0, -10.0, 4.0), color=scenes.gray(1.0))])
+
+
+def _check_smooth_shading(img, tol8, frac):
+    """img: linear 1728x3072x3 frame; main.go renders at 4x and calls Image.Downsample(4)."""
+    ref8 = read_png_rgb8(os.path.join(GOLD, "ref_smooth_shading_rendering.png"))
+    assert ref8.shape == (432, 768, 3)
+    lin = np.clip(img.reshape(432, 4, 768, 4, 3).mean(axis=(1, 3)), 0, 1)
+    ours8 = (np.where(lin <= 0.0031308, 12.92 * lin, 1.055 * lin ** (1 / 2.4) - 0.055) * 255.999).astype(np.int64)
+    rows = slice(0, 268)  # the labels start below the spheres
+    r, o = ref8[rows].astype(np.int64), ours8[rows]
+    lit_r, lit_o = r.sum(axis=2) > 0, o.sum(axis=2) > 0
+    assert 0.3 < lit_r.mean() < 0.5
+    assert (lit_r == lit_o).mean() > 0.9995, (lit_r == lit_o).mean()  # same silhouettes
+    d = np.abs(r - o).max(axis=2)
+    both = lit_r & lit_o
+    assert (d[both] <= tol8).mean() > frac, ((d[both] <= tol8).mean(), d[both].max())
+    # each sphere separately: flat facets on the left, smooth interpolation on the right
+    for cols in (slice(0, 384), slice(384, 768)):
+        m = both[:, cols]
+        ratio = srgb_expand(o[:, cols][m]).mean() / srgb_expand(r[:, cols][m]).mean()
+        assert abs(ratio - 1) < 0.003, ratio
+
+
+def test_vertex_normals_restatement():
+    """meshes.VertexNormals against a plain-loop restatement of mesh_ops.go:146-169."""
+    import math
+    from model3d_b200 import meshes
+    tris = meshes.NewMeshIcosphere((0.3, -0.1, 0.2), 1.5, 3)
+    got = meshes.VertexNormals(tris)
+    sums = {}
+    for t in tris:
+        e = [t[0] - t[1], t[1] - t[2], t[2] - t[0]]
+        e = [v / math.sqrt(float(v @ v)) for v in e]
+        nrm = np.cross(t[1] - t[0], t[2] - t[0])
+        nrm = nrm / math.sqrt(float(nrm @ nrm))
+        for i in range(3):
+            theta = math.acos(max(-1.0, min(1.0, -float(e[(i + 2) % 3] @ e[i]))))
+            k = tuple(t[i].tolist())
+            sums[k] = sums.get(k, np.zeros(3)) + nrm * theta
+    for ti, t in enumerate(tris):
+        for i in range(3):
+            v = sums[tuple(t[i].tolist())]
+            assert np.allclose(got[ti, i], v / math.sqrt(float(v @ v)), atol=1e-12)
+    # on a sphere the vertex normals point away from the centre
+    radial = (tris - np.array([0.3, -0.1, 0.2])) / 1.5
+    assert np.abs(got - radial).max() < 0.02
+
+
+def test_oracle_matches_the_references_smooth_shading_rendering(oracle):
+    spec = _smooth_shading_spec()
+    osc = scenes.build_oracle(spec)
+    cam = spec["camera"]
+    ocam = oracle.camera_at(cam["src"], cam["dst"], cam["fov"])
+    ol = oracle.PointLight()
+    ol.origin[:] = spec["lights"][0]["origin"]
+    ol.color[:] = (1.0, 1.0, 1.0)
+    _check_smooth_shading(osc.render_raycast(ocam, [ol], 3072, 1728, threads=8)["img"], 1, 0.995)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_the_references_smooth_shading_rendering(built):
+    from model3d_b200 import render3d as R
+    spec = _smooth_shading_spec()
+    psc = scenes.build_product(spec)
+    cam = spec["camera"]
+    img = R.Image(3072, 1728)
+    rc = R.RayCaster(Camera=R.NewCameraAt(cam["src"], cam["dst"], cam["fov"]),
+                     Lights=[R.PointLight(Origin=spec["lights"][0]["origin"], Color=(1.0, 1.0, 1.0))])
+    rc.Render(img, psc)
+    _check_smooth_shading(np.asarray(img.Data, np.float64).reshape(1728, 3072, 3), 1, 0.99)
