@@ -500,6 +500,17 @@ void orc_material_sample_source(void *s, int32_t mat, uint64_t seed, const doubl
     for (int k = 0; k < 3; k++) out[i * 3 + k] = v[k];
   }
 }
+// sampleAroundUniform / densityAroundUniform (focus_point.go:155-177): n directions in the cone
+// around `direction` and their densities (for the restated TestSampleAroundUniform)
+void orc_sample_around_uniform(uint64_t seed, double min_cos, const double direction[3], int64_t n,
+                               double *out /*n*3*/, double *density /*n*/) {
+  Rng g(seed);
+  for (int64_t i = 0; i < n; i++) {
+    V3 v = sample_around_uniform(g, min_cos, v3(direction));
+    for (int k = 0; k < 3; k++) out[i * 3 + k] = v[k];
+    density[i] = density_around_uniform(min_cos, v3(direction), v);
+  }
+}
 void orc_material_sample_dest(void *s, int32_t mat, uint64_t seed, const double normal[3],
                               const double source[3], int64_t n, double *out /*n*3*/) {
   auto *sc = (Scene *)s;

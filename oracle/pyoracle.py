@@ -442,6 +442,15 @@ class Scene:
         return out
 
 
+def sample_around_uniform(seed, min_cos, direction, n):
+    """sampleAroundUniform + densityAroundUniform (focus_point.go:155-177): (directions [n,3], densities [n])."""
+    out = np.zeros((n, 3))
+    dens = np.zeros(n)
+    lib().orc_sample_around_uniform(C.c_uint64(seed), C.c_double(min_cos), _d3(direction), C.c_int64(n),
+                                    _p(out, f64p), _p(dens, f64p))
+    return out, dens
+
+
 def camera_at(src, dst, fov):
     cam = Camera()
     lib().orc_camera_at(_d3(src), _d3(dst), C.c_double(fov), C.byref(cam))
