@@ -1,7 +1,8 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY (see vec.hpp header for the parity status: pinned
-// statistically by the reference's committed cornell_box renderings and by the reference's
-// own property tests restated in tests/test_oracle_collide.py; per-ray outputs otherwise
-// "parity unpinned" -- no Go toolchain).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see vec.hpp header for the parity status: pinned by the
+// renderings the reference commits -- statistically by cornell_box / showcase, pixel for pixel by
+// the deterministic smooth_shading RayCaster image -- and by the reference's own property tests
+// restated in tests/test_oracle_collide.py; per-ray outputs as numbers otherwise "parity
+// unpinned" -- no Go toolchain).
 //
 // float64 CPU restatement of the reference's collision path:
 //   Ray / RayCollision               model3d/collisions.go:12-46

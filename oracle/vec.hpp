@@ -11,12 +11,19 @@
 //      tests/golden/): the oracle's path tracer reproduces them statistically -- z-scores of mean
 //      0.04 and rms 1.05 over the 200x200 image, image means equal to 0.04 %
 //      (tests/test_reference_golden.py).  That scene exercises mesh BVH first hits, analytic
-//      spheres, every material kind, the focus point and the recursive tracer;
+//      spheres, every material kind, the focus point and the recursive tracer.  Likewise
+//      examples/renderings/showcase/output.png (BASELINE config 4; block means within 1.2 % median
+//      with the vase, whose mesh is missing, masked) and -- deterministically --
+//      examples/renderings/smooth_shading/rendering.png: the RayCaster image of two icospheres
+//      (flat and interpolated normals, Phong material, point light, 4x downsampling), which the
+//      oracle reproduces with identical silhouettes and 99.994 % of the 82,696 lit pixels equal
+//      at 8 bits.  That image fixes, per pixel, which triangle is hit first and its normal;
 //  (2) by restating the reference's own property tests (tests/test_oracle_*.py,
 //      tests/test_marching_cubes.py); the reference ships no golden vectors for this path
 //      (SURVEY.md section 8c).
-// Deterministic per-ray outputs (triangle ids, t) have no bit-level reference output to compare
-// with: for those the oracle remains "parity unpinned" beyond (1) and (2).
+// Deterministic per-ray outputs as numbers (triangle ids, t) have no reference output to compare
+// with beyond what the deterministic image in (1) implies: for those the oracle remains "parity
+// unpinned" beyond (1) and (2).
 #pragma once
 #include <cmath>
 #include <cstdint>
