@@ -80,8 +80,19 @@ func MeshToCollider(ctx *Context, m *model3d.Mesh) (*MeshCollider, error) {
 	return MeshToColliderBuild(ctx, m, BuildHostSAH)
 }
 
+// MeshToInterpNormalCollider replaces model3d.MeshToInterpNormalCollider (collisions.go:147-162):
+// collision normals are interpolated from the mesh's vertex normals (Mesh.VertexNormals,
+// mesh_ops.go:146-169, computed by the reference's own code here) instead of flat per triangle.
+func MeshToInterpNormalCollider(ctx *Context, m *model3d.Mesh) (*MeshCollider, error) {
+	return meshToCollider(ctx, m, BuildHostSAH, true)
+}
+
 // MeshToColliderBuild is MeshToCollider with an explicit BVH builder.
 func MeshToColliderBuild(ctx *Context, m *model3d.Mesh, buildFlags uint32) (*MeshCollider, error) {
+	return meshToCollider(ctx, m, buildFlags, false)
+}
+
+func meshToCollider(ctx *Context, m *model3d.Mesh, buildFlags uint32, interpNormals bool) (*MeshCollider, error) {
 	tris := m.TriangleSlice()
 	flat := make([]float32, 0, len(tris)*9)
 	for _, t := range tris {
@@ -89,12 +100,26 @@ func MeshToColliderBuild(ctx *Context, m *model3d.Mesh, buildFlags uint32) (*Mes
 			flat = append(flat, float32(p.X), float32(p.Y), float32(p.Z))
 		}
 	}
+	var normals []float32
+	if interpNormals {
+		vn := m.VertexNormals()
+		normals = make([]float32, 0, len(tris)*9)
+		for _, t := range tris {
+			for _, p := range t {
+				n := vn.Value(p)
+				normals = append(normals, float32(n.X), float32(n.Y), float32(n.Z))
+			}
+		}
+	}
 	res := &MeshCollider{Triangles: tris}
-	var ptr *C.float
+	var ptr, nptr *C.float
 	if len(flat) > 0 {
 		ptr = (*C.float)(unsafe.Pointer(&flat[0]))
 	}
-	if err := status(C.m3d_mesh_create(ctx.h, ptr, C.int64_t(len(tris)), nil, C.uint32_t(buildFlags), &res.h)); err != nil {
+	if len(normals) > 0 {
+		nptr = (*C.float)(unsafe.Pointer(&normals[0]))
+	}
+	if err := status(C.m3d_mesh_create(ctx.h, ptr, C.int64_t(len(tris)), nptr, C.uint32_t(buildFlags), &res.h)); err != nil {
 		return nil, err
 	}
 	var mn, mx [3]C.double
