@@ -33,3 +33,14 @@ def test_reference_arm_c1_line():
 
 def test_reference_arm_other_ranks_print_nothing():
     assert run(["--impl", "reference", "--workload", "c1", "--steps", "1"], env={"RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_reference_arm_path_tracing_line():
+    """The path-tracing reference arm (oracle renderer on a bounded frame) keeps the same contract."""
+    lines = run(["--impl", "reference", "--workload", "c4", "--steps", "1", "--warmup", "0"])
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert KEYS <= set(d), KEYS - set(d)
+    assert d["metric"] == "path_traced_Msamples_per_s" and d["unit"] == "Msamples/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and "spp" in d["cpu_baseline"]["sample"]
+    assert "showcase" in d["config"]["workload"]
