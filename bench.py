@@ -149,16 +149,17 @@ C4_WORKLOAD = "C4 showcase (examples/renderings/showcase, 326,136 triangles in 7
 WORKLOAD_NAME = {"c3": C3_WORKLOAD, "c4": C4_WORKLOAD, "c5": C5_WORKLOAD}
 
 
-def cornell_tracer(spp, workload="c3", seed=1234):
+def cornell_tracer(spp, workload="c3", seed=1234, ctx=None):
     from model3d_b200 import examples
+    kw = {"ctx": ctx} if ctx is not None else {}
     if workload == "c4":
         spec = examples.showcase(hd=True)
-        psc = examples.build_product(spec)
+        psc = examples.build_product(spec, **kw)
         tr = examples.product_tracer(spec, psc, spec["max_depth"], spp, cutoff=spec["cutoff"],
                                      antialias=spec["antialias"], seed=seed)
         return spec, psc, tr
     spec = examples.cornell_box()
-    psc = examples.build_product(spec)
+    psc = examples.build_product(spec, **kw)
     if workload == "c5":
         tr = examples.product_bidir(spec, psc, num_samples=spp, seed=seed, **C5_KW)
     else:
@@ -166,10 +167,135 @@ def cornell_tracer(spp, workload="c3", seed=1234):
     return spec, psc, tr
 
 
+def path_measure(wl, spp, size, steps, warmup, rank, world, local_rank, reduce_mode="fused", lib_devices=0):
+    """Times one path-tracing workload: `steps` frames of W x H x spp samples, samples sharded by
+    index over the GPUs (strong scaling), CUDA events on the launching stream, max over ranks.
+
+    How the per-pixel sums of the shards meet (the only exchange step of the path):
+      one process per GPU (torchrun), reduce_mode "fused": every rank's path_flush kernel adds
+          straight into rank 0's accumulator (CUDA IPC mapping over NVLink, red.add; model3d_b200/
+          distributed.SharedAccumulator); a 4-byte all_reduce per frame is the only NCCL call;
+      reduce_mode "nccl": local accumulators + one NCCL reduce per frame (round 1, kept for A/B);
+      one process, lib_devices > 1: m3d_ctx_create_multi -- the library shards and reduces inside
+          m3d_render_path / m3d_render_bidir (one host thread per device, peer-mapped red.add).
+    Returns a dict (identical on every rank)."""
+    import torch
+    import torch.distributed as dist
+    from model3d_b200 import _native as N, distributed as D
+    dev = torch.device("cuda", local_rank)
+    ctx = N.MultiContext(list(range(lib_devices))) if lib_devices > 1 else N.default_context(local_rank)
+    W = H = size
+    spec, psc, tr = cornell_tracer(spp, wl, ctx=ctx)
+    if wl == "c4":
+        W, H = spec["size"]  # "HD" 960x640 (showcase/main.go:61-69)
+    part, my_spp = D.sample_shard(spp, rank, world)
+    stream = torch.cuda.current_stream().cuda_stream
+    fused = world > 1 and reduce_mode == "fused"
+    sa = None
+    fused_note = ""
+    if fused:
+        # every rank must take the same path: agree on whether the IPC mapping came up everywhere
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            sa = D.SharedAccumulator(W * H * 12, rank, world, D._CudaIpcBackend(ctx), nbuf=2)
+        except Exception as e:
+            ok.zero_()
+            fused_note = "fused flush unavailable (%s); " % str(e)[:120]
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if sa is not None:
+                sa.close()
+            sa, fused = None, False
+            fused_note = fused_note or "fused flush unavailable on another rank; "
+    if fused:
+        accs = [torch.as_tensor(D.DevicePointer(sa.ptr(k), (H, W, 3)), device=dev) if rank == 0 else None
+                for k in range(2)]
+    else:
+        accs = [torch.zeros((H, W, 3), dtype=torch.float32, device=dev)]
+    mean = torch.empty((H, W, 3), dtype=torch.float32, device=dev) if rank == 0 else None
+    info = {"rays": 0, "launches": 0}
+    marks = []
+
+    def step(k, timed):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
+        if timed:
+            ev[0].record()
+        if fused:
+            st = tr.RenderSumsDevice(W, H, psc, sa.ptr(k), partition=part + (N.PART_ATOMIC,),
+                                     sample_count=my_spp, stream=stream)
+        else:
+            accs[0].zero_()
+            st = tr.RenderSumsDevice(W, H, psc, accs[0].data_ptr(), partition=part, sample_count=my_spp,
+                                     stream=stream)
+        if timed:
+            ev[1].record()
+        if fused:
+            sa.barrier(dev)  # every rank's flush has landed in rank 0's memory
+            if rank == 0:
+                torch.mul(accs[k % 2], 1.0 / spp, out=mean)  # colorSum / numSamples (ray_renderer.go:150)
+                accs[k % 2].zero_()
+        else:
+            if world > 1:
+                dist.reduce(accs[0], dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                torch.mul(accs[0], 1.0 / spp, out=mean)
+        if timed:
+            ev[2].record()
+            marks.append(ev)
+        info["rays"], info["launches"] = st["rays"], st["launches"]
+
+    for k in range(warmup):
+        step(k, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(steps):
+        step(warmup + k, True)
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    render_ms = sum(e[0].elapsed_time(e[1]) for e in marks) / steps
+    sync_ms = sum(e[1].elapsed_time(e[2]) for e in marks) / steps
+    t = torch.tensor([ev0.elapsed_time(ev1) / steps, float(info["rays"]), render_ms, sync_ms],
+                     dtype=torch.float64, device=dev)
+    per_rank = [[float(x) for x in t.tolist()]]
+    if world > 1:
+        dist.barrier()
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank = [[float(x) for x in g.tolist()] for g in gathered]
+    ms = max(r[0] for r in per_rank)
+    total_rays = sum(r[1] for r in per_rank)
+    checksum = float(mean.sum().item()) if rank == 0 else 0.0
+    if sa is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        del accs
+        sa.close()
+    n_dev = max(world, lib_devices, 1)
+    return {"W": W, "H": H, "spp": spp, "ms_per_step": ms, "total_rays": total_rays, "clocks": clocks,
+            "launches": int(info["launches"]), "n_devices": n_dev,
+            "render_ms_per_rank": [round(r[2], 3) for r in per_rank],
+            "reduce_wait_ms_per_rank": [round(r[3], 3) for r in per_rank],
+            "image_mean": checksum / (W * H * 3),
+            "reduce": fused_note + ("none (one GPU)" if n_dev == 1 else
+                       "library: m3d_ctx_create_multi, peer-mapped red.add inside path_flush" if lib_devices > 1 else
+                       "fused: path_flush red.add into rank 0's accumulator over a CUDA IPC / NVLink mapping, "
+                       "one 4-byte all_reduce per frame as the barrier" if fused else
+                       "nccl: one reduce of the W*H*3 float32 sums per frame"),
+            "tracer": tr, "scene": psc, "spec": spec}
+
+
 def run_path(args):
-    """BASELINE configs[2]: cornell_box, RecursiveRayTracer, 1024x1024 at --spp samples per pixel
-    per step.  N GPUs: samples sharded by index (strong scaling), per-pixel sums reduced to
-    rank 0 with one NCCL reduce, inside the timed region."""
+    """BASELINE configs[2..4]: cornell_box / showcase with the RecursiveRayTracer, cornell_box with
+    the BidirPathTracer, --spp samples per pixel per step.  N GPUs: samples sharded by index
+    (strong scaling); see path_measure for how the shards are reduced."""
     import torch
     import torch.distributed as dist
 
@@ -180,63 +306,22 @@ def run_path(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    from model3d_b200 import _native as N
-    N.default_context(local_rank)
-    W = H = args.size
-    spp = args.spp
-    spec, psc, tr = cornell_tracer(spp, args.workload)
-    if args.workload == "c4":
-        W, H = spec["size"]  # "HD" 960x640 (showcase/main.go:61-69)
-    from model3d_b200 import distributed as D
-    part, my_spp = D.sample_shard(spp, rank, world)
-    acc = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    lib_devices = args.gpus if (world == 1 and args.gpus > 1) else 0  # one process driving several GPUs
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.synchronize()
     torch.cuda.set_stream(tstream)
-    rays = [0]
-    launches = [0]
-
-    def step():
-        acc.zero_()
-        st = tr.RenderSumsDevice(W, H, psc, acc.data_ptr(), partition=part, sample_count=my_spp,
-                                 stream=tstream.cuda_stream)
-        rays[0] = st["rays"]
-        launches[0] = st["launches"]
-        D.reduce_sums(acc, dst=0)
-
-    for _ in range(max(1, min(args.warmup, 3))):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, float(rays[0])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.barrier()
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms, total_rays = float(tmax[0].item()), float(t[1].item())
-    else:
-        total_rays = float(rays[0])
-    ms_step = ms / args.steps
+    m = path_measure(args.workload, args.spp, args.size, args.steps, max(3, args.warmup), rank, world, local_rank,
+                     reduce_mode=args.reduce, lib_devices=lib_devices)
+    W, H, spp, ms_step, total_rays = m["W"], m["H"], m["spp"], m["ms_per_step"], m["total_rays"]
+    tr, psc = m["tracer"], m["scene"]
+    n_dev = m["n_devices"]
     samples = W * H * spp
     value = samples / (ms_step * 1e-3) / 1e6
     if rank == 0:
         # end to end: the host-buffer call (sums copied back to host memory every step)
         e2e = None
         if world == 1 and not args.no_e2e:
+            tr.RenderSums(W, H, psc)
             t0 = time.perf_counter()
             k = max(1, args.steps // 2)
             for _ in range(k):
@@ -246,25 +331,29 @@ def run_path(args):
                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 12,
                    "api": "m3d_render_%s (host image buffers)" % ("bidir" if args.workload == "c5" else "path")}
         line = {
-            "metric": "path_traced_Msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "metric": "path_traced_Msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": n_dev,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME[args.workload], "width": W, "height": H,
                        "spp": spp,
                        "rays_per_sample": total_rays / samples, "Mrays_per_s": total_rays / (ms_step * 1e-3) / 1e6,
-                       "sharding": "sample index, NCCL reduce of the W*H*3 float32 sums to rank 0",
+                       "sharding": "sample index; " + m["reduce"],
+                       "render_ms_per_rank": m["render_ms_per_rank"],
+                       "reduce_wait_ms_per_rank": m["reduce_wait_ms_per_rank"],
                        "l2": "path state streams through HBM (> L2 per batch); scene BVH is L2/L1 resident"},
-            "clocks": clocks, "gpu_launches": int(launches[0]) * args.steps,
+            "clocks": m["clocks"], "gpu_launches": m["launches"] * args.steps * (n_dev if lib_devices else 1),
         }
         if e2e:
             line["e2e"] = e2e
         # Path state that crosses HBM per traced ray: queue entry 40 B written and
         # read, raw hit 16 + 16, hit record 48 + 48, throughput 16 + 16 = 256 B.  The path tracers
         # are bound by issue rate and dependent-load latency, not by this stream; the fraction says so.
+        # N GPUs: the bytes of all GPUs against N times one GPU's peak.
         peak, peak_src = hbm_peak()
         achieved = total_rays * 256.0 / (ms_step * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak * n_dev, "unit": "GB/s",
+                            "frac": achieved / (peak * n_dev), "traffic": None,
+                            "peak_source": peak_src + (" x %d GPUs" % n_dev if n_dev > 1 else ""),
                             "bytes_per_ray": 256.0, "kernel": "trace_first_hit_kernel + path_resolve / path_sample"
                             if args.workload != "c5" else "bidir_connect_kernel + trace_first_hit_kernel"}
         if world == 1 and not args.no_cpu_baseline:
@@ -459,56 +548,29 @@ def run_reference_path(args):
     print(json.dumps(line), flush=True)
 
 
-def secondary_path_metrics(rank, world, dev):
-    """Short path-tracing measurements appended to the headline line (BASELINE metric: 'Mrays/s
-    first-hit AND path-traced samples/s'): cornell_box 1024x1024 with the RecursiveRayTracer (C3,
-    64 spp) and the BidirPathTracer (C5, 16 spp), the showcase scene 960x640 (C4, 64 spp); samples
-    sharded over the ranks, sums reduced to rank 0 inside the timed region.  CUDA-event timed, max
-    over ranks."""
-    import torch
-    import torch.distributed as dist
-    from model3d_b200 import distributed as D
+# BASELINE configs[2..4] at their own sample counts (the driver-run lines must be
+# measured at 256 / 256 / 1024 spp, >= 3 warm-up and >= 5 timed frames each)
+SECONDARY = (("c3", 256), ("c4", 256), ("c5", 1024))
+
+
+def secondary_path_metrics(rank, world, local_rank, reduce_mode="fused", steps=5, warmup=3):
+    """Path-tracing measurements appended to the headline line (BASELINE metric: 'Mrays/s first-hit
+    AND path-traced samples/s'): cornell_box 1024x1024 with the RecursiveRayTracer (C3, 256 spp) and
+    the BidirPathTracer (C5, 1024 spp), the showcase scene 960x640 (C4, 256 spp); samples sharded
+    over the ranks, every rank's flush kernel reducing into rank 0's accumulator inside the timed
+    region.  CUDA-event timed, max over ranks; per-rank render / reduce-wait split reported."""
     out = {}
-    for wl, spp in (("c3", 64), ("c4", 64), ("c5", 16)):
-        W = H = 1024
-        spec, psc, tr = cornell_tracer(spp, wl)
-        if wl == "c4":
-            W, H = spec["size"]  # "HD" 960x640 (showcase/main.go:61-69)
-        part, my_spp = D.sample_shard(spp, rank, world)
-        acc = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
-        stream = torch.cuda.current_stream().cuda_stream
-        rays = 0
-
-        def step():
-            nonlocal rays
-            acc.zero_()
-            st = tr.RenderSumsDevice(W, H, psc, acc.data_ptr(), partition=part, sample_count=my_spp, stream=stream)
-            rays = st["rays"]
-            D.reduce_sums(acc, dst=0)
-
-        step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k = 2
-        ev0.record()
-        for _ in range(k):
-            step()
-        ev1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([ev0.elapsed_time(ev1) / k, float(rays)], dtype=torch.float64, device=dev)
-        if world > 1:
-            tm = t.clone()
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            ms, total_rays = float(tm[0].item()), float(t[1].item())
-        else:
-            ms, total_rays = float(t[0].item()), float(t[1].item())
-        out[wl] = {"workload": WORKLOAD_NAME[wl], "width": W, "height": H, "spp": spp,
-                   "Msamples_per_s": W * H * spp / (ms * 1e-3) / 1e6, "Mrays_per_s": total_rays / (ms * 1e-3) / 1e6,
-                   "ms_per_frame": ms, "scaling": "strong (sample shards + NCCL reduce)"}
-        del psc, tr
+    for wl, spp in SECONDARY:
+        m = path_measure(wl, spp, 1024, steps, warmup, rank, world, local_rank, reduce_mode=reduce_mode)
+        W, H, ms = m["W"], m["H"], m["ms_per_step"]
+        out[wl] = {"workload": WORKLOAD_NAME[wl], "width": W, "height": H, "spp": spp, "steps": steps,
+                   "warmup": warmup,
+                   "Msamples_per_s": W * H * spp / (ms * 1e-3) / 1e6,
+                   "Mrays_per_s": m["total_rays"] / (ms * 1e-3) / 1e6,
+                   "ms_per_frame": ms, "render_ms_per_rank": m["render_ms_per_rank"],
+                   "reduce_wait_ms_per_rank": m["reduce_wait_ms_per_rank"],
+                   "scaling": "strong (sample shards); " + m["reduce"]}
+        del m
     return out
 
 
@@ -527,9 +589,15 @@ def main():
                     help="c2: raw first-hit ray batch (headline); c1: marching-cubes sphere, RayCaster 512x512; "
                          "c3: cornell_box RecursiveRayTracer 1024x1024; c4: showcase HD; "
                          "c5: cornell_box BidirPathTracer 1024x1024")
-    ap.add_argument("--spp", type=int, default=256, help="samples per pixel per step (c3)")
+    ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"],
+                    help="N > 1 path tracing: fused = every rank's flush kernel adds into rank 0's accumulator "
+                         "over NVLink (default); nccl = local accumulators + one NCCL reduce per frame")
+    ap.add_argument("--spp", type=int, default=0,
+                    help="samples per pixel per step (default: the BASELINE value, c3/c4 256, c5 1024)")
     ap.add_argument("--size", type=int, default=1024, help="frame width == height (c3)")
     args = ap.parse_args()
+    if not args.spp:
+        args.spp = 1024 if args.workload == "c5" else 256
     if args.impl == "reference":
         if args.workload in ("c3", "c4", "c5"):
             run_reference_path(args)
@@ -619,67 +687,77 @@ def main():
     ms_step = ms_total / args.steps
     value = world * n / (ms_step * 1e-3) / 1e6
 
-    # end to end through the host-buffer C-ABI call: pinned host inputs, H2D + kernels + D2H
+    # end to end through the host-buffer C-ABI call, H2D + kernels + D2H inside the timed region.
+    # Headline e2e: caller buffers from m3d_host_alloc (pinned; what the cgo binding hands out) and
+    # all of t / prim / normal returned.  Beside it: the same call on pageable numpy arrays (what a
+    # caller gets who ignores m3d_host_alloc) and with only t + prim returned (8 B/ray back).
     e2e = None
     if not args.no_e2e:
-        org_p = torch.from_numpy(org).pin_memory()
-        d_p = torch.from_numpy(d).pin_memory()
-        t_p = torch.empty(n, dtype=torch.float32).pin_memory()
-        prim_p = torch.empty(n, dtype=torch.int32).pin_memory()
-        nrm_p = torch.empty((n, 3), dtype=torch.float32).pin_memory()
         import ctypes as C
         f32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        org_p, d_p = N.host_empty((n, 3), np.float32), N.host_empty((n, 3), np.float32)
+        org_p[:], d_p[:] = org, d
+        t_p, prim_p = N.host_empty(n, np.float32), N.host_empty(n, np.int32)
+        nrm_p = N.host_empty((n, 3), np.float32)
 
-        def e2e_step():
+        def call(o, dd, t, pr, nr):
             N.check(N.lib().m3d_mesh_first_ray_collisions(
-                col.h, C.cast(org_p.data_ptr(), f32p), C.cast(d_p.data_ptr(), f32p), C.c_int64(n),
-                C.cast(t_p.data_ptr(), f32p), C.cast(prim_p.data_ptr(), i32p),
-                C.cast(nrm_p.data_ptr(), f32p), None, C.c_uint32(0), None))
+                col.h, o.ctypes.data_as(f32p), dd.ctypes.data_as(f32p), C.c_int64(n),
+                t.ctypes.data_as(f32p), pr.ctypes.data_as(i32p),
+                nr.ctypes.data_as(f32p) if nr is not None else None, None, C.c_uint32(0), None))
 
-        for _ in range(2):
-            e2e_step()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
+        def timed(fn, reps):
+            for _ in range(2):
+                fn()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            ctx.synchronize()
+            tt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
         e2e_steps = max(2, min(args.steps // 2, 10))
-        for _ in range(e2e_steps):
-            e2e_step()
-        ctx.synchronize()
-        dt = (time.perf_counter() - t0) / e2e_steps
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = timed(lambda: call(org_p, d_p, t_p, prim_p, nrm_p), e2e_steps)
         e2e = {"value": world * n / dt / 1e6, "unit": "Mrays/s", "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 20,
-               "api": "m3d_mesh_first_ray_collisions (host buffers, pinned)"}
-        # what the link allows: the same bytes copied both ways at once with no compute at all
-        # (two streams, pinned memory); e2e / this bound says how well the chunked pipeline hides
-        # the kernels behind the copies
-        if world == 1:
-            d_in = torch.empty(n * 24, dtype=torch.uint8, device=dev)
-            d_out = torch.empty(n * 20, dtype=torch.uint8, device=dev)
-            h_in = org_p.view(torch.uint8).reshape(-1), d_p.view(torch.uint8).reshape(-1)
-            h_out = torch.empty(n * 20, dtype=torch.uint8).pin_memory()
-            s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+               "api": "m3d_mesh_first_ray_collisions (host buffers from m3d_host_alloc: pinned)"}
+        dt_min = timed(lambda: call(org_p, d_p, t_p, prim_p, None), e2e_steps)
+        e2e["t_prim_only"] = {"value": world * n / dt_min / 1e6, "ms_per_step": dt_min * 1e3,
+                              "d2h_bytes_per_step": n * 8}
+        t_g, prim_g, nrm_g = np.empty(n, np.float32), np.empty(n, np.int32), np.empty((n, 3), np.float32)
+        dt_pg = timed(lambda: call(org, d, t_g, prim_g, nrm_g), 2)
+        e2e["pageable"] = {"value": world * n / dt_pg / 1e6, "ms_per_step": dt_pg * 1e3,
+                           "note": "same call on ordinary (pageable) numpy arrays: the driver stages the copies"}
+        assert np.array_equal(prim_g, prim_p)
+        del t_g, prim_g, nrm_g
+        # what the host link allows: the same bytes copied both ways at once with no compute at all
+        # (two streams, pinned memory), all ranks at the same time -- every GPU of the box shares the
+        # host's memory system, so at N > 1 this bound, not the GPUs, is what e2e scales with
+        d_in = torch.empty(n * 24, dtype=torch.uint8, device=dev)
+        d_out = torch.empty(n * 20, dtype=torch.uint8, device=dev)
+        h_in = torch.from_numpy(org_p.view(np.uint8).reshape(-1)), torch.from_numpy(d_p.view(np.uint8).reshape(-1))
+        h_out_np = N.host_empty(n * 20, np.uint8)
+        h_out = torch.from_numpy(h_out_np)
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
-            def copies(reps):
-                torch.cuda.synchronize()
-                t0c = time.perf_counter()
-                for _ in range(reps):
-                    with torch.cuda.stream(s_in):
-                        d_in[:n * 12].copy_(h_in[0], non_blocking=True)
-                        d_in[n * 12:].copy_(h_in[1], non_blocking=True)
-                    with torch.cuda.stream(s_out):
-                        h_out.copy_(d_out, non_blocking=True)
-                s_in.synchronize()
-                s_out.synchronize()
-                return (time.perf_counter() - t0c) / reps
-            copies(2)
-            cb = copies(5)
-            e2e["copy_bound_ms"] = cb * 1e3
-            e2e["frac_of_copy_bound"] = cb / dt
-            del d_in, d_out, h_out
+        def copies():
+            with torch.cuda.stream(s_in):
+                d_in[:n * 12].copy_(h_in[0], non_blocking=True)
+                d_in[n * 12:].copy_(h_in[1], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out.copy_(d_out, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+        cb = timed(copies, 5)
+        e2e["copy_bound_ms"] = cb * 1e3
+        e2e["frac_of_copy_bound"] = cb / dt
+        e2e["copy_bound_note"] = "%d rank(s) copying %d MB in + %d MB out each, concurrently, no compute" % (
+            world, n * 24 >> 20, n * 20 >> 20)
+        del d_in, d_out, h_out, h_out_np, h_in
 
     # mix B: coherent primary rays of a 4096x4096 pinhole camera at (0,-3,0) looking at
     # the origin, fov pi/3.6 -- same mesh, same kernels, reported beside the incoherent headline
@@ -717,7 +795,7 @@ def main():
     secondary = None
     if not args.no_secondary:
         try:
-            secondary = secondary_path_metrics(rank, world, dev)
+            secondary = secondary_path_metrics(rank, world, local_rank, reduce_mode=args.reduce)
         except Exception as e:  # the headline must still be reported
             secondary = {"error": str(e)[:200]}
     if rank == 0:
@@ -745,10 +823,32 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_ray": bytes_per_ray, "kernel": "trace_first_hit_kernel",
-                         "compulsory_stream_GBps": n * RAY_IO_BYTES / (ms_step * 1e-3) / 1e9},
+                         "compulsory_stream_GBps": n * RAY_IO_BYTES / (ms_step * 1e-3) / 1e9,
+                         "frac_hbm_compulsory": n * RAY_IO_BYTES / (ms_step * 1e-3) / 1e9 / peak,
+                         "note": "achieved / frac follow SURVEY 8d (all algorithmic bytes over the HBM copy peak); "
+                                 "the BVH is L2 resident, so the node + triangle fetches are also set against "
+                                 "what L2 delivers on this GPU, measured live (m3d_measure_l2_bandwidth)"},
             "clocks": clocks,
             "gpu_launches": 2 * args.steps,
         }
+        try:
+            # L2 -> SM bandwidth over a working set of the BVH's size: coalesced stream, and the
+            # traversal's own access pattern (32 different 80-byte records per warp instruction)
+            import ctypes as C
+            bvh_mb = max(8, int(info["device_bytes"]) >> 20)
+            l2 = {}
+            for mode, key in ((0, "stream"), (1, "gather")):
+                g = C.c_double()
+                N.check(N.lib().m3d_measure_l2_bandwidth(ctx.h, C.c_int32(mode), C.c_int64(bvh_mb << 20),
+                                                         C.c_int32(3), C.byref(g)))
+                l2[key] = g.value
+            fetch = n * (nodes_per_ray * NODE_BYTES + tris_per_ray * TRI_BYTES) / (ms_step * 1e-3) / 1e9
+            line["roofline"].update({
+                "node_tri_fetch_GBps": fetch, "l2_stream_peak_GBps": l2["stream"], "l2_gather_peak_GBps": l2["gather"],
+                "frac_l2_stream": fetch / l2["stream"], "frac_l2_gather": fetch / l2["gather"],
+                "l2_working_set_MB": bvh_mb})
+        except Exception as e:
+            line["roofline"]["l2_error"] = str(e)[:200]
         if e2e:
             line["e2e"] = e2e
         if mix_b:

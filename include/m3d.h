@@ -17,7 +17,12 @@
  *   - "triangle id" == index of the triangle in the caller's array
  *     (the reference identifies triangles by pointer, model3d/collisions.go:39-46);
  *   - there is NO CPU fallback: without a CUDA device every compute entry point
- *     fails with M3D_ERR_CUDA.
+ *     fails with M3D_ERR_CUDA;
+ *   - thread safety: every call on a context (or on a mesh / scene built from it) takes the
+ *     context's lock, so handles may be shared between threads like the reference's Colliders
+ *     and Objects ("safe for concurrency", model3d/collisions.go:51); calls on ONE context run one
+ *     after another -- use one context per thread (or a multi-device context) for parallelism.
+ *     m3d_last_error() is per thread: read it on the thread whose call failed.
  */
 #ifndef M3D_H_
 #define M3D_H_
@@ -28,7 +33,7 @@
 extern "C" {
 #endif
 
-#define M3D_ABI_VERSION 4
+#define M3D_ABI_VERSION 5
 
 typedef enum {
   M3D_OK = 0,
@@ -51,6 +56,19 @@ const char *m3d_last_error(void);
 
 /* device < 0 -> current CUDA device. */
 int32_t m3d_ctx_create(int32_t device, m3d_ctx **out);
+/* A context over n devices of this node (devices[0] is the primary; NULL/n<=0 -> all visible
+ * devices).  Replaces the reference's goroutine scheduler (render3d/concurrency.go:17-43,
+ * ray_renderer.go:25-56) across GPUs: meshes and scenes built on it are replicated on every
+ * device; m3d_mesh_first_ray_collisions splits the ray batch into contiguous slices,
+ * m3d_render_raycast renders row bands, m3d_render_path / m3d_render_bidir shard the samples of
+ * every pixel by index (adaptive renders: row bands), one host thread per device, and every
+ * device's flush kernel adds its per-pixel sums straight into the primary's accumulator over
+ * NVLink peer mappings (system-scope red.add) -- no collective afterwards.  The image does not
+ * depend on the number of devices (Philox streams are keyed by pixel and sample index) beyond
+ * float32 summation order.  Needs peer access between the primary and every other device,
+ * else M3D_ERR_UNSUPPORTED. */
+int32_t m3d_ctx_create_multi(const int32_t *devices, int32_t n, m3d_ctx **out);
+int32_t m3d_ctx_num_devices(const m3d_ctx *ctx);
 void m3d_ctx_destroy(m3d_ctx *ctx);
 int32_t m3d_ctx_device(const m3d_ctx *ctx);
 int32_t m3d_ctx_synchronize(m3d_ctx *ctx);
@@ -281,9 +299,15 @@ typedef struct {
 
 /* Work partition for multi-GPU: this call renders rows [row_begin,row_end) of the
  * frame and samples [sample_begin, sample_begin+sample_count) of every pixel. */
+#define M3D_PART_ATOMIC 1u /* several GPUs flush into ONE accumulator at the same time: the
+                              per-pixel sums are added with system-scope red.add (the output
+                              pointer may be another GPU's memory, mapped by peer access inside a
+                              multi-device context or by m3d_ipc_open across processes) */
 typedef struct {
   int32_t row_begin, row_end; /* 0,0 == whole frame */
   int64_t sample_begin;       /* first Philox sample index of this shard */
+  uint32_t flags;             /* M3D_PART_* */
+  uint32_t _pad;
 } m3d_partition;
 
 /* (*RayCaster).Render (render3d/raycast.go:15-39).
@@ -398,6 +422,38 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam,
 int32_t m3d_finalize_image_device(m3d_ctx *ctx, const void *d_sum, int64_t num_pixels,
                                   double inv_samples, void *d_mean, void *d_srgb8,
                                   void *stream);
+
+/* ---- memory the caller shares with the library --------------------------------
+ * Pinned host memory: host-buffer calls reach the PCIe rate only from page-locked buffers
+ * (pageable memory is staged by the driver: about half the rate, and copies stop overlapping).
+ * A Go / C caller allocates its ray and hit arrays here (the cgo binding wraps the pointer in a
+ * slice with unsafe.Slice) or registers arrays it already owns. */
+int32_t m3d_host_alloc(int64_t bytes, void **out);
+int32_t m3d_host_free(void *ptr);
+int32_t m3d_host_register(void *ptr, int64_t bytes);
+int32_t m3d_host_unregister(void *ptr);
+
+/* Device buffers owned by the library (zero-filled) and their export to the other processes of a
+ * one-process-per-GPU job: rank 0 allocates the frame accumulator and exports it, every other
+ * rank opens it and passes the mapped pointer as d_rgb_sum with M3D_PART_ATOMIC, so that its
+ * flush kernel reduces into rank 0's memory over NVLink.  handle: M3D_IPC_HANDLE_BYTES bytes. */
+#define M3D_IPC_HANDLE_BYTES 64
+int32_t m3d_device_alloc(m3d_ctx *ctx, int64_t bytes, void **d_ptr);
+int32_t m3d_device_free(m3d_ctx *ctx, void *d_ptr);
+int32_t m3d_ipc_export(m3d_ctx *ctx, void *d_ptr, uint8_t *handle);
+int32_t m3d_ipc_open(m3d_ctx *ctx, const uint8_t *handle, void **d_ptr);
+int32_t m3d_ipc_close(m3d_ctx *ctx, void *d_ptr);
+
+/* ---- diagnostics ---------------------------------------------------------------
+ * On-chip bandwidth microbenchmarks for the roofline of the traversal kernel (the BVH
+ * is L2 resident, node / triangle fetches are bounded by L2 -> SM bandwidth, not HBM).
+ *   mode 0: every SM streams a working set of working_set_bytes (choose it < L2, > the L1s) with
+ *           coalesced 16-byte loads that bypass L1;
+ *   mode 1: every lane reads whole pseudo-random 80-byte records (the wide-node access pattern:
+ *           32 different nodes per warp instruction).
+ * Best of `repeats` timed launches, GB/s.  Not on any product path. */
+int32_t m3d_measure_l2_bandwidth(m3d_ctx *ctx, int32_t mode, int64_t working_set_bytes,
+                                 int32_t repeats, double *gb_per_s);
 
 #ifdef __cplusplus
 }

@@ -67,8 +67,13 @@ class Transform(C.Structure):
     _fields_ = [("matrix", C.c_double * 9), ("offset", C.c_double * 3)]
 
 
+PART_ATOMIC = 1
+IPC_HANDLE_BYTES = 64
+
+
 class Partition(C.Structure):
-    _fields_ = [("row_begin", C.c_int32), ("row_end", C.c_int32), ("sample_begin", C.c_int64)]
+    _fields_ = [("row_begin", C.c_int32), ("row_end", C.c_int32), ("sample_begin", C.c_int64),
+                ("flags", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class FocusPoint(C.Structure):
@@ -109,6 +114,9 @@ SYMBOLS = [
     "m3d_scene_build", "m3d_scene_destroy", "m3d_scene_bounds", "m3d_scene_cast",
     "m3d_render_raycast", "m3d_render_raycast_device", "m3d_render_path", "m3d_render_path_device",
     "m3d_render_bidir", "m3d_render_bidir_device", "m3d_finalize_image_device",
+    "m3d_measure_l2_bandwidth", "m3d_ctx_create_multi", "m3d_ctx_num_devices",
+    "m3d_host_alloc", "m3d_host_free", "m3d_host_register", "m3d_host_unregister",
+    "m3d_device_alloc", "m3d_device_free", "m3d_ipc_export", "m3d_ipc_open", "m3d_ipc_close",
 ]
 
 _lib = None
@@ -165,6 +173,84 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class MultiContext(Context):
+    """m3d_ctx over several devices of this node (m3d_ctx_create_multi): meshes and scenes built on
+    it are replicated, first-hit batches are sliced and renders sharded over the devices, and the
+    per-pixel sums meet in device 0's accumulator inside the flush kernels (NVLink red.add)."""
+
+    def __init__(self, devices=None):
+        self.h = C.c_void_p()
+        if devices is None:
+            check(lib().m3d_ctx_create_multi(None, C.c_int32(0), C.byref(self.h)))
+        else:
+            arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            check(lib().m3d_ctx_create_multi(arr, C.c_int32(len(devices)), C.byref(self.h)))
+
+    @property
+    def num_devices(self):
+        return int(lib().m3d_ctx_num_devices(self.h))
+
+
+class _PinnedBlock:
+    """Owner of one m3d_host_alloc block; numpy views keep it alive through .base."""
+
+    def __init__(self, nbytes):
+        self.nbytes = max(int(nbytes), 1)
+        p = C.c_void_p()
+        check(lib().m3d_host_alloc(C.c_int64(self.nbytes), C.byref(p)))
+        self.ptr = p.value
+
+    @property
+    def __array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().m3d_host_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def host_empty(shape, dtype):
+    """numpy array in pinned (page-locked) host memory from m3d_host_alloc: what the host-buffer
+    calls need to reach the PCIe rate.  Freed when the array and all of its views are gone."""
+    import numpy as np
+    dt = np.dtype(dtype)
+    count = int(np.prod(shape))
+    block = _PinnedBlock(count * dt.itemsize)
+    return np.asarray(block)[:count * dt.itemsize].view(dt).reshape(shape)
+
+
+def device_alloc(ctx, nbytes):
+    """Zero-filled device buffer owned by the library (a plain cudaMalloc, exportable over IPC)."""
+    p = C.c_void_p()
+    check(lib().m3d_device_alloc(ctx.h, C.c_int64(nbytes), C.byref(p)))
+    return p.value
+
+
+def device_free(ctx, ptr):
+    check(lib().m3d_device_free(ctx.h, C.c_void_p(ptr)))
+
+
+def ipc_export(ctx, ptr):
+    h = (C.c_uint8 * IPC_HANDLE_BYTES)()
+    check(lib().m3d_ipc_export(ctx.h, C.c_void_p(ptr), h))
+    return bytes(h)
+
+
+def ipc_open(ctx, handle):
+    h = (C.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(handle)
+    p = C.c_void_p()
+    check(lib().m3d_ipc_open(ctx.h, h, C.byref(p)))
+    return p.value
+
+
+def ipc_close(ctx, ptr):
+    check(lib().m3d_ipc_close(ctx.h, C.c_void_p(ptr)))
 
 
 _default_ctx = {}

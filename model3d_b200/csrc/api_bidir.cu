@@ -89,6 +89,18 @@ int32_t carve_bidir_buffers(m3d_ctx *ctx, int64_t cap, int De, int Dl, BidirBuff
 
 }  // namespace
 
+static int32_t render_bidir_one_device(m3d_scene *scene, const m3d_camera *cam, const m3d_area_light *lights,
+                                       int32_t num_lights, const m3d_bidir_params *params, int32_t width,
+                                       int32_t height, const m3d_partition *part, int32_t sample_count,
+                                       void *d_rgb_sum, void *d_rgb_sumsq, void *stream, m3d_stats *stats);
+
+namespace m3d {
+int32_t shard_render(m3d_scene *scene, bool adaptive, int32_t height, const m3d_partition *part,
+                     int32_t sample_count, cudaStream_t stream, m3d_stats *stats,
+                     const std::function<int32_t(m3d_scene *, const m3d_partition &, int32_t, cudaStream_t,
+                                                 m3d_stats *)> &one);  // api_path.cu
+}
+
 extern "C" {
 
 int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m3d_area_light *lights,
@@ -98,6 +110,25 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
   if (!scene || !cam || !params || !lights || num_lights <= 0 || width <= 0 || height <= 0 || !d_rgb_sum ||
       sample_count < 0)
     return fail(M3D_ERR_INVALID_ARG, "m3d_render_bidir: bad arguments");
+  M3D_LOCK(scene->ctx);
+  if (!scene->replicas.empty() && sample_count > 0) {
+    const bool adaptive = params->min_samples != 0 && params->max_stddev != 0;
+    return shard_render(scene, adaptive, height, part, sample_count, (cudaStream_t)stream, stats,
+                        [&](m3d_scene *si, const m3d_partition &pi, int32_t count, cudaStream_t s, m3d_stats *st) {
+                          return render_bidir_one_device(si, cam, lights, num_lights, params, width, height, &pi,
+                                                         count, d_rgb_sum, d_rgb_sumsq, s, st);
+                        });
+  }
+  return render_bidir_one_device(scene, cam, lights, num_lights, params, width, height, part, sample_count,
+                                 d_rgb_sum, d_rgb_sumsq, stream, stats);
+}
+
+}  // extern "C"
+
+static int32_t render_bidir_one_device(m3d_scene *scene, const m3d_camera *cam, const m3d_area_light *lights,
+                                       int32_t num_lights, const m3d_bidir_params *params, int32_t width,
+                                       int32_t height, const m3d_partition *part, int32_t sample_count,
+                                       void *d_rgb_sum, void *d_rgb_sumsq, void *stream, m3d_stats *stats) {
   const int max_depth = params->max_depth;
   const int max_ld = params->max_light_depth != 0 ? params->max_light_depth : max_depth;  // bidir.go:257-262
   if (max_depth < 1 || max_ld < 1) return fail(M3D_ERR_INVALID_ARG, "MaxDepth and MaxLightDepth must be >= 1");
@@ -199,6 +230,7 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
   bp.min_depth = params->min_depth;
   bp.cutoff = (float)params->cutoff;
   bp.antialias = (float)params->antialias;
+  bp.eps = params->epsilon > 1e-7 ? (float)params->epsilon : 0.f;  // DefaultEpsilon 1e-8 -> surface skip ids
   bp.roulette_delta = params->roulette_delta;
   bp.power_heuristic = params->power_heuristic;
   bp.seed = params->seed;
@@ -219,12 +251,11 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
 #ifndef M3D_BIDIR_BUDGET_GB
 #define M3D_BIDIR_BUDGET_GB 64  // device memory for one batch's path vertices / work lists (of 180 GB)
 #endif
-  static int batch_log2 = 0;  // M3D_BIDIR_BATCH_LOG2: samples per batch (tuning runs)
-  if (!batch_log2) {
+  static const int batch_log2 = [] {  // M3D_BIDIR_BATCH_LOG2: samples per batch (tuning runs)
     const char *e = getenv("M3D_BIDIR_BATCH_LOG2");
-    batch_log2 = e ? atoi(e) : 22;
-    if (batch_log2 < 10 || batch_log2 > 22) batch_log2 = 22;
-  }
+    const int v = e ? atoi(e) : 22;
+    return (v < 10 || v > 22) ? 22 : v;
+  }();
   // at most half of what is free on the device right now (beyond what this context already holds)
   size_t free_b = 0, total_b = 0;
   M3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -304,9 +335,21 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
                                   buf.accum, (float *)d_rgb_sum, run_batch, &samples_taken))
       return rc;
   } else {
+    // M3D_PART_ATOMIC: other GPUs flush into the same accumulator at the same time.  A pixel range
+    // that takes several batches keeps its partial sums in local memory and only its last batch
+    // adds to the shared accumulator (with red.add, over NVLink when it lives on another GPU).
+    FlushPlan fp;
+    fp.atomic = part && (part->flags & M3D_PART_ATOMIC);
+    if (fp.atomic && sample_count > std::max<int64_t>(1, cap / nP_max)) {
+      M3D_CUDA(ctx->scratch[11].reserve((size_t)nP_max * 6 * sizeof(float)));
+      fp.carry = ctx->scratch[11].as<float>();
+      fp.carry_sq = fp.carry + (size_t)nP_max * 3;
+    }
     for (int64_t p0 = 0; p0 < npix; p0 += nP_max) {
       const int64_t nP = std::min(nP_max, npix - p0);
       const int64_t S_max = std::max<int64_t>(1, cap / nP);
+      if (fp.carry && sample_count > S_max)
+        M3D_CUDA(cudaMemsetAsync(fp.carry, 0, (size_t)nP_max * 6 * sizeof(float), s));
       for (int64_t s0 = 0; s0 < sample_count; s0 += S_max) {
         PathBatch b;
         b.W = width;
@@ -315,7 +358,8 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
         b.S = (int32_t)std::min<int64_t>(S_max, sample_count - s0);
         b.sample0 = (uint32_t)(sample_begin + s0);
         if (int32_t rc = run_batch(b)) return rc;
-        launch_path_flush(b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
+        flush_batch(fp, b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s0 == 0,
+                    s0 + S_max >= sample_count, s);
         launches++;
       }
     }
@@ -334,6 +378,8 @@ int32_t m3d_render_bidir_device(m3d_scene *scene, const m3d_camera *cam, const m
   return M3D_OK;
 }
 
+extern "C" {
+
 int32_t m3d_render_bidir(m3d_scene *scene, const m3d_camera *cam, const m3d_area_light *lights, int32_t num_lights,
                          const m3d_bidir_params *params, int32_t width, int32_t height,
                          const m3d_partition *part, int32_t sample_count, float *rgb_sum, float *rgb_sumsq,
@@ -341,6 +387,7 @@ int32_t m3d_render_bidir(m3d_scene *scene, const m3d_camera *cam, const m3d_area
   if (!scene || !rgb_sum || width <= 0 || height <= 0)
     return fail(M3D_ERR_INVALID_ARG, "m3d_render_bidir: bad arguments");
   m3d_ctx *ctx = scene->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)width * height * 3 * sizeof(float);
   M3D_CUDA(ctx->scratch[3].reserve(bytes * 2));

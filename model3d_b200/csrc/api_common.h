@@ -4,6 +4,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -80,11 +82,20 @@ struct m3d_ctx {
   cudaStream_t copy_in = nullptr;      // H2D
   cudaStream_t copy_out = nullptr;     // D2H
   // scratch reused by host-buffer calls (grown on demand, never shrunk)
-  m3d::DevBuf scratch[12];
+  m3d::DevBuf scratch[14];
   m3d::DevBuf counters;       // [0..3] node/triangle statistics, then kWorkSlots work counters
   unsigned work_slot = 0;
   static constexpr int kWorkSlots = 64;
+  // Every entry point that touches scratch / streams / counters holds this lock for the whole
+  // call: the reference's Collider and Object methods are "safe for concurrency"
+  // (model3d/collisions.go:51) and its consumers call them from many goroutines at once, so calls
+  // on one context serialise here (recursive: host-buffer calls nest the device-buffer ones).
+  std::recursive_mutex mu;
+  // Multi-device context (m3d_ctx_create_multi): this context is device 0 of the group and owns
+  // the contexts of the other devices.  Meshes and scenes built on it carry one replica per member.
+  std::vector<m3d_ctx *> members;
 };
+#define M3D_LOCK(ctx) std::lock_guard<std::recursive_mutex> m3d_lock_((ctx)->mu)
 
 namespace m3d {
 // Device u64 work counter for one persistent-kernel launch (rotating pool so that launches
@@ -96,6 +107,7 @@ unsigned long long *stats_counters(m3d_ctx *ctx, cudaStream_t s);
 
 struct m3d_mesh {
   m3d_ctx *ctx = nullptr;
+  std::vector<m3d_mesh *> replicas;  // multi-device context: copies on ctx->members[i] (owned)
   m3d::DevBuf nodes, tris, vnormals;
   m3d::DeviceBVH bvh;
   m3d_mesh_info info{};
@@ -103,6 +115,25 @@ struct m3d_mesh {
 };
 
 namespace m3d {
+// ---- multi-device contexts (api_multi.cu) ----------------------------------------------------
+inline int group_size(const m3d_ctx *c) { return 1 + (int)c->members.size(); }
+inline m3d_ctx *group_member(m3d_ctx *c, int i) { return i == 0 ? c : c->members[(size_t)i - 1]; }
+// Runs fn(i) for i in [0, n): i == 0 on the calling thread, the others on one host thread each
+// (the reference schedules its pixels over NumCPU goroutines, render3d/concurrency.go:17-43; here a
+// thread drives one GPU).  Returns the first failing status and makes its message this thread's
+// m3d_last_error().
+int32_t parallel_members(int n, const std::function<int32_t(int)> &fn);
+// Copies a device buffer of `src_device` into `dst` on dst_ctx's device (peer copy over NVLink).
+int32_t replicate_buffer(m3d_ctx *dst_ctx, DevBuf &dst, const DevBuf &src, int src_device);
+// Gives a mesh built on a multi-device context its replicas (no-op for single-device contexts).
+int32_t replicate_mesh(m3d_mesh *mesh);
+// [begin, end) of part i when n items are split into `parts` nearly equal contiguous ranges
+inline void split_range(int64_t n, int parts, int i, int64_t *begin, int64_t *end) {
+  const int64_t base = n / parts, extra = n % parts;
+  *begin = base * i + (i < extra ? i : extra);
+  *end = *begin + base + (i < extra ? 1 : 0);
+}
+
 // Device LBVH (lbvh.cu): binary hierarchy from Morton codes, downloaded for the wide collapse.
 int32_t lbvh_build_binary(m3d_ctx *ctx, const float *tris, int64_t n, std::vector<BinaryNode> &nodes,
                           std::vector<int32_t> &order, int32_t *root_out, double *device_ms);

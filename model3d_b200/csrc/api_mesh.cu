@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "api_common.h"
+#include "trace_core.cuh"
 
 namespace m3d {
 
@@ -141,6 +142,8 @@ int32_t m3d_ctx_create(int32_t device, m3d_ctx **out) {
 
 void m3d_ctx_destroy(m3d_ctx *ctx) {
   if (!ctx) return;
+  for (m3d_ctx *mc : ctx->members) m3d_ctx_destroy(mc);
+  ctx->members.clear();
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -152,6 +155,9 @@ int32_t m3d_ctx_device(const m3d_ctx *ctx) { return ctx ? ctx->device : -1; }
 
 int32_t m3d_ctx_synchronize(m3d_ctx *ctx) {
   if (!ctx) return fail(M3D_ERR_INVALID_ARG, "ctx is NULL");
+  M3D_LOCK(ctx);
+  for (m3d_ctx *mc : ctx->members)
+    if (int32_t rc = m3d_ctx_synchronize(mc)) return rc;
   M3D_CUDA(cudaSetDevice(ctx->device));
   M3D_CUDA(cudaStreamSynchronize(ctx->stream));
   M3D_CUDA(cudaStreamSynchronize(ctx->copy_in));
@@ -161,8 +167,12 @@ int32_t m3d_ctx_synchronize(m3d_ctx *ctx) {
 
 int32_t m3d_ctx_trim(m3d_ctx *ctx) {
   if (!ctx) return fail(M3D_ERR_INVALID_ARG, "ctx is NULL");
+  M3D_LOCK(ctx);
   int32_t rc = m3d_ctx_synchronize(ctx);
   if (rc != M3D_OK) return rc;
+  for (m3d_ctx *mc : ctx->members)
+    if (int32_t rc2 = m3d_ctx_trim(mc)) return rc2;
+  M3D_CUDA(cudaSetDevice(ctx->device));
   for (auto &b : ctx->scratch) b.release();
   return M3D_OK;
 }
@@ -173,6 +183,7 @@ int32_t m3d_mesh_create(m3d_ctx *ctx, const float *tris, int64_t n, const float 
     return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_create: bad arguments");
   if (n > (int64_t)0x7fffff00) return fail(M3D_ERR_INVALID_ARG, "too many triangles (%lld)", (long long)n);
   *out = nullptr;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   for (int64_t i = 0; i < n * 9; i++)
     if (!(tris[i] == tris[i]) || tris[i] > 3e38f || tris[i] < -3e38f)
@@ -201,12 +212,27 @@ int32_t m3d_mesh_create(m3d_ctx *ctx, const float *tris, int64_t n, const float 
     m->bmin[k] = n ? bvh.bounds_min[k] : 0.0;  // nullCollider bounds are zero (collisions.go:360-366)
     m->bmax[k] = n ? bvh.bounds_max[k] : 0.0;
   }
+  // The traversal kernels keep 64 stack entries per ray (10 in shared memory, the rest in local
+  // memory, trace_kernels.cu) and the scalar walkers M3D_STACK_SIZE; a stack entry is one node
+  // group, at most one per level, so a deeper hierarchy could drop pushes silently: refuse it.
+  if (bvh.max_depth > M3D_MAX_BVH_DEPTH) {
+    const int d = bvh.max_depth;
+    delete m;
+    return fail(M3D_ERR_UNSUPPORTED, "BVH depth %d exceeds the traversal stack (%d levels)", d, M3D_MAX_BVH_DEPTH);
+  }
+  if (int32_t rc2 = replicate_mesh(m)) {
+    m3d_mesh_destroy(m);
+    return rc2;
+  }
   *out = m;
   return M3D_OK;
 }
 
 void m3d_mesh_destroy(m3d_mesh *mesh) {
   if (!mesh) return;
+  for (m3d_mesh *r : mesh->replicas) m3d_mesh_destroy(r);
+  mesh->replicas.clear();
+  std::lock_guard<std::recursive_mutex> lock(mesh->ctx->mu);
   cudaSetDevice(mesh->ctx->device);
   delete mesh;
 }
@@ -235,6 +261,7 @@ int32_t m3d_mesh_first_ray_collisions_device(m3d_mesh *mesh, const void *d_org_t
   if (n > (int64_t)0x7ff00000)
     return fail(M3D_ERR_INVALID_ARG, "batch too large (%lld rays); split it", (long long)n);
   m3d_ctx *ctx = mesh->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   TraceLaunch p;
@@ -277,11 +304,54 @@ int32_t m3d_mesh_first_ray_collisions_device(m3d_mesh *mesh, const void *d_org_t
 
 static constexpr int kMaxPipeBuf = 8;
 
+static int32_t first_ray_collisions_one_device(m3d_mesh *mesh, const float *org, const float *dir, int64_t n,
+                                               float *t, int32_t *prim, float *normal, float *bary,
+                                               uint32_t flags, m3d_stats *stats);
+
+static void add_stats(m3d_stats *sum, const m3d_stats &s) {
+  sum->rays += s.rays;
+  sum->hits += s.hits;
+  sum->nodes_visited += s.nodes_visited;
+  sum->tris_tested += s.tris_tested;
+  sum->kernel_ms = std::max(sum->kernel_ms, s.kernel_ms);  // the devices run side by side
+  sum->h2d_bytes += s.h2d_bytes;
+  sum->d2h_bytes += s.d2h_bytes;
+  sum->launches += s.launches;
+  sum->samples += s.samples;
+}
+
 int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const float *dir, int64_t n,
                                       float *t, int32_t *prim, float *normal, float *bary,
                                       uint32_t flags, m3d_stats *stats) {
   if (!mesh || n < 0 || (n > 0 && (!org || !dir)))
     return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_first_ray_collisions: bad arguments");
+  M3D_LOCK(mesh->ctx);
+  const int g = 1 + (int)mesh->replicas.size();
+  // multi-device context: contiguous slices of the ray arrays, one host thread and one copy /
+  // compute pipeline per GPU, no exchange between them
+  if (g > 1 && n >= (int64_t)g * 4096) {
+    std::vector<m3d_stats> st((size_t)g);
+    int32_t rc = parallel_members(g, [&](int i) -> int32_t {
+      int64_t b, e;
+      split_range(n, g, i, &b, &e);
+      m3d_mesh *mi = i == 0 ? mesh : mesh->replicas[(size_t)i - 1];
+      std::lock_guard<std::recursive_mutex> lock(mi->ctx->mu);
+      return first_ray_collisions_one_device(mi, org + 3 * b, dir + 3 * b, e - b, t ? t + b : nullptr,
+                                             prim ? prim + b : nullptr, normal ? normal + 3 * b : nullptr,
+                                             bary ? bary + 3 * b : nullptr, flags, stats ? &st[(size_t)i] : nullptr);
+    });
+    if (stats) {
+      std::memset(stats, 0, sizeof(*stats));
+      for (const m3d_stats &x : st) add_stats(stats, x);
+    }
+    return rc;
+  }
+  return first_ray_collisions_one_device(mesh, org, dir, n, t, prim, normal, bary, flags, stats);
+}
+
+static int32_t first_ray_collisions_one_device(m3d_mesh *mesh, const float *org, const float *dir, int64_t n,
+                                               float *t, int32_t *prim, float *normal, float *bary,
+                                               uint32_t flags, m3d_stats *stats) {
   m3d_ctx *ctx = mesh->ctx;
   M3D_CUDA(cudaSetDevice(ctx->device));
   if (stats) std::memset(stats, 0, sizeof(*stats));
@@ -291,18 +361,17 @@ int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const fl
   // Three stages need three buffers in flight to overlap fully (a fourth absorbs jitter); small
   // chunks keep the exposed pipeline fill (first H2D) and drain (last kernels + D2H) short.
   // M3D_PIPE_CHUNK_LOG2 / M3D_PIPE_NBUF override both for tuning runs.
-  static int64_t kChunk = 0;
-  static int nbuf = 0;
-  if (!kChunk) {
+  static const int64_t kChunk = [] {
     const char *e = getenv("M3D_PIPE_CHUNK_LOG2");
     int lg = e ? atoi(e) : 20;
     if (lg < 14 || lg > 24) lg = 20;
+    return (int64_t)1 << lg;
+  }();
+  static const int nbuf = [] {
     const char *f = getenv("M3D_PIPE_NBUF");
     int nb = f ? atoi(f) : 4;
-    if (nb < 2 || nb > kMaxPipeBuf) nb = 4;
-    nbuf = nb;
-    kChunk = (int64_t)1 << lg;
-  }
+    return (nb < 2 || nb > kMaxPipeBuf) ? 4 : nb;
+  }();
   // per buffer: org3, dir3, org4, dir4, hit0, hit1, out_t, out_prim, out_normal, out_bary
   const size_t per = (size_t)kChunk;
   const size_t sz_in3 = per * 3 * sizeof(float), sz_f4 = per * sizeof(float4);
@@ -428,6 +497,7 @@ int32_t m3d_mesh_ray_collision_counts(m3d_mesh *mesh, const float *org, const fl
     return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_ray_collision_counts: bad arguments");
   if (n > (int64_t)0x7ff00000) return fail(M3D_ERR_INVALID_ARG, "batch too large; split it");
   m3d_ctx *ctx = mesh->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return M3D_OK;
@@ -464,6 +534,7 @@ int32_t m3d_mesh_ray_collisions(m3d_mesh *mesh, const float *org, const float *d
     return fail(M3D_ERR_INVALID_ARG, "m3d_mesh_ray_collisions: bad arguments");
   if (n > (int64_t)0x7ff00000) return fail(M3D_ERR_INVALID_ARG, "batch too large; split it");
   m3d_ctx *ctx = mesh->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   if (stats) std::memset(stats, 0, sizeof(*stats));
   offsets[0] = 0;
@@ -546,6 +617,7 @@ int32_t m3d_mesh_contains(m3d_mesh *mesh, const float *points, int64_t n, double
     if (rc != M3D_OK) return rc;
   }
   m3d_ctx *ctx = mesh->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return M3D_OK;
@@ -592,6 +664,7 @@ int32_t m3d_mesh_sdf(m3d_mesh *mesh, const float *points, int64_t n, float *sdf,
   int32_t rc = check_sdf_depth(mesh, "m3d_mesh_sdf");
   if (rc != M3D_OK) return rc;
   m3d_ctx *ctx = mesh->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return M3D_OK;
@@ -653,6 +726,7 @@ int32_t m3d_mesh_sphere_collisions(m3d_mesh *mesh, const float *centers, const f
   int32_t rc = check_sdf_depth(mesh, "m3d_mesh_sphere_collisions");
   if (rc != M3D_OK) return rc;
   m3d_ctx *ctx = mesh->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return M3D_OK;

@@ -78,6 +78,59 @@ int32_t carve_path_buffers(m3d_ctx *ctx, int64_t cap, int num_lights, PathBuffer
 
 }  // namespace
 
+static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
+                                      int32_t num_lights, const m3d_path_params *params, int32_t width,
+                                      int32_t height, const m3d_partition *part, int32_t sample_count,
+                                      void *d_rgb_sum, void *d_rgb_sumsq, void *stream, m3d_stats *stats);
+
+namespace m3d {
+// Splits a render over the devices of a multi-device scene (shared by the path tracer and the
+// bidirectional tracer): fixed-spp renders by sample index -- every device takes a contiguous
+// range of the absolute sample indices of every pixel, so the load is balanced whatever the
+// scene looks like and the image does not depend on the device count -- adaptive renders
+// (per-pixel early stop) by row band.  Every shard flushes into the one accumulator with
+// M3D_PART_ATOMIC.
+int32_t shard_render(m3d_scene *scene, bool adaptive, int32_t height, const m3d_partition *part,
+                     int32_t sample_count, cudaStream_t stream, m3d_stats *stats,
+                     const std::function<int32_t(m3d_scene *, const m3d_partition &, int32_t, cudaStream_t,
+                                                 m3d_stats *)> &one) {
+  const int g = 1 + (int)scene->replicas.size();
+  int r0 = 0, r1 = height;
+  int64_t s_begin = 0;
+  if (part) {
+    if (!(part->row_begin == 0 && part->row_end == 0)) {
+      r0 = part->row_begin;
+      r1 = part->row_end;
+      if (r0 < 0 || r1 > height || r0 > r1)
+        return fail(M3D_ERR_INVALID_ARG, "bad row partition [%d,%d) of %d rows", r0, r1, height);
+    }
+    s_begin = part->sample_begin;
+  }
+  return render_sharded(scene, stream, stats, [&](int i, m3d_scene *si, cudaStream_t s, m3d_stats *st) -> int32_t {
+    m3d_partition pi{};
+    pi.flags = (part ? part->flags : 0u) | M3D_PART_ATOMIC;
+    int64_t b, e;
+    int32_t count = sample_count;
+    if (adaptive) {
+      split_range(r1 - r0, g, i, &b, &e);
+      if (b == e) return M3D_OK;
+      pi.row_begin = r0 + (int32_t)b;
+      pi.row_end = r0 + (int32_t)e;
+      pi.sample_begin = s_begin;
+    } else {
+      split_range(sample_count, g, i, &b, &e);
+      if (b == e) return M3D_OK;
+      pi.row_begin = r0;
+      pi.row_end = r1;
+      if (r0 == 0 && r1 == 0) return M3D_OK;  // empty frame
+      pi.sample_begin = s_begin + b;
+      count = (int32_t)(e - b);
+    }
+    return one(si, pi, count, s, st);
+  });
+}
+}  // namespace m3d
+
 extern "C" {
 
 int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
@@ -87,6 +140,25 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   if (!scene || !cam || !params || width <= 0 || height <= 0 || !d_rgb_sum || num_lights < 0 ||
       (num_lights > 0 && !lights) || sample_count < 0)
     return fail(M3D_ERR_INVALID_ARG, "m3d_render_path: bad arguments");
+  M3D_LOCK(scene->ctx);
+  if (!scene->replicas.empty() && sample_count > 0) {
+    const bool adaptive = params->min_samples != 0 && params->max_stddev != 0;
+    return shard_render(scene, adaptive, height, part, sample_count, (cudaStream_t)stream, stats,
+                        [&](m3d_scene *si, const m3d_partition &pi, int32_t count, cudaStream_t s, m3d_stats *st) {
+                          return render_path_one_device(si, cam, lights, num_lights, params, width, height, &pi,
+                                                        count, d_rgb_sum, d_rgb_sumsq, s, st);
+                        });
+  }
+  return render_path_one_device(scene, cam, lights, num_lights, params, width, height, part, sample_count,
+                                d_rgb_sum, d_rgb_sumsq, stream, stats);
+}
+
+}  // extern "C"
+
+static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
+                                      int32_t num_lights, const m3d_path_params *params, int32_t width,
+                                      int32_t height, const m3d_partition *part, int32_t sample_count,
+                                      void *d_rgb_sum, void *d_rgb_sumsq, void *stream, m3d_stats *stats) {
   if (params->num_focus_points < 0 || params->num_focus_points > M3D_MAX_FOCUS_POINTS)
     return fail(M3D_ERR_UNSUPPORTED, "at most %d focus points are supported", M3D_MAX_FOCUS_POINTS);
   // rayRenderer.HasConvergenceCheck (ray_renderer.go:153-155) without the Convergence callback
@@ -125,6 +197,7 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   pp.num_lights = num_lights;
   pp.cutoff = (float)params->cutoff;
   pp.antialias = (float)params->antialias;
+  pp.eps = params->epsilon > 1e-7 ? (float)params->epsilon : 0.f;  // DefaultEpsilon 1e-8 -> surface skip ids
   pp.seed = params->seed;
   for (int i = 0; i < pp.num_focus; i++) {
     const m3d_focus_point &f = params->focus[i];
@@ -140,12 +213,11 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   if (pp.cutoff > 1.f) return M3D_OK;  // recurse() returns black at depth 0 (raytrace.go:139-142)
 
   // batch geometry: nP pixels x S samples <= cap slots
-  static int batch_log2 = 0;  // M3D_PATH_BATCH_LOG2: path slots per batch (tuning runs)
-  if (!batch_log2) {
+  static const int batch_log2 = [] {  // M3D_PATH_BATCH_LOG2: path slots per batch (tuning runs)
     const char *e = getenv("M3D_PATH_BATCH_LOG2");
-    batch_log2 = e ? atoi(e) : 26;
-    if (batch_log2 < 10 || batch_log2 > 28) batch_log2 = 26;
-  }
+    const int v = e ? atoi(e) : 26;
+    return (v < 10 || v > 28) ? 26 : v;
+  }();
   // <= 48 GB of the 180 GB for the path state (192 B per slot + 68 B per point light), and queue
   // positions / shadow-ray counts stay below 2^31
   const int64_t per_slot = 192 + 68 * (int64_t)num_lights;
@@ -248,9 +320,21 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
                                   buf.accum, (float *)d_rgb_sum, run_batch, &samples_taken))
       return rc;
   } else {
+    // M3D_PART_ATOMIC: other GPUs flush into the same accumulator at the same time.  A pixel range
+    // that takes several batches keeps its partial sums in local memory and only its last batch
+    // adds to the shared accumulator (with red.add, over NVLink when it lives on another GPU).
+    FlushPlan fp;
+    fp.atomic = part && (part->flags & M3D_PART_ATOMIC);
+    if (fp.atomic && sample_count > std::max<int64_t>(1, cap / nP_max)) {
+      M3D_CUDA(ctx->scratch[11].reserve((size_t)nP_max * 6 * sizeof(float)));
+      fp.carry = ctx->scratch[11].as<float>();
+      fp.carry_sq = fp.carry + (size_t)nP_max * 3;
+    }
     for (int64_t p0 = 0; p0 < npix; p0 += nP_max) {
       const int64_t nP = std::min(nP_max, npix - p0);
       const int64_t S_max = std::max<int64_t>(1, cap / nP);
+      if (fp.carry && sample_count > S_max)
+        M3D_CUDA(cudaMemsetAsync(fp.carry, 0, (size_t)nP_max * 6 * sizeof(float), s));
       for (int64_t s0 = 0; s0 < sample_count; s0 += S_max) {
         PathBatch b;
         b.W = width;
@@ -259,7 +343,8 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
         b.S = (int32_t)std::min<int64_t>(S_max, sample_count - s0);
         b.sample0 = (uint32_t)(sample_begin + s0);
         if (int32_t rc = run_batch(b)) return rc;
-        launch_path_flush(b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s);
+        flush_batch(fp, b, buf.accum, (float *)d_rgb_sum, (float *)d_rgb_sumsq, s0 == 0,
+                    s0 + S_max >= sample_count, s);
         launches++;
       }
     }
@@ -279,6 +364,8 @@ int32_t m3d_render_path_device(m3d_scene *scene, const m3d_camera *cam, const m3
   return M3D_OK;
 }
 
+extern "C" {
+
 int32_t m3d_render_path(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
                         int32_t num_lights, const m3d_path_params *params, int32_t width, int32_t height,
                         const m3d_partition *part, int32_t sample_count, float *rgb_sum, float *rgb_sumsq,
@@ -286,6 +373,7 @@ int32_t m3d_render_path(m3d_scene *scene, const m3d_camera *cam, const m3d_point
   if (!scene || !rgb_sum || width <= 0 || height <= 0)
     return fail(M3D_ERR_INVALID_ARG, "m3d_render_path: bad arguments");
   m3d_ctx *ctx = scene_ctx(scene);
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)width * height * 3 * sizeof(float);
   M3D_CUDA(ctx->scratch[3].reserve(bytes * 2));

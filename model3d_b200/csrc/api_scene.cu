@@ -9,6 +9,7 @@
 #include "api_common.h"
 #include "scene.h"
 #include "scene_host.h"
+#include "trace_core.cuh"
 
 using namespace m3d;
 
@@ -290,6 +291,7 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
   if (b->objects.empty()) return fail(M3D_ERR_INVALID_ARG, "scene has no objects");
   if (b->objects.size() > 0x7fffff) return fail(M3D_ERR_INVALID_ARG, "too many objects");
   m3d_ctx *ctx = b->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   std::unique_ptr<m3d_scene> sc(new m3d_scene());
   sc->ctx = ctx;
@@ -363,6 +365,9 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
   in.prim_ids = prim_ids.data();
   in.obj_ids = obj_ids.data();
   if (int32_t rc = build_bvh_with_flags(ctx, in, build_flags, bvh)) return rc;
+  if (bvh.max_depth > M3D_MAX_BVH_DEPTH)  // see m3d_mesh_create: deeper trees would overflow the traversal stacks
+    return fail(M3D_ERR_UNSUPPORTED, "BVH depth %d exceeds the traversal stack (%d levels)", bvh.max_depth,
+                M3D_MAX_BVH_DEPTH);
   sc->leaf_of_merged.assign((size_t)ntri, -1);
   for (size_t li = 0; li < bvh.tris.size(); li++)
     sc->leaf_of_merged[(size_t)(sc->object_tri_begin[bvh.tris[li].object] + bvh.tris[li].prim)] = (int32_t)li;
@@ -432,12 +437,20 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
   sc->info.max_depth = bvh.max_depth;
   sc->info.build_ms = bvh.build_ms;
   sc->info.sah_cost = bvh.sah_cost;
-  *out = sc.release();
+  m3d_scene *raw = sc.release();
+  if (int32_t rc = replicate_scene(raw)) {
+    m3d_scene_destroy(raw);
+    return rc;
+  }
+  *out = raw;
   return M3D_OK;
 }
 
 void m3d_scene_destroy(m3d_scene *scene) {
   if (!scene) return;
+  for (m3d_scene *r : scene->replicas) m3d_scene_destroy(r);
+  scene->replicas.clear();
+  std::lock_guard<std::recursive_mutex> lock(scene->ctx->mu);
   cudaSetDevice(scene->ctx->device);
   delete scene;
 }
@@ -456,6 +469,7 @@ int32_t m3d_scene_cast(m3d_scene *scene, const float *org, const float *dir, int
   if (!scene || n < 0 || (n > 0 && (!org || !dir))) return fail(M3D_ERR_INVALID_ARG, "m3d_scene_cast: bad arguments");
   if (n > (int64_t)0x7ff00000) return fail(M3D_ERR_INVALID_ARG, "batch too large; split it");
   m3d_ctx *ctx = scene->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return M3D_OK;
@@ -509,11 +523,44 @@ int32_t m3d_scene_cast(m3d_scene *scene, const float *org, const float *dir, int
   return M3D_OK;
 }
 
+static int32_t raycast_one_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
+                                  int32_t num_lights, int32_t width, int32_t height,
+                                  const m3d_partition *part, void *d_rgb, void *stream, m3d_stats *stats);
+
 int32_t m3d_render_raycast_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
                                   int32_t num_lights, int32_t width, int32_t height,
                                   const m3d_partition *part, void *d_rgb, void *stream, m3d_stats *stats) {
   if (!scene || !cam || width <= 0 || height <= 0 || !d_rgb || num_lights < 0 || (num_lights > 0 && !lights))
     return fail(M3D_ERR_INVALID_ARG, "m3d_render_raycast: bad arguments");
+  M3D_LOCK(scene->ctx);
+  // Multi-device context: row bands, every device writes its band straight into the primary's
+  // image over the NVLink peer mapping (disjoint rows: plain stores).  Small frames stay on the
+  // primary: a 512 x 512 frame is 0.2 ms of GPU work, less than waking the other devices costs.
+  const int g = 1 + (int)scene->replicas.size();
+  if (g > 1 && (int64_t)width * height >= ((int64_t)1 << 21)) {
+    int r0 = 0, r1 = height;
+    if (part && !(part->row_begin == 0 && part->row_end == 0)) {
+      r0 = part->row_begin;
+      r1 = part->row_end;
+      if (r0 < 0 || r1 > height || r0 > r1)
+        return fail(M3D_ERR_INVALID_ARG, "bad row partition [%d,%d) of %d rows", r0, r1, height);
+    }
+    return render_sharded(scene, (cudaStream_t)stream, stats, [&](int i, m3d_scene *si, cudaStream_t s, m3d_stats *st) {
+      int64_t b, e;
+      split_range(r1 - r0, g, i, &b, &e);
+      if (b == e) return (int32_t)M3D_OK;
+      m3d_partition pi{};
+      pi.row_begin = r0 + (int32_t)b;
+      pi.row_end = r0 + (int32_t)e;
+      return raycast_one_device(si, cam, lights, num_lights, width, height, &pi, d_rgb, s, st);
+    });
+  }
+  return raycast_one_device(scene, cam, lights, num_lights, width, height, part, d_rgb, stream, stats);
+}
+
+static int32_t raycast_one_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
+                                  int32_t num_lights, int32_t width, int32_t height,
+                                  const m3d_partition *part, void *d_rgb, void *stream, m3d_stats *stats) {
   m3d_ctx *ctx = scene->ctx;
   M3D_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
@@ -575,6 +622,7 @@ int32_t m3d_render_raycast(m3d_scene *scene, const m3d_camera *cam, const m3d_po
                            float *rgb, m3d_stats *stats) {
   if (!scene || !rgb || width <= 0 || height <= 0) return fail(M3D_ERR_INVALID_ARG, "m3d_render_raycast: bad arguments");
   m3d_ctx *ctx = scene->ctx;
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)width * height * 3 * sizeof(float);
   M3D_CUDA(ctx->scratch[3].reserve(bytes));
@@ -595,6 +643,7 @@ int32_t m3d_render_raycast(m3d_scene *scene, const m3d_camera *cam, const m3d_po
 int32_t m3d_finalize_image_device(m3d_ctx *ctx, const void *d_sum, int64_t num_pixels, double inv_samples,
                                   void *d_mean, void *d_srgb8, void *stream) {
   if (!ctx || !d_sum || num_pixels < 0) return fail(M3D_ERR_INVALID_ARG, "m3d_finalize_image_device: bad arguments");
+  M3D_LOCK(ctx);
   M3D_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
   launch_finalize_image((const float *)d_sum, num_pixels * 3, (float)inv_samples, (float *)d_mean,

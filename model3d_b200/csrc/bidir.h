@@ -15,6 +15,7 @@ constexpr int kBidirMaxDepth = 16;  // per sub-path; joined paths have at most 3
 struct DeviceBidirParams {
   int32_t max_depth, max_light_depth, min_depth;
   float cutoff, antialias;
+  float eps;  // BidirPathTracer.Epsilon above float32 resolution, else 0 (see DevicePathParams.eps)
   double roulette_delta, power_heuristic;
   uint64_t seed;
   int32_t num_lights;

@@ -257,7 +257,8 @@ bidir_shade_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffe
       pos0 = __shfl_sync(0xffffffffu, pos0, __ffs(live) - 1);
       if (alive) {
         const int pos = pos0 + __popc(live & ((1u << lane) - 1u));
-        buf.org[nxt][pos] = make_float4(v.point.x, v.point.y, v.point.z, 0.f);
+        // bounceRay (bidir.go:243-255): unit direction, origin eps along it
+        buf.org[nxt][pos] = make_float4(v.point.x, v.point.y, v.point.z, bp.eps);
         buf.dir[nxt][pos] = make_float4(next_dir.x, next_dir.y, next_dir.z, INFINITY);
         buf.skip[nxt][pos] = v.surf;
         buf.queue[nxt][pos] = slot;
@@ -343,7 +344,7 @@ bidir_light_raygen_kernel(DeviceScene sc, DeviceBidirParams bp, const DeviceArea
   eval_vertex(sc, v, 0);
   store_vertex(buf.lv, buf.Dl, buf.cap, 0, slot, v);
   buf.nl[slot] = 1;
-  buf.org[0][slot] = make_float4(v.point.x, v.point.y, v.point.z, 0.f);
+  buf.org[0][slot] = make_float4(v.point.x, v.point.y, v.point.z, bp.eps);
   buf.dir[0][slot] = make_float4(v.dest.x, v.dest.y, v.dest.z, INFINITY);
   buf.skip[0][slot] = v.surf;
   buf.queue[0][slot] = slot;
@@ -647,8 +648,10 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
   // parameter interval) since float32 cannot express the reference's 1e-8 offsets
   const int pos = warp_aggregated_alloc(buf.counts + 2);
   const V3f dirn = diff * (1.f / dist);
-  buf.corg[pos] = make_float4(ev.point.x, ev.point.y, ev.point.z, 0.f);
-  buf.cdir[pos] = make_float4(dirn.x, dirn.y, dirn.z, dist * (1.f - 2e-4f));
+  // with a user Epsilon: the ray starts eps after the eye vertex and is blocked iff
+  // Scale < dist - 2 eps from there (bidir.go:144-152), i.e. t in [eps, dist - eps)
+  buf.corg[pos] = make_float4(ev.point.x, ev.point.y, ev.point.z, bp.eps);
+  buf.cdir[pos] = make_float4(dirn.x, dirn.y, dirn.z, fminf(dist * (1.f - 2e-4f), dist - bp.eps));
   buf.cskip[pos] = ev.surf;
   buf.cpay[pos] = make_float4((float)color.x, (float)color.y, (float)color.z, __int_as_float(slot));
 }

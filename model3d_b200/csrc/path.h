@@ -22,6 +22,12 @@ struct DevicePathParams {
   int32_t num_focus;
   int32_t num_lights;
   float cutoff, antialias;
+  // RecursiveRayTracer.Epsilon (raytrace.go:217-229: bounce / shadow origins move eps along the
+  // ray).  The default 1e-8 is below float32 resolution and is replaced by the exact surface skip
+  // ids; a larger user value is honoured ON TOP of them as the rays' tmin (in units of |dir|), so
+  // that coplanar / duplicated surfaces within eps of the start point are stepped over like in
+  // the reference.  0: skip ids only.
+  float eps;
   uint64_t seed;
   DeviceFocus focus[4];
 };
@@ -75,5 +81,32 @@ void launch_path_shadow_resolve(const DeviceScene &sc, const DevicePathParams &p
 // per pixel: add the S per-sample colours (and their squares) into the frame accumulators
 void launch_path_flush(const PathBatch &b, const float4 *accum, float *rgb_sum, float *rgb_sumsq,
                        cudaStream_t stream);
+// Shared-accumulator mode (M3D_PART_ATOMIC): several GPUs flush into one frame accumulator.
+// A pixel range that takes several batches keeps its partial sums in `carry` (3 floats per batch
+// position, local memory); the last batch adds carry + its own sums to the shared accumulator with
+// system-scope red.add (over NVLink when the accumulator lives on another GPU).
+void launch_path_flush_carry(const PathBatch &b, const float4 *accum, float *carry, float *carry_sq,
+                             cudaStream_t stream);
+void launch_path_flush_red(const PathBatch &b, const float4 *accum, float *rgb_sum, float *rgb_sumsq,
+                           float *carry, float *carry_sq, cudaStream_t stream);
+
+// The flush sequence of the non-adaptive batch loops (api_path.cu, api_bidir.cu): chooses between
+// the three kernels above.  `atomic`: M3D_PART_ATOMIC; carry buffers hold 3 * nP floats (zeroed by
+// the caller at the start of every pixel range that takes more than one batch) or are null.
+struct FlushPlan {
+  bool atomic = false;
+  float *carry = nullptr, *carry_sq = nullptr;
+};
+inline void flush_batch(const FlushPlan &f, const PathBatch &b, const float4 *accum, float *rgb_sum, float *rgb_sumsq,
+                        bool first_of_range, bool last_of_range, cudaStream_t stream) {
+  if (!f.atomic) {
+    launch_path_flush(b, accum, rgb_sum, rgb_sumsq, stream);
+  } else if (last_of_range) {
+    launch_path_flush_red(b, accum, rgb_sum, rgb_sumsq, first_of_range ? nullptr : f.carry,
+                          first_of_range || !rgb_sumsq ? nullptr : f.carry_sq, stream);
+  } else {
+    launch_path_flush_carry(b, accum, f.carry, rgb_sumsq ? f.carry_sq : nullptr, stream);
+  }
+}
 
 }  // namespace m3d

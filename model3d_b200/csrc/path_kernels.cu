@@ -179,7 +179,9 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
           const V3f c = shade_collision(lt, nrm, light_dir) * brdf * tv;
           const size_t si = (size_t)q * pp.num_lights + l;
           const bool useful = !is_zero(c);
-          buf.sorg[si] = make_float4(point.x, point.y, point.z, useful ? 0.f : 1.f);
+          // bounceRay(point, lightDirection): the origin moves eps along the unit direction (raytrace.go:217-229)
+          const float s_tmin = pp.eps > 0.f ? pp.eps * rsqrtf(dot(light_dir, light_dir)) : 0.f;
+          buf.sorg[si] = make_float4(point.x, point.y, point.z, useful ? s_tmin : 1.f);
           buf.sdir[si] = make_float4(light_dir.x, light_dir.y, light_dir.z, useful ? 1.f : -1.f);
           buf.sskip[si] = h.surf;
           buf.spay[si] = make_float4(c.x, c.y, c.z, __int_as_float(slot));
@@ -346,7 +348,8 @@ path_sample_kernel(DeviceScene sc, DevicePathParams pp, PathBatch b, PathBuffers
       pos0 = __shfl_sync(0xffffffffu, pos0, __ffs(live) - 1);
       if (alive) {
         const int pos = pos0 + __popc(live & ((1u << lane) - 1u));
-        buf.org[nxt][pos] = make_float4(point.x, point.y, point.z, 0.f);
+        const float b_tmin = pp.eps > 0.f ? pp.eps * rsqrtf(dot(next_dir, next_dir)) : 0.f;
+        buf.org[nxt][pos] = make_float4(point.x, point.y, point.z, b_tmin);
         buf.dir[nxt][pos] = make_float4(next_dir.x, next_dir.y, next_dir.z, INFINITY);
         buf.skip[nxt][pos] = surf;
         buf.queue[nxt][pos] = slot;
@@ -385,9 +388,31 @@ path_shadow_resolve_kernel(DeviceScene sc, DevicePathParams pp, PathBuffers buf,
   }
 }
 
+// colorSum (+ squares) per pixel over the S samples of a batch (ray_renderer.go:125-127,150).
+//   FLUSH_ADD     dst[pixel] += sum                 (one GPU owns dst)
+//   FLUSH_CARRY   carry[p]   += sum                 (p = position in the batch: the local partial
+//                                                    sums of a pixel range that takes several batches)
+//   FLUSH_RED     dst[pixel] (+)= carry[p] + sum    with red.add: dst is the frame accumulator that
+//                 several GPUs flush into at once, usually rank 0's memory mapped over NVLink
+//                 (peer access / CUDA IPC), so the cross-GPU reduce of the per-pixel sums
+//                  happens inside this kernel, tile by tile, instead of in a
+//                 collective afterwards.  System-scope reductions: the adds of different GPUs meet
+//                 in the owning GPU's L2.
+enum { FLUSH_ADD = 0, FLUSH_CARRY = 1, FLUSH_RED = 2 };
+
+__device__ __forceinline__ void red_add_sys(float *addr, float v) {
+  asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_sys_v4(float *addr, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
 path_flush_kernel(PathBatch b, const float4 *__restrict__ accum, float *__restrict__ rgb_sum,
-                  float *__restrict__ rgb_sumsq) {
+                  float *__restrict__ rgb_sumsq, float *__restrict__ carry, float *__restrict__ carry_sq) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= b.nP) return;
   float sx = 0.f, sy = 0.f, sz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
@@ -400,14 +425,98 @@ path_flush_kernel(PathBatch b, const float4 *__restrict__ accum, float *__restri
     qy += a.y * a.y;
     qz += a.z * a.z;
   }
+  if (MODE == FLUSH_CARRY) {
+    const size_t c = (size_t)p * 3;
+    carry[c] += sx;
+    carry[c + 1] += sy;
+    carry[c + 2] += sz;
+    if (carry_sq) {
+      carry_sq[c] += qx;
+      carry_sq[c + 1] += qy;
+      carry_sq[c + 2] += qz;
+    }
+    return;
+  }
   const size_t o = (size_t)batch_pixel(b, p) * 3;
-  rgb_sum[o] += sx;
-  rgb_sum[o + 1] += sy;
-  rgb_sum[o + 2] += sz;
-  if (rgb_sumsq) {
-    rgb_sumsq[o] += qx;
-    rgb_sumsq[o + 1] += qy;
-    rgb_sumsq[o + 2] += qz;
+  if (MODE == FLUSH_ADD) {
+    rgb_sum[o] += sx;
+    rgb_sum[o + 1] += sy;
+    rgb_sum[o + 2] += sz;
+    if (rgb_sumsq) {
+      rgb_sumsq[o] += qx;
+      rgb_sumsq[o + 1] += qy;
+      rgb_sumsq[o + 2] += qz;
+    }
+  } else {
+    if (carry) {
+      const size_t c = (size_t)p * 3;
+      sx += carry[c];
+      sy += carry[c + 1];
+      sz += carry[c + 2];
+      if (carry_sq) {
+        qx += carry_sq[c];
+        qy += carry_sq[c + 1];
+        qz += carry_sq[c + 2];
+      }
+    }
+    red_add_sys(rgb_sum + o, sx);
+    red_add_sys(rgb_sum + o + 1, sy);
+    red_add_sys(rgb_sum + o + 2, sz);
+    if (rgb_sumsq) {
+      red_add_sys(rgb_sumsq + o, qx);
+      red_add_sys(rgb_sumsq + o + 1, qy);
+      red_add_sys(rgb_sumsq + o + 2, qz);
+    }
+  }
+}
+
+// FLUSH_RED for a contiguous pixel range whose first pixel is a multiple of four: one thread sums
+// four consecutive pixels and pushes their 12 floats as three 16-byte vector reductions (a warp
+// covers 1.5 KB of the remote accumulator per instruction triple instead of 384 scattered bytes).
+__global__ void __launch_bounds__(256)
+path_flush_red4_kernel(PathBatch b, const float4 *__restrict__ accum, float *__restrict__ rgb_sum,
+                       float *__restrict__ rgb_sumsq, const float *__restrict__ carry,
+                       const float *__restrict__ carry_sq) {
+  const int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (p4 >= b.nP) return;
+  float su[12], sq[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) su[k] = sq[k] = 0.f;
+  const int np = b.nP - p4 < 4 ? b.nP - p4 : 4;
+  for (int s = 0; s < b.S; s++) {
+    const float4 *row = accum + (size_t)s * b.nP + p4;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (j < np) {
+        const float4 a = __ldcs(row + j);
+        su[3 * j] += a.x;
+        su[3 * j + 1] += a.y;
+        su[3 * j + 2] += a.z;
+        sq[3 * j] += a.x * a.x;
+        sq[3 * j + 1] += a.y * a.y;
+        sq[3 * j + 2] += a.z * a.z;
+      }
+  }
+  if (carry) {
+    for (int k = 0; k < 3 * np; k++) {
+      su[k] += carry[(size_t)p4 * 3 + k];
+      if (carry_sq) sq[k] += carry_sq[(size_t)p4 * 3 + k];
+    }
+  }
+  const size_t o = (size_t)(b.pix0 + p4) * 3;  // multiple of 12 floats: 16-byte aligned
+  if (np == 4) {
+#pragma unroll
+    for (int v = 0; v < 3; v++) red_add_sys_v4(rgb_sum + o + 4 * v, su[4 * v], su[4 * v + 1], su[4 * v + 2], su[4 * v + 3]);
+    if (rgb_sumsq) {
+#pragma unroll
+      for (int v = 0; v < 3; v++)
+        red_add_sys_v4(rgb_sumsq + o + 4 * v, sq[4 * v], sq[4 * v + 1], sq[4 * v + 2], sq[4 * v + 3]);
+    }
+  } else {
+    for (int k = 0; k < 3 * np; k++) {
+      red_add_sys(rgb_sum + o + k, su[k]);
+      if (rgb_sumsq) red_add_sys(rgb_sumsq + o + k, sq[k]);
+    }
   }
 }
 
@@ -432,12 +541,12 @@ static int shade_grid(K kernel, int64_t n) {
 
 void launch_path_resolve(const DeviceScene &sc, const DevicePathParams &pp, const DevicePointLight *lights,
                          const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream) {
-  static int grid_full[2] = {0, 0};
+  // resident-grid sizes, computed once (thread-safe static initialisation: renders may run on
+  // several host threads, one per device)
+  static const int grid_full[2] = {shade_grid(path_resolve_kernel<false>, (int64_t)1 << 40),
+                                   shade_grid(path_resolve_kernel<true>, (int64_t)1 << 40)};
   const int64_t n = (int64_t)b.nP * b.S;
   const int li = pp.num_lights > 0 ? 1 : 0;
-  if (!grid_full[li])
-    grid_full[li] = li ? shade_grid(path_resolve_kernel<true>, (int64_t)1 << 40)
-                       : shade_grid(path_resolve_kernel<false>, (int64_t)1 << 40);
   const int64_t want = (n + kShadeBlock - 1) / kShadeBlock;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_full[li], want));
   if (li)
@@ -449,13 +558,9 @@ void launch_path_resolve(const DeviceScene &sc, const DevicePathParams &pp, cons
 void launch_path_sample(int kind, const DeviceScene &sc, const DevicePathParams &pp, const PathBatch &b,
                         const PathBuffers &buf, int cur, int depth, cudaStream_t stream) {
   const int64_t n = (int64_t)b.nP * b.S;
-  static int grids[4] = {0, 0, 0, 0};
-  if (!grids[0]) {
-    grids[0] = shade_grid(path_sample_kernel<0>, (int64_t)1 << 40);
-    grids[1] = shade_grid(path_sample_kernel<1>, (int64_t)1 << 40);
-    grids[2] = shade_grid(path_sample_kernel<2>, (int64_t)1 << 40);
-    grids[3] = shade_grid(path_sample_kernel<3>, (int64_t)1 << 40);
-  }
+  static const int grids[4] = {
+      shade_grid(path_sample_kernel<0>, (int64_t)1 << 40), shade_grid(path_sample_kernel<1>, (int64_t)1 << 40),
+      shade_grid(path_sample_kernel<2>, (int64_t)1 << 40), shade_grid(path_sample_kernel<3>, (int64_t)1 << 40)};
   const int64_t want = (n + kShadeBlock - 1) / kShadeBlock;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grids[kind], want));
   switch (kind) {
@@ -475,7 +580,30 @@ void launch_path_shadow_resolve(const DeviceScene &sc, const DevicePathParams &p
 void launch_path_flush(const PathBatch &b, const float4 *accum, float *rgb_sum, float *rgb_sumsq,
                        cudaStream_t stream) {
   if (b.nP <= 0) return;
-  path_flush_kernel<<<(unsigned)((b.nP + 255) / 256), 256, 0, stream>>>(b, accum, rgb_sum, rgb_sumsq);
+  path_flush_kernel<FLUSH_ADD><<<(unsigned)((b.nP + 255) / 256), 256, 0, stream>>>(b, accum, rgb_sum, rgb_sumsq,
+                                                                                    nullptr, nullptr);
+}
+
+void launch_path_flush_carry(const PathBatch &b, const float4 *accum, float *carry, float *carry_sq,
+                             cudaStream_t stream) {
+  if (b.nP <= 0) return;
+  path_flush_kernel<FLUSH_CARRY><<<(unsigned)((b.nP + 255) / 256), 256, 0, stream>>>(b, accum, nullptr, nullptr,
+                                                                                      carry, carry_sq);
+}
+
+void launch_path_flush_red(const PathBatch &b, const float4 *accum, float *rgb_sum, float *rgb_sumsq,
+                           float *carry, float *carry_sq, cudaStream_t stream) {
+  if (b.nP <= 0) return;
+  const bool aligned = !b.pixels && (b.pix0 & 3) == 0 && ((uintptr_t)rgb_sum & 15) == 0 &&
+                       ((uintptr_t)rgb_sumsq & 15) == 0;
+  if (aligned) {
+    const int threads = (b.nP + 3) / 4;
+    path_flush_red4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(b, accum, rgb_sum, rgb_sumsq,
+                                                                                   carry, carry_sq);
+  } else {
+    path_flush_kernel<FLUSH_RED><<<(unsigned)((b.nP + 255) / 256), 256, 0, stream>>>(b, accum, rgb_sum, rgb_sumsq,
+                                                                                      carry, carry_sq);
+  }
 }
 
 }  // namespace m3d

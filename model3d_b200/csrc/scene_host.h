@@ -8,6 +8,7 @@
 
 struct m3d_scene {
   m3d_ctx *ctx = nullptr;
+  std::vector<m3d_scene *> replicas;  // multi-device context: copies on ctx->members[i] (owned)
   m3d::DevBuf nodes, tris, vnormals, shapes, objects, materials;
   m3d::DeviceScene dev;
   std::vector<m3d::DeviceShape> host_shapes;
@@ -21,3 +22,16 @@ struct m3d_scene {
   double bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
   m3d_mesh_info info{};
 };
+
+namespace m3d {
+// Gives a scene built on a multi-device context its replicas (api_multi.cu).
+int32_t replicate_scene(m3d_scene *scene);
+// Runs one render call per device of the scene's multi-device context, side by side:
+// fn(i, replica i, stream, stats) on one host thread each.  The primary renders on `stream` (or
+// its context's stream), the others on their own; they first wait (on the device) for everything
+// the caller enqueued on the primary's stream, e.g. the clearing of the shared accumulator.
+// Every fn must return with its stream idle (the m3d_render_*_device bodies do), so when this
+// returns every device's contribution has landed in the primary's memory.  stats (optional): summed.
+int32_t render_sharded(m3d_scene *scene, cudaStream_t stream, m3d_stats *stats,
+                       const std::function<int32_t(int, m3d_scene *, cudaStream_t, m3d_stats *)> &fn);
+}  // namespace m3d

@@ -157,6 +157,9 @@ struct TraceCounters {
 };
 
 #define M3D_STACK_SIZE 32
+// deepest wide BVH the traversal stacks cover (one pending node group per level); builds beyond it
+// are refused at m3d_mesh_create / m3d_scene_build instead of dropping pushes silently
+#define M3D_MAX_BVH_DEPTH (M3D_STACK_SIZE - 1)
 
 M3D_HD float max3f(float a, float b, float c) {
 #if defined(__CUDA_ARCH__)

@@ -439,13 +439,12 @@ namespace {
 template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS, bool HAS_SKIP>
 static void launch_trace_instance(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
   // persistent grid: as many blocks as stay resident
-  static int blocks_per_sm = 0;
-  if (!blocks_per_sm) {
+  static const int blocks_per_sm = [] {
     int b = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         &b, trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS, HAS_SKIP>, kTraceBlock, 0);
-    blocks_per_sm = b > 0 ? b : 1;
-  }
+    return b > 0 ? b : 1;
+  }();
   long long want = (p.n + kTraceBlock - 1) / kTraceBlock;
   long long grid = (long long)device_sm_count() * blocks_per_sm;
   if (grid > want) grid = want;
@@ -466,17 +465,15 @@ void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p_in, cudaSt
   if (p_in.n <= 0) return;
   // register budget of the traversal kernel: 6 resident blocks/SM (80 registers, no spills)
   // measured best on B200; M3D_TRACE_MINB=7|8 selects the tighter variants for tuning runs
-  static int minb = 0;
-  if (!minb) {
+  static const int minb = [] {
     const char *e = getenv("M3D_TRACE_MINB");
-    minb = e ? atoi(e) : 6;
-    if (minb < 5 || minb > 8) minb = 6;
-  }
-  static int tri_rounds_env = -1;
-  if (tri_rounds_env < 0) {
+    const int v = e ? atoi(e) : 6;
+    return (v < 5 || v > 8) ? 6 : v;
+  }();
+  static const int tri_rounds_env = [] {
     const char *e = getenv("M3D_TRACE_TRI_ROUNDS");
-    tri_rounds_env = e ? atoi(e) : 0;
-  }
+    return e ? atoi(e) : 0;
+  }();
   const TraceLaunch &p = p_in;
   // tiny hierarchies (cornell_box: 72 triangles in 4 nodes) spend their time in the triangle phase
   const int tri_rounds = tri_rounds_env > 0 ? tri_rounds_env : (bvh.num_nodes <= kTinySceneNodes ? 2 : 1);

@@ -156,12 +156,11 @@ struct Builder2 {
 constexpr double kCostNode = 1.0;
 // relative cost of one triangle test; M3D_BVH_CPRIM overrides it for tuning runs
 static double cost_prim() {
-  static double v = -1;
-  if (v < 0) {
+  static const double v = [] {
     const char *e = getenv("M3D_BVH_CPRIM");
-    v = e ? atof(e) : 0.3;
-    if (!(v > 0)) v = 0.3;
-  }
+    const double x = e ? atof(e) : 0.3;
+    return x > 0 ? x : 0.3;
+  }();
   return v;
 }
 #define kCostPrim (cost_prim())

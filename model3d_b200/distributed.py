@@ -60,3 +60,88 @@ def reduce_sums(acc: torch.Tensor, dst: int = 0) -> torch.Tensor:
 def finalize_mean(acc: torch.Tensor, total_samples: int) -> torch.Tensor:
     """colorSum.Scale(1/numSamples) (render3d/ray_renderer.go:150) after the reduce."""
     return acc / float(total_samples)
+
+
+# ---- fused flush + reduce: one accumulator in rank 0's memory ------------------------------------
+
+class _CudaIpcBackend:
+    """Accumulators are plain cudaMalloc blocks of rank 0 (m3d_device_alloc), mapped into the other
+    ranks' address spaces with CUDA IPC (m3d_ipc_export / m3d_ipc_open); over NVLink on a B200 box."""
+
+    def __init__(self, ctx):
+        from . import _native as N
+        self.N, self.ctx = N, ctx
+
+    def alloc(self, nbytes):
+        return self.N.device_alloc(self.ctx, nbytes)
+
+    def export(self, ptr):
+        return self.N.ipc_export(self.ctx, ptr)
+
+    def open(self, handle):
+        return self.N.ipc_open(self.ctx, handle)
+
+    def close(self, ptr):
+        self.N.ipc_close(self.ctx, ptr)
+
+    def free(self, ptr):
+        self.N.device_free(self.ctx, ptr)
+
+
+class SharedAccumulator:
+    """`nbuf` frame accumulators that live in rank 0's memory and that EVERY rank's flush kernel
+    adds into (m3d_partition.flags = M3D_PART_ATOMIC): the cross-GPU reduce of the per-pixel sums
+    happens inside path_flush (red.add over the NVLink mapping), tile by tile, instead of in a
+    collective after the render.  Replaces `reduce_sums` for the one-process-per-GPU launch.
+
+    Protocol per frame k (all on the ranks' streams, no host synchronisation):
+        every rank     render + flush into ptr(k)
+        every rank     barrier()                    (a 4-byte all_reduce: every flush has landed)
+        rank 0         consume ptr(k), then clear it
+    With nbuf >= 2 a rank that runs ahead flushes frame k+1 into the other buffer, which rank 0
+    cleared before it entered barrier k, so one barrier per frame is enough."""
+
+    def __init__(self, nbytes, rank, world, backend, nbuf=2, src=0):
+        self.rank, self.world, self.backend, self.nbuf, self.src = rank, world, backend, nbuf, src
+        self.nbytes = int(nbytes)
+        self.owner = rank == src
+        handles = [None] * nbuf
+        self.ptrs = []
+        err = None
+        if self.owner:
+            try:
+                self.ptrs = [backend.alloc(self.nbytes) for _ in range(nbuf)]
+                if world > 1:
+                    handles = [backend.export(p) for p in self.ptrs]
+            except Exception as e:  # the other ranks wait in the broadcast: tell them before raising
+                err, handles = e, [None] * nbuf
+        if world > 1:
+            dist.broadcast_object_list(handles, src=src)
+            if not self.owner:
+                if handles[0] is None:
+                    raise RuntimeError("rank %d could not export its accumulators" % src)
+                self.ptrs = [backend.open(h) for h in handles]
+        if err is not None:
+            raise err
+
+    def ptr(self, k):
+        return self.ptrs[k % self.nbuf]
+
+    def barrier(self, device=None):
+        """Cross-rank ordering point on the current stream (NCCL) or the host (gloo)."""
+        if self.world > 1:
+            t = torch.zeros(1, dtype=torch.float32, device=device)
+            dist.all_reduce(t)
+
+    def close(self):
+        for p in self.ptrs:
+            (self.backend.free if self.owner else self.backend.close)(p)
+        self.ptrs = []
+
+
+class DevicePointer:
+    """Wraps a raw device pointer for torch.as_tensor (the __cuda_array_interface__ protocol)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}

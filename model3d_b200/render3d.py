@@ -328,17 +328,13 @@ class Scene:
 
 
 def _as_scene(obj, ctx=None):
+    """A Scene is used as is; any other object tree is compiled for this call only, like the
+    reference re-reads the object on every Render (callers that render the same objects many
+    times build a Scene once and pass it: no hidden cache that could go stale when the object
+    tree, a material or a mesh is edited between renders)."""
     if isinstance(obj, Scene):
         return obj
-    cached = getattr(obj, "_m3d_scene", None) if not isinstance(obj, (list, tuple)) or isinstance(obj, JoinedObject) else None
-    if cached is not None:
-        return cached
-    sc = Scene(obj, ctx)
-    try:
-        obj._m3d_scene = sc
-    except Exception:
-        pass
-    return sc
+    return Scene(obj, ctx)
 
 
 # ---- camera (camera.go) --------------------------------------------------------------------
@@ -578,7 +574,8 @@ def _samples_partition(partition):
     """(row_begin, row_end, sample_begin) or None -> m3d_partition pointer (or None)."""
     if partition is None:
         return None
-    return N.Partition(int(partition[0]), int(partition[1]), int(partition[2]))
+    flags = int(partition[3]) if len(partition) > 3 else 0
+    return N.Partition(int(partition[0]), int(partition[1]), int(partition[2]), flags, 0)
 
 
 @dataclass

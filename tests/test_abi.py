@@ -28,7 +28,7 @@ def test_python_symbol_list_matches_header():
 
 
 def test_abi_version(built):
-    assert built.m3d_abi_version() == 4
+    assert built.m3d_abi_version() == 5
 
 
 def test_struct_sizes_match_header(built):
@@ -81,3 +81,17 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 for b in banned:
                     assert b not in txt, "%s references the oracle (%s)" % (f, b)
+
+
+def test_multi_context_and_shared_memory_fail_loudly_without_gpu(built):
+    """m3d_ctx_create_multi / m3d_host_alloc have no CPU stand-in either."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from model3d_b200 import _native as N
+    with pytest.raises(N.M3DError) as ei:
+        N.MultiContext()
+    assert ei.value.code == 3
+    p = C.c_void_p()
+    assert built.m3d_host_alloc(C.c_int64(4096), C.byref(p)) != 0
+    assert built.m3d_ctx_num_devices(None) == 0

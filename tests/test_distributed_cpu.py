@@ -73,3 +73,86 @@ def test_two_rank_reduce_matches_single_process(tmp_path):
         full += sample_colour(W, H, s)
     assert np.allclose(got["mean"], full / spp, rtol=1e-6, atol=1e-7)
     assert np.array_equal(got["band"], sample_colour(W, H, 0))
+
+
+# ---- SharedAccumulator: the fused flush+reduce protocol of the one-process-per-GPU launch -------
+# On the GPU box the accumulators are cudaMalloc blocks of rank 0 mapped by CUDA IPC and the adds
+# are red.add inside path_flush; here POSIX shared memory and a lock-protected numpy add stand in
+# for them, so that the handle exchange, the double buffering and the one-barrier-per-frame
+# ordering run with world_size 2 on CPU.
+
+class _ShmBackend:
+    def __init__(self):
+        from multiprocessing import shared_memory
+        self.shm_mod = shared_memory
+        self.blocks = {}
+
+    def alloc(self, nbytes):
+        b = self.shm_mod.SharedMemory(create=True, size=nbytes)
+        b.buf[:nbytes] = bytes(nbytes)
+        self.blocks[id(b)] = b
+        return id(b)
+
+    def export(self, ptr):
+        return self.blocks[ptr].name.encode()
+
+    def open(self, handle):
+        b = self.shm_mod.SharedMemory(name=handle.decode())
+        self.blocks[id(b)] = b
+        return id(b)
+
+    def array(self, ptr, shape):
+        return np.ndarray(shape, np.float32, buffer=self.blocks[ptr].buf)
+
+    def close(self, ptr):
+        self.blocks.pop(ptr).close()
+
+    def free(self, ptr):
+        b = self.blocks.pop(ptr)
+        b.close()
+        b.unlink()
+
+
+def _shared_worker(rank, world, port, W, H, spp, frames, out_path, lock):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        be = _ShmBackend()
+        sa = D.SharedAccumulator(W * H * 3 * 4, rank, world, be, nbuf=2)
+        (rb, re, s0), cnt = D.sample_shard(spp, rank, world)
+        means = []
+        for k in range(frames):
+            part = np.zeros((H, W, 3), np.float32)
+            for s in range(s0, s0 + cnt):
+                part += sample_colour(W, H, s + 1000 * k)
+            with lock:  # stands in for the atomicity of red.add
+                be.array(sa.ptr(k), (H, W, 3))[...] += part
+            sa.barrier()
+            if rank == 0:
+                a = be.array(sa.ptr(k), (H, W, 3))
+                means.append((a / spp).copy())
+                a[...] = 0
+        dist.barrier()
+        sa.close()
+        if rank == 0:
+            np.save(out_path, np.stack(means))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_accumulator_protocol_two_ranks(tmp_path):
+    W, H, spp, world, frames = 16, 6, 9, 2, 5
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    out = str(tmp_path / "means.npy")
+    lock = mp.get_context("spawn").Lock()
+    mp.spawn(_shared_worker, args=(world, port, W, H, spp, frames, out, lock), nprocs=world, join=True)
+    got = np.load(out)
+    for k in range(frames):
+        full = np.zeros((H, W, 3), np.float32)
+        for s in range(spp):
+            full += sample_colour(W, H, s + 1000 * k)
+        assert np.allclose(got[k], full / spp, rtol=1e-5, atol=1e-6), k
