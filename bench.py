@@ -243,6 +243,8 @@ def path_measure(wl, spp, size, steps, warmup, rank, world, local_rank, reduce_m
             ev[2].record()
             marks.append(ev)
         info["rays"], info["launches"] = st["rays"], st["launches"]
+        if timed:
+            info["kernel_ms"] = info.get("kernel_ms", 0.0) + st["kernel_ms"] / steps
 
     for k in range(warmup):
         step(k, False)
@@ -262,8 +264,8 @@ def path_measure(wl, spp, size, steps, warmup, rank, world, local_rank, reduce_m
     clocks = sampler.stop() if rank == 0 else None
     render_ms = sum(e[0].elapsed_time(e[1]) for e in marks) / steps
     sync_ms = sum(e[1].elapsed_time(e[2]) for e in marks) / steps
-    t = torch.tensor([ev0.elapsed_time(ev1) / steps, float(info["rays"]), render_ms, sync_ms],
-                     dtype=torch.float64, device=dev)
+    t = torch.tensor([ev0.elapsed_time(ev1) / steps, float(info["rays"]), render_ms, sync_ms,
+                      info.get("kernel_ms", 0.0)], dtype=torch.float64, device=dev)
     per_rank = [[float(x) for x in t.tolist()]]
     if world > 1:
         dist.barrier()
@@ -283,6 +285,7 @@ def path_measure(wl, spp, size, steps, warmup, rank, world, local_rank, reduce_m
             "launches": int(info["launches"]), "n_devices": n_dev,
             "render_ms_per_rank": [round(r[2], 3) for r in per_rank],
             "reduce_wait_ms_per_rank": [round(r[3], 3) for r in per_rank],
+            "kernel_ms_per_rank": [round(r[4], 3) for r in per_rank],
             "image_mean": checksum / (W * H * 3),
             "reduce": fused_note + ("none (one GPU)" if n_dev == 1 else
                        "library: m3d_ctx_create_multi, peer-mapped red.add inside path_flush" if lib_devices > 1 else
@@ -340,6 +343,7 @@ def run_path(args):
                        "sharding": "sample index; " + m["reduce"],
                        "render_ms_per_rank": m["render_ms_per_rank"],
                        "reduce_wait_ms_per_rank": m["reduce_wait_ms_per_rank"],
+                       "kernel_ms_per_rank": m["kernel_ms_per_rank"], "image_mean": m["image_mean"],
                        "l2": "path state streams through HBM (> L2 per batch); scene BVH is L2/L1 resident"},
             "clocks": m["clocks"], "gpu_launches": m["launches"] * args.steps * (n_dev if lib_devices else 1),
         }
@@ -449,15 +453,33 @@ def run_c1(args):
                 "clocks": clocks, "gpu_launches": int(launches[0]) * args.steps}
         if e2e:
             line["e2e"] = e2e
+        # algorithmic bytes per primary ray, counted on the same camera rays (untimed pass)
+        dirs = R.CasterRays(rc.Camera, W, H).astype(np.float32)
+        orgs = np.tile(np.asarray(cam["src"], np.float32), (W * H, 1))
+        cst = psc.Cast(orgs, dirs, counters=True)["stats"]
+        v_nodes, t_tris = cst["nodes_visited"] / (W * H), cst["tris_tested"] / (W * H)
+        b_ray = RAY_IO_BYTES + v_nodes * NODE_BYTES + t_tris * TRI_BYTES + 12  # + the pixel written
+        peak, peak_src = hbm_peak()
+        achieved = W * H * b_ray / (ms_step * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+                            "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src,
+                            "bytes_per_ray": b_ray, "nodes_per_ray": v_nodes, "tris_per_ray": t_tris,
+                            "kernel": "raygen_camera + trace_first_hit_kernel + finish_scene_hits + shade_raycast",
+                            "note": "a 262,144-ray frame is four dependent launches of ~50 us: launch latency, "
+                                    "not bandwidth, bounds it (the same kernels reach 0.61 on the 2^24-ray batch)"}
+        if world == 1 and not args.no_cpu_baseline:
+            ref = c1_cpu_rate(3)
+            line["cpu_baseline"] = {"value": ref[0], "unit": "Mrays/s", "cores": ref[2], "kind": "port",
+                                    "sample": "the full 512x512 frame, 3 frames",
+                                    "note": "C++ float64 restatement of the Go RayCaster on all host threads"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_reference_c1(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def c1_cpu_rate(frames):
+    """The oracle's RayCaster (float64 restatement of raycast.go:15-39) on the C1 scene, all host
+    threads: (Mrays/s, seconds per frame, threads)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import scenes
     from oracle import pyoracle as O
@@ -470,12 +492,20 @@ def run_reference_c1(args):
     ol = O.PointLight()
     ol.origin[:], ol.color[:], ol.quad_dropoff = lt["origin"], lt["color"], 0
     W = H = 512
-    k = max(1, args.steps)
+    k = max(1, frames)
     t0 = time.perf_counter()
     for _ in range(k):
         osc.render_raycast(ocam, [ol], W, H, threads=threads)
     dt = (time.perf_counter() - t0) / k
-    rate = W * H / dt / 1e6
+    return W * H / dt / 1e6, dt, threads
+
+
+def run_reference_c1(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    W = H = 512
+    rate, dt, threads = c1_cpu_rate(min(max(1, args.steps), 10))
     line = {"impl": "reference", "metric": "first_hit_Mrays_per_s", "value": rate, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -256,16 +256,26 @@ static int32_t render_bidir_one_device(m3d_scene *scene, const m3d_camera *cam, 
     const int v = e ? atoi(e) : 22;
     return (v < 10 || v > 22) ? 22 : v;
   }();
-  // at most half of what is free on the device right now (beyond what this context already holds)
-  size_t free_b = 0, total_b = 0;
-  M3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const size_t budget = std::min<size_t>((size_t)M3D_BIDIR_BUDGET_GB << 30, (free_b + ctx->scratch[6].bytes) / 2);
-  int64_t cap = (int64_t)std::min<size_t>((size_t)1 << batch_log2, budget / per_slot);
+  // at most half of what is free on the device right now (beyond what this context already holds);
+  // cudaMemGetInfo only when the batch does not fit what the last call of the same depths carved
+  // (it costs 10-40 ms when several devices / processes share peer mappings)
   const int64_t total = npix * sample_count;
-  cap = std::max<int64_t>(1, std::min(cap, total));
+  const int64_t depth_key = (int64_t)max_depth * 1024 + max_ld;
+  int64_t cap = std::min<int64_t>((int64_t)1 << batch_log2, total);
+  if (!(ctx->bidir_carved_key == depth_key && cap <= ctx->bidir_carved_cap && ctx->scratch[6].bytes > 0)) {
+    size_t free_b = 0, total_b = 0;
+    M3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = std::min<size_t>((size_t)M3D_BIDIR_BUDGET_GB << 30, (free_b + ctx->scratch[6].bytes) / 2);
+    cap = std::min<int64_t>(cap, (int64_t)(budget / per_slot));
+  }
+  cap = std::max<int64_t>(1, cap);
   const int64_t nP_max = std::min(npix, cap);
   BidirBuffers buf;
   if (int32_t rc = carve_bidir_buffers(ctx, cap, max_depth, max_ld, buf)) return rc;
+  if (!(ctx->bidir_carved_key == depth_key && cap <= ctx->bidir_carved_cap)) {
+    ctx->bidir_carved_key = depth_key;
+    ctx->bidir_carved_cap = cap;
+  }
   M3D_CUDA(cudaMemsetAsync(buf.ray_total, 0, sizeof(unsigned long long), s));
   const DeviceCamera dc = device_camera(*cam, width, height);
 

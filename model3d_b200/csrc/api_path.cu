@@ -3,6 +3,7 @@
 // pipeline: raygen -> [trace -> shade/compact (-> shadow trace -> shadow resolve)] x depth
 // -> flush, batch by batch, all enqueued on one stream with device-side queue lengths
 // (no host round trip between bounces).
+#include <chrono>
 #include <cstdlib>
 #include <algorithm>
 #include <cmath>
@@ -183,6 +184,10 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
       return fail(M3D_ERR_INVALID_ARG, "sample range out of bounds");
   }
   if (stats) std::memset(stats, 0, sizeof(*stats));
+  static const bool dbg = getenv("M3D_DEBUG_T") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_entry = now();
+  double t_carved = 0, t_enq = 0;
   const int64_t npix = (int64_t)width * (row_end - row_begin);
   if (npix == 0 || sample_count == 0) return M3D_OK;
   if (adaptive && (sample_begin != 0 || sample_count != params->num_samples || d_rgb_sumsq))
@@ -221,13 +226,21 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
   // <= 48 GB of the 180 GB for the path state (192 B per slot + 68 B per point light), and queue
   // positions / shadow-ray counts stay below 2^31
   const int64_t per_slot = 192 + 68 * (int64_t)num_lights;
-  // ... and at most half of what is free on the device right now (beyond what this context already holds)
-  size_t free_b = 0, total_b = 0;
-  M3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  const int64_t budget = std::min<int64_t>((int64_t)48 << 30, (int64_t)((free_b + ctx->scratch[4].bytes) / 2));
+  // ... and at most half of what is free on the device right now (beyond what this context already
+  // holds).  cudaMemGetInfo is only asked when the scratch allocation would have to grow: it takes
+  // 10-40 ms when several devices / processes share peer mappings (measured: 2 x B200, r2).
+  const int64_t total = npix * sample_count;
+  const int64_t want_slots = std::min<int64_t>(
+      total, std::min<int64_t>((int64_t)1 << batch_log2, ((int64_t)1 << 30) / std::max<int64_t>(1, num_lights)));
+  int64_t budget = (int64_t)48 << 30;
+  // carve_path_buffers pads every array to 256 bytes: 32 arrays
+  if ((int64_t)ctx->scratch[4].bytes < want_slots * per_slot + 32 * 256) {
+    size_t free_b = 0, total_b = 0;
+    M3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    budget = std::min<int64_t>(budget, (int64_t)((free_b + ctx->scratch[4].bytes) / 2));
+  }
   const int64_t kMaxSlots = std::min<int64_t>(std::min<int64_t>((int64_t)1 << batch_log2, budget / per_slot),
                                               ((int64_t)1 << 30) / std::max<int64_t>(1, num_lights));
-  const int64_t total = npix * sample_count;
   const int64_t cap = std::min(total, std::max<int64_t>(kMaxSlots, 1));
   const int64_t nP_max = std::min(npix, cap);
   PathBuffers buf;
@@ -247,6 +260,7 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
     M3D_CUDA(cudaMemcpyAsync(d_lights, hl.data(), hl.size() * sizeof(DevicePointLight), cudaMemcpyHostToDevice, s));
   }
   M3D_CUDA(cudaMemsetAsync(buf.ray_total, 0, sizeof(unsigned long long), s));
+  t_carved = now();
   const DeviceCamera dc = device_camera(*cam, width, height);
 
   // material kinds that occur in the scene: one sampling kernel per kind and bounce
@@ -350,10 +364,14 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
     }
   }
   tm.stop(s);
+  t_enq = now();
   // host-side tables (lights) must outlive the async copies; stats need the counters
   unsigned long long rays = 0;
   M3D_CUDA(cudaMemcpyAsync(&rays, buf.ray_total, sizeof(rays), cudaMemcpyDeviceToHost, s));
   M3D_CUDA(cudaStreamSynchronize(s));
+  if (dbg)
+    fprintf(stderr, "[m3d] render_path: setup %.3f ms, enqueue %.3f ms, wait %.3f ms (cap %lld)\n", t_carved - t_entry,
+            t_enq - t_carved, now() - t_enq, (long long)cap);
   M3D_CUDA(cudaGetLastError());
   if (stats) {
     stats->rays = (int64_t)rays;

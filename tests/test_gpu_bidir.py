@@ -60,6 +60,27 @@ def test_bidir_cornell_box_mesh_light(built, oracle):
     assert stats["rays"] > W * H * 1024 * 2
 
 
+def test_bidir_cornell_box_c5_literal_parameters(built, oracle):
+    """BASELINE config 5 at its OWN parameters -- MaxDepth 10, MinDepth 3, RouletteDelta 0.2,
+    PowerHeuristic 2, Antialias 1, Cutoff 1e-4 (bench.py C5_KW), the ceiling light as
+    MeshAreaLight -- on a small frame: per-pixel statistical parity with the float64 oracle's
+    restatement of bidir.go:101-576, and the same scene through the path tracer's estimator
+    (the reference's own BDPT test compares the two, bidir_test.go:12-65)."""
+    import bench
+    assert bench.C5_KW["max_depth"] == 10 and bench.C5_KW["min_depth"] == 3 and bench.C5_KW["roulette_delta"] == 0.2
+    spec = scenes.cornell_box()
+    osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
+    W = H = 40
+    ref = oracle_bidir(oracle, spec, osc, W, H, 1024, **bench.C5_KW)
+    mean, var, stats = gpu_bidir(spec, psc, W, H, 4096, **bench.C5_KW)
+    assert ref["mean"].mean() > 0.05
+    check_statistical_parity(mean, var, ref["mean"], ref["var_of_mean"])
+    # eye sub-paths up to depth 10 and light sub-paths up to depth 10 really ran
+    assert stats["rays"] > W * H * 4096 * 4
+    # image means agree to Monte-Carlo accuracy (a biased deep-path weight would show here)
+    assert abs(mean.mean() - ref["mean"].mean()) < 0.01 * ref["mean"].mean() + 4 * np.sqrt(var.sum() + ref["var_of_mean"].sum()) / mean.size
+
+
 def test_bidir_glass_scene_dirac_lobes(built, oracle):
     """Specular chains (refraction + Fresnel reflection) through the float64 MIS weights:
     the Dirac magnitudes (2e8 per specular vertex) must cancel exactly as in the reference."""

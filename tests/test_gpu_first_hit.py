@@ -18,21 +18,30 @@ def rays(rng, n, scale=1.0):
     return o, d.astype(np.float32)
 
 
-def check_parity(oracle, tris32, org, d, got, vnormals=None):
+FLIP_LOG = []  # (label, rays, hit/miss flips, hits won by a different triangle): printed at the end
+
+
+def check_parity(oracle, tris32, org, d, got, vnormals=None, label="", max_flips=None):
     ref = oracle.Collider(tris32, vnormals).first_hits(org, d, threads=8)
     hit_o, hit_g = ref["prim"] >= 0, got.Triangle >= 0
-    # A hit/miss flip is only acceptable for grazing hits: the ray passes within 1e-4
-    # (barycentric) of the boundary of the triangle that one side reports, i.e. it clips a
-    # silhouette edge, or it is nearly parallel to the triangle.  Such rays must be rare.
+    # Hit/miss flips.  The float32 triangle test hands every ray inside its rounding-error band
+    # (and every nearly parallel one) to the reference's own float64 arithmetic on the same
+    # inputs, so the accept / reject decisions are the oracle's: a flip can only come from a
+    # ray that clips a silhouette edge within the few-ulp slack of the quantised child boxes'
+    # tmax pruning.  Allowed: at most one per 10^5 rays (north_star: "identical except for ties
+    # or grazing hits"), each of them grazing: within 1e-6 (barycentric) of the boundary of the
+    # triangle one side reports, or parallel to it within 1e-6.  The count is logged.
     flip = np.nonzero(hit_o != hit_g)[0]
-    assert len(flip) <= max(1, 2e-5 * len(hit_o)), "hit/miss mismatches: %d" % len(flip)
+    limit = max(1, int(1e-5 * len(hit_o))) if max_flips is None else max_flips
+    both = hit_o & hit_g
+    FLIP_LOG.append((label, len(hit_o), len(flip), int((both & (ref["prim"] != got.Triangle)).sum())))
+    assert len(flip) <= limit, "hit/miss mismatches: %d of %d rays" % (len(flip), len(hit_o))
     dn = d.astype(np.float64) / np.linalg.norm(d.astype(np.float64), axis=1, keepdims=True)
     for i in flip:
         bary = ref["bary"][i] if hit_o[i] else got.Barycentric[i].astype(np.float64)
         nrm = ref["normal"][i] if hit_o[i] else got.Normal[i].astype(np.float64)
-        grazing = bary.min() < 1e-4 or abs(float(nrm @ dn[i])) < 1e-3
+        grazing = bary.min() < 1e-6 or abs(float(nrm @ dn[i])) < 1e-6
         assert grazing, "non-grazing hit/miss flip at ray %d (bary %s)" % (i, bary)
-    both = hit_o & hit_g
     same = both & (ref["prim"] == got.Triangle)
     rel = np.abs(got.Scale - ref["t"]) / np.maximum(np.abs(ref["t"]), 1e-30)
     assert rel[same].max(initial=0) < T_REL
@@ -231,7 +240,47 @@ def test_full_size_c2_properties(built, oracle):
     idx = rng.choice(n, 200000, replace=False)
     sub = type(got)(Collides=got.Collides[idx], Scale=got.Scale[idx], Normal=got.Normal[idx],
                     Triangle=got.Triangle[idx], Barycentric=got.Barycentric[idx])
-    check_parity(oracle, tris, org[idx], d[idx], sub)
+    # observed on B200 (round 2): 0 hit/miss flips in the 200,000-ray sample; hold it to that
+    check_parity(oracle, tris, org[idx], d[idx], sub, label="C2 200k sample", max_flips=0)
+
+
+def test_zz_report_flip_counts():
+    """Not a check: prints what the parity tests of this module observed (run pytest with -rP or
+    read gpurun_out/first_hit_flips.log)."""
+    import os
+    lines = ["%-28s rays %8d  hit/miss flips %3d  different-triangle ties %4d" % r for r in FLIP_LOG]
+    print("\n".join(lines))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        open(os.path.join("gpurun_out", "first_hit_flips.log"), "w").write("\n".join(lines) + "\n")
+    except OSError:
+        pass
+
+
+def test_stl_file_to_device_hits(built, oracle, tmp_path):
+    """a binary STL file (the reference's examples/renderings/cornell_box/diamond.stl,
+    committed byte for byte as tests/golden/ref_cornell_box_diamond.stl), also gzip-compressed
+    like the showcase models, -> fileformats.ReadSTL -> MeshCollider -> first hits == oracle."""
+    import gzip
+    import os
+    import shutil
+    from model3d_b200 import MeshCollider, fileformats
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cornell_box_diamond.stl")
+    gz = str(tmp_path / "diamond.stl.gz")
+    with open(src, "rb") as f, gzip.open(gz, "wb") as g:
+        shutil.copyfileobj(f, g)
+    rng = np.random.default_rng(77)
+    for path in (src, gz):
+        tris = fileformats.ReadSTL(path).astype(np.float32)
+        assert tris.shape == (46, 3, 3)
+        assert np.array_equal(tris, np.load(os.path.join(os.path.dirname(src), "diamond_tris.npy")).astype(np.float32))
+        c = tris.reshape(-1, 3).mean(0)
+        size = float(np.abs(tris.reshape(-1, 3) - c).max())
+        org = (c + rng.normal(size=(100000, 3)) * size * 1.5).astype(np.float32)
+        d = rng.normal(size=(100000, 3)).astype(np.float32)
+        got = MeshCollider(tris).FirstRayCollisions(org, d)
+        ref, same = check_parity(oracle, tris, org, d, got, label="diamond.stl")
+        assert same.sum() > 5000
 
 
 def test_ray_collision_counts_and_contains(built, oracle):

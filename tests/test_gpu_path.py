@@ -105,6 +105,37 @@ def test_path_point_lights_and_shadows(built, oracle):
     run_case(oracle, spec, 40, 30, n_gpu=512, n_ref=256, max_depth=2, lights=lights)
 
 
+def test_path_epsilon_steps_over_coincident_surfaces(built, oracle):
+    """RecursiveRayTracer.Epsilon (raytrace.go:217-229): bounce and shadow origins move eps along
+    the ray, which is what lets a ray leave a surface that is DUPLICATED in another object (two
+    meshes with coincident faces).  The GPU path honours a user Epsilon above float32 resolution
+    as the rays' tmin on top of its exact skip ids: with Epsilon 1e-3 the doubled floor is lit
+    exactly like the oracle's, shadow rays included."""
+    from model3d_b200 import render3d as R
+    m_l = scenes.lambert(diffuse=scenes.gray(0.6))
+    slab = scenes.mesh_rect_tris((-3, -3, -0.5), (3, 3, 0.0)).astype(np.float32)
+    post = scenes.mesh_rect_tris((0.5, 0.5, 0.0), (1.0, 1.0, 1.5)).astype(np.float32)
+    spec = dict(objects=[dict(kind="mesh", tris=slab, material=m_l), dict(kind="mesh", tris=slab.copy(), material=m_l),
+                         dict(kind="mesh", tris=post, material=m_l)],
+                camera=dict(src=(0.5, -4.0, 5.0), dst=(0.0, 0.0, 0.0), fov=np.pi / 3))
+    light = dict(origin=(-2.0, -1.0, 6.0), color=(30.0, 30.0, 30.0))
+    W, H, eps = 48, 36, 1e-3
+    osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
+    cam = spec["camera"]
+    ocam = oracle.camera_at(cam["src"], cam["dst"], cam["fov"])
+    pp = scenes.oracle_path_params(spec, osc, 2, 256, seed=4)
+    pp.epsilon = eps
+    ol = oracle.PointLight()
+    ol.origin[:], ol.color[:], ol.quad_dropoff = light["origin"], light["color"], 0
+    ref = osc.render_path(ocam, [ol], pp, W, H, threads=8)
+    tr = scenes.product_tracer(spec, psc, 2, 512, seed=5, lights=[R.PointLight(Origin=light["origin"], Color=light["color"])])
+    tr.Epsilon = eps
+    mean, var, _ = gpu_mean_var(tr, psc, W, H, 512)
+    assert ref["mean"].mean() > 0.1  # the floor is lit in the reference's arithmetic
+    check_statistical_parity(mean, var, ref["mean"], ref["var_of_mean"])
+    assert abs(mean.mean() - ref["mean"].mean()) < 0.02 * ref["mean"].mean()
+
+
 def test_path_depth0_equals_shadowed_raycast(built, oracle):
     """MaxDepth 0 is deterministic (no sampling): must match the oracle to float32 rounding."""
     spec = scenes.mixed_scene()
