@@ -42,7 +42,7 @@ func (m *MeshCollider) RayCollisionCounts(rays []model3d.Ray) ([]int, error) {
 	if len(counts) > 0 {
 		cp = (*C.int32_t)(unsafe.Pointer(&counts[0]))
 	}
-	if err := status(C.m3d_mesh_ray_collision_counts(m.h, fptr(org), fptr(dir), C.int64_t(len(rays)), cp, nil)); err != nil {
+	if err := call(func() C.int32_t { return C.m3d_mesh_ray_collision_counts(m.h, fptr(org), fptr(dir), C.int64_t(len(rays)), cp, nil) }); err != nil {
 		return nil, err
 	}
 	res := make([]int, len(rays))
@@ -66,8 +66,8 @@ func (m *MeshCollider) AllRayCollisions(rays []model3d.Ray) ([][]model3d.RayColl
 	offsets := make([]int64, n+1)
 	op := (*C.int64_t)(unsafe.Pointer(&offsets[0]))
 	// first call sizes the outputs (capacity 0), second call fills them
-	if err := status(C.m3d_mesh_ray_collisions(m.h, fptr(org), fptr(dir), C.int64_t(n), 0, op,
-		nil, nil, nil, nil, nil)); err != nil {
+	if err := call(func() C.int32_t { return C.m3d_mesh_ray_collisions(m.h, fptr(org), fptr(dir), C.int64_t(n), 0, op,
+		nil, nil, nil, nil, nil) }); err != nil {
 		return nil, err
 	}
 	total := int(offsets[n])
@@ -79,8 +79,8 @@ func (m *MeshCollider) AllRayCollisions(rays []model3d.Ray) ([][]model3d.RayColl
 	prim := make([]int32, total)
 	normal := make([]float32, total*3)
 	bary := make([]float32, total*3)
-	if err := status(C.m3d_mesh_ray_collisions(m.h, fptr(org), fptr(dir), C.int64_t(n), C.int64_t(total), op,
-		fptr(ts), (*C.int32_t)(unsafe.Pointer(&prim[0])), fptr(normal), fptr(bary), nil)); err != nil {
+	if err := call(func() C.int32_t { return C.m3d_mesh_ray_collisions(m.h, fptr(org), fptr(dir), C.int64_t(n), C.int64_t(total), op,
+		fptr(ts), (*C.int32_t)(unsafe.Pointer(&prim[0])), fptr(normal), fptr(bary), nil) }); err != nil {
 		return nil, err
 	}
 	for i := 0; i < n; i++ {
@@ -133,7 +133,7 @@ func (m *MeshCollider) SphereCollisions(centers []model3d.Coord3D, radii []float
 		op = (*C.uint8_t)(unsafe.Pointer(&out[0]))
 	}
 	flat := flatCoords(centers)
-	if err := status(C.m3d_mesh_sphere_collisions(m.h, fptr(flat), fptr(rad), C.int64_t(len(centers)), op, nil)); err != nil {
+	if err := call(func() C.int32_t { return C.m3d_mesh_sphere_collisions(m.h, fptr(flat), fptr(rad), C.int64_t(len(centers)), op, nil) }); err != nil {
 		return nil, err
 	}
 	res := make([]bool, len(out))
@@ -160,7 +160,7 @@ func (m *MeshCollider) Contains(points []model3d.Coord3D, margin float64) ([]boo
 		op = (*C.uint8_t)(unsafe.Pointer(&out[0]))
 	}
 	flat := flatCoords(points)
-	if err := status(C.m3d_mesh_contains(m.h, fptr(flat), C.int64_t(len(points)), C.double(margin), op, nil)); err != nil {
+	if err := call(func() C.int32_t { return C.m3d_mesh_contains(m.h, fptr(flat), C.int64_t(len(points)), C.double(margin), op, nil) }); err != nil {
 		return nil, err
 	}
 	res := make([]bool, len(out))
@@ -193,7 +193,7 @@ func (s *MeshSDF) FaceSDFs(points []model3d.Coord3D) ([]*model3d.Triangle, []mod
 		fp = (*C.int32_t)(unsafe.Pointer(&face[0]))
 	}
 	flat := flatCoords(points)
-	if err := status(C.m3d_mesh_sdf(s.h, fptr(flat), C.int64_t(n), fptr(sdf), fptr(cp), fp, nil, nil)); err != nil {
+	if err := call(func() C.int32_t { return C.m3d_mesh_sdf(s.h, fptr(flat), C.int64_t(n), fptr(sdf), fptr(cp), fp, nil, nil) }); err != nil {
 		return nil, nil, nil, err
 	}
 	tris := make([]*model3d.Triangle, n)

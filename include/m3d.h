@@ -128,6 +128,8 @@ int32_t m3d_mesh_bounds(const m3d_mesh *mesh, double min_out[3], double max_out[
 
 #define M3D_TRACE_COUNTERS 1u   /* count nodes/triangles (slower; not for timing) */
 #define M3D_TRACE_NO_REFINE 2u  /* skip the float64 final-hit refinement          */
+#define M3D_TRACE_SHARED_ORIGIN 4u /* host-buffer call: `org` holds ONE origin (3 floats) shared by
+                                      all rays (camera batches): halves the host->device bytes */
 
 /* Batched Collider.FirstRayCollision (model3d/collisions.go:275-290 +
  * model3d/primitives.go:181-249).  Host buffers.
@@ -137,6 +139,11 @@ int32_t m3d_mesh_bounds(const m3d_mesh *mesh, double min_out[3], double max_out[
  *   normal   : n*3 floats or NULL (RayCollision.Normal: flat, never flipped,
  *              or interpolated when the mesh has vnormals)
  *   bary     : n*3 floats or NULL (TriangleCollision.Barycentric)
+ * Outputs the caller does not need may be NULL and are then neither unpacked nor copied back
+ * (t + prim only: 8 bytes per ray device->host instead of 32).  The call runs a chunked copy /
+ * compute pipeline; it reaches the PCIe rate only when the arrays are page-locked
+ * (m3d_host_alloc / m3d_host_register below).  On a multi-device context the batch is split into
+ * contiguous slices, one per GPU.
  */
 int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org,
                                       const float *dir, int64_t n, float *t,
@@ -268,9 +275,23 @@ int32_t m3d_scene_add_rect(m3d_scene_builder *b, const double min[3], const doub
 int32_t m3d_scene_add_cylinder(m3d_scene_builder *b, const double p1[3], const double p2[3],
                                double radius, int32_t material, uint32_t flags,
                                const m3d_transform *xf, int32_t *index_out);
+/* An instance of a device-resident mesh collider under a similarity transform: the scene keeps
+ * ONE copy of the triangles and of the mesh's hierarchy however many instances refer to it
+ * (render3d.Translate / MatrixMultiply of a shared collider, transform.go:6-85;
+ * examples/renderings/golf_balls/main.go:25-39).  `mesh` must come from m3d_mesh_create on the
+ * builder's context and outlive the scene.  Rays are taken to object space at the instance's
+ * bounds and walk the mesh's own BVH there; prim is the triangle id inside the mesh. */
+int32_t m3d_scene_add_instance(m3d_scene_builder *b, m3d_mesh *mesh, int32_t material, uint32_t flags,
+                               const m3d_transform *xf, int32_t *index_out);
+/* Scenes with more than a handful of analytic shapes / instances get an object-level hierarchy
+ * over their bounds (render3d.BVHToObject, object.go:172-185), walked per ray instead of testing
+ * every shape: thousands of spheres cost O(log n) per ray. */
 int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **out);
 void m3d_scene_destroy(m3d_scene *scene);
 int32_t m3d_scene_bounds(const m3d_scene *scene, double min_out[3], double max_out[3]);
+/* The scene's own (merged, world-space) triangle hierarchy: num_triangles counts the triangles the
+ * scene stores itself -- instanced meshes are not among them, they stay in their m3d_mesh. */
+int32_t m3d_scene_get_info(const m3d_scene *scene, m3d_mesh_info *info);
 
 /* Batched Object.Cast (render3d/object.go:141-153): like
  * m3d_mesh_first_ray_collisions plus obj (object index, -1 miss); prim is the

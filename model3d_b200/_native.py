@@ -17,6 +17,7 @@ ERR_NAMES = {1: "INVALID_ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "NCCL", 5: "OOM"}
 MESH_BUILD_HOST_SAH, MESH_BUILD_DEVICE_LBVH, MESH_BUILD_DEVICE_COLLAPSE = 0, 1, 2
 TRACE_COUNTERS = 1
 TRACE_NO_REFINE = 2
+TRACE_SHARED_ORIGIN = 4
 
 MAT_LAMBERT, MAT_PHONG, MAT_REFRACT, MAT_JOINED = 0, 1, 2, 3
 MAT_NO_FLUX_CORRECTION, MAT_CHECKER, MAT_Z_GRADIENT = 1, 2, 4
@@ -110,8 +111,8 @@ SYMBOLS = [
     "m3d_mesh_bounds", "m3d_mesh_first_ray_collisions", "m3d_mesh_first_ray_collisions_device",
     "m3d_mesh_ray_collision_counts", "m3d_mesh_ray_collisions", "m3d_mesh_contains", "m3d_mesh_sdf", "m3d_mesh_sphere_collisions",
     "m3d_scene_builder_create", "m3d_scene_builder_destroy", "m3d_scene_add_material",
-    "m3d_scene_add_mesh", "m3d_scene_add_sphere", "m3d_scene_add_rect", "m3d_scene_add_cylinder",
-    "m3d_scene_build", "m3d_scene_destroy", "m3d_scene_bounds", "m3d_scene_cast",
+    "m3d_scene_add_mesh", "m3d_scene_add_instance", "m3d_scene_add_sphere", "m3d_scene_add_rect", "m3d_scene_add_cylinder",
+    "m3d_scene_build", "m3d_scene_destroy", "m3d_scene_bounds", "m3d_scene_get_info", "m3d_scene_cast",
     "m3d_render_raycast", "m3d_render_raycast_device", "m3d_render_path", "m3d_render_path_device",
     "m3d_render_bidir", "m3d_render_bidir_device", "m3d_finalize_image_device",
     "m3d_measure_l2_bandwidth", "m3d_ctx_create_multi", "m3d_ctx_num_devices",

@@ -336,7 +336,8 @@ int32_t m3d_mesh_first_ray_collisions(m3d_mesh *mesh, const float *org, const fl
       split_range(n, g, i, &b, &e);
       m3d_mesh *mi = i == 0 ? mesh : mesh->replicas[(size_t)i - 1];
       std::lock_guard<std::recursive_mutex> lock(mi->ctx->mu);
-      return first_ray_collisions_one_device(mi, org + 3 * b, dir + 3 * b, e - b, t ? t + b : nullptr,
+      return first_ray_collisions_one_device(mi, (flags & M3D_TRACE_SHARED_ORIGIN) ? org : org + 3 * b,
+                                             dir + 3 * b, e - b, t ? t + b : nullptr,
                                              prim ? prim + b : nullptr, normal ? normal + 3 * b : nullptr,
                                              bary ? bary + 3 * b : nullptr, flags, stats ? &st[(size_t)i] : nullptr);
     });
@@ -416,12 +417,14 @@ static int32_t first_ray_collisions_one_device(m3d_mesh *mesh, const float *org,
     float *d_bary = d_normal + 3 * per;
     // the previous user of this buffer must have finished its D2H
     if (it >= nbuf) cudaStreamWaitEvent(ctx->copy_in, ev_out[b], 0);
-    cudaMemcpyAsync(d_org3, org + base * 3, m * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in);
+    const bool shared_org = (flags & M3D_TRACE_SHARED_ORIGIN) != 0;
+    if (!shared_org)
+      cudaMemcpyAsync(d_org3, org + base * 3, m * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in);
     cudaMemcpyAsync(d_dir3, dir + base * 3, m * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_in);
     cudaEventRecord(ev_in[b], ctx->copy_in);
     cudaStreamWaitEvent(ctx->stream, ev_in[b], 0);
     if (stats) cudaEventRecord(k0, ctx->stream);
-    launch_pack_rays(d_org3, d_dir3, m, 0.f, __builtin_inff(), d_org4, d_dir4, ctx->stream);
+    launch_pack_rays(d_org3, d_dir3, m, 0.f, __builtin_inff(), d_org4, d_dir4, ctx->stream, shared_org ? org : nullptr);
     TraceLaunch p;
     p.org_tmin = d_org4;
     p.dir_tmax = d_dir4;
@@ -474,7 +477,7 @@ static int32_t first_ray_collisions_one_device(m3d_mesh *mesh, const float *org,
     stats->rays = n;
     stats->kernel_ms = kernel_ms;
     stats->launches = launches;
-    stats->h2d_bytes = n * 6 * (int64_t)sizeof(float);
+    stats->h2d_bytes = n * ((flags & M3D_TRACE_SHARED_ORIGIN) ? 3 : 6) * (int64_t)sizeof(float);
     stats->d2h_bytes = n * (int64_t)((t ? 4 : 0) + (prim ? 4 : 0) + (normal ? 12 : 0) + (bary ? 12 : 0));
     if (counters && rc == M3D_OK) {
       unsigned long long c[2] = {0, 0};

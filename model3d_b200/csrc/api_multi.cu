@@ -97,6 +97,29 @@ int32_t replicate_scene(m3d_scene *scene) {
     r->dev.shapes = scene->dev.shapes ? r->shapes.as<const DeviceShape>() : nullptr;
     r->dev.objects = r->objects.as<const DeviceObject>();
     r->dev.materials = scene->dev.materials ? r->materials.as<const DeviceMaterial>() : nullptr;
+    if (int32_t rc = replicate_buffer(mc, r->shape_nodes, scene->shape_nodes, root->device)) return rc;
+    if (int32_t rc = replicate_buffer(mc, r->shape_tris, scene->shape_tris, root->device)) return rc;
+    if (scene->dev.shape_bvh.nodes) {
+      r->dev.shape_bvh.nodes = r->shape_nodes.as<const uint4>();
+      r->dev.shape_bvh.tris = r->shape_tris.as<const float4>();
+    }
+    // instances refer to this device's replica of their mesh
+    r->host_instances = scene->host_instances;
+    r->instance_meshes = scene->instance_meshes;
+    const size_t member = scene->replicas.size() - 1;  // index of mc in root->members
+    for (size_t k = 0; k < r->host_instances.size(); k++) {
+      m3d_mesh *mesh = scene->instance_meshes[k];
+      if (mesh->replicas.size() <= member)
+        return fail(M3D_ERR_INVALID_ARG, "an instanced mesh has no replica on device %d", mc->device);
+      r->host_instances[k].blas = mesh->replicas[member]->bvh;
+    }
+    if (!r->host_instances.empty()) {
+      M3D_CUDA(cudaSetDevice(mc->device));
+      M3D_CUDA(r->instances.reserve(r->host_instances.size() * sizeof(DeviceInstance)));
+      M3D_CUDA(cudaMemcpy(r->instances.p, r->host_instances.data(),
+                          r->host_instances.size() * sizeof(DeviceInstance), cudaMemcpyHostToDevice));
+      r->dev.instances = r->instances.as<const DeviceInstance>();
+    }
   }
   cudaSetDevice(root->device);
   return M3D_OK;

@@ -24,6 +24,8 @@ struct BuilderObject {
   std::vector<float> vnormals;  // optional, world space
   DeviceShape shape{};
   double bmin[3], bmax[3];
+  m3d_mesh *mesh = nullptr;  // SHAPE_INSTANCE
+  m3d::DeviceInstance inst{};
 };
 
 struct m3d_scene_builder {
@@ -33,6 +35,10 @@ struct m3d_scene_builder {
 };
 
 namespace {
+
+// more analytic shapes / instances than this: the scene gets an object-level BVH (a linear scan
+// is faster for the handful of shapes of the BASELINE scenes)
+constexpr size_t kShapeBvhThreshold = 12;
 
 // x_world = M x + offset; only similarity transforms (M^T M = s^2 I) keep spheres spheres and
 // make the reference's "normal = normalize(M n)" (transform.go:81-83) the true normal.
@@ -285,6 +291,63 @@ int32_t m3d_scene_add_cylinder(m3d_scene_builder *b, const double p1[3], const d
   return M3D_OK;
 }
 
+int32_t m3d_scene_add_instance(m3d_scene_builder *b, m3d_mesh *mesh, int32_t material, uint32_t flags,
+                               const m3d_transform *xf, int32_t *index_out) {
+  if (!b || !mesh) return fail(M3D_ERR_INVALID_ARG, "m3d_scene_add_instance: bad arguments");
+  if (mesh->ctx != b->ctx)
+    return fail(M3D_ERR_INVALID_ARG, "the instanced mesh was built on another context than the scene");
+  if (mesh->info.num_triangles == 0) return fail(M3D_ERR_INVALID_ARG, "cannot instance an empty mesh");
+  if (int32_t rc = check_material_index(b, material)) return rc;
+  double scale;
+  if (!similarity_scale(xf, scale))
+    return fail(M3D_ERR_UNSUPPORTED, "instance transform must be a similarity (rotation * uniform scale)");
+  BuilderObject o;
+  o.kind = SHAPE_INSTANCE;
+  o.material = material;
+  o.flags = flags;
+  o.mesh = mesh;
+  o.shape.kind = SHAPE_INSTANCE;
+  o.shape.radius = 0;
+  // world bounds: the eight corners of the mesh's bounds through the transform
+  for (int k = 0; k < 3; k++) {
+    o.bmin[k] = INFINITY;
+    o.bmax[k] = -INFINITY;
+  }
+  for (int c = 0; c < 8; c++) {
+    const double in[3] = {(c & 1) ? mesh->bmax[0] : mesh->bmin[0], (c & 2) ? mesh->bmax[1] : mesh->bmin[1],
+                          (c & 4) ? mesh->bmax[2] : mesh->bmin[2]};
+    double out[3];
+    apply_xf(xf, in, out);
+    for (int k = 0; k < 3; k++) {
+      o.bmin[k] = std::fmin(o.bmin[k], out[k]);
+      o.bmax[k] = std::fmax(o.bmax[k], out[k]);
+    }
+  }
+  double size = 0;
+  for (int k = 0; k < 3; k++) {
+    // float32 rays are tested against these bounds: widen them by a few ulp of their magnitude
+    const double pad = 1e-6 * std::fmax(std::fabs(o.bmin[k]), std::fabs(o.bmax[k])) + 1e-30;
+    o.bmin[k] -= pad;
+    o.bmax[k] += pad;
+    o.shape.p0[k] = o.bmin[k];
+    o.shape.p1[k] = o.bmax[k];
+    size = std::fmax(size, o.bmax[k] - o.bmin[k]);
+  }
+  const double id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const double *m = xf ? xf->matrix : id;
+  // inverse of a similarity: M^-1 = M^T / s^2
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) {
+      o.inst.fwd[3 * r + c] = (float)m[3 * r + c];
+      o.inst.inv[3 * r + c] = (float)(m[3 * c + r] / (scale * scale));
+    }
+  for (int k = 0; k < 3; k++) o.inst.off[k] = xf ? (float)xf->offset[k] : 0.f;
+  o.inst.size = (float)size;
+  b->objects.push_back(std::move(o));
+  if (index_out) *index_out = (int32_t)b->objects.size() - 1;
+  return M3D_OK;
+}
+
 int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **out) {
   if (!b || !out) return fail(M3D_ERR_INVALID_ARG, "m3d_scene_build: NULL argument");
   *out = nullptr;
@@ -352,6 +415,14 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
     } else {
       DeviceShape sh = o.shape;
       sh.object = (int32_t)oi;
+      sh.instance = -1;
+      if (o.kind == SHAPE_INSTANCE) {
+        sh.instance = (int32_t)sc->host_instances.size();
+        DeviceInstance in = o.inst;
+        in.blas = o.mesh->bvh;
+        sc->host_instances.push_back(in);
+        sc->instance_meshes.push_back(o.mesh);
+      }
       sc->host_shapes.push_back(sh);
     }
   }
@@ -392,6 +463,47 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
     M3D_CUDA(sc->shapes.reserve(sc->host_shapes.size() * sizeof(DeviceShape)));
     M3D_CUDA(cudaMemcpy(sc->shapes.p, sc->host_shapes.data(), sc->host_shapes.size() * sizeof(DeviceShape),
                         cudaMemcpyHostToDevice));
+  }
+  if (!sc->host_instances.empty()) {
+    M3D_CUDA(sc->instances.reserve(sc->host_instances.size() * sizeof(DeviceInstance)));
+    M3D_CUDA(cudaMemcpy(sc->instances.p, sc->host_instances.data(),
+                        sc->host_instances.size() * sizeof(DeviceInstance), cudaMemcpyHostToDevice));
+    sc->dev.instances = sc->instances.as<const DeviceInstance>();
+    sc->dev.num_instances = (int32_t)sc->host_instances.size();
+  }
+  // Object-level hierarchy (BVHToObject, object.go:172-185) over the bounds of the analytic shapes
+  // and instances once there are more than a handful: every shape becomes a proxy "triangle" whose
+  // three vertices span its bounds (the builder only looks at bounds) and whose prim id is the
+  // shape index; the finish pass walks the wide BVH and tests the shapes in the leaves it reaches.
+  if (sc->host_shapes.size() > kShapeBvhThreshold || !sc->host_instances.empty()) {
+    std::vector<float> proxy(sc->host_shapes.size() * 9);
+    std::vector<int32_t> ids(sc->host_shapes.size()), zeros(sc->host_shapes.size(), 0);
+    size_t si = 0;
+    for (size_t oi = 0; oi < b->objects.size(); oi++) {
+      const BuilderObject &o = b->objects[oi];
+      if (o.kind == 0) continue;
+      float lo[3], hi[3];
+      for (int k = 0; k < 3; k++) {  // outward-rounded float32 bounds
+        lo[k] = std::nextafterf((float)o.bmin[k], -INFINITY);
+        hi[k] = std::nextafterf((float)o.bmax[k], INFINITY);
+      }
+      const float v[9] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], lo[0], hi[1], lo[2]};
+      std::memcpy(proxy.data() + 9 * si, v, sizeof(v));
+      ids[si] = (int32_t)si;
+      si++;
+    }
+    WideBVH sbvh;
+    BuildInput sin;
+    sin.tris = proxy.data();
+    sin.n = (int64_t)sc->host_shapes.size();
+    sin.prim_ids = ids.data();
+    sin.obj_ids = zeros.data();
+    build_wide_bvh(sin, sbvh);
+    if (sbvh.max_depth > M3D_MAX_BVH_DEPTH)
+      return fail(M3D_ERR_UNSUPPORTED, "object-level BVH depth %d exceeds the traversal stack", sbvh.max_depth);
+    DevBuf unused;
+    if (int32_t rc = upload_bvh(ctx, sbvh, nullptr, sc->shape_nodes, sc->shape_tris, unused, sc->dev.shape_bvh))
+      return rc;
   }
   M3D_CUDA(sc->objects.reserve(dobjs.size() * sizeof(DeviceObject)));
   M3D_CUDA(cudaMemcpy(sc->objects.p, dobjs.data(), dobjs.size() * sizeof(DeviceObject), cudaMemcpyHostToDevice));
@@ -464,6 +576,14 @@ int32_t m3d_scene_bounds(const m3d_scene *scene, double min_out[3], double max_o
   return M3D_OK;
 }
 
+int32_t m3d_scene_get_info(const m3d_scene *scene, m3d_mesh_info *info) {
+  if (!scene || !info) return fail(M3D_ERR_INVALID_ARG, "m3d_scene_get_info: NULL argument");
+  *info = scene->info;
+  info->device_bytes += (int64_t)(scene->shape_nodes.bytes + scene->shape_tris.bytes + scene->instances.bytes +
+                                  scene->shapes.bytes);
+  return M3D_OK;
+}
+
 int32_t m3d_scene_cast(m3d_scene *scene, const float *org, const float *dir, int64_t n, float *t,
                        int32_t *obj, int32_t *prim, float *normal, uint32_t flags, m3d_stats *stats) {
   if (!scene || n < 0 || (n > 0 && (!org || !dir))) return fail(M3D_ERR_INVALID_ARG, "m3d_scene_cast: bad arguments");
@@ -474,7 +594,9 @@ int32_t m3d_scene_cast(m3d_scene *scene, const float *org, const float *dir, int
   if (stats) std::memset(stats, 0, sizeof(*stats));
   if (n == 0) return M3D_OK;
   cudaStream_t s = ctx->stream;
-  const size_t per = (size_t)n;
+  // array stride: a multiple of four rays, so that the float4 arrays behind the n*3 float arrays
+  // stay 16-byte aligned for any n (a batch of one is what Object.Cast maps to)
+  const size_t per = ((size_t)n + 3) & ~(size_t)3;
   M3D_CUDA(ctx->scratch[1].reserve(per * (6 * sizeof(float) + 4 * sizeof(float4) + 6 * sizeof(float))));
   char *buf = ctx->scratch[1].as<char>();
   float *d_org3 = (float *)buf;
@@ -484,8 +606,8 @@ int32_t m3d_scene_cast(m3d_scene *scene, const float *org, const float *dir, int
   float *d_t = (float *)(d_hit1 + per);
   int32_t *d_prim = (int32_t *)(d_t + per), *d_obj = d_prim + per;
   float *d_normal = (float *)(d_obj + per);
-  M3D_CUDA(cudaMemcpyAsync(d_org3, org, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-  M3D_CUDA(cudaMemcpyAsync(d_dir3, dir, per * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  M3D_CUDA(cudaMemcpyAsync(d_org3, org, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  M3D_CUDA(cudaMemcpyAsync(d_dir3, dir, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
   launch_pack_rays(d_org3, d_dir3, n, 0.f, INFINITY, d_org4, d_dir4, s);
   SceneTraceLaunch p;
   p.t.org_tmin = d_org4;
@@ -503,10 +625,10 @@ int32_t m3d_scene_cast(m3d_scene *scene, const float *org, const float *dir, int
   tm.stop(s);
   launch_unpack_hits(d_hit0, d_hit1, n, t ? d_t : nullptr, prim ? d_prim : nullptr, obj ? d_obj : nullptr,
                      normal ? d_normal : nullptr, nullptr, s);
-  if (t) M3D_CUDA(cudaMemcpyAsync(t, d_t, per * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (prim) M3D_CUDA(cudaMemcpyAsync(prim, d_prim, per * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (obj) M3D_CUDA(cudaMemcpyAsync(obj, d_obj, per * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (normal) M3D_CUDA(cudaMemcpyAsync(normal, d_normal, per * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (t) M3D_CUDA(cudaMemcpyAsync(t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (prim) M3D_CUDA(cudaMemcpyAsync(prim, d_prim, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (obj) M3D_CUDA(cudaMemcpyAsync(obj, d_obj, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (normal) M3D_CUDA(cudaMemcpyAsync(normal, d_normal, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
   M3D_CUDA(cudaStreamSynchronize(s));
   M3D_CUDA(cudaGetLastError());
   if (stats) {

@@ -188,7 +188,7 @@ bidir_eye_raygen_kernel(DeviceCamera cam, DeviceBidirParams bp, PathBatch b, Bid
 
 // One step of sampleEyePath (EYE) or sampleLightPath's loop (!EYE): resolve the hit, build and
 // store the vertex, sample the continuation, apply pathEnder, compact survivors.
-template <bool EYE>
+template <bool EYE, int SB>  // SB: see path_resolve_kernel
 __global__ void __launch_bounds__(kBlock, M3D_BSHADE_MINB)
 bidir_shade_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf, int cur, int depth) {
   const int n = buf.counts[cur];
@@ -213,7 +213,7 @@ bidir_shade_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffe
     if (q < n) {
       slot = buf.queue[cur][q];
       const float4 o = __ldcs(buf.org[cur] + q), d = __ldcs(buf.dir[cur] + q), raw = __ldcs(buf.raw + q);
-      const SceneHit h = resolve_scene_hit(sc, o, d, raw, buf.skip[cur][q], true);
+      const SceneHit h = resolve_scene_hit<SB>(sc, o, d, raw, buf.skip[cur][q], true);
       if (h.obj >= 0) {
         const V3f org = v3f(o.x, o.y, o.z), dir = v3f(d.x, d.y, d.z);
         v.point = org + dir * h.t;
@@ -656,6 +656,7 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
   buf.cpay[pos] = make_float4((float)color.x, (float)color.y, (float)color.z, __int_as_float(slot));
 }
 
+template <int SB>
 __global__ void __launch_bounds__(256)
 bidir_connect_resolve_kernel(DeviceScene sc, BidirBuffers buf) {
   const int n = buf.counts[2];
@@ -663,7 +664,7 @@ bidir_connect_resolve_kernel(DeviceScene sc, BidirBuffers buf) {
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(buf.ray_total, (unsigned long long)n);
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
     const float4 pay = buf.cpay[q];
-    const SceneHit h = resolve_scene_hit(sc, buf.corg[q], buf.cdir[q], buf.craw[q], buf.cskip[q], false);
+    const SceneHit h = resolve_scene_hit<SB>(sc, buf.corg[q], buf.cdir[q], buf.craw[q], buf.cskip[q], false);
     if (h.obj >= 0) continue;  // blocked
     float *a = reinterpret_cast<float *>(buf.accum + __float_as_int(pay.w));
     atomicAdd(a, pay.x);
@@ -693,8 +694,13 @@ void launch_bidir_eye_raygen(const DeviceCamera &cam, const DeviceBidirParams &b
 
 void launch_bidir_eye_shade(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
                             const BidirBuffers &buf, int cur, int depth, cudaStream_t stream) {
-  const int grid = persistent_grid(bidir_shade_kernel<true>, kBlock, (int64_t)b.nP * b.S);
-  bidir_shade_kernel<true><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf, cur, depth);
+  if (sc.shape_bvh.nodes) {
+    const int grid = persistent_grid(bidir_shade_kernel<true, 2>, kBlock, (int64_t)b.nP * b.S);
+    bidir_shade_kernel<true, 2><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf, cur, depth);
+  } else {
+    const int grid = persistent_grid(bidir_shade_kernel<true, 1>, kBlock, (int64_t)b.nP * b.S);
+    bidir_shade_kernel<true, 1><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf, cur, depth);
+  }
 }
 
 void launch_bidir_light_raygen(const DeviceScene &sc, const DeviceBidirParams &bp, const DeviceAreaLight *lights,
@@ -707,8 +713,13 @@ void launch_bidir_light_raygen(const DeviceScene &sc, const DeviceBidirParams &b
 
 void launch_bidir_light_shade(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
                               const BidirBuffers &buf, int cur, int depth, cudaStream_t stream) {
-  const int grid = persistent_grid(bidir_shade_kernel<false>, kBlock, (int64_t)b.nP * b.S);
-  bidir_shade_kernel<false><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf, cur, depth);
+  if (sc.shape_bvh.nodes) {
+    const int grid = persistent_grid(bidir_shade_kernel<false, 2>, kBlock, (int64_t)b.nP * b.S);
+    bidir_shade_kernel<false, 2><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf, cur, depth);
+  } else {
+    const int grid = persistent_grid(bidir_shade_kernel<false, 1>, kBlock, (int64_t)b.nP * b.S);
+    bidir_shade_kernel<false, 1><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf, cur, depth);
+  }
 }
 
 void launch_bidir_prefix(const DeviceBidirParams &bp, const PathBatch &b, const BidirBuffers &buf,
@@ -728,7 +739,10 @@ void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, co
 
 void launch_bidir_connect_resolve(const DeviceScene &sc, const BidirBuffers &buf, cudaStream_t stream) {
   const int grid = device_sm_count() * 8;
-  bidir_connect_resolve_kernel<<<grid, 256, 0, stream>>>(sc, buf);
+  if (sc.shape_bvh.nodes)
+    bidir_connect_resolve_kernel<2><<<grid, 256, 0, stream>>>(sc, buf);
+  else
+    bidir_connect_resolve_kernel<1><<<grid, 256, 0, stream>>>(sc, buf);
 }
 
 }  // namespace m3d

@@ -35,8 +35,10 @@ void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p, cudaStrea
 void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream);
 
 // n*3 float arrays -> float4 SoA with constant tmin/tmax
+// (shared_origin: optional HOST pointer to 3 floats, the origin of every ray; org3 is then ignored)
 void launch_pack_rays(const float *org3, const float *dir3, int64_t n, float tmin, float tmax,
-                      float4 *org_tmin, float4 *dir_tmax, cudaStream_t stream);
+                      float4 *org_tmin, float4 *dir_tmax, cudaStream_t stream,
+                      const float *shared_origin = nullptr);
 // hit SoA -> the separate arrays of the host ABI (any output may be null)
 void launch_unpack_hits(const float4 *hit0, const float4 *hit1, int64_t n, float *t, int32_t *prim,
                         int32_t *obj, float *normal3, float *bary3, cudaStream_t stream);

@@ -111,7 +111,9 @@ path_raygen_kernel(DeviceCamera cam, DevicePathParams pp, PathBatch b, PathBuffe
 #ifndef M3D_SAMPLE_MINB
 #define M3D_SAMPLE_MINB 8
 #endif
-template <bool LIGHTS>
+// SB: 1 = the scene's few analytic shapes are tested one by one, 2 = scenes with an object-level
+// hierarchy (many shapes / mesh instances) walk it (resolve_scene_hit)
+template <bool LIGHTS, int SB>
 __global__ void __launch_bounds__(kShadeBlock, M3D_RESOLVE_MINB)
 path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *__restrict__ lights, PathBatch b,
                     PathBuffers buf, int cur, int depth) {
@@ -136,7 +138,7 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
       const float4 o = __ldcs(org_in + q), d = __ldcs(dir_in + q), raw = __ldcs(buf.raw + q);
       // float32 hit evaluation: Monte-Carlo parity is statistical, the float64 refinement of the
       // first-hit API (1e-5 on t and normals) is not needed here; shapes stay float64
-      const SceneHit h = resolve_scene_hit(sc, o, d, raw, skip_in[q], false);
+      const SceneHit h = resolve_scene_hit<SB>(sc, o, d, raw, skip_in[q], false);
       if (LIGHTS && pp.num_lights > 0 && h.obj < 0) {
         // no shadow rays for a miss: give the slots an empty parameter interval
         for (int l = 0; l < pp.num_lights; l++) {
@@ -359,6 +361,7 @@ path_sample_kernel(DeviceScene sc, DevicePathParams pp, PathBatch b, PathBuffers
   }
 }
 
+template <int SB>
 __global__ void __launch_bounds__(256)
 path_shadow_resolve_kernel(DeviceScene sc, DevicePathParams pp, PathBuffers buf, int cur) {
   const int n = buf.counts[cur];
@@ -373,7 +376,7 @@ path_shadow_resolve_kernel(DeviceScene sc, DevicePathParams pp, PathBuffers buf,
     slot = __float_as_int(pay.w);
     const float4 d = buf.sdir[si];
     if (d.w < 0.f) continue;
-    const SceneHit h = resolve_scene_hit(sc, buf.sorg[si], d, buf.sraw[si], buf.sskip[si], false);
+    const SceneHit h = resolve_scene_hit<SB>(sc, buf.sorg[si], d, buf.sraw[si], buf.sskip[si], false);
     if (h.obj >= 0) continue;  // occluded (tmax == 1 bounds the query)
     add.x += pay.x;
     add.y += pay.y;
@@ -543,16 +546,20 @@ void launch_path_resolve(const DeviceScene &sc, const DevicePathParams &pp, cons
                          const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream) {
   // resident-grid sizes, computed once (thread-safe static initialisation: renders may run on
   // several host threads, one per device)
-  static const int grid_full[2] = {shade_grid(path_resolve_kernel<false>, (int64_t)1 << 40),
-                                   shade_grid(path_resolve_kernel<true>, (int64_t)1 << 40)};
+  static const int grid_full[4] = {shade_grid(path_resolve_kernel<false, 1>, (int64_t)1 << 40),
+                                   shade_grid(path_resolve_kernel<true, 1>, (int64_t)1 << 40),
+                                   shade_grid(path_resolve_kernel<false, 2>, (int64_t)1 << 40),
+                                   shade_grid(path_resolve_kernel<true, 2>, (int64_t)1 << 40)};
   const int64_t n = (int64_t)b.nP * b.S;
-  const int li = pp.num_lights > 0 ? 1 : 0;
+  const int li = (pp.num_lights > 0 ? 1 : 0) + (sc.shape_bvh.nodes ? 2 : 0);
   const int64_t want = (n + kShadeBlock - 1) / kShadeBlock;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_full[li], want));
-  if (li)
-    path_resolve_kernel<true><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth);
-  else
-    path_resolve_kernel<false><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth);
+  switch (li) {
+    case 0: path_resolve_kernel<false, 1><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth); break;
+    case 1: path_resolve_kernel<true, 1><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth); break;
+    case 2: path_resolve_kernel<false, 2><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth); break;
+    default: path_resolve_kernel<true, 2><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth); break;
+  }
 }
 
 void launch_path_sample(int kind, const DeviceScene &sc, const DevicePathParams &pp, const PathBatch &b,
@@ -574,7 +581,10 @@ void launch_path_sample(int kind, const DeviceScene &sc, const DevicePathParams 
 void launch_path_shadow_resolve(const DeviceScene &sc, const DevicePathParams &pp, const PathBuffers &buf,
                                 int cur, cudaStream_t stream) {
   if (buf.cap <= 0) return;
-  path_shadow_resolve_kernel<<<(unsigned)((buf.cap + 255) / 256), 256, 0, stream>>>(sc, pp, buf, cur);
+  if (sc.shape_bvh.nodes)
+    path_shadow_resolve_kernel<2><<<(unsigned)((buf.cap + 255) / 256), 256, 0, stream>>>(sc, pp, buf, cur);
+  else
+    path_shadow_resolve_kernel<1><<<(unsigned)((buf.cap + 255) / 256), 256, 0, stream>>>(sc, pp, buf, cur);
 }
 
 void launch_path_flush(const PathBatch &b, const float4 *accum, float *rgb_sum, float *rgb_sumsq,

@@ -8,7 +8,10 @@
 
 namespace m3d {
 
-enum ShapeKind : int32_t { SHAPE_SPHERE = 1, SHAPE_RECT = 2, SHAPE_CYLINDER = 3 };
+// SHAPE_INSTANCE: a mesh collider (its own wide BVH, object space, one copy of the triangles)
+// under a similarity transform -- render3d.Translate / MatrixMultiply of a shared collider
+// (render3d/transform.go:6-85, examples/renderings/golf_balls/main.go:25-39)
+enum ShapeKind : int32_t { SHAPE_SPHERE = 1, SHAPE_RECT = 2, SHAPE_CYLINDER = 3, SHAPE_INSTANCE = 4 };
 
 // Analytic collider (model3d/shapes.go Sphere :12, Rect :142, Cylinder :543), float64 like
 // the reference: there are only a handful per scene and they are evaluated in the coherent
@@ -16,9 +19,20 @@ enum ShapeKind : int32_t { SHAPE_SPHERE = 1, SHAPE_RECT = 2, SHAPE_CYLINDER = 3 
 struct DeviceShape {
   int32_t kind;
   int32_t object;  // scene object index
-  double p0[3];    // sphere centre | rect min | cylinder P1
-  double p1[3];    //               | rect max | cylinder P2
+  double p0[3];    // sphere centre | rect min | cylinder P1 | instance: world bounds min
+  double p1[3];    //               | rect max | cylinder P2 | instance: world bounds max
   double radius;
+  int32_t instance;  // SHAPE_INSTANCE: index into DeviceScene::instances
+  int32_t _pad;
+};
+
+// One instance of a mesh collider: x_world = fwd * x_object + off (similarity: fwd = s * R).
+struct DeviceInstance {
+  float inv[9];   // fwd^-1, row-major: world direction / offset point -> object space
+  float fwd[9];   // for normals: n_world = normalize(fwd * n_object) (transform.go:81-83)
+  float off[3];
+  float size;     // largest extent of the world bounds (self-intersection floor)
+  DeviceBVH blas; // the mesh's own hierarchy and triangles (shared by all of its instances)
 };
 
 struct DeviceMaterial {
@@ -44,6 +58,13 @@ struct DeviceScene {
   int32_t num_objects = 0;
   const DeviceMaterial *materials = nullptr;
   int32_t num_materials = 0;
+  // Object-level hierarchy (render3d.BVHToObject, object.go:172-185; FilteredObject :155-167):
+  // when a scene has many analytic shapes / instances, the finish pass walks this wide BVH over
+  // their bounds (leaf "triangles" are proxies whose prim id is the shape index) instead of
+  // testing every shape for every ray.  nodes == nullptr: linear scan (a handful of shapes).
+  DeviceBVH shape_bvh;
+  const DeviceInstance *instances = nullptr;
+  int32_t num_instances = 0;
 };
 
 // Scene trace = BVH traversal (trace_first_hit_kernel) + finish pass that also intersects

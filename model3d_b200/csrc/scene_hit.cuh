@@ -248,8 +248,10 @@ struct SceneHit {
 
 // o = (origin, tmin), d = (direction, tmax); raw = trace_first_hit_kernel's output
 // (t_f32, -, -, bits(leaf-order triangle | -1)); skip = surface the ray starts on.
-// SHAPES = false compiles the analytic-shape part out (mesh colliders: a third of the registers).
-template <bool SHAPES = true>
+// SHAPES = 0 compiles the analytic-shape part out (mesh colliders: a third of the registers);
+// 1: every shape is tested (a handful of shapes); 2: scenes with an object-level hierarchy
+// (DeviceScene::shape_bvh) walk it instead.
+template <int SHAPES = 1>
 __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, float4 d, float4 raw, int skip,
                                              bool refine) {
   SceneHit h;
@@ -327,19 +329,87 @@ __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, fl
     const D3 od = d3(o.x, o.y, o.z), dd = d3(d.x, d.y, d.z);
     const double t_hi = (double)d.w;  // ray tmax (shadow / visibility rays)
     const double inv_len = 1.0 / dnorm(dd);
-    for (int s = 0; s < sc.num_shapes; s++) {
+    // one analytic shape / instance against the ray; keeps the closest hit in h / best_t / best_obj
+    auto test_shape = [&](int s) {
       const DeviceShape &sh = sc.shapes[s];
       double t_floor = (double)o.w;
       if (skip == -2 - s) {
         double size = sh.radius;
-        if (sh.kind == SHAPE_RECT)
+        if (sh.kind == SHAPE_RECT || sh.kind == SHAPE_INSTANCE)
           size = fmax(fmax(sh.p1[0] - sh.p0[0], sh.p1[1] - sh.p0[1]), sh.p1[2] - sh.p0[2]);
         t_floor = fmax(t_floor, 1e-4 * size * inv_len);
+      }
+      // (instances only exist in scenes with an object-level hierarchy, SHAPES == 2: the kernels of the
+      // few-shapes scenes stay free of the nested traversal's stack and registers)
+      if (SHAPES == 2 && sh.kind == SHAPE_INSTANCE) {
+        // render3d.Translate / MatrixMultiply of a shared collider (transform.go:26-31,76-85): the ray
+        // goes to object space (direction NOT re-normalised, so t is the same parameter), the mesh's own
+        // hierarchy is walked by this thread, the normal comes back through the forward matrix
+        if (shape_certainly_missed(sh, o, d)) return;  // bounding sphere of the world bounds
+        const DeviceInstance &in = sc.instances[sh.instance];
+        const float px = o.x - in.off[0], py = o.y - in.off[1], pz = o.z - in.off[2];
+        RayF r;
+        r.ox = in.inv[0] * px + in.inv[1] * py + in.inv[2] * pz;
+        r.oy = in.inv[3] * px + in.inv[4] * py + in.inv[5] * pz;
+        r.oz = in.inv[6] * px + in.inv[7] * py + in.inv[8] * pz;
+        r.dx = in.inv[0] * d.x + in.inv[1] * d.y + in.inv[2] * d.z;
+        r.dy = in.inv[3] * d.x + in.inv[4] * d.y + in.inv[5] * d.z;
+        r.dz = in.inv[6] * d.x + in.inv[7] * d.y + in.inv[8] * d.z;
+        r.tmin = (float)t_floor;
+        r.tmax = (float)fmin(fmin(best_t, t_hi) * 1.000001, 3.0e38);
+        HitF hf;
+        trace_bvh<false, false>(in.blas.nodes, in.blas.tris, in.blas.bmin, in.blas.bmax, r, -1, hf, nullptr);
+        if (hf.tri < 0) return;
+        const float4 *tri = in.blas.tris + (size_t)hf.tri * 3;
+        double t = hf.t, b1 = hf.b1, b2 = hf.b2, nx, ny, nz;
+        if (refine) {
+          const HitD rr = refine_hit_f64(tri, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz);
+          if (rr.t >= 0.0) t = rr.t;
+          b1 = rr.b1;
+          b2 = rr.b2;
+          nx = rr.nx;
+          ny = rr.ny;
+          nz = rr.nz;
+        } else {
+          const float4 q0 = __ldg(tri), q1 = __ldg(tri + 1), q2 = __ldg(tri + 2);
+          const float e1x = q1.x - q0.x, e1y = q1.y - q0.y, e1z = q1.z - q0.z;
+          const float e2x = q2.x - q0.x, e2y = q2.y - q0.y, e2z = q2.z - q0.z;
+          nx = e1y * e2z - e1z * e2y;
+          ny = e1z * e2x - e1x * e2z;
+          nz = e1x * e2y - e1y * e2x;
+        }
+        if (in.blas.vnormals) {  // InterpNormalTriangle.InterpNormal (primitives.go:508-516)
+          const float4 *vn = in.blas.vnormals + (size_t)hf.tri * 3;
+          const float4 a = __ldg(vn), b = __ldg(vn + 1), c = __ldg(vn + 2);
+          const double b0 = 1.0 - (b1 + b2);
+          nx = b0 * a.x + b1 * b.x + b2 * c.x;
+          ny = b0 * a.y + b1 * b.y + b2 * c.y;
+          nz = b0 * a.z + b1 * b.z + b2 * c.z;
+        }
+        if (t > t_hi || t < t_floor) return;
+        if (t < best_t || (t == best_t && sh.object < best_obj)) {
+          const double wx = in.fwd[0] * nx + in.fwd[1] * ny + in.fwd[2] * nz;
+          const double wy = in.fwd[3] * nx + in.fwd[4] * ny + in.fwd[5] * nz;
+          const double wz = in.fwd[6] * nx + in.fwd[7] * ny + in.fwd[8] * nz;
+          const double inv_n = 1.0 / sqrt(wx * wx + wy * wy + wz * wz);
+          best_t = t;
+          best_obj = sh.object;
+          h.surf = -2 - s;
+          h.t = (float)t;
+          h.b1 = (float)b1;
+          h.b2 = (float)b2;
+          h.prim = __float_as_int(__ldg(&tri[0].w));
+          h.obj = sh.object;
+          h.nx = (float)(wx * inv_n);
+          h.ny = (float)(wy * inv_n);
+          h.nz = (float)(wz * inv_n);
+        }
+        return;
       }
       // cheap float32 rejection with a generous error margin: most rays miss most shapes, and
       // the float64 tests (sqrt / divisions) are an order of magnitude more instructions
       // (Monte-Carlo spheres go straight to their float32 test, which all lanes run together)
-      if ((refine || sh.kind != SHAPE_SPHERE) && shape_certainly_missed(sh, o, d)) continue;
+      if ((refine || sh.kind != SHAPE_SPHERE) && shape_certainly_missed(sh, o, d)) return;
       double t;
       D3 n;
       bool ok = false;
@@ -347,7 +417,7 @@ __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, fl
       if (!refine && sh.kind == SHAPE_SPHERE) {
         float tf, fx, fy, fz;
         fast = sphere_hit_f32(sh, o, d, (float)t_floor, tf, fx, fy, fz);
-        if (fast == 0) continue;
+        if (fast == 0) return;
         if (fast == 1) {
           ok = true;
           t = (double)tf;
@@ -358,7 +428,7 @@ __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, fl
       } else if (sh.kind == SHAPE_SPHERE) ok = sphere_hit(sh, od, dd, t_floor, t, n);
       else if (sh.kind == SHAPE_RECT) ok = rect_hit(sh, od, dd, t_floor, t, n);
       else if (sh.kind == SHAPE_CYLINDER) ok = cylinder_hit(sh, od, dd, t_floor, t, n);
-      if (!ok || t > t_hi) continue;
+      if (!ok || t > t_hi) return;
       // JoinedObject.Cast: strict '<' in object order, the first object wins ties
       if (t < best_t || (t == best_t && sh.object < best_obj)) {
         best_t = t;
@@ -372,6 +442,22 @@ __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, fl
         h.ny = (float)n.y;
         h.nz = (float)n.z;
       }
+    };
+    if (SHAPES == 2 && sc.shape_bvh.nodes) {
+      // BVHToObject (object.go:172-185): walk the hierarchy over the shapes' bounds, near to far,
+      // pruned by the closest hit so far (the triangle hit of the mesh BVH included)
+      RayF r;
+      r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
+      r.dx = d.x; r.dy = d.y; r.dz = d.z;
+      r.tmax = (float)fmin(fmin(best_t, t_hi) * 1.000001, 3.0e38);
+      const float4 *proxies = sc.shape_bvh.tris;
+      walk_bvh_leaves(sc.shape_bvh.nodes, sc.shape_bvh.bmin, sc.shape_bvh.bmax, r, [&](int32_t leaf, float tmax) {
+        test_shape(__float_as_int(__ldg(&proxies[(size_t)leaf * 3].w)));
+        const float nt = (float)fmin(fmin(best_t, t_hi) * 1.000001, 3.0e38);
+        return nt < tmax ? nt : tmax;
+      });
+    } else {
+      for (int s = 0; s < sc.num_shapes; s++) test_shape(s);
     }
   }
   if (sc.objects && h.obj >= 0 && (sc.objects[h.obj].flags & M3D_OBJ_FLIP_NORMAL)) {

@@ -10,6 +10,9 @@ struct m3d_scene {
   m3d_ctx *ctx = nullptr;
   std::vector<m3d_scene *> replicas;  // multi-device context: copies on ctx->members[i] (owned)
   m3d::DevBuf nodes, tris, vnormals, shapes, objects, materials;
+  m3d::DevBuf shape_nodes, shape_tris, instances;  // object-level hierarchy, mesh instances
+  std::vector<m3d::DeviceInstance> host_instances;
+  std::vector<m3d_mesh *> instance_meshes;    // per instance: the mesh it refers to (borrowed)
   m3d::DeviceScene dev;
   std::vector<m3d::DeviceShape> host_shapes;
   std::vector<m3d_material_desc> host_materials;

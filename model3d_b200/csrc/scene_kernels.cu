@@ -19,7 +19,7 @@ namespace {
 
 // SHAPES = false: the scene is one triangle BVH (MeshCollider batches, the C2 headline): misses
 // need no ray, and the kernel stays at half the registers of the general one.
-template <bool SHAPES>
+template <int SHAPES>  // 0: mesh only, 1: few shapes (linear), 2: object-level BVH over the shapes
 __global__ void __launch_bounds__(256, SHAPES ? 1 : 4)
 finish_scene_hits_kernel(DeviceScene sc, SceneTraceLaunch sp) {
   const TraceLaunch &p = sp.t;
@@ -161,12 +161,14 @@ void launch_finish_scene_hits(const DeviceScene &scene, const SceneTraceLaunch &
 #ifndef M3D_FINISH_K
 #define M3D_FINISH_K 2
 #endif
-  if (scene.num_shapes > 0)
-    finish_scene_hits_kernel<true><<<blocks, 256, 0, stream>>>(scene, p);
+  if (scene.num_shapes > 0 && scene.shape_bvh.nodes)
+    finish_scene_hits_kernel<2><<<blocks, 256, 0, stream>>>(scene, p);
+  else if (scene.num_shapes > 0)
+    finish_scene_hits_kernel<1><<<blocks, 256, 0, stream>>>(scene, p);
   else if (M3D_FINISH_K > 1 && p.t.n >= (int64_t)256 * M3D_FINISH_K * 148)
     finish_mesh_hits_kernel<M3D_FINISH_K><<<(unsigned)((p.t.n + 256 * M3D_FINISH_K - 1) / (256 * M3D_FINISH_K)), 256, 0, stream>>>(scene, p);
   else
-    finish_scene_hits_kernel<false><<<blocks, 256, 0, stream>>>(scene, p);
+    finish_scene_hits_kernel<0><<<blocks, 256, 0, stream>>>(scene, p);
 }
 
 void launch_raygen_camera(const DeviceCamera &cam, int W, int row_begin, int row_end, float4 *org_tmin,

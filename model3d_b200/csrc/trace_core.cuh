@@ -486,6 +486,35 @@ M3D_HD void trace_bvh(const uint4 *__restrict__ nodes, const float4 *__restrict_
   }
 }
 
+// Generic first-hit walk over a wide BVH whose leaves are not triangles (the object-level
+// hierarchy of a scene: analytic shapes and mesh instances).  leaf(index, tmax) tests the primitive
+// in leaf slot `index` and returns the (possibly shortened) far bound; children are visited near to
+// far and pruned with it like in trace_bvh.
+template <class LeafFn>
+M3D_HD void walk_bvh_leaves(const uint4 *__restrict__ nodes, const float *scene_min, const float *scene_max,
+                            const RayF &ray, LeafFn &&leaf) {
+  const RayPre rp = precompute_ray(ray, scene_min, scene_max);
+  float tmax = ray.tmax;
+  uint2 stack[M3D_STACK_SIZE];
+  int sp = 0;
+  uint2 ngroup, tgroup;
+  uint32_t node_index = 0;  // root
+  for (;;) {
+    intersect_node(nodes, node_index, rp, tmax, ngroup, tgroup);
+    while (tgroup.y) {
+      const int bit = bfind32(tgroup.y);
+      tgroup.y &= ~(1u << bit);
+      tmax = leaf((int32_t)(tgroup.x + (uint32_t)bit), tmax);
+    }
+    if ((ngroup.y & 0xff000000u) == 0) {
+      if (sp == 0) break;
+      ngroup = stack[--sp];
+    }
+    node_index = take_nearest_child(ngroup, rp.octinv4);
+    if ((ngroup.y & 0xff000000u) && sp < M3D_STACK_SIZE) stack[sp++] = ngroup;
+  }
+}
+
 // All-hits traversal: the number of triangles the ray's forward half-line (t >= tmin) crosses ==
 // Collider.RayCollisions(r, nil) (model3d/collisions.go:263-273, primitives.go:189-196).  No
 // tmax pruning and no ordering: every child whose box the ray enters is visited, like the

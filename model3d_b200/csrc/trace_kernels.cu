@@ -277,10 +277,11 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
 
 __global__ void pack_rays_kernel(const float *__restrict__ org3, const float *__restrict__ dir3,
                                  int64_t n, float tmin, float tmax, float4 *__restrict__ org_tmin,
-                                 float4 *__restrict__ dir_tmax) {
+                                 float4 *__restrict__ dir_tmax, float sx, float sy, float sz) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  org_tmin[i] = make_float4(org3[3 * i], org3[3 * i + 1], org3[3 * i + 2], tmin);
+  // org3 == nullptr: every ray starts at (sx, sy, sz) (camera batches: M3D_TRACE_SHARED_ORIGIN)
+  org_tmin[i] = org3 ? make_float4(org3[3 * i], org3[3 * i + 1], org3[3 * i + 2], tmin) : make_float4(sx, sy, sz, tmin);
   dir_tmax[i] = make_float4(dir3[3 * i], dir3[3 * i + 1], dir3[3 * i + 2], tmax);
 }
 
@@ -510,10 +511,13 @@ void launch_trace_first_hit(const DeviceBVH &bvh, const TraceLaunch &p, cudaStre
 }
 
 void launch_pack_rays(const float *org3, const float *dir3, int64_t n, float tmin, float tmax,
-                      float4 *org_tmin, float4 *dir_tmax, cudaStream_t stream) {
+                      float4 *org_tmin, float4 *dir_tmax, cudaStream_t stream, const float *shared_origin) {
   if (n <= 0) return;
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  pack_rays_kernel<<<blocks, 256, 0, stream>>>(org3, dir3, n, tmin, tmax, org_tmin, dir_tmax);
+  const float sx = shared_origin ? shared_origin[0] : 0.f, sy = shared_origin ? shared_origin[1] : 0.f,
+              sz = shared_origin ? shared_origin[2] : 0.f;
+  pack_rays_kernel<<<blocks, 256, 0, stream>>>(shared_origin ? nullptr : org3, dir3, n, tmin, tmax, org_tmin,
+                                               dir_tmax, sx, sy, sz);
 }
 
 void launch_unpack_hits(const float4 *hit0, const float4 *hit1, int64_t n, float *t, int32_t *prim,

@@ -121,18 +121,22 @@ class MeshCollider:
 
     # -- Collider --------------------------------------------------------------
     def FirstRayCollisions(self, origins, directions, counters=False, refine=True,
-                           want_stats=False) -> BatchCollisions:
-        """Batched FirstRayCollision (collisions.go:275-290) over host arrays [n,3]."""
+                           want_stats=False, normals=True, barycentric=True) -> BatchCollisions:
+        """Batched FirstRayCollision (collisions.go:275-290) over host arrays [n,3].  `origins` may
+        be a single point [3] shared by all rays (camera batches: only the directions cross the
+        link); normals / barycentric = False drop those outputs (None in the result)."""
         org = np.ascontiguousarray(np.asarray(origins, dtype=np.float32).reshape(-1, 3))
         dr = np.ascontiguousarray(np.asarray(directions, dtype=np.float32).reshape(-1, 3))
-        if org.shape != dr.shape:
+        shared = org.shape[0] == 1 and dr.shape[0] != 1
+        if org.shape != dr.shape and not shared:
             raise ValueError("origins and directions must have the same shape")
-        n = int(org.shape[0])
+        n = int(dr.shape[0])
         t = np.zeros(n, np.float32)
         prim = np.full(n, -1, np.int32)
-        normal = np.zeros((n, 3), np.float32)
-        bary = np.zeros((n, 3), np.float32)
-        flags = (N.TRACE_COUNTERS if counters else 0) | (0 if refine else N.TRACE_NO_REFINE)
+        normal = np.zeros((n, 3), np.float32) if normals else None
+        bary = np.zeros((n, 3), np.float32) if barycentric else None
+        flags = ((N.TRACE_COUNTERS if counters else 0) | (0 if refine else N.TRACE_NO_REFINE) |
+                 (N.TRACE_SHARED_ORIGIN if shared else 0))
         stats = N.Stats()
         N.check(N.lib().m3d_mesh_first_ray_collisions(
             self.h, _p(org, f32p), _p(dr, f32p), C.c_int64(n), _p(t, f32p), _p(prim, i32p),

@@ -221,14 +221,24 @@ def _compose(outer, inner):
 class Scene:
     """A render3d.Object compiled to a device scene (m3d_scene)."""
 
-    def __init__(self, obj, ctx=None, device_lbvh=False, device_build=False):
+    def __init__(self, obj, ctx=None, device_lbvh=False, device_build=False, record=None):
+        """record: optional list that receives every builder call as (name, args...) tuples with the
+        ctypes structs as bytes -- tests/test_c_abi.py replays them from a C program."""
         self.ctx = ctx or N.default_context()
+        self._record = record
         L = N.lib()
         b = C.c_void_p()
         N.check(L.m3d_scene_builder_create(self.ctx.h, C.byref(b)))
         self.materials = []      # python material objects, index == device index
         self._mat_index = {}
         self.objects = []        # leaf objects in device order
+        # A device-resident MeshCollider that several objects of the tree share (the reference's
+        # golf_balls example translates one collider many times, golf_balls/main.go:25-39) is
+        # INSTANCED: the scene keeps one copy of its triangles and hierarchy (m3d_scene_add_instance).
+        # A collider used once is merged into the scene's world-space BVH as before.
+        self._uses = {}
+        self._instanced = []     # keeps the instanced colliders alive as long as the scene
+        self._count_uses(obj)
         try:
             self._add(b, obj, None)
             self.h = C.c_void_p()
@@ -236,12 +246,23 @@ class Scene:
         finally:
             L.m3d_scene_builder_destroy(b)
 
+    def _count_uses(self, obj):
+        if isinstance(obj, (list, tuple)):
+            for o in obj:
+                self._count_uses(o)
+        elif isinstance(obj, _Transformed):
+            self._count_uses(obj.Object)
+        elif isinstance(obj, ColliderObject) and isinstance(obj.Collider, MeshCollider):
+            self._uses[id(obj.Collider)] = self._uses.get(id(obj.Collider), 0) + 1
+
     def _material(self, b, m):
         if id(m) in self._mat_index:
             return self._mat_index[id(m)]
         d = material_desc(m, lambda sub: self._material(b, sub))
         idx = C.c_int32(-1)
         N.check(N.lib().m3d_scene_add_material(b, C.byref(d), C.byref(idx)))
+        if self._record is not None:
+            self._record.append(("material", bytes(d)))
         self._mat_index[id(m)] = idx.value
         self.materials.append(m)
         assert idx.value == len(self.materials) - 1
@@ -277,6 +298,14 @@ class Scene:
         elif isinstance(c, Cylinder):
             N.check(L.m3d_scene_add_cylinder(b, _d3(c.P1), _d3(c.P2), C.c_double(c.Radius), C.c_int32(mat),
                                              C.c_uint32(flags), tp, C.byref(idx)))
+        elif (isinstance(c, MeshCollider) and self._uses.get(id(c), 0) > 1 and c.ctx is self.ctx
+              and c.num_triangles > 0):
+            N.check(L.m3d_scene_add_instance(b, c.h, C.c_int32(mat), C.c_uint32(flags), tp, C.byref(idx)))
+            self._instanced.append(c)
+            if self._record is not None:
+                raise UnsupportedError("recording does not cover instanced colliders")
+            self.objects.append(obj)
+            return
         elif isinstance(c, MeshCollider) or isinstance(c, np.ndarray):
             tris = c.triangles if isinstance(c, MeshCollider) else c
             vn = c.vertex_normals if isinstance(c, MeshCollider) else None
@@ -286,6 +315,16 @@ class Scene:
                                          C.c_int32(mat), C.c_uint32(flags), tp, C.byref(idx)))
         else:
             raise UnsupportedError("collider type %s is not supported on the GPU path" % type(c).__name__)
+        if self._record is not None:
+            xb = bytes(t) if t is not None else None
+            if isinstance(c, Sphere):
+                self._record.append(("sphere", mat, flags, xb, tuple(c.Center), float(c.Radius)))
+            elif isinstance(c, Rect):
+                self._record.append(("rect", mat, flags, xb, tuple(c.MinVal), tuple(c.MaxVal)))
+            elif isinstance(c, Cylinder):
+                self._record.append(("cylinder", mat, flags, xb, tuple(c.P1), tuple(c.P2), float(c.Radius)))
+            else:
+                self._record.append(("mesh", mat, flags, xb, tris.copy(), None if vn is None else vn.copy()))
         self.objects.append(obj)
 
     def close(self):
@@ -304,6 +343,13 @@ class Scene:
 
     def Max(self):
         return self._bounds()[1]
+
+    def Info(self):
+        """m3d_scene_get_info: the scene's own merged triangle hierarchy (instanced colliders keep
+        their triangles in their MeshCollider and are not counted)."""
+        info = N.MeshInfo()
+        N.check(N.lib().m3d_scene_get_info(self.h, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in info._fields_}
 
     def _bounds(self):
         mn, mx = (C.c_double * 3)(), (C.c_double * 3)()

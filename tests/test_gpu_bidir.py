@@ -74,11 +74,16 @@ def test_bidir_cornell_box_c5_literal_parameters(built, oracle):
     ref = oracle_bidir(oracle, spec, osc, W, H, 1024, **bench.C5_KW)
     mean, var, stats = gpu_bidir(spec, psc, W, H, 4096, **bench.C5_KW)
     assert ref["mean"].mean() > 0.05
-    check_statistical_parity(mean, var, ref["mean"], ref["var_of_mean"])
+    # Measured on B200 (scripts/c5_bias_check.py, 32x32, 32768 vs 4096 spp): the GPU BDPT image mean is
+    # 0.9124 +- 0.0002, the oracle's BDPT 0.9108 +- 0.0006, the path tracers of both 0.9118 / 0.9120 --
+    # i.e. GPU BDPT +0.07 % and oracle BDPT -0.13 % around the path-traced value, all far inside the
+    # 0.02 the reference's own BDPT test allows (bidir_test.go:57-63).  At 1024 oracle samples that
+    # 0.18 % shows up as a mean z of 0.17, hence the wider bound on the mean z here.
+    check_statistical_parity(mean, var, ref["mean"], ref["var_of_mean"], max_mean_z=0.3)
     # eye sub-paths up to depth 10 and light sub-paths up to depth 10 really ran
     assert stats["rays"] > W * H * 4096 * 4
     # image means agree to Monte-Carlo accuracy (a biased deep-path weight would show here)
-    assert abs(mean.mean() - ref["mean"].mean()) < 0.01 * ref["mean"].mean() + 4 * np.sqrt(var.sum() + ref["var_of_mean"].sum()) / mean.size
+    assert abs(mean.mean() - ref["mean"].mean()) < 0.005 * ref["mean"].mean() + 4 * np.sqrt(var.sum() + ref["var_of_mean"].sum()) / mean.size
 
 
 def test_bidir_glass_scene_dirac_lobes(built, oracle):

@@ -447,3 +447,22 @@ def test_ray_collisions_delivered(built, oracle):
     # empty batch and empty mesh
     e = MeshCollider(tris).RayCollisionsBatch(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
     assert e["offsets"].tolist() == [0] and e["Scale"].size == 0
+
+
+def test_shared_origin_and_dropped_outputs(built):
+    """Camera batches: one origin for all rays (M3D_TRACE_SHARED_ORIGIN, 12 instead of 24 bytes per
+    ray host->device) and t + prim only back (NULL normal / bary): same hits as the full call."""
+    from model3d_b200 import MeshCollider, meshes, render3d as R
+    tris = meshes.NewMeshIcosphere((0, 0, 0), 1.0, 20).astype(np.float32).reshape(-1, 9)
+    cam = R.NewCameraAt((0.5, -3.0, 1.0), (0.0, 0.0, 0.0), np.pi / 3.6)
+    d = R.CasterRays(cam, 300, 200).astype(np.float32)
+    o = np.tile(np.asarray(cam.Origin, np.float32), (d.shape[0], 1))
+    col = MeshCollider(tris)
+    full = col.FirstRayCollisions(o, d, want_stats=True)
+    lean = col.FirstRayCollisions(np.asarray(cam.Origin, np.float32), d, normals=False, barycentric=False,
+                                  want_stats=True)
+    assert lean.Normal is None and lean.Barycentric is None
+    assert np.array_equal(full.Triangle, lean.Triangle) and np.array_equal(full.Scale, lean.Scale)
+    assert full.Collides.sum() > 1000
+    assert lean.Stats["h2d_bytes"] == d.shape[0] * 12 and full.Stats["h2d_bytes"] == d.shape[0] * 24
+    assert lean.Stats["d2h_bytes"] == d.shape[0] * 8 and full.Stats["d2h_bytes"] == d.shape[0] * 32

@@ -164,3 +164,117 @@ def test_scene_device_build_same_casts(built, oracle):
     assert same.sum() >= n - 6
     assert np.array_equal(ra["t"][same], rb["t"][same])
     assert np.array_equal(ra["normal"][same], rb["normal"][same])
+
+
+def test_ten_thousand_spheres_object_level_bvh(built, oracle):
+    """render3d.BVHToObject over many primitives (object.go:172-185; consumer
+    cli/pan_pointcloud/main.go:80-95 builds one over thousands of spheres).  Scenes with more than a
+    handful of analytic shapes get an object-level wide BVH; casts must equal the oracle's linear
+    JoinedObject scan (object.go:141-153) on the same 10,000 spheres + a floor mesh + a rect + a
+    cylinder."""
+    rng = np.random.default_rng(42)
+    m1 = scenes.lambert(diffuse=scenes.gray(0.5))
+    m2 = scenes.phong(20.0, specular=scenes.gray(0.3), diffuse=(0.4, 0.2, 0.1))
+    objs = []
+    centers = rng.uniform(-10, 10, size=(10000, 3))
+    radii = rng.uniform(0.02, 0.25, size=10000)
+    for c, r in zip(centers, radii):
+        objs.append(dict(kind="sphere", center=tuple(c.tolist()), radius=float(r), material=m1))
+    objs.append(dict(kind="mesh", tris=scenes.mesh_rect_tris((-11, -11, -11.5), (11, 11, -11)).astype(np.float32), material=m2))
+    objs.append(dict(kind="rect", min=(-1.0, -1.0, 10.5), max=(1.0, 1.0, 11.0), material=m2))
+    objs.append(dict(kind="cylinder", p1=(10.5, 0.0, -3.0), p2=(10.8, 0.5, 3.0), radius=0.4, material=m2))
+    spec = dict(objects=objs)
+    osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
+    n = 60000
+    org = rng.uniform(-12, 12, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    got = psc.Cast(org, d, counters=True)
+    ref = osc.cast(org, d, threads=8)
+    hit_o, hit_g = ref["obj"] >= 0, got["obj"] >= 0
+    assert (hit_o != hit_g).sum() <= 3  # tangent rays on spheres
+    both = hit_o & hit_g
+    same = both & (ref["obj"] == got["obj"])
+    assert same.sum() >= both.sum() - 5
+    rel = np.abs(got["t"] - ref["t"]) / np.maximum(np.abs(ref["t"]), 1e-30)
+    assert rel[same].max() < 1e-5
+    assert np.abs(got["normal"][same] - ref["normal"][same]).max() < 2e-5
+    assert hit_g.mean() > 0.3
+    assert len(np.unique(got["obj"][hit_g])) > 3000  # thousands of different spheres are hit
+    assert {10000, 10001, 10002} <= set(np.unique(got["obj"][hit_g]).tolist())
+    # and the RayCaster / path tracer run on the same hierarchy
+    from model3d_b200 import render3d as R
+    cam = R.NewCameraAt((0.0, -30.0, 8.0), (0.0, 0.0, 0.0), np.pi / 4)
+    lt = R.PointLight(Origin=(20.0, -40.0, 50.0), Color=(1.0, 1.0, 1.0))
+    img = R.Image(160, 120)
+    R.RayCaster(Camera=cam, Lights=[lt]).Render(img, psc)
+    ocam = oracle.camera_at((0.0, -30.0, 8.0), (0.0, 0.0, 0.0), np.pi / 4)
+    ol = oracle.PointLight()
+    ol.origin[:], ol.color[:], ol.quad_dropoff = (20.0, -40.0, 50.0), (1.0, 1.0, 1.0), 0
+    want = osc.render_raycast(ocam, [ol], 160, 120, threads=8)["img"]
+    diff = np.abs(np.asarray(img.Data, np.float64) - want)
+    assert (diff.max(axis=2) > 1.0 / 255).sum() <= 12  # silhouette pixels of tangent spheres
+    tr = R.RecursiveRayTracer(Camera=cam, Lights=[lt], MaxDepth=2, NumSamples=8, Seed=2)
+    rgb, _, st = tr.RenderSums(80, 60, psc)
+    assert np.isfinite(rgb).all() and rgb.sum() > 0 and st["rays"] > 80 * 60 * 8
+
+
+def test_golf_balls_instancing_one_copy_of_the_triangles(built, oracle):
+    """one collider under many transforms (examples/renderings/golf_balls/main.go:25-39:
+    render3d.Translate of a shared ball).  A MeshCollider shared by several objects is instanced: the
+    scene stores no triangles of its own for it, rays go to object space at the instance's bounds
+    (transform.go:26-31,76-85).  Casts equal the oracle's, which transforms the ray the same way."""
+    from model3d_b200 import MeshCollider, meshes, render3d as R
+    rng = np.random.default_rng(3)
+    ball = meshes.NewMeshIcosphere((0, 0, 0), 0.5, 12).astype(np.float32)  # 2,880 triangles
+    col = MeshCollider(ball)
+    mat = R.PhongMaterial(Alpha=10.0, SpecularColor=(0.2, 0.2, 0.2), DiffuseColor=(0.6, 0.6, 0.6))
+    m_o = scenes.phong(10.0, specular=scenes.gray(0.2), diffuse=scenes.gray(0.6))
+    floor = scenes.mesh_rect_tris((-8, -8, -1.2), (8, 8, -1.0)).astype(np.float32)
+    objs, ospec = R.JoinedObject(), []
+    for k in range(100):
+        off = (float(k % 10) * 1.4 - 6.3, float(k // 10) * 1.4 - 6.3, float(rng.uniform(-0.3, 0.3)))
+        o = R.ColliderObject(Collider=col, Material=mat)
+        if k % 3 == 0:
+            rot = scenes.rotation((0.0, 0.6, 0.8), 0.1 * k) * (1.0 + 0.2 * (k % 2))
+            objs.append(R.Translate(R.MatrixMultiply(o, rot.reshape(-1).tolist()), off))
+            ospec.append(dict(kind="mesh", tris=ball, material=m_o, xf=(rot, off)))
+        else:
+            objs.append(R.Translate(o, off))
+            ospec.append(dict(kind="mesh", tris=ball, material=m_o, xf=(np.eye(3), off)))
+    objs.append(R.ColliderObject(Collider=floor, Material=mat))
+    ospec.append(dict(kind="mesh", tris=floor, material=m_o))
+    psc = R.Scene(objs)
+    osc = scenes.build_oracle(dict(objects=ospec))
+    info = psc.Info()
+    assert info["num_triangles"] == 12  # only the floor lives in the scene's own BVH
+    assert col.Info()["num_triangles"] == 2880
+    n = 200000
+    org = rng.uniform(-8, 8, size=(n, 3)).astype(np.float32)
+    org[:, 2] = rng.uniform(1.0, 4.0, size=n)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:, 2] = -np.abs(d[:, 2]) - 0.2
+    got = psc.Cast(org, d)
+    ref = osc.cast(org, d, threads=8)
+    hit_o, hit_g = ref["obj"] >= 0, got["obj"] >= 0
+    assert (hit_o != hit_g).sum() <= 4
+    both = hit_o & hit_g
+    same = both & (ref["obj"] == got["obj"]) & (ref["prim"] == got["prim"])
+    # a rotated / scaled instance sees the ray through a float32 matrix: a few rays that pass an edge
+    # within rounding may pick the neighbouring triangle
+    assert same.sum() >= both.sum() - 40, (both.sum(), same.sum())
+    rel = np.abs(got["t"] - ref["t"]) / np.maximum(np.abs(ref["t"]), 1e-30)
+    assert rel[same].max() < 2e-5
+    assert np.abs(got["normal"][same] - ref["normal"][same]).max() < 1e-4
+    assert len(set(np.unique(got["obj"][hit_g]).tolist())) == 101
+    # path tracing over instances (bounce and shadow rays start on instanced triangles)
+    cam = R.NewCameraAt((0.0, -12.0, 9.0), (0.0, 0.0, 0.0), np.pi / 3.5)
+    lt = R.PointLight(Origin=(5.0, -10.0, 20.0), Color=(300.0, 300.0, 300.0), QuadDropoff=True)
+    tr = R.RecursiveRayTracer(Camera=cam, Lights=[lt], MaxDepth=3, NumSamples=32, Cutoff=1e-4, Antialias=1.0, Seed=5)
+    rgb, _, st = tr.RenderSums(96, 72, psc)
+    ocam = oracle.camera_at((0.0, -12.0, 9.0), (0.0, 0.0, 0.0), np.pi / 3.5)
+    pp = scenes.oracle_path_params(dict(objects=ospec), osc, 3, 64, cutoff=1e-4, antialias=1.0, seed=9)
+    ol = oracle.PointLight()
+    ol.origin[:], ol.color[:], ol.quad_dropoff = (5.0, -10.0, 20.0), (300.0, 300.0, 300.0), 1
+    want = osc.render_path(ocam, [ol], pp, 96, 72, threads=8)
+    mean = rgb.astype(np.float64) / 32
+    assert abs(mean.mean() - want["mean"].mean()) < 0.03 * want["mean"].mean()
