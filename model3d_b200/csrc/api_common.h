@@ -85,6 +85,7 @@ struct m3d_ctx {
   m3d::DevBuf scratch[14];
   m3d::DevBuf counters;       // [0..3] node/triangle statistics, then kWorkSlots work counters
   unsigned work_slot = 0;
+  std::vector<char> host_stage;  // small per-call tables staged for async uploads (light lists)
   int64_t bidir_carved_key = -1, bidir_carved_cap = 0;  // depths / batch size scratch[6] was last carved for
   static constexpr int kWorkSlots = 64;
   // Every entry point that touches scratch / streams / counters holds this lock for the whole

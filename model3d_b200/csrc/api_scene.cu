@@ -645,9 +645,12 @@ int32_t m3d_scene_cast(m3d_scene *scene, const float *org, const float *dir, int
   return M3D_OK;
 }
 
+// sync = false: the caller synchronises the stream itself before it returns (the host-buffer call
+// waits once, after its device-to-host copy, instead of twice per frame)
 static int32_t raycast_one_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
                                   int32_t num_lights, int32_t width, int32_t height,
-                                  const m3d_partition *part, void *d_rgb, void *stream, m3d_stats *stats);
+                                  const m3d_partition *part, void *d_rgb, void *stream, m3d_stats *stats,
+                                  bool sync = true);
 
 int32_t m3d_render_raycast_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
                                   int32_t num_lights, int32_t width, int32_t height,
@@ -682,7 +685,8 @@ int32_t m3d_render_raycast_device(m3d_scene *scene, const m3d_camera *cam, const
 
 static int32_t raycast_one_device(m3d_scene *scene, const m3d_camera *cam, const m3d_point_light *lights,
                                   int32_t num_lights, int32_t width, int32_t height,
-                                  const m3d_partition *part, void *d_rgb, void *stream, m3d_stats *stats) {
+                                  const m3d_partition *part, void *d_rgb, void *stream, m3d_stats *stats,
+                                  bool sync) {
   m3d_ctx *ctx = scene->ctx;
   M3D_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
@@ -700,7 +704,12 @@ static int32_t raycast_one_device(m3d_scene *scene, const m3d_camera *cam, const
   float4 *d_org4 = ctx->scratch[2].as<float4>();
   float4 *d_dir4 = d_org4 + n, *d_hit0 = d_dir4 + n, *d_hit1 = d_hit0 + n;
   DevicePointLight *d_lights = (DevicePointLight *)(d_hit1 + n);
-  std::vector<DevicePointLight> hl(num_lights);
+  // the light table is staged in context-owned host memory so that it outlives the async copy
+  // without a synchronisation of its own (calls on a context are serialised by its lock, and every
+  // call waits for the stream before it returns)
+  std::vector<char> &stage = ctx->host_stage;
+  stage.resize(std::max<size_t>(stage.size(), (size_t)(num_lights + 1) * sizeof(DevicePointLight)));
+  DevicePointLight *hl = reinterpret_cast<DevicePointLight *>(stage.data());
   for (int i = 0; i < num_lights; i++) {
     for (int k = 0; k < 3; k++) {
       hl[i].origin[k] = (float)lights[i].origin[k];
@@ -709,7 +718,7 @@ static int32_t raycast_one_device(m3d_scene *scene, const m3d_camera *cam, const
     hl[i].quad_dropoff = lights[i].quad_dropoff;
   }
   if (num_lights)
-    M3D_CUDA(cudaMemcpyAsync(d_lights, hl.data(), hl.size() * sizeof(DevicePointLight), cudaMemcpyHostToDevice, s));
+    M3D_CUDA(cudaMemcpyAsync(d_lights, hl, (size_t)num_lights * sizeof(DevicePointLight), cudaMemcpyHostToDevice, s));
   const DeviceCamera dc = make_device_camera(*cam, width, height);
   GpuTimer tm;
   tm.start(s);
@@ -728,8 +737,7 @@ static int32_t raycast_one_device(m3d_scene *scene, const m3d_camera *cam, const
   launch_shade_raycast(scene->dev, dc, d_lights, num_lights, d_org4, d_dir4, d_hit0, d_hit1, n,
                        (float *)d_rgb + (size_t)row_begin * width * 3, s);
   tm.stop(s);
-  // the host-side light table must outlive the async copy
-  M3D_CUDA(cudaStreamSynchronize(s));
+  if (sync || stats) M3D_CUDA(cudaStreamSynchronize(s));
   M3D_CUDA(cudaGetLastError());
   if (stats) {
     stats->rays = n;
@@ -750,8 +758,12 @@ int32_t m3d_render_raycast(m3d_scene *scene, const m3d_camera *cam, const m3d_po
   M3D_CUDA(ctx->scratch[3].reserve(bytes));
   // pixels whose ray misses keep their previous value (raycast.go:26-28): start from the caller's image
   M3D_CUDA(cudaMemcpyAsync(ctx->scratch[3].p, rgb, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  int32_t rc = m3d_render_raycast_device(scene, cam, lights, num_lights, width, height, part, ctx->scratch[3].p,
-                                         ctx->stream, stats);
+  // one device, or the multi-device dispatch for large frames (which waits for its members)
+  const bool multi = !scene->replicas.empty() && (int64_t)width * height >= ((int64_t)1 << 21);
+  int32_t rc = multi ? m3d_render_raycast_device(scene, cam, lights, num_lights, width, height, part,
+                                                 ctx->scratch[3].p, ctx->stream, stats)
+                     : raycast_one_device(scene, cam, lights, num_lights, width, height, part, ctx->scratch[3].p,
+                                          ctx->stream, stats, /*sync=*/false);
   if (rc != M3D_OK) return rc;
   M3D_CUDA(cudaMemcpyAsync(rgb, ctx->scratch[3].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   M3D_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -2,6 +2,7 @@
 image.go:55-172, camera.go:84-98).  Host-side pieces run on CPU; the renderings themselves
 are GPU tests against the oracle's RayCaster."""
 import math
+import os
 import struct
 import zlib
 
@@ -153,3 +154,27 @@ def test_random_grid_and_rotating_gif(built, oracle, tmp_path):
     ref_img.Data = ref.astype(np.float32)
     diff = np.abs(frames[k].astype(int) - ref_img.Gray8().astype(int))
     assert (diff > 2).sum() <= 40, (diff > 2).sum()  # float32-rotated vertices move silhouettes by < 1 px
+
+
+def test_render_stl_cli_arguments():
+    """cli/render_stl (main.go:17-40): same flags and defaults; a missing operand is a usage error."""
+    from model3d_b200.cli import render_stl
+    with pytest.raises(SystemExit):
+        render_stl.main(["only_one_operand.stl"])
+
+
+@pytest.mark.gpu
+def test_render_stl_cli_on_the_reference_stl(built, tmp_path):
+    """The command end to end on the reference's cornell_box/diamond.stl: STL file -> device BVH ->
+    3x3 grid PNG and a rotating GIF (cli/render_stl/main.go:42-77)."""
+    from model3d_b200.cli import render_stl
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_cornell_box_diamond.stl")
+    png, gif = str(tmp_path / "grid.png"), str(tmp_path / "spin.gif")
+    assert render_stl.main(["--grid-size", "3", "--image-size", "64", "--seed", "1", src, png]) == 0
+    assert render_stl.main(["--image-size", "48", "--frames", "5", "--device-build", src, gif]) == 0
+    raw = open(png, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    import struct
+    w, h = struct.unpack(">II", raw[16:24])
+    assert (w, h) == (192, 192)
+    assert open(gif, "rb").read()[:6] in (b"GIF89a", b"GIF87a")
