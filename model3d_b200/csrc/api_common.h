@@ -139,8 +139,15 @@ inline void split_range(int64_t n, int parts, int i, int64_t *begin, int64_t *en
 // Device LBVH (lbvh.cu): binary hierarchy from Morton codes, downloaded for the wide collapse.
 int32_t lbvh_build_binary(m3d_ctx *ctx, const float *tris, int64_t n, std::vector<BinaryNode> &nodes,
                           std::vector<int32_t> &order, int32_t *root_out, double *device_ms);
+// Where a device build leaves its arrays when they are to stay on the device (lbvh_build_wide).
+struct ResidentBVH {
+  DevBuf *nodes = nullptr, *tris = nullptr, *vnormals = nullptr;
+  const float *vnormals_by_prim = nullptr;  // optional host n*9 per-corner normals, caller order
+  int64_t num_nodes = 0, num_tris = 0;
+};
 // Full device build (lbvh.cu): LBVH + cost-optimal 8-wide collapse + node emission on the device.
-int32_t lbvh_build_wide(m3d_ctx *ctx, const BuildInput &in, double cost_prim_value, WideBVH &out);
+int32_t lbvh_build_wide(m3d_ctx *ctx, const BuildInput &in, double cost_prim_value, WideBVH &out,
+                        ResidentBVH *resident = nullptr);
 // Builds the compressed wide BVH with the builder build_flags selects.
 int32_t build_bvh_with_flags(m3d_ctx *ctx, const BuildInput &in, uint32_t build_flags, WideBVH &out);
 // uploads a built BVH (and optional per-corner normals in caller order, remapped to leaf order)

@@ -192,16 +192,44 @@ int32_t m3d_mesh_create(m3d_ctx *ctx, const float *tris, int64_t n, const float 
   BuildInput in;
   in.tris = tris;
   in.n = n;
-  if (int32_t rc = build_bvh_with_flags(ctx, in, build_flags, bvh)) return rc;
   auto *m = new m3d_mesh();
   m->ctx = ctx;
-  int32_t rc = upload_bvh(ctx, bvh, vnormals, m->nodes, m->tris, m->vnormals, m->bvh);
-  if (rc != M3D_OK) {
-    delete m;
-    return rc;
+  int64_t num_nodes = 0;
+  if ((build_flags & M3D_MESH_BUILD_DEVICE_COLLAPSE) && n > 0) {
+    // whole build on the device, arrays stay there (no round trip through the host)
+    ResidentBVH res;
+    res.nodes = &m->nodes;
+    res.tris = &m->tris;
+    res.vnormals = &m->vnormals;
+    res.vnormals_by_prim = vnormals;
+    if (int32_t rc = lbvh_build_wide(ctx, in, bvh_cost_prim(), bvh, &res)) {
+      delete m;
+      return rc;
+    }
+    m->bvh.nodes = m->nodes.as<const uint4>();
+    m->bvh.tris = m->tris.as<const float4>();
+    m->bvh.vnormals = vnormals ? m->vnormals.as<const float4>() : nullptr;
+    m->bvh.num_nodes = res.num_nodes;
+    m->bvh.num_tris = res.num_tris;
+    for (int k = 0; k < 3; k++) {
+      m->bvh.bmin[k] = bvh.bounds_min[k];
+      m->bvh.bmax[k] = bvh.bounds_max[k];
+    }
+    num_nodes = res.num_nodes;
+  } else {
+    if (int32_t rc = build_bvh_with_flags(ctx, in, build_flags, bvh)) {
+      delete m;
+      return rc;
+    }
+    int32_t rc = upload_bvh(ctx, bvh, vnormals, m->nodes, m->tris, m->vnormals, m->bvh);
+    if (rc != M3D_OK) {
+      delete m;
+      return rc;
+    }
+    num_nodes = (int64_t)bvh.nodes.size();
   }
   m->info.num_triangles = n;
-  m->info.num_nodes = (int64_t)bvh.nodes.size();
+  m->info.num_nodes = num_nodes;
   m->info.node_bytes = sizeof(WideNode);
   m->info.tri_bytes = sizeof(TriRecord);
   m->info.device_bytes = (int64_t)(m->nodes.bytes + m->tris.bytes + m->vnormals.bytes);

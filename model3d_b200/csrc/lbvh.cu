@@ -488,7 +488,22 @@ namespace m3d {
 // resident is a later optimisation).  Node and triangle ranges are handed out with atomics, so
 // the memory order of the nodes of one level may differ from run to run; slots, child order and
 // therefore traversal order and hits do not.
-int32_t lbvh_build_wide(m3d_ctx *ctx, const BuildInput &in, double cost_prim_value, WideBVH &out) {
+// n*9 per-corner normals in caller (prim id) order -> 3 x float4 per triangle in leaf order
+// (what upload_bvh does on the host for the other builders)
+__global__ void lbvh_gather_vnormals_kernel(const TriRecord *__restrict__ wtris, const float *__restrict__ vn_by_prim,
+                                            int n, float4 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *src = vn_by_prim + (size_t)wtris[i].prim * 9;
+  for (int k = 0; k < 3; k++) out[(size_t)i * 3 + k] = make_float4(src[3 * k], src[3 * k + 1], src[3 * k + 2], 0.f);
+}
+
+// resident != nullptr: the finished node / triangle arrays (and the leaf-ordered vertex normals) stay on
+// the device -- device-to-device copies into the mesh's own buffers -- and `out` only carries the
+// counts, bounds, depth and cost; the 56 MB round trip through the host that the shared upload path
+// costs (22 of 46 ms per million triangles) is gone.
+int32_t lbvh_build_wide(m3d_ctx *ctx, const BuildInput &in, double cost_prim_value, WideBVH &out,
+                        ResidentBVH *resident) {
   const int n = (int)in.n;
   cudaStream_t s = ctx->stream;
   const size_t b_tris = (size_t)n * 9 * 4, b_boxes = (size_t)n * 6 * 4, b_keys = (size_t)n * 8, b_ids = (size_t)n * 4;
@@ -561,12 +576,28 @@ int32_t lbvh_build_wide(m3d_ctx *ctx, const BuildInput &in, double cost_prim_val
   }
   M3D_CUDA(cudaGetLastError());
   const int num_wide = end;
-  out.nodes.resize((size_t)num_wide);
-  out.tris.resize((size_t)n);
   BinaryNode root_node;
   float root_cost = 0;
-  M3D_CUDA(cudaMemcpyAsync(out.nodes.data(), d_wide, (size_t)num_wide * sizeof(WideNode), cudaMemcpyDeviceToHost, s));
-  M3D_CUDA(cudaMemcpyAsync(out.tris.data(), d_wtris, (size_t)n * sizeof(TriRecord), cudaMemcpyDeviceToHost, s));
+  if (resident) {
+    M3D_CUDA(resident->nodes->reserve((size_t)num_wide * sizeof(WideNode)));
+    M3D_CUDA(resident->tris->reserve((size_t)n * sizeof(TriRecord)));
+    M3D_CUDA(cudaMemcpyAsync(resident->nodes->p, d_wide, (size_t)num_wide * sizeof(WideNode), cudaMemcpyDeviceToDevice, s));
+    M3D_CUDA(cudaMemcpyAsync(resident->tris->p, d_wtris, (size_t)n * sizeof(TriRecord), cudaMemcpyDeviceToDevice, s));
+    if (resident->vnormals_by_prim) {
+      // the build scratch is free again: stage the caller-order normals in it
+      float *d_vn = (float *)(p + o_tris);  // n*9 floats, the size of the triangle upload
+      M3D_CUDA(resident->vnormals->reserve((size_t)n * 3 * sizeof(float4)));
+      M3D_CUDA(cudaMemcpyAsync(d_vn, resident->vnormals_by_prim, b_tris, cudaMemcpyHostToDevice, s));
+      lbvh_gather_vnormals_kernel<<<blocks, 256, 0, s>>>(d_wtris, d_vn, n, resident->vnormals->as<float4>());
+    }
+    resident->num_nodes = num_wide;
+    resident->num_tris = n;
+  } else {
+    out.nodes.resize((size_t)num_wide);
+    out.tris.resize((size_t)n);
+    M3D_CUDA(cudaMemcpyAsync(out.nodes.data(), d_wide, (size_t)num_wide * sizeof(WideNode), cudaMemcpyDeviceToHost, s));
+    M3D_CUDA(cudaMemcpyAsync(out.tris.data(), d_wtris, (size_t)n * sizeof(TriRecord), cudaMemcpyDeviceToHost, s));
+  }
   M3D_CUDA(cudaMemcpyAsync(&root_node, d_nodes, sizeof(BinaryNode), cudaMemcpyDeviceToHost, s));
   M3D_CUDA(cudaMemcpyAsync(&root_cost, d_cost, 4, cudaMemcpyDeviceToHost, s));
   M3D_CUDA(cudaStreamSynchronize(s));

@@ -161,6 +161,10 @@ def test_interp_normal_collider(built, oracle):
     org, d = rays(rng, 50000)
     got = MeshToInterpNormalCollider(tris, vn).FirstRayCollisions(org, d)
     check_parity(oracle, tris, org, d, got, vnormals=vn.astype(np.float32))
+    # the full device build keeps its arrays on the device and gathers the normals into leaf order there
+    from model3d_b200 import MeshCollider
+    dev = MeshCollider(tris, vertex_normals=vn, device_build=True).FirstRayCollisions(org, d)
+    check_parity(oracle, tris, org, d, dev, vnormals=vn.astype(np.float32), label="vnormals, device build")
 
 
 def test_no_refine_mode_within_contract(built, oracle):
