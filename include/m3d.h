@@ -344,6 +344,19 @@ int32_t m3d_render_raycast_device(m3d_scene *scene, const m3d_camera *cam,
                                   int32_t width, int32_t height, const m3d_partition *part,
                                   void *d_rgb, void *stream, m3d_stats *stats);
 
+/* Many RayCaster frames of one scene in ONE call: view v has its own camera and its own lights
+ * (lights[light_begin[v] .. light_begin[v+1])); every frame starts black, is rendered at
+ * width x height and, with downsample > 1, box-filtered on the device like Image.Downsample
+ * (render3d/image.go:100-120); rgb receives num_views frames of (width/downsample) x
+ * (height/downsample) x 3 floats, view-major, in one device-to-host copy.  What
+ * render3d.SaveRandomGrid / SaveRotatingGIF do view by view (helpers.go:133-236): rows*cols or
+ * `frames` renderings of one object at 2x supersampling.  The BVH is built once, the launch chains of
+ * all views queue up behind each other without host round trips, and on a multi-device context the
+ * views are spread over the GPUs. */
+int32_t m3d_render_raycast_views(m3d_scene *scene, const m3d_camera *cams, int32_t num_views,
+                                 const m3d_point_light *lights, const int32_t *light_begin, int32_t width,
+                                 int32_t height, int32_t downsample, float *rgb, m3d_stats *stats);
+
 typedef enum {
   M3D_FOCUS_PHONG = 0, /* render3d.PhongFocusPoint  (focus_point.go:30-71)  */
   M3D_FOCUS_SPHERE = 1 /* render3d.SphereFocusPoint (focus_point.go:73-153) */

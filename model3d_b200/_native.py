@@ -113,7 +113,7 @@ SYMBOLS = [
     "m3d_scene_builder_create", "m3d_scene_builder_destroy", "m3d_scene_add_material",
     "m3d_scene_add_mesh", "m3d_scene_add_instance", "m3d_scene_add_sphere", "m3d_scene_add_rect", "m3d_scene_add_cylinder",
     "m3d_scene_build", "m3d_scene_destroy", "m3d_scene_bounds", "m3d_scene_get_info", "m3d_scene_cast",
-    "m3d_render_raycast", "m3d_render_raycast_device", "m3d_render_path", "m3d_render_path_device",
+    "m3d_render_raycast", "m3d_render_raycast_device", "m3d_render_raycast_views", "m3d_render_path", "m3d_render_path_device",
     "m3d_render_bidir", "m3d_render_bidir_device", "m3d_finalize_image_device",
     "m3d_measure_l2_bandwidth", "m3d_ctx_create_multi", "m3d_ctx_num_devices",
     "m3d_host_alloc", "m3d_host_free", "m3d_host_register", "m3d_host_unregister",

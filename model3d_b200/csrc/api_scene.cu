@@ -774,6 +774,121 @@ int32_t m3d_render_raycast(m3d_scene *scene, const m3d_camera *cam, const m3d_po
   return M3D_OK;
 }
 
+// Renders views [v0, v1) of a view batch on one device into d_out (view-major, downsampled frames).
+static int32_t raycast_views_one_device(m3d_scene *scene, const m3d_camera *cams, int v0, int v1,
+                                        const m3d_point_light *lights, const int32_t *light_begin, int32_t width,
+                                        int32_t height, int32_t factor, float *rgb_host, m3d_stats *stats) {
+  m3d_ctx *ctx = scene->ctx;
+  M3D_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  const int nv = v1 - v0;
+  if (nv <= 0) return M3D_OK;
+  const int64_t n = (int64_t)width * height;
+  const int ow = width / factor, oh = height / factor;
+  const size_t out_floats = (size_t)ow * oh * 3;
+  const int nl_total = light_begin[v1] - light_begin[v0];
+  // scratch: rays + hits of one frame, the full-resolution frame, all downsampled frames, all lights
+  const size_t b_rays = (size_t)n * 4 * sizeof(float4), b_frame = (size_t)n * 3 * sizeof(float),
+               b_out = out_floats * nv * sizeof(float), b_lights = (size_t)(nl_total + 1) * sizeof(DevicePointLight);
+  M3D_CUDA(ctx->scratch[12].reserve(b_rays + b_frame + b_out + b_lights + 1024));
+  char *base = ctx->scratch[12].as<char>();
+  float4 *d_org4 = (float4 *)base, *d_dir4 = d_org4 + n, *d_hit0 = d_dir4 + n, *d_hit1 = d_hit0 + n;
+  float *d_frame = (float *)(base + b_rays);
+  float *d_out = (float *)(base + b_rays + b_frame);
+  DevicePointLight *d_lights = (DevicePointLight *)(base + b_rays + b_frame + ((b_out + 255) & ~(size_t)255));
+  std::vector<char> &stage = ctx->host_stage;
+  stage.resize(std::max<size_t>(stage.size(), b_lights));
+  DevicePointLight *hl = reinterpret_cast<DevicePointLight *>(stage.data());
+  for (int i = 0; i < nl_total; i++) {
+    const m3d_point_light &L = lights[light_begin[v0] + i];
+    for (int k = 0; k < 3; k++) {
+      hl[i].origin[k] = (float)L.origin[k];
+      hl[i].color[k] = (float)L.color[k];
+    }
+    hl[i].quad_dropoff = L.quad_dropoff;
+  }
+  if (nl_total)
+    M3D_CUDA(cudaMemcpyAsync(d_lights, hl, (size_t)nl_total * sizeof(DevicePointLight), cudaMemcpyHostToDevice, s));
+  GpuTimer tm;
+  tm.start(s);
+  int64_t launches = 0;
+  for (int v = v0; v < v1; v++) {
+    const DeviceCamera dc = make_device_camera(cams[v], width, height);
+    // a fresh image is black where rays miss (NewImage, image.go:24-31; raycast.go:26-28 leaves those pixels)
+    M3D_CUDA(cudaMemsetAsync(d_frame, 0, b_frame, s));
+    launch_raygen_camera(dc, width, 0, height, d_org4, d_dir4, s);
+    SceneTraceLaunch p;
+    p.t.org_tmin = d_org4;
+    p.t.dir_tmax = d_dir4;
+    p.t.n = n;
+    p.t.hit0 = d_hit0;
+    p.t.hit1 = d_hit1;
+    p.t.refine = true;
+    p.t.counters = nullptr;
+    p.t.ray_counter = next_work_counter(ctx);
+    if (!p.t.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
+    launch_trace_scene(scene->dev, p, s);
+    launch_shade_raycast(scene->dev, dc, d_lights + (light_begin[v] - light_begin[v0]),
+                         light_begin[v + 1] - light_begin[v], d_org4, d_dir4, d_hit0, d_hit1, n, d_frame, s);
+    float *dst = d_out + out_floats * (size_t)(v - v0);
+    if (factor > 1)
+      launch_downsample_image(d_frame, width, height, factor, dst, s);
+    else
+      M3D_CUDA(cudaMemcpyAsync(dst, d_frame, b_frame, cudaMemcpyDeviceToDevice, s));
+    launches += 5;
+  }
+  tm.stop(s);
+  M3D_CUDA(cudaMemcpyAsync(rgb_host + out_floats * (size_t)v0, d_out, b_out, cudaMemcpyDeviceToHost, s));
+  M3D_CUDA(cudaStreamSynchronize(s));
+  M3D_CUDA(cudaGetLastError());
+  if (stats) {
+    stats->rays = n * nv;
+    stats->kernel_ms = tm.ms();
+    stats->launches = launches;
+    stats->d2h_bytes = (int64_t)b_out;
+  }
+  return M3D_OK;
+}
+
+int32_t m3d_render_raycast_views(m3d_scene *scene, const m3d_camera *cams, int32_t num_views,
+                                 const m3d_point_light *lights, const int32_t *light_begin, int32_t width,
+                                 int32_t height, int32_t downsample, float *rgb, m3d_stats *stats) {
+  if (!scene || !cams || num_views < 0 || !light_begin || width <= 0 || height <= 0 || downsample < 1 || !rgb)
+    return fail(M3D_ERR_INVALID_ARG, "m3d_render_raycast_views: bad arguments");
+  if (width % downsample || height % downsample)
+    return fail(M3D_ERR_INVALID_ARG, "image size %d x %d cannot be divided evenly by factor %d", width, height,
+                downsample);  // image.go:101-104
+  for (int v = 0; v < num_views; v++)
+    if (light_begin[v + 1] < light_begin[v] || (light_begin[v + 1] > light_begin[v] && !lights))
+      return fail(M3D_ERR_INVALID_ARG, "m3d_render_raycast_views: bad light ranges");
+  M3D_LOCK(scene->ctx);
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (num_views == 0) return M3D_OK;
+  const int g = 1 + (int)scene->replicas.size();
+  if (g > 1 && num_views > 1) {
+    // the views are independent frames: spread them over the devices (no exchange at all)
+    std::vector<m3d_stats> st((size_t)g);
+    const int32_t rc = parallel_members(g, [&](int i) -> int32_t {
+      int64_t b, e;
+      split_range(num_views, g, i, &b, &e);
+      m3d_scene *si = i == 0 ? scene : scene->replicas[(size_t)i - 1];
+      std::lock_guard<std::recursive_mutex> lock(si->ctx->mu);
+      return raycast_views_one_device(si, cams, (int)b, (int)e, lights, light_begin, width, height, downsample, rgb,
+                                      &st[(size_t)i]);
+    });
+    if (stats)
+      for (const m3d_stats &x : st) {
+        stats->rays += x.rays;
+        stats->kernel_ms = std::max(stats->kernel_ms, x.kernel_ms);
+        stats->launches += x.launches;
+        stats->d2h_bytes += x.d2h_bytes;
+      }
+    return rc;
+  }
+  return raycast_views_one_device(scene, cams, 0, num_views, lights, light_begin, width, height, downsample, rgb, stats);
+}
+
 int32_t m3d_finalize_image_device(m3d_ctx *ctx, const void *d_sum, int64_t num_pixels, double inv_samples,
                                   void *d_mean, void *d_srgb8, void *stream) {
   if (!ctx || !d_sum || num_pixels < 0) return fail(M3D_ERR_INVALID_ARG, "m3d_finalize_image_device: bad arguments");

@@ -103,6 +103,9 @@ void launch_shade_raycast(const DeviceScene &scene, const DeviceCamera &cam, con
                           const float4 *hit0, const float4 *hit1, int64_t n, float *rgb,
                           cudaStream_t stream);
 
+// Image.Downsample (image.go:100-120): factor x factor box filter of a W x H x 3 image
+void launch_downsample_image(const float *src, int W, int H, int factor, float *dst, cudaStream_t stream);
+
 // colorSum/numSamples and optional sRGB-8 (ray_renderer.go:150, image.go:125-145)
 void launch_finalize_image(const float *sum, int64_t num_values, float inv_samples, float *mean,
                            uint8_t *srgb8, cudaStream_t stream);

@@ -153,7 +153,33 @@ __global__ void finalize_image_kernel(const float *__restrict__ sum, int64_t n, 
   }
 }
 
+// Image.Downsample (image.go:100-120): box filter, sum in float64 like the reference, * 1/f^2
+__global__ void downsample_image_kernel(const float *__restrict__ src, int W, int H, int f, float *__restrict__ dst) {
+  const int ow = W / f, oh = H / f;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ow * oh) return;
+  const int ox = i % ow, oy = i / ow;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int k = 0; k < f; k++)
+    for (int l = 0; l < f; l++) {
+      const float *p = src + ((size_t)(oy * f + k) * W + (ox * f + l)) * 3;
+      s0 += p[0];
+      s1 += p[1];
+      s2 += p[2];
+    }
+  const double w = 1.0 / (double)(f * f);
+  dst[(size_t)i * 3] = (float)(s0 * w);
+  dst[(size_t)i * 3 + 1] = (float)(s1 * w);
+  dst[(size_t)i * 3 + 2] = (float)(s2 * w);
+}
+
 }  // namespace
+
+void launch_downsample_image(const float *src, int W, int H, int factor, float *dst, cudaStream_t stream) {
+  const int n = (W / factor) * (H / factor);
+  if (n <= 0) return;
+  downsample_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, W, H, factor, dst);
+}
 
 void launch_finish_scene_hits(const DeviceScene &scene, const SceneTraceLaunch &p, cudaStream_t stream) {
   if (p.t.n <= 0) return;

@@ -100,15 +100,20 @@ def SaveRandomGrid(path, obj, rows, cols, imgSize, colorFunc=None, seed=None):
     center = (mn + mx) / 2
     rng = np.random.default_rng(seed)
     full = R.Image(cols * imgSize, rows * imgSize)
+    casters = []
+    for _ in range(rows * cols):
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        casters.append(R.RayCaster(Camera=DirectionalCamera(sc, d, helperFieldOfView),
+                                   Lights=[R.PointLight(Origin=tuple(center + d * 1000), Color=R.NewColor(1.0))]))
+    # all rows x cols views in one call: one BVH, the views' launch chains back to back, the 2x
+    # supersampled frames box-filtered on the device, one copy back (spread over the GPUs of a
+    # multi-device context)
+    views, _ = R.RayCaster.RenderViews(casters, imgSize * helperAntialias, imgSize * helperAntialias, sc,
+                                       downsample=helperAntialias)
     for i in range(rows):
         for j in range(cols):
-            d = rng.normal(size=3)
-            d /= np.linalg.norm(d)
-            caster = R.RayCaster(Camera=DirectionalCamera(sc, d, helperFieldOfView),
-                                 Lights=[R.PointLight(Origin=tuple(center + d * 1000), Color=R.NewColor(1.0))])
-            sub = R.Image(imgSize * helperAntialias, imgSize * helperAntialias)
-            caster.Render(sub, sc)
-            full.CopyFrom(sub.Downsample(helperAntialias), j * imgSize, i * imgSize)
+            full.Data[i * imgSize:(i + 1) * imgSize, j * imgSize:(j + 1) * imgSize] = views[i * cols + j]
     if path is not None:
         full.Save(path)
     return full
@@ -152,7 +157,7 @@ def SaveRotatingGIF(path, obj, axis, cameraDir, imgSize, frames, fps, colorFunc=
             furthest = cam
     offset = np.asarray(furthest.Origin, np.float64) - center
     light = center + offset * 1000
-    out = []
+    casters = []
     for rot in rots:
         inv = rot.T  # counter-rotate camera and light about the centre instead of the object
 
@@ -162,9 +167,12 @@ def SaveRotatingGIF(path, obj, axis, cameraDir, imgSize, frames, fps, colorFunc=
 
         cam = R.Camera(Origin=back(furthest.Origin), ScreenX=back(furthest.ScreenX, True),
                        ScreenY=back(furthest.ScreenY, True), FieldOfView=furthest.FieldOfView)
-        caster = R.RayCaster(Camera=cam, Lights=[R.PointLight(Origin=back(light), Color=R.NewColor(1.0))])
+        casters.append(R.RayCaster(Camera=cam, Lights=[R.PointLight(Origin=back(light), Color=R.NewColor(1.0))]))
+    views, _ = R.RayCaster.RenderViews(casters, imgSize, imgSize, sc)  # all frames in one call
+    out = []
+    for v in views:
         img = R.Image(imgSize, imgSize)
-        caster.Render(img, sc)
+        img.Data = np.array(v)
         out.append(img.Gray8())
     if path is not None:
         write_gif(path, out, int(math.ceil(100 / fps)))

@@ -571,6 +571,29 @@ class RayCaster:
         img.Data = data
         return {k: getattr(stats, k) for k, _ in stats._fields_}
 
+    @staticmethod
+    def RenderViews(casters, width, height, obj, downsample=1):
+        """Many RayCaster frames of one object in one library call (m3d_render_raycast_views): view
+        v is rendered like casters[v].Render into a fresh (black) width x height image and, with
+        downsample > 1, box-filtered like Image.Downsample.  Returns (float32 [V, H/f, W/f, 3], stats).
+        What SaveRandomGrid / SaveRotatingGIF render view by view in the reference
+        (helpers.go:133-236); on a multi-device context the views are spread over the GPUs."""
+        sc = _as_scene(obj)
+        nv = len(casters)
+        cams = (N.Camera * max(1, nv))(*[c.Camera._c() for c in casters])
+        all_lights = [l for c in casters for l in c.Lights]
+        begin = np.zeros(nv + 1, np.int32)
+        for v, c in enumerate(casters):
+            begin[v + 1] = begin[v] + len(c.Lights)
+        lights = _lights(all_lights)
+        out = N.host_empty((nv, height // downsample, width // downsample, 3), np.float32) if nv else \
+            np.zeros((0, height // downsample, width // downsample, 3), np.float32)
+        stats = N.Stats()
+        N.check(N.lib().m3d_render_raycast_views(sc.h, cams, C.c_int32(nv), lights, _p(begin, i32p), C.c_int32(width),
+                                                 C.c_int32(height), C.c_int32(downsample), _p(out, f32p),
+                                                 C.byref(stats)))
+        return out, {k: getattr(stats, k) for k, _ in stats._fields_}
+
     def RenderDevice(self, width, height, obj, d_rgb, partition=None, stream=0):
         """Render into a device buffer (pointer to W*H*3 float32; pixels whose ray misses keep
         their value, raycast.go:26-28): what a multi-GPU driver gathers by row band."""

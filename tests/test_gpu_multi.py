@@ -219,3 +219,15 @@ def test_multi_context_raycast_large_frame():
         imgs.append(np.array(img.Data))
     assert np.array_equal(imgs[0], imgs[1])
     assert imgs[0].sum() > 0
+
+
+@needs2
+def test_multi_context_render_views_spread_over_devices():
+    from model3d_b200 import _native as N, helpers as H, render3d as R
+    spec = scenes.c1_scene(n=10)
+    outs = []
+    for ctx in (N.Context(0), N.MultiContext(list(range(_num_gpus())))):
+        psc = scenes.build_product(spec, ctx=ctx)
+        g = H.SaveRandomGrid(None, psc, 3, 3, 48, seed=4)
+        outs.append(np.array(g.Data))
+    assert np.array_equal(outs[0], outs[1]) and outs[0].sum() > 0

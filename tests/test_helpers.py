@@ -178,3 +178,28 @@ def test_render_stl_cli_on_the_reference_stl(built, tmp_path):
     w, h = struct.unpack(">II", raw[16:24])
     assert (w, h) == (192, 192)
     assert open(gif, "rb").read()[:6] in (b"GIF89a", b"GIF87a")
+
+
+@pytest.mark.gpu
+def test_render_views_equals_frame_by_frame(built):
+    """m3d_render_raycast_views (what SaveRandomGrid / SaveRotatingGIF now use): every view equals
+    RayCaster.Render into a fresh image followed by Image.Downsample, bit for bit."""
+    spec = scenes.c1_scene(n=10)
+    psc = scenes.build_product(spec)
+    rng = np.random.default_rng(8)
+    casters = []
+    for k in range(5):
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        casters.append(R.RayCaster(Camera=H.DirectionalCamera(psc, d, H.helperFieldOfView),
+                                   Lights=[R.PointLight(Origin=tuple(d * 1000), Color=R.NewColor(1.0))] * (1 + k % 2)))
+    views, st = R.RayCaster.RenderViews(casters, 96, 64, psc, downsample=2)
+    assert views.shape == (5, 32, 48, 3) and st["rays"] == 5 * 96 * 64
+    for c, v in zip(casters, views):
+        img = R.Image(96, 64)
+        c.Render(img, psc)
+        assert np.array_equal(img.Downsample(2).Data, v)
+    full, _ = R.RayCaster.RenderViews(casters[:2], 40, 40, psc)
+    img = R.Image(40, 40)
+    casters[1].Render(img, psc)
+    assert np.array_equal(img.Data, full[1]) and full[1].sum() > 0
