@@ -51,6 +51,9 @@ int32_t carve_bidir_buffers(m3d_ctx *ctx, int64_t cap, int De, int Dl, BidirBuff
   const size_t o_work = take(c * (size_t)De * (size_t)(Dl + 1) * 4);
   const size_t o_counts = take(64);
   const size_t o_class = take((size_t)De * (size_t)(Dl + 1) * 4);
+  const size_t o_chunk = take((c / 256 + 1) * 4);
+  const MisTab mt{De, Dl};
+  const size_t o_mt = take(c * 8 * (size_t)mt.entries());
   M3D_CUDA(ctx->scratch[6].reserve(total));
   char *p = ctx->scratch[6].as<char>();
   b.cap = cap;
@@ -83,6 +86,8 @@ int32_t carve_bidir_buffers(m3d_ctx *ctx, int64_t cap, int De, int Dl, BidirBuff
   b.work = (uint32_t *)(p + o_work);
   b.counts = (int *)(p + o_counts);
   b.class_counts = (int *)(p + o_class);
+  b.chunk_counts = (int *)(p + o_chunk);
+  b.mistab = (double *)(p + o_mt);
   b.ray_total = (unsigned long long *)(p + o_counts + 32);
   return M3D_OK;
 }

@@ -65,6 +65,9 @@ struct BidirBuffers {
   float4 *misA;
   double2 *misB;
   float *misC;
+  // per-sample tables of the MIS sums (bidir_kernels.cu, "MIS weights in O(1) per connection"),
+  // entry-major: mistab[entry * cap + slot], entries enumerated by MisTab
+  double *mistab;
   // connection (visibility) rays of all (i, j) pairs of the batch, compacted
   float4 *corg, *cdir, *craw, *cpay;
   int32_t *cskip;
@@ -72,8 +75,25 @@ struct BidirBuffers {
   // (i, j) class: class c = (i-1) * (max_light_depth+1) + j owns work[c*cap, c*cap + class_counts[c])
   uint32_t *work;
   int *class_counts;
+  // chunked layout (bidir_kernels.cu, M3D_CONNECT_CHUNKED): the items of samples [256 b, 256 b + 256) are
+  // work[256 b * classes, ... + chunk_counts[b]), ordered by class
+  int *chunk_counts;
   int *counts;     // [0],[1] queue lengths, [2] connection rays
   unsigned long long *ray_total;
+};
+
+// Entry numbering of BidirBuffers::mistab for sub-path capacities De (eye) and Dl (light).
+struct MisTab {
+  int De, Dl;
+  __host__ __device__ int tri(int x) const { return x * (x + 1) / 2; }
+  __host__ __device__ int lt(int t) const { return t - 1; }                                  // t = 1..Dl
+  __host__ __device__ int slp(int j) const { return Dl + j - 1; }                            // j = 1..Dl
+  __host__ __device__ int h(int j, int t_lo) const { return 2 * Dl + tri(j - 3) + t_lo - 1; }  // j = 3..Dl, t_lo = 1..j-2
+  __host__ __device__ int eye0() const { return 2 * Dl + tri(Dl > 2 ? Dl - 2 : 0); }
+  __host__ __device__ int ge(int e) const { return eye0() + e; }                             // e = 1..De-1
+  __host__ __device__ int rsp(int e) const { return eye0() + De + e; }                       // e = 0..De-2
+  __host__ __device__ int k(int i, int m_lo) const { return eye0() + 2 * De + tri(i - 3) + m_lo; }  // i = 3..De+1, m_lo = 0..i-3
+  __host__ __device__ int entries() const { return eye0() + 2 * De + tri(De > 1 ? De - 1 : 0); }
 };
 
 void launch_bidir_eye_raygen(const DeviceCamera &cam, const DeviceBidirParams &bp, const PathBatch &b,

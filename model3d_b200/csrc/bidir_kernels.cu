@@ -14,6 +14,8 @@
 // Dirac-lobe magnitude 2/cosineEpsilon = 2e8 per specular vertex (material.go:401-462), which
 // overflows float32 after 5 vertices: they are carried as (finite, delta-coefficient) pairs per
 // vertex and combined in float64, exactly like the reference's float64 arithmetic.
+#include <cstdio>
+
 #include "bidir.h"
 #include "materials.cuh"
 #include "scene_hit.cuh"
@@ -23,6 +25,14 @@
 #endif
 #ifndef M3D_BCONNECT_MINB
 #define M3D_BCONNECT_MINB 8
+#endif
+// Work list of the connection stage grouped by CHUNK (the 256 consecutive samples of one
+// bidir_prefix block) and, inside a chunk, by (i, j) class.  0: one list per class over the whole batch.
+#ifndef M3D_CONNECT_CHUNKED
+#define M3D_CONNECT_CHUNKED 0
+#endif
+#ifndef M3D_CONNECT_PARTS
+#define M3D_CONNECT_PARTS 32  // connection blocks per chunk (each strides over the chunk's items)
 #endif
 
 namespace m3d {
@@ -158,6 +168,7 @@ bidir_eye_raygen_kernel(DeviceCamera cam, DeviceBidirParams bp, PathBatch b, Bid
     buf.counts[0] = (int)n;
     buf.counts[1] = 0;
     buf.counts[2] = 0;
+    buf.counts[4] = buf.counts[5] = 0;  // M3D_CONNECT_CHECK: mismatching / checked MIS weights
   }
   if (slot < (int64_t)buf.De * (buf.Dl + 1)) buf.class_counts[slot] = 0;
   if (slot >= n) return;
@@ -352,15 +363,46 @@ bidir_light_raygen_kernel(DeviceScene sc, DeviceBidirParams bp, const DeviceArea
   buf.ender_roul[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
 }
 
-// Per-vertex scalars of the MIS computation (bidir.go:421-471), written once per sub-path
-// vertex by bidir_prefix_kernel so that the connection threads load 32 bytes per vertex (two
-// 16-byte loads) instead of the 112-byte vertex record:
-//   misA = (point.xyz, sourceDot)   misB = (sourceDensity, destDensity, destDot, -) as float32,
-//   densities incl. the Dirac magnitudes (M3D_MIS_F32=0: float64 pairs + misC = destDot, 36 bytes)
-// Eye vertices occupy depths [0, De), light vertices [De, De+Dl) of the mis arrays.
-#ifndef M3D_MIS_F32
-#define M3D_MIS_F32 1
+// ---- MIS weights in O(1) per connection ------------------------------------------------------
+// The weight of a connection is the sum, over every way t of splitting the JOINED path x_0 .. x_{n-1}
+// (light end first) into t light-sampled and n - t eye-sampled vertices, of that strategy's density
+// (`densities`, bidir.go:421-471) under the power / balance heuristic (bidir.go:118-131).  The joined
+// path of item (i, j) is light[0..j-2], JL, JE, eye[i-2..0], where only the two junction vertices JL, JE
+// are re-evaluated (combinePaths, bidir.go:532-572); every other vertex keeps the densities of its own
+// sub-path.  With T_t = (density of sampling x_0..x_{t-1} from the light) * area(x_{t-1}, x_t) /
+// destDot(x_{t-1}) and acc_t = product of sourceDensity(x_k), k > t, the strategy densities are
+// acc_t * T_t (t >= 1) and acc_0, and they factor into per-sub-path partial products times junction terms:
+//   t <= j-2 : LT[t] * sd(L_{t+1}) .. sd(L_{j-2}) * sd(JL) * sd(JE) * EP[i-1]
+//   t == j-1 : LT[j-1] * sd(JE) * EP[i-1]
+//   t == j   : the connection's own density
+//   t == j+1 : ld1 * GE[i-1] * EP[i-2],   ld1 = LD[j] * dd(JL) * sourceDot(JE) / destDot(JL)
+//   t >= j+2 : ld1 * dd(JE) * RSP[i-2] * RS[i-3] .. RS[m+1] * GE[m+1] * EP[m],   m = n-1-t
+//   t == 0   : SLP[j] * sd(JL) * sd(JE) * EP[i-1]
+// (LD = lightpre density, EP = eyepre density, LT[t] = LD[t] * area(L_{t-1}, L_t) / destDot(L_{t-1}),
+// GE[e] = area(E_e, E_{e-1}) / destDot(E_e), RSP[e] = sourceDot(E_e) / destDot(E_{e+1}), RS[e] =
+// dd(E_{e+1}) * RSP[e], SLP[j] = sd(L_1) .. sd(L_{j-2}).)  The heuristic's power is multiplicative, so the
+// sums over t <= j-2 and over t >= j+2 are per-sample tables
+//   H[j][t_lo] = sum_{t=t_lo}^{j-2} g(LT[t] * sd(L_{t+1}) .. sd(L_{j-2}))
+//   K[i][m_lo] = sum_{m=m_lo}^{i-3} g(RS[i-3] .. RS[m+1] * GE[m+1] * EP[m])
+// (g(x) = x^ph, x for the balance heuristic) with one-step recurrences in j and i; the lower limits carry
+// the reference's depth limits (a strategy needs n - t <= MaxDepth eye vertices and t <= MaxLightDepth
+// light vertices).  bidir_prefix_kernel fills the tables (O(depth^2) per sample), a connection reads seven
+// entries instead of walking its joined path twice (O(depth) dependent 32-byte gathers per item, 40 % of
+// the connection kernel's stall samples, and a 33-entry float64 array in local memory).
+// M3D_CONNECT_CHECK=1 also keeps the path walk and reports items whose two weights differ.
+#ifndef M3D_CONNECT_CHECK
+#define M3D_CONNECT_CHECK 0
 #endif
+__device__ __forceinline__ double mis_pow(double x, double ph) {
+  return ph == 0.0 ? x : (ph == 2.0 ? x * x : pow(x, ph));
+}
+__device__ __forceinline__ double area_between(V3f a, V3f b) {
+  const double dx = (double)a.x - b.x, dy = (double)a.y - b.y, dz = (double)a.z - b.z;
+  return kFourPi * (dx * dx + dy * dy + dz * dz);
+}
+
+#if M3D_CONNECT_CHECK
+// compact per-vertex records of the path walk (check build only)
 struct Mis {
   double sd, dd;
   float sdot, ddot;
@@ -380,24 +422,13 @@ __device__ __forceinline__ Mis mis_of(const BVert &v) {
 __device__ __forceinline__ void store_mis(const BidirBuffers &buf, int depth, int slot, const Mis &m) {
   const size_t o = (size_t)depth * buf.cap + slot;
   buf.misA[o] = make_float4(m.px, m.py, m.pz, m.sdot);
-#if M3D_MIS_F32
-  // single densities (<= a few times the 2e8 Dirac magnitude) fit float32 at 6e-8 relative; only
-  // their products along a path need float64, and those are formed in the connection kernel
-  reinterpret_cast<float4 *>(buf.misB)[o] = make_float4((float)m.sd, (float)m.dd, m.ddot, 0.f);
-#else
   buf.misB[o] = make_double2(m.sd, m.dd);
   buf.misC[o] = m.ddot;
-#endif
 }
 __device__ __forceinline__ Mis load_mis(const BidirBuffers &buf, int depth, int slot) {
   const size_t o = (size_t)depth * buf.cap + slot;
   const float4 a = buf.misA[o];
-#if M3D_MIS_F32
-  const float4 bf = reinterpret_cast<const float4 *>(buf.misB)[o];
-  const double2 b = make_double2((double)bf.x, (double)bf.y);
-#else
   const double2 b = buf.misB[o];
-#endif
   Mis m;
   m.px = a.x;
   m.py = a.y;
@@ -405,17 +436,14 @@ __device__ __forceinline__ Mis load_mis(const BidirBuffers &buf, int depth, int 
   m.sdot = a.w;
   m.sd = b.x;
   m.dd = b.y;
-#if M3D_MIS_F32
-  m.ddot = bf.z;
-#else
   m.ddot = buf.misC[o];
-#endif
   return m;
 }
 __device__ __forceinline__ double out_area(const Mis &a, const Mis &b) {
   const double dx = (double)a.px - b.px, dy = (double)a.py - b.py, dz = (double)a.pz - b.pz;
   return kFourPi * (dx * dx + dy * dy + dz * dz);
 }
+#endif
 
 struct D3c {
   double x, y, z;
@@ -426,7 +454,7 @@ struct D3c {
 // (eye prefix i, light prefix j) pair becomes an independent work item:
 //   eyepre[i-1]   = (eyeDensity, eyeBSDF.xyz) as they stand when the outer loop reaches i
 //   lightpre[j-1] = (density / eyeDensity, lightBSDF.xyz) as they stand when the inner loop reaches j
-// One thread per sample; also writes the compact MIS records.
+// One thread per sample; also fills the per-sample MIS tables (see above).
 __global__ void __launch_bounds__(256)
 bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
   __shared__ int s_cnt[kBidirMaxDepth * (kBidirMaxDepth + 1)], s_base[kBidirMaxDepth * (kBidirMaxDepth + 1)];
@@ -439,8 +467,14 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
   if (slot < n_slots) {
     ne = buf.ne[slot];
     nl = buf.nl[slot];
+    const MisTab mt{buf.De, buf.Dl};
+    const double ph = bp.power_heuristic;
+    auto tab = [&](int entry) -> double & { return buf.mistab[(size_t)entry * buf.cap + slot]; };
     double eye_density = 1.0;
     D3c eye_bsdf = {1.0, 1.0, 1.0};
+    double ep_prev = 1.0;             // EP[i-2] while vertex E_{i-1} is handled
+    double krow[kBidirMaxDepth];      // K[i+1][.], carried from row to row
+    BVert pv;
     for (int i = 1; i <= ne; i++) {
       const BVert v = load_vertex(buf.ev, buf.De, buf.cap, i - 1, slot);
       double *st = buf.eyepre + ((size_t)(i - 1) * buf.cap + slot) * 4;
@@ -448,15 +482,36 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
       st[1] = eye_bsdf.x;
       st[2] = eye_bsdf.y;
       st[3] = eye_bsdf.z;
+#if M3D_CONNECT_CHECK
       store_mis(buf, i - 1, slot, mis_of(v));
+#endif
+      if (i >= 2) {
+        // v = E_e, pv = E_{e-1}, e = i-1
+        const double ddv = (double)dest_dot(v);
+        const double ge = area_between(v.point, pv.point) / ddv;
+        const double rsp = (double)source_dot(pv) / ddv;
+        tab(mt.ge(i - 1)) = ge;
+        tab(mt.rsp(i - 2)) = rsp;
+        // K[i+1][m] = g(RS[i-2]) K[i][m] + g(GE[i-1] EP[i-2]),  m = 0 .. i-2
+        const double grs = mis_pow(full_dd(v) * rsp, ph), gnew = mis_pow(ge * ep_prev, ph);
+        for (int m = 0; m <= i - 2; m++) {
+          const double kv = (m <= i - 3 ? grs * krow[m] : 0.0) + gnew;
+          krow[m] = kv;
+          tab(mt.k(i + 1, m)) = kv;
+        }
+      }
       const double sdv = (double)source_dot(v);
+      ep_prev = eye_density;
       eye_density *= full_sd(v);
       eye_bsdf.x *= ((double)v.bsdf_fin.x + (double)v.bsdf_del.x * kDeltaMag) * sdv;
       eye_bsdf.y *= ((double)v.bsdf_fin.y + (double)v.bsdf_del.y * kDeltaMag) * sdv;
       eye_bsdf.z *= ((double)v.bsdf_fin.z + (double)v.bsdf_del.z * kDeltaMag) * sdv;
+      pv = v;
     }
     double density = 0.0;
     D3c light_bsdf = {0.0, 0.0, 0.0};
+    double lt_prev = 0.0, slp = 1.0;  // LT[j-2], SLP[j] while vertex L_{j-1} is handled
+    double hrow[kBidirMaxDepth];      // H[j][.]
     BVert prev;
     for (int j = 1; j <= nl; j++) {
       const BVert lj = load_vertex(buf.lv, buf.Dl, buf.cap, j - 1, slot);
@@ -466,6 +521,21 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
         light_bsdf.y = lj.emission.y;
         light_bsdf.z = lj.emission.z;
       } else {
+        // LT[j-1] from LD[j-1] (density before this step); prev = L_{j-2}
+        const double lt = density * area_between(prev.point, lj.point) / (double)dest_dot(prev);
+        tab(mt.lt(j - 1)) = lt;
+        if (j >= 3) {
+          const double sdp = full_sd(prev);
+          slp *= sdp;
+          // H[j][t_lo] = g(sd(L_{j-2})) H[j-1][t_lo] + g(LT[j-2]),  t_lo = 1 .. j-2
+          const double gs = mis_pow(sdp, ph), gl = mis_pow(lt_prev, ph);
+          for (int t = 1; t <= j - 2; t++) {
+            const double hv = (t <= j - 3 ? gs * hrow[t - 1] : 0.0) + gl;
+            hrow[t - 1] = hv;
+            tab(mt.h(j, t)) = hv;
+          }
+        }
+        lt_prev = lt;
         density *= full_dd(prev);
         density *= (double)source_dot(lj) / (double)dest_dot(prev);
         if (j > 2) {
@@ -478,24 +548,60 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
         light_bsdf.y *= sdj;
         light_bsdf.z *= sdj;
       }
+      tab(mt.slp(j)) = slp;
       double *st = buf.lightpre + ((size_t)(j - 1) * buf.cap + slot) * 4;
       st[0] = density;
       st[1] = light_bsdf.x;
       st[2] = light_bsdf.y;
       st[3] = light_bsdf.z;
+#if M3D_CONNECT_CHECK
       store_mis(buf, buf.De + j - 1, slot, mis_of(lj));
+#endif
       prev = lj;
     }
   }
   // Work list of the connection stage: one item per (i, j) pair of this sample, packed
   // slot | i << 22 | j << 27 (slots < 2^22, depths <= 16) and grouped by (i, j) class, so that the threads of a warp of the
   // connection kernel walk joined paths of the same length (uniform loops) and read their
-  // vertices from consecutive slots (coalesced).  Block-level counting sort: count per class in
-  // shared memory, reserve the block's range of every class with one global atomic, scatter.
+  // vertices from neighbouring slots.  Block-level counting sort: count per class in shared memory,
+  // place the classes one after the other, scatter.
   __syncthreads();
   for (int i = 1; i <= ne; i++)
     for (int j = 0; j <= nl; j++) atomicAdd(&s_cnt[(i - 1) * row + j], 1);
   __syncthreads();
+#if M3D_CONNECT_CHUNKED
+  // The block's items stay together (segment blockIdx.x of the work array, classes back to back):
+  // the connection blocks of one chunk run next to each other in time, so the ~0.9 MB of path
+  // vertices, running products and MIS records of these 256 samples are fetched from HBM once and
+  // then served by L2 to all ~40 items per sample (one list per class over the whole batch swept
+  // the batch's 10+ GB of path state through L2 once per class).
+  if (threadIdx.x < 32) {
+    const int per = (n_classes + 31) / 32;
+    const int c0 = (int)threadIdx.x * per, c1 = min(c0 + per, n_classes);
+    int sum = 0;
+    for (int c = c0; c < c1; c++) sum += s_cnt[c];
+    int incl = sum;
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if ((int)threadIdx.x >= off) incl += v;
+    }
+    int run = incl - sum;
+    for (int c = c0; c < c1; c++) {
+      s_base[c] = run;
+      run += s_cnt[c];
+      s_cnt[c] = 0;
+    }
+    if (threadIdx.x == 31) buf.chunk_counts[blockIdx.x] = incl;
+  }
+  __syncthreads();
+  uint32_t *seg = buf.work + (size_t)blockIdx.x * blockDim.x * n_classes;
+  for (int i = 1; i <= ne; i++)
+    for (int j = 0; j <= nl; j++) {
+      const int c = (i - 1) * row + j;
+      const int r = atomicAdd(&s_cnt[c], 1);
+      seg[s_base[c] + r] = (uint32_t)slot | ((uint32_t)i << 22) | ((uint32_t)j << 27);
+    }
+#else
   for (int c = threadIdx.x; c < n_classes; c += blockDim.x) {
     s_base[c] = s_cnt[c] > 0 ? atomicAdd(buf.class_counts + c, s_cnt[c]) : 0;
     s_cnt[c] = 0;
@@ -507,16 +613,13 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
       const int r = atomicAdd(&s_cnt[c], 1);
       buf.work[(size_t)c * buf.cap + s_base[c] + r] = (uint32_t)slot | ((uint32_t)i << 22) | ((uint32_t)j << 27);
     }
+#endif
 }
 
-// allPathCombinations (bidir.go:476-530) + rayColor's callback (bidir.go:113-158): one thread
-// per (eye prefix length i, light prefix length j, sample); threads of a warp share (i, j).
-__global__ void __launch_bounds__(kBlock, M3D_BCONNECT_MINB)
-bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
-  // grid: x over the items of a class, y = class; most blocks of a sparsely filled class exit here
-  const int cls = (int)blockIdx.y, rank = (int)(blockIdx.x * kBlock + threadIdx.x);
-  if (rank >= buf.class_counts[cls]) return;
-  const uint32_t item = buf.work[(size_t)cls * buf.cap + rank];
+// allPathCombinations (bidir.go:476-530) + rayColor's callback (bidir.go:113-158) for one
+// (eye prefix length i, light prefix length j, sample) work item.
+__device__ __forceinline__ void connect_item(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
+                                             const BidirBuffers &buf, uint32_t item) {
   const int slot = (int)(item & 0x3fffffu);
   const int i = (int)((item >> 22) & 31u);
   const int j = (int)(item >> 27);
@@ -529,8 +632,16 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
   const double ph = bp.power_heuristic;
   const int n = i + j;
 
-  // joined path (combinePaths bidir.go:532-572): light[0..j-2], JL, JE, eye[i-2..0] for j >= 1,
-  // eye[i-1..0] for j == 0
+  const MisTab mt{buf.De, buf.Dl};
+  auto tab = [&](int entry) -> double { return buf.mistab[(size_t)entry * buf.cap + slot]; };
+  // f(x) = (x / density^((ph-1)/ph))^ph, the heuristic's term of a strategy of density x, normalised like
+  // the reference's so that the sums stay inside float64; f(x y) = f(x) g(y)
+  auto heur_scale = [&](double density) -> double {
+    return ph == 0.0 ? 1.0 : (ph == 2.0 ? rsqrt(density) : pow(density, -(ph - 1.0) / ph));
+  };
+#if M3D_CONNECT_CHECK
+  // the path walk the tables replace: joined path light[0..j-2], JL, JE, eye[i-2..0] for j >= 1,
+  // eye[i-1..0] for j == 0; pass 1 from the light end (term[t]), pass 2 from the eye end (acc)
   Mis JL, JE;
   auto at = [&](int k) -> Mis {
     if (j == 0) return load_mis(buf, i - 1 - k, slot);
@@ -539,18 +650,10 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
     if (k == j) return JE;
     return load_mis(buf, i - 1 - (k - j), slot);
   };
-  // sum over every way of splitting the joined path into a light and an eye part
-  // (densities, bidir.go:421-471) under the power / balance heuristic (bidir.go:118-131)
-  auto mis_weight = [&](double density, double emis0_sum) -> double {
-    const double s = ph == 0.0 ? 1.0 : (ph == 2.0 ? rsqrt(density) : pow(density, -(ph - 1.0) / ph));
+  auto walk_weight = [&](double density, double emis0_sum) -> double {
+    const double s = heur_scale(density);
     double weight = 0.0;
-    auto f = [&](double d) {
-      if (ph == 0.0) weight += d;
-      else if (ph == 2.0) weight += (d * s) * (d * s);
-      else weight += pow(d * s, ph);
-    };
-    // pass 1, from the light end: the light-side density of every split, times the geometry
-    // term of the connecting edge; term[t] belongs to the split with t light-sampled vertices
+    auto f = [&](double d) { weight += mis_pow(d * s, ph); };
     double term[2 * kBidirMaxDepth + 1];
     if (n > 1) {
       double ld = emis0_sum / bp.total_light;
@@ -566,7 +669,6 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
         m0 = m1;
         m1 = m2;
       }
-      // pass 2, from the eye end: acc = product of the source densities beyond the split
       double acc = 1.0;
       for (int k = n - 1; k >= 1; k--) {
         if (k < t && term[k] != 0.0) f(acc * term[k]);
@@ -578,6 +680,14 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
     }
     return weight;
   };
+  auto check_weight = [&](double w, double w_walk) {
+    atomicAdd(buf.counts + 5, 1);
+    const bool both_bad = !(w > 0.0 && w < INFINITY) && !(w_walk > 0.0 && w_walk < INFINITY);
+    if (both_bad || fabs(w - w_walk) <= 1e-9 * fabs(w_walk)) return;
+    if (atomicAdd(buf.counts + 4, 1) < 16)
+      printf("MIS weight mismatch: slot %d i %d j %d tables %.17g walk %.17g\n", slot, i, j, w, w_walk);
+  };
+#endif
 
   if (j == 0) {
     // the eye path itself reached an emitter (bidir.go:486-491)
@@ -586,7 +696,17 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
     const D3c cur = {ev.emission.x * eye_bsdf.x * r, ev.emission.y * eye_bsdf.y * r, ev.emission.z * eye_bsdf.z * r};
     if (cur.x + cur.y + cur.z < 1e-8) return;
     const double es = (double)ev.emission.x + ev.emission.y + ev.emission.z;
-    const double w = mis_weight(eye_density, es);
+    // pure eye path E_{i-1} .. E_0: strategy 0 has density EP[i-1]; strategies t = 1 .. min(i-1,
+    // MaxLightDepth) are f(es / total) K[i+1][m_lo] (the t >= j+2 sum with nothing re-evaluated)
+    const double s = heur_scale(eye_density);
+    double w = mis_pow(eye_density * s, ph);  // n = i <= MaxDepth always
+    if (i >= 2) {
+      const int m_lo = max(0, i - 1 - max_ld);
+      if (m_lo <= i - 2) w += mis_pow(es / bp.total_light * s, ph) * tab(mt.k(i + 1, m_lo));
+    }
+#if M3D_CONNECT_CHECK
+    check_weight(w, walk_weight(eye_density, es));
+#endif
     if (!(w > 0.0 && w < INFINITY)) return;
     float *a = reinterpret_cast<float *>(buf.accum + slot);
     atomicAdd(a, (float)(cur.x / w));
@@ -626,9 +746,34 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
     inten.z *= (double)jl.bsdf_fin.z;
   }
   if (inten.x + inten.y + inten.z < 1e-8) return;
+  // the strategies of the joined path (see "MIS weights in O(1) per connection")
+  const double jl_sd = full_sd(jl), jl_dd = full_dd(jl), je_sd = full_sd(je), je_dd = full_dd(je);
+  const double s = heur_scale(cur_density);
+  // t == j, this connection's own strategy (the edge length in float64 like every other edge of the sums)
+  double w = mis_pow(lst[0] * area_between(jl.point, je.point) / (double)dd * eye_density * s, ph);
+  const double tail = je_sd * eye_density;                  // sd(JE) * EP[i-1]
+  const int t_lo = max(1, n - bp.max_depth);
+  if (j >= 2) {
+    const double tail2 = jl_sd * tail;
+    if (n <= bp.max_depth) w += mis_pow(tab(mt.slp(j)) * tail2 * s, ph);            // t == 0
+    if (j >= 3 && t_lo <= j - 2) w += mis_pow(tail2 * s, ph) * tab(mt.h(j, t_lo));  // t <= j-2
+    if (t_lo <= j - 1) w += mis_pow(tab(mt.lt(j - 1)) * tail * s, ph);              // t == j-1
+  } else if (n <= bp.max_depth) {
+    w += mis_pow(tail * s, ph);  // t == 0 with j == 1: x_0 = JL is not eye-sampled
+  }
+  if (i >= 2 && j + 1 <= max_ld) {
+    const double ld1 = lst[0] * jl_dd * (double)sd / (double)dd;  // sd = sourceDot(JE), dd = destDot(JL)
+    w += mis_pow(ld1 * tab(mt.ge(i - 1)) * buf.eyepre[((size_t)(i - 2) * buf.cap + slot) * 4] * s, ph);  // t == j+1
+    if (i >= 3 && j + 2 <= max_ld) {
+      const int m_lo = max(0, n - 1 - max_ld);
+      if (m_lo <= i - 3) w += mis_pow(ld1 * je_dd * tab(mt.rsp(i - 2)) * s, ph) * tab(mt.k(i, m_lo));  // t >= j+2
+    }
+  }
+#if M3D_CONNECT_CHECK
   JL = mis_of(jl);
   JE = mis_of(je);
-  const double w = mis_weight(cur_density, l0_sum);
+  check_weight(w, walk_weight(cur_density, l0_sum));
+#endif
   if (!(w > 0.0 && w < INFINITY)) return;
   D3c color = {inten.x / w, inten.y / w, inten.z / w};
   const double brightness = fmax(fmax(color.x, color.y), color.z);
@@ -656,12 +801,34 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
   buf.cpay[pos] = make_float4((float)color.x, (float)color.y, (float)color.z, __int_as_float(slot));
 }
 
+// One thread per work item; threads of a warp share (i, j) except where two classes meet.
+__global__ void __launch_bounds__(kBlock, M3D_BCONNECT_MINB)
+bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
+#if M3D_CONNECT_CHUNKED
+  // M3D_CONNECT_PARTS consecutive blocks share a chunk and stride over its items
+  const int chunk = (int)(blockIdx.x / M3D_CONNECT_PARTS), part = (int)(blockIdx.x % M3D_CONNECT_PARTS);
+  const int count = buf.chunk_counts[chunk];
+  const uint32_t *seg = buf.work + (size_t)chunk * 256 * (bp.max_depth * (bp.max_light_depth + 1));
+  for (int k = part * kBlock + (int)threadIdx.x; k < count; k += M3D_CONNECT_PARTS * kBlock)
+    connect_item(sc, bp, b, buf, seg[k]);
+#else
+  // grid: x over the items of a class, y = class; most blocks of a sparsely filled class exit here
+  const int cls = (int)blockIdx.y, rank = (int)(blockIdx.x * kBlock + threadIdx.x);
+  if (rank >= buf.class_counts[cls]) return;
+  connect_item(sc, bp, b, buf, buf.work[(size_t)cls * buf.cap + rank]);
+#endif
+}
+
 template <int SB>
 __global__ void __launch_bounds__(256)
 bidir_connect_resolve_kernel(DeviceScene sc, BidirBuffers buf) {
   const int n = buf.counts[2];
   const int stride = gridDim.x * blockDim.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(buf.ray_total, (unsigned long long)n);
+#if M3D_CONNECT_CHECK
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    printf("MIS check: %d of %d connection weights differ from the path walk\n", buf.counts[4], buf.counts[5]);
+#endif
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
     const float4 pay = buf.cpay[q];
     const SceneHit h = resolve_scene_hit<SB>(sc, buf.corg[q], buf.cdir[q], buf.craw[q], buf.cskip[q], false);
@@ -733,7 +900,11 @@ void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, co
                           const BidirBuffers &buf, cudaStream_t stream) {
   const int64_t n = (int64_t)b.nP * b.S;
   if (n <= 0) return;
+#if M3D_CONNECT_CHUNKED
+  const unsigned grid = (unsigned)((n + 255) / 256) * M3D_CONNECT_PARTS;  // chunks of bidir_prefix_kernel's 256 samples
+#else
   const dim3 grid((unsigned)((n + kBlock - 1) / kBlock), (unsigned)(bp.max_depth * (bp.max_light_depth + 1)));
+#endif
   bidir_connect_kernel<<<grid, kBlock, 0, stream>>>(sc, bp, b, buf);
 }
 

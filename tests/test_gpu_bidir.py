@@ -109,6 +109,19 @@ def test_bidir_balance_heuristic_and_light_depth(built, oracle):
     check_statistical_parity(mean, var, ref["mean"], ref["var_of_mean"])
 
 
+def test_bidir_general_power_heuristic_with_binding_depth_limits(built, oracle):
+    """PowerHeuristic 3 (neither the balance sum nor the squared special case) with MaxDepth 4 /
+    MaxLightDepth 2: most joined paths are cut by one of the two limits, which is where the per-sample
+    MIS tables of the connection stage (H[j][t_lo], K[i][m_lo]) take their lower limits from."""
+    spec = scenes.cornell_box()
+    osc, psc = scenes.build_oracle(spec), scenes.build_product(spec)
+    kw = dict(max_depth=4, max_light_depth=2, min_depth=2, power_heuristic=3.0)
+    W = H = 24
+    ref = oracle_bidir(oracle, spec, osc, W, H, 384, **kw)
+    mean, var, _ = gpu_bidir(spec, psc, W, H, 1024, **kw)
+    check_statistical_parity(mean, var, ref["mean"], ref["var_of_mean"])
+
+
 def test_bidir_partitions_add_up(built):
     spec = scenes.cornell_box()
     psc = scenes.build_product(spec)
