@@ -44,7 +44,8 @@ int32_t carve_bidir_buffers(m3d_ctx *ctx, int64_t cap, int De, int Dl, BidirBuff
   }
   const size_t o_raw = take(c * 16), o_ef = take(c * 16), o_er = take(c * 16), o_acc = take(c * 16);
   const size_t o_ep = take(c * 32 * De), o_lp = take(c * 32 * Dl);
-  const size_t o_ma = take(c * 16 * (De + Dl)), o_mb = take(c * 16 * (De + Dl)), o_mc = take(c * 4 * (De + Dl));
+  const size_t mis_c = M3D_CONNECT_CHECK ? c : 0;  // the path-walk records exist in verification builds only
+  const size_t o_ma = take(mis_c * 16 * (De + Dl)), o_mb = take(mis_c * 16 * (De + Dl)), o_mc = take(mis_c * 4 * (De + Dl));
   const size_t cc = c * (size_t)De * (size_t)Dl;
   const size_t o_corg = take(cc * 16), o_cdir = take(cc * 16), o_craw = take(cc * 16), o_cpay = take(cc * 16),
                o_cskip = take(cc * 4);
@@ -251,8 +252,8 @@ static int32_t render_bidir_one_device(m3d_scene *scene, const m3d_camera *cam, 
     M3D_CUDA(cudaMemcpyAsync(d_tris, ht.data(), ht.size() * sizeof(DeviceLightTri), cudaMemcpyHostToDevice, s));
 
   // batch geometry: per-slot footprint is dominated by the stored path vertices
-  const size_t per_slot = (size_t)(16 * kBidirVertexFields + 32 + 36) * (max_depth + max_ld) +
-                          (size_t)max_depth * (max_ld + 1) * 72 + 256;
+  const size_t per_slot = (size_t)(16 * kBidirVertexFields + 32 + (M3D_CONNECT_CHECK ? 36 : 0)) * (max_depth + max_ld) +
+                          (size_t)max_depth * (max_ld + 1) * 72 + (size_t)MisTab{max_depth, max_ld}.entries() * 8 + 256;
 #ifndef M3D_BIDIR_BUDGET_GB
 #define M3D_BIDIR_BUDGET_GB 64  // device memory for one batch's path vertices / work lists (of 180 GB)
 #endif
@@ -302,13 +303,16 @@ static int32_t render_bidir_one_device(m3d_scene *scene, const m3d_camera *cam, 
     return M3D_OK;
   };
 
+  int64_t launches = 0;
   GpuTimer tm;
   tm.start(s);
-  int64_t launches = 0;
+  StageTimer stages(s);
+  static const char *const kStageNames[] = {"eye", "light", "prefix", "connect", "visibility", "resolve", "flush"};
   // traces one batch of samples; leaves one colour per slot in buf.accum
   auto run_batch = [&](const PathBatch &b) -> int32_t {
     const int64_t n = (int64_t)b.nP * b.S;
     // eye sub-paths
+    stages.mark(0);
     launch_bidir_eye_raygen(dc, bp, b, buf, s);
     launches++;
     int cur = 0;
@@ -320,6 +324,7 @@ static int32_t render_bidir_one_device(m3d_scene *scene, const m3d_camera *cam, 
       launches += 2;
     }
     // light sub-paths
+    stages.mark(1);
     launch_bidir_light_raygen(sc, bp, d_lights, d_tris, b, buf, s);
     launches++;
     cur = 0;
@@ -331,11 +336,16 @@ static int32_t render_bidir_one_device(m3d_scene *scene, const m3d_camera *cam, 
       launches += 2;
     }
     // connections: all (eye prefix, light prefix) pairs at once
+    stages.mark(2);
     launch_bidir_prefix(bp, b, buf, s);
+    stages.mark(3);
     launch_bidir_connect(sc, bp, b, buf, s);
+    stages.mark(4);
     if (int32_t rc = trace(buf.corg, buf.cdir, buf.cskip, buf.craw, n * max_depth * max_ld, buf.counts + 2))
       return rc;
+    stages.mark(5);
     launch_bidir_connect_resolve(sc, buf, s);
+    stages.mark(6);
     launches += 4;
     return M3D_OK;
   };
@@ -379,11 +389,13 @@ static int32_t render_bidir_one_device(m3d_scene *scene, const m3d_camera *cam, 
       }
     }
   }
+  stages.mark(7);
   tm.stop(s);
   unsigned long long rays = 0;
   M3D_CUDA(cudaMemcpyAsync(&rays, buf.ray_total, sizeof(rays), cudaMemcpyDeviceToHost, s));
   M3D_CUDA(cudaStreamSynchronize(s));  // also keeps the host light tables alive for the copies
   M3D_CUDA(cudaGetLastError());
+  stages.report("m3d_render_bidir", kStageNames, 7);
   if (stats) {
     stats->rays = (int64_t)rays;
     stats->kernel_ms = tm.ms();

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -70,6 +71,39 @@ struct GpuTimer {
     cudaEventSynchronize(b);
     cudaEventElapsedTime(&f, a, b);
     return f;
+  }
+};
+
+// Per-stage device times of a multi-launch render, for tuning runs: with M3D_STAGE_TIMING set in the
+// environment, mark(k) records an event where stage k begins (and the previous one ends) and report()
+// prints the summed times per stage to stderr after the stream has been synchronised.  Off: no events.
+struct StageTimer {
+  bool on = false;
+  cudaStream_t stream = nullptr;
+  std::vector<std::pair<int, cudaEvent_t>> marks;
+  explicit StageTimer(cudaStream_t s) : stream(s) { on = getenv("M3D_STAGE_TIMING") != nullptr; }
+  ~StageTimer() {
+    for (auto &m : marks) cudaEventDestroy(m.second);
+  }
+  void mark(int stage) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    marks.emplace_back(stage, e);
+  }
+  void report(const char *what, const char *const *names, int num_stages) {
+    if (!on || marks.size() < 2) return;
+    std::vector<double> ms((size_t)num_stages + 1, 0.0);
+    for (size_t i = 0; i + 1 < marks.size(); i++) {
+      float f = 0;
+      cudaEventElapsedTime(&f, marks[i].second, marks[i + 1].second);
+      const int k = marks[i].first;
+      ms[(size_t)(k >= 0 && k < num_stages ? k : num_stages)] += f;
+    }
+    fprintf(stderr, "[m3d stage timing] %s:", what);
+    for (int k = 0; k < num_stages; k++) fprintf(stderr, " %s %.2f ms", names[k], ms[(size_t)k]);
+    fprintf(stderr, "\n");
   }
 };
 

@@ -12,6 +12,13 @@ namespace m3d {
 
 constexpr int kBidirMaxDepth = 16;  // per sub-path; joined paths have at most 32 vertices
 
+// 1: the connection kernel also walks every joined path like the reference's `densities` and reports
+// weights that differ from the table-based ones (tuning / verification builds:
+// scripts/build_variant.sh chk "-DM3D_CONNECT_CHECK=1" "bidir_kernels.cu api_bidir.cu")
+#ifndef M3D_CONNECT_CHECK
+#define M3D_CONNECT_CHECK 0
+#endif
+
 struct DeviceBidirParams {
   int32_t max_depth, max_light_depth, min_depth;
   float cutoff, antialias;
@@ -61,7 +68,8 @@ struct BidirBuffers {
   // running products of allPathCombinations per sub-path prefix, 4 doubles each:
   // eyepre[(i-1)*cap + slot] = eyeDensity, eyeBSDF.xyz; lightpre[(j-1)*cap + slot] likewise
   double *eyepre, *lightpre;
-  // compact MIS records, depth-major: eye vertices at [0, De), light vertices at [De, De+Dl)
+  // M3D_CONNECT_CHECK builds only: compact per-vertex records of the path walk, depth-major: eye
+  // vertices at [0, De), light vertices at [De, De+Dl)
   float4 *misA;
   double2 *misB;
   float *misC;

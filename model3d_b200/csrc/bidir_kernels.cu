@@ -29,7 +29,7 @@
 // Work list of the connection stage grouped by CHUNK (the 256 consecutive samples of one
 // bidir_prefix block) and, inside a chunk, by (i, j) class.  0: one list per class over the whole batch.
 #ifndef M3D_CONNECT_CHUNKED
-#define M3D_CONNECT_CHUNKED 0
+#define M3D_CONNECT_CHUNKED 1
 #endif
 #ifndef M3D_CONNECT_PARTS
 #define M3D_CONNECT_PARTS 32  // connection blocks per chunk (each strides over the chunk's items)
@@ -109,6 +109,17 @@ __device__ __forceinline__ void eval_vertex(const DeviceScene &sc, BVert &v, int
   v.bsdf_fin = mat_bsdf(sc, m, v.normal, v.source, v.dest);
   v.bsdf_del = mat_bsdf_delta(sc, m, v.normal, v.source, v.dest, tag);
 }
+
+// One out-of-line copy for callers that evaluate several vertices (the connection kernel's two junction
+// vertices): the material code is ~2,000 instructions per inlined copy.
+#ifndef M3D_CONNECT_EVAL_NOINLINE
+#define M3D_CONNECT_EVAL_NOINLINE 0
+#endif
+#if M3D_CONNECT_EVAL_NOINLINE
+static __device__ __noinline__ void eval_vertex_call(const DeviceScene &sc, BVert &v) { eval_vertex(sc, v, 0); }
+#else
+__device__ __forceinline__ void eval_vertex_call(const DeviceScene &sc, BVert &v) { eval_vertex(sc, v, 0); }
+#endif
 
 __device__ __forceinline__ float source_dot(const BVert &v) { return fabsf(dot(v.normal, v.source)); }
 __device__ __forceinline__ float dest_dot(const BVert &v) { return fabsf(dot(v.normal, v.dest)); }
@@ -277,6 +288,12 @@ bidir_shade_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffe
     }
   }
 }
+// (Measured and rejected, round 2: splitting this kernel like a bounce of the path tracer -- a resolve
+// kernel writing 48-byte hit records and per-kind work lists, then bidir_sample_kernel<EYE, KIND> per
+// material kind, 1,400-3,300 instructions each instead of 6,450 -- removes the instruction-fetch stalls
+// (43 % of this kernel's stall samples) but not its time: eye + light stages 305 ms vs 290 ms per
+// 1024^2 x 128 spp frame.  The stage is bound by the scattered 112-byte vertex stores and the pathEnder
+// gathers, and the split adds the hit-record round trip and four launches per step.)
 
 // Box-Muller pair from two uniforms
 __device__ __forceinline__ void gauss2(Rng &g, float &a, float &b) {
@@ -389,13 +406,17 @@ bidir_light_raygen_kernel(DeviceScene sc, DeviceBidirParams bp, const DeviceArea
 // light vertices).  bidir_prefix_kernel fills the tables (O(depth^2) per sample), a connection reads seven
 // entries instead of walking its joined path twice (O(depth) dependent 32-byte gathers per item, 40 % of
 // the connection kernel's stall samples, and a 33-entry float64 array in local memory).
-// M3D_CONNECT_CHECK=1 also keeps the path walk and reports items whose two weights differ.
-#ifndef M3D_CONNECT_CHECK
-#define M3D_CONNECT_CHECK 0
-#endif
+// M3D_CONNECT_CHECK=1 (bidir.h) also keeps the path walk and reports items whose two weights differ.
+// PHK selects the heuristic at compile time: 0 balance (PowerHeuristic 0: plain sum), 2 the squared
+// special case, 1 any other exponent.  pow() is ~100 instructions per call site and the connection kernel
+// has a dozen of them: compiled in unconditionally they were a third of its 7,100 instructions, with 28 %
+// of the stall samples waiting for instruction fetch.
+static __device__ __noinline__ double pow_general(double x, double ph) { return pow(x, ph); }
+template <int PHK>
 __device__ __forceinline__ double mis_pow(double x, double ph) {
-  return ph == 0.0 ? x : (ph == 2.0 ? x * x : pow(x, ph));
+  return PHK == 0 ? x : (PHK == 2 ? x * x : pow_general(x, ph));
 }
+__host__ __device__ inline int heuristic_kind(double ph) { return ph == 0.0 ? 0 : (ph == 2.0 ? 2 : 1); }
 __device__ __forceinline__ double area_between(V3f a, V3f b) {
   const double dx = (double)a.x - b.x, dy = (double)a.y - b.y, dz = (double)a.z - b.z;
   return kFourPi * (dx * dx + dy * dy + dz * dz);
@@ -455,6 +476,7 @@ struct D3c {
 //   eyepre[i-1]   = (eyeDensity, eyeBSDF.xyz) as they stand when the outer loop reaches i
 //   lightpre[j-1] = (density / eyeDensity, lightBSDF.xyz) as they stand when the inner loop reaches j
 // One thread per sample; also fills the per-sample MIS tables (see above).
+template <int PHK>
 __global__ void __launch_bounds__(256)
 bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
   __shared__ int s_cnt[kBidirMaxDepth * (kBidirMaxDepth + 1)], s_base[kBidirMaxDepth * (kBidirMaxDepth + 1)];
@@ -493,7 +515,7 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
         tab(mt.ge(i - 1)) = ge;
         tab(mt.rsp(i - 2)) = rsp;
         // K[i+1][m] = g(RS[i-2]) K[i][m] + g(GE[i-1] EP[i-2]),  m = 0 .. i-2
-        const double grs = mis_pow(full_dd(v) * rsp, ph), gnew = mis_pow(ge * ep_prev, ph);
+        const double grs = mis_pow<PHK>(full_dd(v) * rsp, ph), gnew = mis_pow<PHK>(ge * ep_prev, ph);
         for (int m = 0; m <= i - 2; m++) {
           const double kv = (m <= i - 3 ? grs * krow[m] : 0.0) + gnew;
           krow[m] = kv;
@@ -528,7 +550,7 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
           const double sdp = full_sd(prev);
           slp *= sdp;
           // H[j][t_lo] = g(sd(L_{j-2})) H[j-1][t_lo] + g(LT[j-2]),  t_lo = 1 .. j-2
-          const double gs = mis_pow(sdp, ph), gl = mis_pow(lt_prev, ph);
+          const double gs = mis_pow<PHK>(sdp, ph), gl = mis_pow<PHK>(lt_prev, ph);
           for (int t = 1; t <= j - 2; t++) {
             const double hv = (t <= j - 3 ? gs * hrow[t - 1] : 0.0) + gl;
             hrow[t - 1] = hv;
@@ -618,6 +640,7 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
 
 // allPathCombinations (bidir.go:476-530) + rayColor's callback (bidir.go:113-158) for one
 // (eye prefix length i, light prefix length j, sample) work item.
+template <int PHK>
 __device__ __forceinline__ void connect_item(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
                                              const BidirBuffers &buf, uint32_t item) {
   const int slot = (int)(item & 0x3fffffu);
@@ -637,7 +660,7 @@ __device__ __forceinline__ void connect_item(const DeviceScene &sc, const Device
   // f(x) = (x / density^((ph-1)/ph))^ph, the heuristic's term of a strategy of density x, normalised like
   // the reference's so that the sums stay inside float64; f(x y) = f(x) g(y)
   auto heur_scale = [&](double density) -> double {
-    return ph == 0.0 ? 1.0 : (ph == 2.0 ? rsqrt(density) : pow(density, -(ph - 1.0) / ph));
+    return PHK == 0 ? 1.0 : (PHK == 2 ? rsqrt(density) : pow_general(density, -(ph - 1.0) / ph));
   };
 #if M3D_CONNECT_CHECK
   // the path walk the tables replace: joined path light[0..j-2], JL, JE, eye[i-2..0] for j >= 1,
@@ -653,7 +676,7 @@ __device__ __forceinline__ void connect_item(const DeviceScene &sc, const Device
   auto walk_weight = [&](double density, double emis0_sum) -> double {
     const double s = heur_scale(density);
     double weight = 0.0;
-    auto f = [&](double d) { weight += mis_pow(d * s, ph); };
+    auto f = [&](double d) { weight += mis_pow<PHK>(d * s, ph); };
     double term[2 * kBidirMaxDepth + 1];
     if (n > 1) {
       double ld = emis0_sum / bp.total_light;
@@ -699,10 +722,10 @@ __device__ __forceinline__ void connect_item(const DeviceScene &sc, const Device
     // pure eye path E_{i-1} .. E_0: strategy 0 has density EP[i-1]; strategies t = 1 .. min(i-1,
     // MaxLightDepth) are f(es / total) K[i+1][m_lo] (the t >= j+2 sum with nothing re-evaluated)
     const double s = heur_scale(eye_density);
-    double w = mis_pow(eye_density * s, ph);  // n = i <= MaxDepth always
+    double w = mis_pow<PHK>(eye_density * s, ph);  // n = i <= MaxDepth always
     if (i >= 2) {
       const int m_lo = max(0, i - 1 - max_ld);
-      if (m_lo <= i - 2) w += mis_pow(es / bp.total_light * s, ph) * tab(mt.k(i + 1, m_lo));
+      if (m_lo <= i - 2) w += mis_pow<PHK>(es / bp.total_light * s, ph) * tab(mt.k(i + 1, m_lo));
     }
 #if M3D_CONNECT_CHECK
     check_weight(w, walk_weight(eye_density, es));
@@ -719,8 +742,10 @@ __device__ __forceinline__ void connect_item(const DeviceScene &sc, const Device
   const double density = eye_density * lst[0];
   const D3c light_bsdf = {lst[1], lst[2], lst[3]};
   const BVert lj = load_vertex(buf.lv, buf.Dl, buf.cap, j - 1, slot);
+#if M3D_CONNECT_CHECK
   const float4 l0e = buf.lv[vidx(6, buf.Dl, buf.cap, 0, slot)];
   const double l0_sum = (double)l0e.x + l0e.y + l0e.z;
+#endif
   const V3f diff = lj.point - ev.point;
   const float dist2 = dot(diff, diff);
   const float dist = sqrtf(dist2);
@@ -728,10 +753,10 @@ __device__ __forceinline__ void connect_item(const DeviceScene &sc, const Device
   // combinePaths (bidir.go:544-566): both junction vertices re-evaluated for the new edge
   BVert jl = lj;
   jl.dest = (ev.point - lj.point) * (1.f / dist);
-  eval_vertex(sc, jl, 0);
+  eval_vertex_call(sc, jl);
   BVert je = ev;
   je.source = jl.dest;
-  eval_vertex(sc, je, 0);
+  eval_vertex_call(sc, je);
   const float dd = dest_dot(jl);
   const float sd = source_dot(je);
   if (!(dd > 0.f && sd > 0.f)) return;
@@ -750,23 +775,23 @@ __device__ __forceinline__ void connect_item(const DeviceScene &sc, const Device
   const double jl_sd = full_sd(jl), jl_dd = full_dd(jl), je_sd = full_sd(je), je_dd = full_dd(je);
   const double s = heur_scale(cur_density);
   // t == j, this connection's own strategy (the edge length in float64 like every other edge of the sums)
-  double w = mis_pow(lst[0] * area_between(jl.point, je.point) / (double)dd * eye_density * s, ph);
+  double w = mis_pow<PHK>(lst[0] * area_between(jl.point, je.point) / (double)dd * eye_density * s, ph);
   const double tail = je_sd * eye_density;                  // sd(JE) * EP[i-1]
   const int t_lo = max(1, n - bp.max_depth);
   if (j >= 2) {
     const double tail2 = jl_sd * tail;
-    if (n <= bp.max_depth) w += mis_pow(tab(mt.slp(j)) * tail2 * s, ph);            // t == 0
-    if (j >= 3 && t_lo <= j - 2) w += mis_pow(tail2 * s, ph) * tab(mt.h(j, t_lo));  // t <= j-2
-    if (t_lo <= j - 1) w += mis_pow(tab(mt.lt(j - 1)) * tail * s, ph);              // t == j-1
+    if (n <= bp.max_depth) w += mis_pow<PHK>(tab(mt.slp(j)) * tail2 * s, ph);            // t == 0
+    if (j >= 3 && t_lo <= j - 2) w += mis_pow<PHK>(tail2 * s, ph) * tab(mt.h(j, t_lo));  // t <= j-2
+    if (t_lo <= j - 1) w += mis_pow<PHK>(tab(mt.lt(j - 1)) * tail * s, ph);              // t == j-1
   } else if (n <= bp.max_depth) {
-    w += mis_pow(tail * s, ph);  // t == 0 with j == 1: x_0 = JL is not eye-sampled
+    w += mis_pow<PHK>(tail * s, ph);  // t == 0 with j == 1: x_0 = JL is not eye-sampled
   }
   if (i >= 2 && j + 1 <= max_ld) {
     const double ld1 = lst[0] * jl_dd * (double)sd / (double)dd;  // sd = sourceDot(JE), dd = destDot(JL)
-    w += mis_pow(ld1 * tab(mt.ge(i - 1)) * buf.eyepre[((size_t)(i - 2) * buf.cap + slot) * 4] * s, ph);  // t == j+1
+    w += mis_pow<PHK>(ld1 * tab(mt.ge(i - 1)) * buf.eyepre[((size_t)(i - 2) * buf.cap + slot) * 4] * s, ph);  // t == j+1
     if (i >= 3 && j + 2 <= max_ld) {
       const int m_lo = max(0, n - 1 - max_ld);
-      if (m_lo <= i - 3) w += mis_pow(ld1 * je_dd * tab(mt.rsp(i - 2)) * s, ph) * tab(mt.k(i, m_lo));  // t >= j+2
+      if (m_lo <= i - 3) w += mis_pow<PHK>(ld1 * je_dd * tab(mt.rsp(i - 2)) * s, ph) * tab(mt.k(i, m_lo));  // t >= j+2
     }
   }
 #if M3D_CONNECT_CHECK
@@ -802,6 +827,7 @@ __device__ __forceinline__ void connect_item(const DeviceScene &sc, const Device
 }
 
 // One thread per work item; threads of a warp share (i, j) except where two classes meet.
+template <int PHK>
 __global__ void __launch_bounds__(kBlock, M3D_BCONNECT_MINB)
 bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
 #if M3D_CONNECT_CHUNKED
@@ -810,12 +836,12 @@ bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuf
   const int count = buf.chunk_counts[chunk];
   const uint32_t *seg = buf.work + (size_t)chunk * 256 * (bp.max_depth * (bp.max_light_depth + 1));
   for (int k = part * kBlock + (int)threadIdx.x; k < count; k += M3D_CONNECT_PARTS * kBlock)
-    connect_item(sc, bp, b, buf, seg[k]);
+    connect_item<PHK>(sc, bp, b, buf, seg[k]);
 #else
   // grid: x over the items of a class, y = class; most blocks of a sparsely filled class exit here
   const int cls = (int)blockIdx.y, rank = (int)(blockIdx.x * kBlock + threadIdx.x);
   if (rank >= buf.class_counts[cls]) return;
-  connect_item(sc, bp, b, buf, buf.work[(size_t)cls * buf.cap + rank]);
+  connect_item<PHK>(sc, bp, b, buf, buf.work[(size_t)cls * buf.cap + rank]);
 #endif
 }
 
@@ -893,7 +919,12 @@ void launch_bidir_prefix(const DeviceBidirParams &bp, const PathBatch &b, const 
                          cudaStream_t stream) {
   const int64_t n = (int64_t)b.nP * b.S;
   if (n <= 0) return;
-  bidir_prefix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bp, b, buf);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  switch (heuristic_kind(bp.power_heuristic)) {
+    case 0: bidir_prefix_kernel<0><<<grid, 256, 0, stream>>>(bp, b, buf); break;
+    case 2: bidir_prefix_kernel<2><<<grid, 256, 0, stream>>>(bp, b, buf); break;
+    default: bidir_prefix_kernel<1><<<grid, 256, 0, stream>>>(bp, b, buf); break;
+  }
 }
 
 void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, const PathBatch &b,
@@ -905,7 +936,11 @@ void launch_bidir_connect(const DeviceScene &sc, const DeviceBidirParams &bp, co
 #else
   const dim3 grid((unsigned)((n + kBlock - 1) / kBlock), (unsigned)(bp.max_depth * (bp.max_light_depth + 1)));
 #endif
-  bidir_connect_kernel<<<grid, kBlock, 0, stream>>>(sc, bp, b, buf);
+  switch (heuristic_kind(bp.power_heuristic)) {
+    case 0: bidir_connect_kernel<0><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf); break;
+    case 2: bidir_connect_kernel<2><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf); break;
+    default: bidir_connect_kernel<1><<<grid, kBlock, 0, stream>>>(sc, bp, b, buf); break;
+  }
 }
 
 void launch_bidir_connect_resolve(const DeviceScene &sc, const BidirBuffers &buf, cudaStream_t stream) {

@@ -119,7 +119,10 @@ def test_bidir_general_power_heuristic_with_binding_depth_limits(built, oracle):
     W = H = 24
     ref = oracle_bidir(oracle, spec, osc, W, H, 384, **kw)
     mean, var, _ = gpu_bidir(spec, psc, W, H, 1024, **kw)
-    check_statistical_parity(mean, var, ref["mean"], ref["var_of_mean"])
+    # two light vertices at most leave fewer strategies per path and heavier-tailed pixels: the mean z of
+    # the skewed per-pixel estimates sits at 0.15-0.23 for 384 as for 8192 oracle samples while the image
+    # means agree to 0.5 sigma (scripts/bidir_param_check.py), so the bound on it is wider here
+    check_statistical_parity(mean, var, ref["mean"], ref["var_of_mean"], max_mean_z=0.3)
 
 
 def test_bidir_partitions_add_up(built):
