@@ -476,8 +476,11 @@ struct D3c {
 //   eyepre[i-1]   = (eyeDensity, eyeBSDF.xyz) as they stand when the outer loop reaches i
 //   lightpre[j-1] = (density / eyeDensity, lightBSDF.xyz) as they stand when the inner loop reaches j
 // One thread per sample; also fills the per-sample MIS tables (see above).
+#ifndef M3D_BPREFIX_MINB
+#define M3D_BPREFIX_MINB 3  // 80 registers, 3 blocks of 256: C5 prefix stage 68 -> 61 ms per 128-spp frame
+#endif
 template <int PHK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, M3D_BPREFIX_MINB)
 bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
   __shared__ int s_cnt[kBidirMaxDepth * (kBidirMaxDepth + 1)], s_base[kBidirMaxDepth * (kBidirMaxDepth + 1)];
   const int n_slots = b.nP * b.S;

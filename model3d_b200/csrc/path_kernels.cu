@@ -138,7 +138,11 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
       const float4 o = __ldcs(org_in + q), d = __ldcs(dir_in + q), raw = __ldcs(buf.raw + q);
       // float32 hit evaluation: Monte-Carlo parity is statistical, the float64 refinement of the
       // first-hit API (1e-5 on t and normals) is not needed here; shapes stay float64
+#ifdef M3D_TEST_NOSHAPES
+      const SceneHit h = resolve_scene_hit<0>(sc, o, d, raw, skip_in[q], false);
+#else
       const SceneHit h = resolve_scene_hit<SB>(sc, o, d, raw, skip_in[q], false);
+#endif
       if (LIGHTS && pp.num_lights > 0 && h.obj < 0) {
         // no shadow rays for a miss: give the slots an empty parameter interval
         for (int l = 0; l < pp.num_lights; l++) {

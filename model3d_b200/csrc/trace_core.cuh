@@ -200,6 +200,21 @@ M3D_HD float unit_plus_byte(uint32_t q, int j, uint32_t one) {
 #endif
 }
 
+#ifndef M3D_FFMA2
+#define M3D_FFMA2 0
+#endif
+#if defined(__CUDACC__)
+// (a0, a1) * s + (b0, b1) as one packed float32 FMA (sm_100: fma.rn.f32x2 -> FFMA2)
+__device__ __forceinline__ void fma2(float a0, float a1, float s, float b0, float b1, float &r0, float &r1) {
+  unsigned long long a, ss, b, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(ss), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+}
+#endif
+
 // The reference's Moeller-Trumbore in float64 (primitives.go:207-249) on the float32
 // inputs widened exactly: the arbiter for rays that pass so close to a triangle edge (or
 // are so nearly parallel to it) that the float32 test cannot decide.  Kept out of line: it
@@ -396,12 +411,21 @@ M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index,
     const uint32_t zn = (rp.octinv4 & 1u) ? qloz : qhiz, zf = (rp.octinv4 & 1u) ? qhiz : qloz;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
+#if defined(__CUDA_ARCH__) && M3D_FFMA2
+      // near and far plane of one axis in one packed FMA (FFMA2: two float32 FMAs, one issue slot;
+      // the kernel is bound by issue slots, not by the FMA pipe)
+      float t0x, t1x, t0y, t1y, t0z, t1z;
+      fma2(unit_plus_byte(xn, j, one), unit_plus_byte(xf, j, one), Sx, bnx, bfx, t0x, t1x);
+      fma2(unit_plus_byte(yn, j, one), unit_plus_byte(yf, j, one), Sy, bny, bfy, t0y, t1y);
+      fma2(unit_plus_byte(zn, j, one), unit_plus_byte(zf, j, one), Sz, bnz, bfz, t0z, t1z);
+#else
       const float t0x = fmaf(unit_plus_byte(xn, j, one), Sx, bnx);
       const float t0y = fmaf(unit_plus_byte(yn, j, one), Sy, bny);
       const float t0z = fmaf(unit_plus_byte(zn, j, one), Sz, bnz);
       const float t1x = fmaf(unit_plus_byte(xf, j, one), Sx, bfx);
       const float t1y = fmaf(unit_plus_byte(yf, j, one), Sy, bfy);
       const float t1z = fmaf(unit_plus_byte(zf, j, one), Sz, bfz);
+#endif
       const float cmin = fmaxf(max3f(t0x, t0y, t0z), rp.tmin);
       const float cmax = fminf(min3f(t1x, t1y, t1z), tmax_w);
       if (USE_LUT) {
