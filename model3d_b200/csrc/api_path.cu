@@ -269,11 +269,14 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
   for (int32_t mi : scene->object_material) kinds_present |= 1u << (unsigned)scene->host_materials[(size_t)mi].kind;
   GpuTimer tm;
   tm.start(s);
+  StageTimer stages(s);  // M3D_STAGE_TIMING=1: device time per kernel type, printed to stderr
+  static const char *const kStageNames[] = {"raygen", "trace", "resolve", "sample", "shadow", "flush"};
   int64_t launches = 0;
   // traces one batch: raygen -> [trace -> shade (-> shadow trace -> resolve)] x depth; leaves one
   // colour per slot in buf.accum
   auto run_batch = [&](const PathBatch &b) -> int32_t {
     const int64_t n = (int64_t)b.nP * b.S;
+    stages.mark(0);
     launch_path_raygen(dc, pp, b, buf, s);
     launches++;
     int cur = 0;
@@ -290,8 +293,11 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
       t.skip_tris = buf.skip[cur];
       t.ray_counter = next_work_counter(ctx);
       if (!t.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
+      stages.mark(1);
       launch_trace_bvh_only(sc.bvh, t, s);
+      stages.mark(2);
       launch_path_resolve(sc, pp, d_lights, b, buf, cur, depth, s);
+      stages.mark(3);
       launches += 2;
       if (depth < pp.max_depth)
         for (int k = 0; k < 4; k++)
@@ -299,6 +305,7 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
             launch_path_sample(k, sc, pp, b, buf, cur, depth, s);
             launches++;
           }
+      stages.mark(4);
       if (num_lights > 0) {
         TraceLaunch ts;
         ts.org_tmin = buf.sorg;
@@ -321,6 +328,7 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
       M3D_CUDA(cudaMemsetAsync(buf.counts + 4, 0, 4 * sizeof(int), s));
       cur ^= 1;
     }
+    stages.mark(5);
     return M3D_OK;
   };
   int64_t samples_taken = npix * sample_count;
@@ -363,6 +371,7 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
       }
     }
   }
+  stages.mark(6);
   tm.stop(s);
   t_enq = now();
   // host-side tables (lights) must outlive the async copies; stats need the counters
@@ -373,6 +382,7 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
     fprintf(stderr, "[m3d] render_path: setup %.3f ms, enqueue %.3f ms, wait %.3f ms (cap %lld)\n", t_carved - t_entry,
             t_enq - t_carved, now() - t_enq, (long long)cap);
   M3D_CUDA(cudaGetLastError());
+  stages.report("m3d_render_path", kStageNames, 6);
   if (stats) {
     stats->rays = (int64_t)rays;
     stats->kernel_ms = tm.ms();

@@ -537,6 +537,9 @@ int32_t m3d_scene_build(m3d_scene_builder *b, uint32_t build_flags, m3d_scene **
   }
   sc->dev.shapes = sc->shapes.as<const DeviceShape>();
   sc->dev.num_shapes = (int32_t)sc->host_shapes.size();
+  sc->dev.spheres_only = 1;
+  for (const DeviceShape &sh : sc->host_shapes)
+    if (sh.kind != SHAPE_SPHERE) sc->dev.spheres_only = 0;
   sc->dev.objects = sc->objects.as<const DeviceObject>();
   sc->dev.num_objects = (int32_t)dobjs.size();
   sc->dev.materials = sc->materials.as<const DeviceMaterial>();

@@ -83,9 +83,14 @@ struct MatAt {
   V3f diffuse;  // of the top-level material (procedural variants resolved)
 };
 
+// material `index` at `point` (procedural variants resolved)
+__device__ __forceinline__ MatAt material_at_index(const DeviceScene &sc, int32_t index, V3f point);
 __device__ __forceinline__ MatAt material_at(const DeviceScene &sc, int32_t object, V3f point) {
+  return material_at_index(sc, sc.objects[object].material, point);
+}
+__device__ __forceinline__ MatAt material_at_index(const DeviceScene &sc, int32_t index, V3f point) {
   MatAt m;
-  m.index = sc.objects[object].material;
+  m.index = index;
   const DeviceMaterial &d = sc.materials[m.index];
   m.diffuse = v3f(d.diffuse);
   if (d.flags & M3D_MAT_CHECKER) {

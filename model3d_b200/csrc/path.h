@@ -55,7 +55,7 @@ struct PathBuffers {
   int32_t *skip[2], *queue[2];
   float4 *raw;
   float4 *thr, *accum;
-  // hit records of the current bounce, in queue order: (point, surface id), (normal, object),
+  // hit records of the current bounce, in queue order: (point, surface id), (normal, material index),
   // (direction to the viewer, slot); and the per-material-kind work lists of queue positions
   float4 *hrA, *hrB, *hrC;
   int32_t *klist[4];

@@ -113,14 +113,15 @@ path_raygen_kernel(DeviceCamera cam, DevicePathParams pp, PathBatch b, PathBuffe
 #endif
 // SB: 1 = the scene's few analytic shapes are tested one by one, 2 = scenes with an object-level
 // hierarchy (many shapes / mesh instances) walk it (resolve_scene_hit)
-template <bool LIGHTS, int SB>
-__global__ void __launch_bounds__(kShadeBlock, M3D_RESOLVE_MINB)
+#ifndef M3D_RESOLVE_SPHERES_MINB
+#define M3D_RESOLVE_SPHERES_MINB 4
+#endif
+template <bool LIGHTS, int SB>  // SB = 3: scenes whose analytic shapes are all spheres (no point lights)
+__global__ void __launch_bounds__(kShadeBlock, SB == 3 ? M3D_RESOLVE_SPHERES_MINB : M3D_RESOLVE_MINB)
 path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight *__restrict__ lights, PathBatch b,
                     PathBuffers buf, int cur, int depth) {
   const int n = buf.counts[cur];
   const unsigned lane = threadIdx.x & 31u;
-  const int warps_total = (gridDim.x * kShadeBlock) >> 5;
-  const int warp_id = (blockIdx.x * kShadeBlock + threadIdx.x) >> 5;
   const float4 *__restrict__ org_in = buf.org[cur];
   const float4 *__restrict__ dir_in = buf.dir[cur];
   const int32_t *__restrict__ skip_in = buf.skip[cur];
@@ -130,19 +131,25 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
     buf.counts[2] = n * pp.num_lights;
   }
 
-  for (int base = warp_id * 32; base < n; base += warps_total * 32) {
-    const int q = base + (int)lane;
+  // List appends of the spheres-only instantiation are aggregated per block (one global atomic per block
+  // and kind instead of one per warp: the per-kind counters are single addresses that every warp of the
+  // grid adds to; measured on C3: resolve stage 14.6 -> 13.5 ms per 1024^2 x 64 spp frame).  The general
+  // instantiation keeps the per-warp form: its rare float64 shape tests make the block barriers cost more
+  // than the atomics (C4: 12.1 -> 12.9 ms with them).
+  constexpr bool kBlockAgg = SB == 3;
+  __shared__ int s_wcnt[2][4][kShadeBlock / 32];
+  __shared__ int s_kbase[2][4];
+  const int wib = (int)(threadIdx.x >> 5);
+  int parity = 0;
+  for (int bbase = (int)blockIdx.x * kShadeBlock; bbase < n; bbase += (int)gridDim.x * kShadeBlock, parity ^= 1) {
+    const int q = bbase + (int)threadIdx.x;
     int kind = -1;  // material kind whose sampler continues this path, -1: the path ends
     if (q < n) {
       const int slot = queue_in[q];
       const float4 o = __ldcs(org_in + q), d = __ldcs(dir_in + q), raw = __ldcs(buf.raw + q);
       // float32 hit evaluation: Monte-Carlo parity is statistical, the float64 refinement of the
       // first-hit API (1e-5 on t and normals) is not needed here; shapes stay float64
-#ifdef M3D_TEST_NOSHAPES
-      const SceneHit h = resolve_scene_hit<0>(sc, o, d, raw, skip_in[q], false);
-#else
       const SceneHit h = resolve_scene_hit<SB>(sc, o, d, raw, skip_in[q], false);
-#endif
       if (LIGHTS && pp.num_lights > 0 && h.obj < 0) {
         // no shadow rays for a miss: give the slots an empty parameter interval
         for (int l = 0; l < pp.num_lights; l++) {
@@ -195,20 +202,46 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
         if (depth < pp.max_depth) {
           kind = sc.materials[m.index].kind;
           buf.hrA[q] = make_float4(point.x, point.y, point.z, __int_as_float(h.surf));
-          buf.hrB[q] = make_float4(nrm.x, nrm.y, nrm.z, __int_as_float(h.obj));
+          buf.hrB[q] = make_float4(nrm.x, nrm.y, nrm.z, __int_as_float(m.index));  // the material, not the object:
+                                                                                 // one gather less in the sampler
           buf.hrC[q] = make_float4(dest.x, dest.y, dest.z, __int_as_float(slot));
         }
       }
     }
-    // append to the per-kind work lists (one atomic per warp and kind present in the warp)
+    if (kBlockAgg) {
+      // append to the per-kind work lists: one global atomic per block and kind
+      unsigned mine = 0u;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const unsigned m = __ballot_sync(0xffffffffu, kind == k);
-      if (m) {
-        int pos0 = 0;
-        if (lane == (unsigned)(__ffs(m) - 1)) pos0 = atomicAdd(buf.counts + 4 + k, __popc(m));
-        pos0 = __shfl_sync(0xffffffffu, pos0, __ffs(m) - 1);
-        if (kind == k) buf.klist[k][pos0 + __popc(m & ((1u << lane) - 1u))] = q;
+      for (int k = 0; k < 4; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, kind == k);
+        if (lane == 0) s_wcnt[parity][k][wib] = __popc(m);
+        if (kind == k) mine = m;
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kShadeBlock / 32; w++) tot += s_wcnt[parity][threadIdx.x][w];
+        s_kbase[parity][threadIdx.x] = tot ? atomicAdd(buf.counts + 4 + (int)threadIdx.x, tot) : 0;
+      }
+      __syncthreads();
+      if (kind >= 0) {
+        int off = s_kbase[parity][kind];
+        for (int w = 0; w < wib; w++) off += s_wcnt[parity][kind][w];
+        buf.klist[kind][off + __popc(mine & ((1u << lane) - 1u))] = q;
+      }
+      // (the next trip writes the other half of s_wcnt / s_kbase; its first barrier orders it after these reads)
+    } else {
+      // one atomic per warp and kind present in the warp
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, kind == k);
+        if (m) {
+          int pos0 = 0;
+          if (lane == (unsigned)(__ffs(m) - 1)) pos0 = atomicAdd(buf.counts + 4 + k, __popc(m));
+          pos0 = __shfl_sync(0xffffffffu, pos0, __ffs(m) - 1);
+          if (kind == k) buf.klist[k][pos0 + __popc(m & ((1u << lane) - 1u))] = q;
+        }
       }
     }
   }
@@ -263,13 +296,11 @@ __global__ void __launch_bounds__(kShadeBlock, M3D_SAMPLE_MINB)
 path_sample_kernel(DeviceScene sc, DevicePathParams pp, PathBatch b, PathBuffers buf, int cur, int depth) {
   const int n = buf.counts[4 + KIND];
   const unsigned lane = threadIdx.x & 31u;
-  const int warps_total = (gridDim.x * kShadeBlock) >> 5;
-  const int warp_id = (blockIdx.x * kShadeBlock + threadIdx.x) >> 5;
   const int nxt = cur ^ 1;
   const int32_t *__restrict__ list = buf.klist[KIND];
 
-  for (int base = warp_id * 32; base < n; base += warps_total * 32) {
-    const int li = base + (int)lane;
+  for (int bbase = (int)blockIdx.x * kShadeBlock; bbase < n; bbase += (int)gridDim.x * kShadeBlock) {
+    const int li = bbase + (int)threadIdx.x;
     bool alive = false;
     int slot = 0, surf = -1;
     V3f point = v3f(0.f, 0.f, 0.f), next_dir = v3f(0.f, 0.f, 1.f);
@@ -281,7 +312,7 @@ path_sample_kernel(DeviceScene sc, DevicePathParams pp, PathBatch b, PathBuffers
       surf = __float_as_int(ra.w);
       const V3f nrm = v3f(rb.x, rb.y, rb.z), dest = v3f(rc.x, rc.y, rc.z);
       slot = __float_as_int(rc.w);
-      const MatAt m = material_at(sc, __float_as_int(rb.w), point);
+      const MatAt m = material_at_index(sc, __float_as_int(rb.w), point);
       thr = buf.thr[slot];
       const V3f tv = v3f(thr.x, thr.y, thr.z);
       Rng g;
@@ -348,6 +379,8 @@ path_sample_kernel(DeviceScene sc, DevicePathParams pp, PathBatch b, PathBuffers
     }
     // compaction: surviving lanes take consecutive positions of the next queue
     const unsigned live = __ballot_sync(0xffffffffu, alive);
+    // one atomic per warp (aggregating the warps of a block behind two barriers measured slower here:
+    // C3 sample stage 16.1 -> 16.5 ms, C4 9.05 -> 9.37 ms)
     if (live) {
       int pos0 = 0;
       if (lane == (unsigned)(__ffs(live) - 1)) pos0 = atomicAdd(buf.counts + nxt, __popc(live));
@@ -550,18 +583,21 @@ void launch_path_resolve(const DeviceScene &sc, const DevicePathParams &pp, cons
                          const PathBatch &b, const PathBuffers &buf, int cur, int depth, cudaStream_t stream) {
   // resident-grid sizes, computed once (thread-safe static initialisation: renders may run on
   // several host threads, one per device)
-  static const int grid_full[4] = {shade_grid(path_resolve_kernel<false, 1>, (int64_t)1 << 40),
+  static const int grid_full[5] = {shade_grid(path_resolve_kernel<false, 1>, (int64_t)1 << 40),
                                    shade_grid(path_resolve_kernel<true, 1>, (int64_t)1 << 40),
                                    shade_grid(path_resolve_kernel<false, 2>, (int64_t)1 << 40),
-                                   shade_grid(path_resolve_kernel<true, 2>, (int64_t)1 << 40)};
+                                   shade_grid(path_resolve_kernel<true, 2>, (int64_t)1 << 40),
+                                   shade_grid(path_resolve_kernel<false, 3>, (int64_t)1 << 40)};
   const int64_t n = (int64_t)b.nP * b.S;
-  const int li = (pp.num_lights > 0 ? 1 : 0) + (sc.shape_bvh.nodes ? 2 : 0);
+  int li = (pp.num_lights > 0 ? 1 : 0) + (sc.shape_bvh.nodes ? 2 : 0);
+  if (li == 0 && sc.spheres_only) li = 4;
   const int64_t want = (n + kShadeBlock - 1) / kShadeBlock;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_full[li], want));
   switch (li) {
     case 0: path_resolve_kernel<false, 1><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth); break;
     case 1: path_resolve_kernel<true, 1><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth); break;
     case 2: path_resolve_kernel<false, 2><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth); break;
+    case 4: path_resolve_kernel<false, 3><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth); break;
     default: path_resolve_kernel<true, 2><<<grid, kShadeBlock, 0, stream>>>(sc, pp, lights, b, buf, cur, depth); break;
   }
 }

@@ -54,6 +54,7 @@ struct DeviceScene {
   DeviceBVH bvh;  // all mesh objects merged, world space; triangle records carry object ids
   const DeviceShape *shapes = nullptr;
   int32_t num_shapes = 0;
+  int32_t spheres_only = 0;  // every analytic shape is a sphere (kernels without the rect / cylinder code)
   const DeviceObject *objects = nullptr;
   int32_t num_objects = 0;
   const DeviceMaterial *materials = nullptr;

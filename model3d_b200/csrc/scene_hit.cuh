@@ -167,6 +167,26 @@ static __device__ __noinline__ bool cylinder_hit(const DeviceShape &s, D3 o_in, 
   return ok;
 }
 
+// The float64 tests behind a float32 interface, out of line: the Monte-Carlo renderers (statistical
+// parity) keep no float64 state across their shape loop, which is what had their resolve kernels at the
+// 128-register limit.
+static __device__ __noinline__ bool shape_hit_from_f32(const DeviceShape &sh, float4 o, float4 d, float t_floor,
+                                                       float &t_out, float &nx, float &ny, float &nz) {
+  const D3 od = d3(o.x, o.y, o.z), dd = d3(d.x, d.y, d.z);
+  double t;
+  D3 n;
+  bool ok = false;
+  if (sh.kind == SHAPE_SPHERE) ok = sphere_hit(sh, od, dd, (double)t_floor, t, n);
+  else if (sh.kind == SHAPE_RECT) ok = rect_hit(sh, od, dd, (double)t_floor, t, n);
+  else if (sh.kind == SHAPE_CYLINDER) ok = cylinder_hit(sh, od, dd, (double)t_floor, t, n);
+  if (!ok) return false;
+  t_out = (float)t;
+  nx = (float)n.x;
+  ny = (float)n.y;
+  nz = (float)n.z;
+  return true;
+}
+
 // Conservative float32 pre-test: true only if the ray's supporting line provably misses the
 // shape's bounding sphere (sphere: the shape itself).  Margin 1e-4 relative covers float32
 // rounding of the discriminant with two orders of magnitude to spare.
@@ -237,6 +257,69 @@ __device__ __forceinline__ int sphere_hit_f32(const DeviceShape &sh, float4 o, f
   return 1;
 }
 
+// Rect.FirstRayCollision (shapes.go:177-247) in float32 for the Monte-Carlo renderers: the slab test of
+// bvh.go:322-351 with the face taken from the binding axis.  Returns 0 miss, 1 hit, 2 undecided (a
+// decision within the float32 error of its threshold: grazing an edge, a root next to t_floor, the
+// origin on a face plane of a parallel ray): the caller falls back to the float64 test.
+__device__ __forceinline__ int rect_hit_f32(const DeviceShape &sh, float4 o, float4 d, float t_floor, float &t,
+                                            float &nx, float &ny, float &nz) {
+  const float oo[3] = {o.x, o.y, o.z}, dv[3] = {d.x, d.y, d.z};
+  float tmin = -INFINITY, tmax = INFINITY, emin = 0.f, emax = 0.f;
+  int amin = 0, amax = 0;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float mn = (float)sh.p0[a], mx = (float)sh.p1[a];
+    const float perr = 2e-7f * (fabsf(mn) + fabsf(mx) + fabsf(oo[a]));  // rounding of mn - o, mx - o and of mn, mx
+    if (dv[a] == 0.f) {
+      if (fabsf(oo[a] - mn) <= perr || fabsf(oo[a] - mx) <= perr) return 2;
+      if (oo[a] < mn || oo[a] > mx) return 0;
+      continue;
+    }
+    const float inv = 1.0f / dv[a];
+    float t1 = (mn - oo[a]) * inv, t2 = (mx - oo[a]) * inv;
+    if (t1 > t2) {
+      const float tmp = t1;
+      t1 = t2;
+      t2 = tmp;
+    }
+    const float e = perr * fabsf(inv) + 1e-6f * (fabsf(t1) + fabsf(t2));
+    if (t2 < -e) return 0;  // bvh.go:341-343
+    if (t2 <= e) return 2;
+    if (t1 > tmin) {
+      tmin = t1;
+      emin = e;
+      amin = a;
+    }
+    if (t2 < tmax) {
+      tmax = t2;
+      emax = e;
+      amax = a;
+    }
+  }
+  if (tmax < tmin - (emin + emax) || tmax < t_floor - emax) return 0;
+  if (tmax <= tmin + (emin + emax) || tmax <= t_floor + emax) return 2;
+  if (fabsf(tmin - t_floor) <= emin) return 2;
+  const bool enter = tmin >= t_floor;
+  t = enter ? tmin : tmax;
+  const int axis = enter ? amin : amax;
+  // the face: entering through the low side when moving up the axis, leaving through the high side
+  const float d_axis = axis == 0 ? d.x : (axis == 1 ? d.y : d.z);
+  const float sign = (d_axis > 0.f) == enter ? -1.f : 1.f;
+  // a second face within the error of the hit point (edge / corner): the float64 rule picks by distance
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (a == axis) continue;
+    const float c = oo[a] + dv[a] * t;
+    const float mn = (float)sh.p0[a], mx = (float)sh.p1[a];
+    const float tol = 4e-6f * (fabsf(mn) + fabsf(mx) + fabsf(oo[a]) + fabsf(dv[a] * t));
+    if (fabsf(c - mn) <= tol || fabsf(c - mx) <= tol) return 2;
+  }
+  nx = axis == 0 ? sign : 0.f;
+  ny = axis == 1 ? sign : 0.f;
+  nz = axis == 2 ? sign : 0.f;
+  return 1;
+}
+
 // Result of resolving one scene ray: the closest of the BVH's raw triangle hit and the
 // analytic shapes.  surf: leaf-order triangle index, or -2-shape index, or -1 (miss).
 struct SceneHit {
@@ -250,7 +333,8 @@ struct SceneHit {
 // (t_f32, -, -, bits(leaf-order triangle | -1)); skip = surface the ray starts on.
 // SHAPES = 0 compiles the analytic-shape part out (mesh colliders: a third of the registers);
 // 1: every shape is tested (a handful of shapes); 2: scenes with an object-level hierarchy
-// (DeviceScene::shape_bvh) walk it instead.
+// (DeviceScene::shape_bvh) walk it instead; 3: like 1 for scenes whose shapes are all spheres
+// (DeviceScene::spheres_only; Monte-Carlo renderers only: no rect / cylinder code in the kernel).
 template <int SHAPES = 1>
 __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, float4 d, float4 raw, int skip,
                                              bool refine) {
@@ -325,7 +409,62 @@ __device__ inline SceneHit resolve_scene_hit(const DeviceScene &sc, float4 o, fl
     }
     best_obj = obj;
   }
-  if (SHAPES && sc.num_shapes > 0) {
+  if ((SHAPES == 1 || SHAPES == 3) && !refine && sc.num_shapes > 0) {
+    // Monte-Carlo renderers, a handful of shapes: float32 state only (spheres by their float32 test, the
+    // float64 tests out of line behind the bounding-sphere rejection)
+    float best_tf = tri_idx >= 0 ? raw.x : INFINITY;
+    const float inv_len_f = rsqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    for (int s = 0; s < sc.num_shapes; s++) {
+      const DeviceShape &sh = sc.shapes[s];
+      float t_floor = o.w;
+      if (skip == -2 - s) {
+        float size = (float)sh.radius;
+        if (SHAPES != 3 && sh.kind == SHAPE_RECT)
+          size = fmaxf(fmaxf((float)(sh.p1[0] - sh.p0[0]), (float)(sh.p1[1] - sh.p0[1])), (float)(sh.p1[2] - sh.p0[2]));
+        t_floor = fmaxf(t_floor, 1e-4f * size * inv_len_f);
+      }
+      float tf, fx, fy, fz;
+      int fast = 2;
+      if (sh.kind == SHAPE_SPHERE) {
+        fast = sphere_hit_f32(sh, o, d, t_floor, tf, fx, fy, fz);
+        if (fast == 0) continue;
+      } else if (SHAPES == 3) {
+        continue;  // not reached: spheres only
+      } else if (sh.kind == SHAPE_RECT) {
+        fast = rect_hit_f32(sh, o, d, t_floor, tf, fx, fy, fz);
+        if (fast == 0) continue;
+      } else if (shape_certainly_missed(sh, o, d)) {
+        continue;
+      }
+      if (fast == 2) {
+        if (SHAPES == 3) {  // a grazing sphere: the float64 sphere test alone
+          double td;
+          D3 nd;
+          if (!sphere_hit(sh, d3(o.x, o.y, o.z), d3(d.x, d.y, d.z), (double)t_floor, td, nd)) continue;
+          tf = (float)td;
+          fx = (float)nd.x;
+          fy = (float)nd.y;
+          fz = (float)nd.z;
+        } else if (!shape_hit_from_f32(sh, o, d, t_floor, tf, fx, fy, fz)) {
+          continue;
+        }
+      }
+      if (tf > d.w) continue;  // ray tmax (shadow / visibility rays)
+      // JoinedObject.Cast: strict '<' in object order, the first object wins ties
+      if (tf < best_tf || (tf == best_tf && sh.object < best_obj)) {
+        best_tf = tf;
+        best_obj = sh.object;
+        h.surf = -2 - s;
+        h.t = tf;
+        h.b1 = h.b2 = 0.f;
+        h.prim = 0;
+        h.obj = sh.object;
+        h.nx = fx;
+        h.ny = fy;
+        h.nz = fz;
+      }
+    }
+  } else if (SHAPES && sc.num_shapes > 0) {
     const D3 od = d3(o.x, o.y, o.z), dd = d3(d.x, d.y, d.z);
     const double t_hi = (double)d.w;  // ray tmax (shadow / visibility rays)
     const double inv_len = 1.0 / dnorm(dd);

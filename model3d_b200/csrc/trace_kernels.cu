@@ -35,13 +35,19 @@ constexpr int kWarpsPerBlock = kTraceBlock / 32;
 #ifndef M3D_TINY_MINB
 #define M3D_TINY_MINB 6  // resident blocks per SM of the tiny-scene instantiation (two triangle rounds)
 #endif
+#ifndef M3D_TINY_TRI_ROUNDS
+// triangle tests per trip of the tiny-scene instantiation; measured on C3 (trace stage of a 1024^2 x 64 spp
+// frame): 2 rounds 16.7 ms, 3 17.3, 4 14.9 (the only count whose instantiation stays nearly spill-free),
+// 5 16.1, 6 16.4, 8 17.1
+#define M3D_TINY_TRI_ROUNDS 4
+#endif
 #ifndef M3D_MASK_LUT
 #define M3D_MASK_LUT 1  // child hit bits from a shared-memory table (ALU-pipe relief): C2 2.405 -> 2.347 ms
 #endif
 constexpr int kSmemStack = M3D_SMEM_STACK;  // stack entries per thread kept in shared memory
 constexpr int kLocalStack = 64 - kSmemStack;  // overflow entries (local memory; untouched for sane trees)
 constexpr int kRayBatch = M3D_RAY_BATCH;  // rays a warp claims per global atomic
-constexpr int kTinySceneNodes = 32;       // at most this many wide nodes: two triangle rounds per trip
+constexpr int kTinySceneNodes = 32;       // at most this many wide nodes: several triangle rounds per trip
 #ifndef M3D_PREFETCH_NEXT_NODE
 #define M3D_PREFETCH_NEXT_NODE 0  // measured on B200: 2.58 -> 3.98 ms per 2^24 rays (L1 prefetches throttle the LSU)
 #endif
@@ -477,12 +483,12 @@ void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p_in, cudaSt
   }();
   const TraceLaunch &p = p_in;
   // tiny hierarchies (cornell_box: 72 triangles in 4 nodes) spend their time in the triangle phase
-  const int tri_rounds = tri_rounds_env > 0 ? tri_rounds_env : (bvh.num_nodes <= kTinySceneNodes ? 2 : 1);
+  const int tri_rounds = tri_rounds_env > 0 ? tri_rounds_env : (bvh.num_nodes <= kTinySceneNodes ? M3D_TINY_TRI_ROUNDS : 1);
   cudaMemsetAsync(p.ray_counter, 0, sizeof(unsigned long long), stream);
   if (p.counters) {
     launch_trace_variant<true, 6>(bvh, p, stream);
   } else if (tri_rounds >= 2) {
-    launch_trace_variant<false, M3D_TINY_MINB, 2>(bvh, p, stream);
+    launch_trace_variant<false, M3D_TINY_MINB, M3D_TINY_TRI_ROUNDS>(bvh, p, stream);
   } else if (minb == 5) {
     launch_trace_variant<false, 5>(bvh, p, stream);
   } else if (minb == 8) {
