@@ -215,6 +215,28 @@ __device__ __forceinline__ void fma2(float a0, float a1, float s, float b0, floa
 }
 #endif
 
+// M3D_L2_HINT (tuning builds): bit 0 = node loads, bit 1 = triangle loads carry an L2 evict_last
+// cache policy (createpolicy folds into the load's descriptor: no register cost), so that the ray /
+// hit streams passing through L2 evict each other instead of the hierarchy.
+#ifndef M3D_L2_HINT
+#define M3D_L2_HINT 0
+#endif
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint4 ldg_keep_u4(const uint4 *p) {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  uint4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_keep_f4(const float4 *p) {
+  const uint4 v = ldg_keep_u4(reinterpret_cast<const uint4 *>(p));
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+#endif
+
 // The reference's Moeller-Trumbore in float64 (primitives.go:207-249) on the float32
 // inputs widened exactly: the arbiter for rays that pass so close to a triangle edge (or
 // are so nearly parallel to it) that the float32 test cannot decide.  Kept out of line: it
@@ -310,7 +332,9 @@ M3D_HD bool intersect_tri_loaded(const float4 *__restrict__ tri, const float4 q0
 
 M3D_HD bool intersect_tri(const float4 *__restrict__ tri, const RayPre &rp, float tmax, float &t_out,
                           float &b1, float &b2) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && (M3D_L2_HINT & 2)
+  const float4 q0 = ldg_keep_f4(tri), q1 = ldg_keep_f4(tri + 1), q2 = ldg_keep_f4(tri + 2);
+#elif defined(__CUDA_ARCH__)
   const float4 q0 = __ldg(tri), q1 = __ldg(tri + 1), q2 = __ldg(tri + 2);
 #else
   const float4 q0 = tri[0], q1 = tri[1], q2 = tri[2];
@@ -376,6 +400,9 @@ M3D_HD void intersect_node(const uint4 *__restrict__ nodes, uint32_t node_index,
       : "=r"(n2.x), "=r"(n2.y), "=r"(n2.z), "=r"(n2.w), "=r"(n3.x), "=r"(n3.y), "=r"(n3.z), "=r"(n3.w)
       : "l"(np + 2));
   const uint4 n4 = __ldg(np + 4);
+#elif defined(__CUDA_ARCH__) && (M3D_L2_HINT & 1)
+  const uint4 n0 = ldg_keep_u4(np), n1 = ldg_keep_u4(np + 1), n2 = ldg_keep_u4(np + 2), n3 = ldg_keep_u4(np + 3),
+              n4 = ldg_keep_u4(np + 4);
 #elif defined(__CUDA_ARCH__)
   const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
 #else

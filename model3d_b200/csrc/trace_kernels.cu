@@ -5,6 +5,7 @@
 //                              (Ray{Origin,Direction}, collisions.go:12-15;
 //                              RayCollision / TriangleCollision, collisions.go:19-46)
 //                              and the device float4 SoA layout.
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -485,6 +486,51 @@ void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p_in, cudaSt
   // tiny hierarchies (cornell_box: 72 triangles in 4 nodes) spend their time in the triangle phase
   const int tri_rounds = tri_rounds_env > 0 ? tri_rounds_env : (bvh.num_nodes <= kTinySceneNodes ? M3D_TINY_TRI_ROUNDS : 1);
   cudaMemsetAsync(p.ray_counter, 0, sizeof(unsigned long long), stream);
+  // M3D_L2_PERSIST_MB (tuning runs): the traversal kernel runs with an access-policy window that
+  // marks the node array (M3D_L2_WINDOW=tris: the triangle records) as persisting in L2
+  // (read per launch so that one tuning process can sweep the settings)
+  const char *l2_env = getenv("M3D_L2_PERSIST_MB");
+  const int l2_mb = l2_env ? atoi(l2_env) : 0;
+  const bool l2_window = l2_mb > 0 && bvh.num_nodes > kTinySceneNodes;
+  if (l2_window) {
+    const char *we = getenv("M3D_L2_WINDOW");
+    const bool on_tris = we && we[0] == 't';
+    const char *re = getenv("M3D_L2_HITRATIO");
+    const float ratio = re ? (float)atof(re) : 1.0f;
+    static int applied_mb = -1;
+    static size_t max_window = 0;
+    if (applied_mb != l2_mb) {
+      int dev = 0, max_persist = 0, max_win = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      size_t want = (size_t)l2_mb << 20;
+      if (want > (size_t)max_persist) want = (size_t)max_persist;
+      const cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      fprintf(stderr, "m3d: L2 persisting set-aside %zu MB (device max %d MB, max window %d MB): %s\n", want >> 20,
+              max_persist >> 20, max_win >> 20, cudaGetErrorString(e));
+      max_window = (size_t)max_win;
+      applied_mb = l2_mb;
+    }
+    cudaStreamAttrValue v = {};
+    size_t bytes = on_tris ? (size_t)bvh.num_tris * 48 : (size_t)bvh.num_nodes * M3D_NODE_BYTES;
+    v.accessPolicyWindow.base_ptr = on_tris ? (void *)bvh.tris : (void *)bvh.nodes;
+    v.accessPolicyWindow.num_bytes = bytes < max_window ? bytes : max_window;
+    v.accessPolicyWindow.hitRatio = ratio;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
+  }
+  struct WindowReset {
+    cudaStream_t s;
+    bool on;
+    ~WindowReset() {
+      if (!on) return;
+      cudaStreamAttrValue v = {};
+      v.accessPolicyWindow.num_bytes = 0;
+      cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
+    }
+  } window_reset{stream, l2_window};
   if (p.counters) {
     launch_trace_variant<true, 6>(bvh, p, stream);
   } else if (tri_rounds >= 2) {
