@@ -47,21 +47,59 @@ __device__ __forceinline__ float sum3(V3f a) { return a.x + a.y + a.z; }
 // coords.go:431-434 (n is unit already on every call site here)
 __device__ __forceinline__ V3f reflect_about(V3f n, V3f c1) { return (c1 + n * (-2.f * dot(n, c1))) * -1.f; }
 
-// coords.go:388-421
-static __device__ __noinline__ void ortho_basis(V3f c, V3f &b1o, V3f &b2o) {
+// Reciprocal square root / square root through the SFU alone (MUFU.RSQ / MUFU.SQRT, ~2 ulp): for the
+// Monte-Carlo sampling formulas only, whose results feed an estimator with 1e-2 .. 1e-3 noise; the
+// deterministic shading paths keep normalize() / sqrtf().
+#ifndef M3D_FAST_SQRT
+#define M3D_FAST_SQRT 1
+#endif
+#ifndef M3D_FAST_NORMALIZE
+#define M3D_FAST_NORMALIZE 1
+#endif
+#ifndef M3D_FAST_SINCOS
+#define M3D_FAST_SINCOS 1
+#endif
+__device__ __forceinline__ float sqrt_fast(float x) {
+#if M3D_FAST_SQRT
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+__device__ __forceinline__ V3f normalize_fast(V3f a) {
+#if M3D_FAST_NORMALIZE
+  return a * rsqrtf(dot(a, a));
+#else
+  return a * (1.0f / sqrtf(dot(a, a)));
+#endif
+}
+
+// coords.go:388-421.  The reference divides the first basis vector by the largest component before
+// normalising it; the direction is the same without the division.  b1 is orthogonal to c by
+// construction, so b1 x c only needs the (near-unit) length of c divided out.
+// (Out-of-line helpers take and return VALUES: a reference parameter would force the caller's object
+// into local memory for the call, and with it every other access to that object.)
+struct Basis {
+  V3f x, z;
+};
+static __device__ __noinline__ Basis ortho_basis(V3f c) {
   const float ax = fabsf(c.x), ay = fabsf(c.y), az = fabsf(c.z);
   V3f b1 = v3f(0.f, 0.f, 0.f);
   if (ax > ay && ax > az) {
-    b1.x = c.y / ax;
-    b1.y = -c.x / ax;
+    b1.x = c.y;
+    b1.y = -c.x;
   } else {
-    const float m = ay > az ? ay : az;
-    b1.y = c.z / m;
-    b1.z = -c.y / m;
+    b1.y = c.z;
+    b1.z = -c.y;
   }
+  b1 = normalize_fast(b1);
   const V3f b2 = v3f(b1.y * c.z - b1.z * c.y, b1.z * c.x - b1.x * c.z, b1.x * c.y - b1.y * c.x);
-  b1o = normalize(b1);
-  b2o = normalize(b2);
+  Basis r;
+  r.x = b1;
+  r.z = normalize_fast(b2);
+  return r;
 }
 
 // x^y for x in [0, 1], y >= 0 through the SFU (lg2.approx / ex2.approx): a dozen instructions
@@ -73,7 +111,17 @@ __device__ __forceinline__ float pow_unit(float x, float y) {
   return exp2f(y * __log2f(x));
 }
 // sin and cos of 2*pi*u without libm's large-argument slow path
-__device__ __forceinline__ void sincos_2pi(float u, float *s, float *c) { sincospif(2.f * u, s, c); }
+// (u in [0, 1): the angle is folded to [-pi, pi) where MUFU.SIN / MUFU.COS are accurate to ~5e-7
+// absolute; sin(2 pi u) = -sin(2 pi (u - 1/2)), likewise for the cosine)
+__device__ __forceinline__ void sincos_2pi(float u, float *s, float *c) {
+#if M3D_FAST_SINCOS
+  const float a = 6.283185307179586f * (u - 0.5f);
+  *s = -__sinf(a);
+  *c = -__cosf(a);
+#else
+  sincospif(2.f * u, s, c);
+#endif
+}
 
 constexpr float kCosEps = 1e-8f;  // cosineEpsilon material.go:10
 
@@ -189,6 +237,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// One Philox block, out of line (ten rounds, ~80 instructions per call site otherwise); values in, values out, so
+// that the generator's state stays in registers.
+static __device__ __noinline__ uint4 philox_block(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t domain,
+                                                  uint32_t k0, uint32_t k1) {
+  return philox4x32_10(make_uint4(pixel, sample, block, domain), make_uint2(k0, k1));
+}
+
 struct Rng {
   uint2 key;
   uint32_t pixel, sample, block, domain;
@@ -202,8 +257,8 @@ struct Rng {
     block = 0;
     have = 0;
   }
-  __device__ __noinline__ void refill() {
-    buf = philox4x32_10(make_uint4(pixel, sample, block++, domain), key);
+  __device__ __forceinline__ void refill() {
+    buf = philox_block(pixel, sample, block++, domain, key.x, key.y);
     have = 4;
   }
   __device__ __forceinline__ uint32_t bits() {
@@ -223,16 +278,18 @@ constexpr float kTwoPi = 6.283185307179586f;
 // Tag of the direction a sampler produced: which Dirac lobe(s) of which sub-material.
 constexpr int kLobeRefract = 1, kLobeReflect = 2;  // bits 0..1; sub-material index in bits 2..3
 
-// material.go:136-151
-static __device__ __noinline__ V3f lambert_sample(Rng &g, V3f normal) {
-  const float u = g.f32();
-  const float cos_lat = sqrtf(u), sin_lat = sqrtf(1.f - u);
+// material.go:136-151 (u, v: the two uniforms the reference draws)
+static __device__ __noinline__ V3f lambert_direction(float u, float v, V3f normal) {
+  const float cos_lat = sqrt_fast(u), sin_lat = sqrt_fast(1.f - u);
   float sl, cl;
-  sincos_2pi(g.f32(), &sl, &cl);
-  V3f xa, za;
-  ortho_basis(normal, xa, za);
-  const V3f lon_point = xa * cl + za * sl;
+  sincos_2pi(v, &sl, &cl);
+  const Basis b = ortho_basis(normal);
+  const V3f lon_point = b.x * cl + b.z * sl;
   return normal * -cos_lat + lon_point * sin_lat;
+}
+__device__ __forceinline__ V3f lambert_sample(Rng &g, V3f normal) {
+  const float u = g.f32(), v = g.f32();
+  return lambert_direction(u, v, normal);
 }
 // material.go:153-159
 __device__ __forceinline__ float lambert_density(V3f normal, V3f source) {
@@ -240,16 +297,18 @@ __device__ __forceinline__ float lambert_density(V3f normal, V3f source) {
   return nd < 0.f ? 0.f : 4.f * nd;
 }
 // material.go:274-323
-static __device__ __noinline__ V3f sample_around_direction(Rng &g, float alpha, V3f direction) {
-  V3f xa, za;
-  ortho_basis(direction, xa, za);
-  const float u = g.f32(), v = g.f32();
+static __device__ __noinline__ V3f direction_around(float u, float v, float alpha, V3f direction) {
+  const Basis b = ortho_basis(direction);
   float sl, cl;
   sincos_2pi(u, &sl, &cl);
   const float cos_lat = pow_unit(v, 1.f / (alpha + 1.f));
-  const float sin_lat = sqrtf(fmaxf(0.f, 1.f - cos_lat * cos_lat));
-  const V3f lon_point = xa * cl + za * sl;
+  const float sin_lat = sqrt_fast(fmaxf(0.f, 1.f - cos_lat * cos_lat));
+  const V3f lon_point = b.x * cl + b.z * sl;
   return direction * cos_lat + lon_point * sin_lat;
+}
+__device__ __forceinline__ V3f sample_around_direction(Rng &g, float alpha, V3f direction) {
+  const float u = g.f32(), v = g.f32();
+  return direction_around(u, v, alpha, direction);
 }
 // material.go:328-335: 2(a+1) / v^(1/(a+1) - 1) with v = d^(a+1), i.e. 2(a+1) d^a
 __device__ __forceinline__ float density_around_direction(float alpha, V3f direction, V3f sample) {
@@ -285,31 +344,57 @@ __device__ __forceinline__ float reflect_amount(float ior, V3f normal, V3f sourc
 }
 
 // SampleSource of a non-joined material; lobe: Dirac lobes the direction belongs to.
-static __device__ __noinline__ V3f simple_sample_source(const DeviceMaterial &d, V3f diffuse, Rng &g, V3f normal,
-                                                    V3f dest, int &lobe) {
-  lobe = 0;
-  if (d.kind == M3D_MAT_LAMBERT) return lambert_sample(g, normal);
+// coin / u / v: the random numbers of the branch taken (Phong: coin, then the sampler's two uniforms;
+// Lambert: u, v; Refract: u), drawn by the inlined wrapper below.
+struct SampledDir {
+  V3f dir;
+  int lobe;
+};
+static __device__ __noinline__ SampledDir simple_source_direction(const DeviceMaterial &d, V3f diffuse, uint32_t coin,
+                                                               float u, float v, V3f normal, V3f dest) {
+  SampledDir r;
+  r.lobe = 0;
+  if (d.kind == M3D_MAT_LAMBERT) {
+    r.dir = lambert_direction(u, v, normal);
+    return r;
+  }
   if (d.kind == M3D_MAT_PHONG) {  // material.go:230-236,251-256
-    if (is_zero(diffuse) || (g.bits() & 1u) == 0u) {
+    if (is_zero(diffuse) || (coin & 1u) == 0u) {
       const V3f reflection = reflect_about(normal, dest) * -1.f;
-      return sample_around_direction(g, d.alpha, reflection);
+      r.dir = direction_around(u, v, d.alpha, reflection);
+      return r;
     }
-    return lambert_sample(g, normal);
+    r.dir = lambert_direction(u, v, normal);
+    return r;
   }
   // RefractMaterial material.go:425-439
   bool tir;
   const V3f refracted = refract_inverse(d.ior, normal, dest, tir);
   if (is_zero(v3f(d.specular))) {
-    lobe = kLobeRefract;
-    return refracted;
+    r.lobe = kLobeRefract;
+    r.dir = refracted;
+    return r;
   }
   const float refl = reflect_amount(d.ior, normal, dest);
-  if (g.f32() > refl) {
-    lobe = tir ? (kLobeRefract | kLobeReflect) : kLobeRefract;
-    return refracted;
+  if (u > refl) {
+    r.lobe = tir ? (kLobeRefract | kLobeReflect) : kLobeRefract;
+    r.dir = refracted;
+    return r;
   }
-  lobe = tir ? (kLobeRefract | kLobeReflect) : kLobeReflect;
-  return reflect_about(normal, dest) * -1.f;
+  r.lobe = tir ? (kLobeRefract | kLobeReflect) : kLobeReflect;
+  r.dir = reflect_about(normal, dest) * -1.f;
+  return r;
+}
+__device__ __forceinline__ V3f simple_sample_source(const DeviceMaterial &d, V3f diffuse, Rng &g, V3f normal,
+                                                    V3f dest, int &lobe) {
+  // the numbers are drawn whether or not the branch uses them: streams are per (pixel, sample, bounce)
+  // and a Philox block holds four, so nothing is saved by drawing lazily
+  const uint32_t coin = d.kind == M3D_MAT_PHONG && !is_zero(diffuse) ? g.bits() : 0u;
+  const float u = g.f32();
+  const float v = d.kind == M3D_MAT_REFRACT ? 0.f : g.f32();
+  const SampledDir r = simple_source_direction(d, diffuse, coin, u, v, normal, dest);
+  lobe = r.lobe;
+  return r.dir;
 }
 
 struct Density {

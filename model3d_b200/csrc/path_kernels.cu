@@ -12,6 +12,19 @@
 // Traversal between the stages is trace_first_hit_kernel (trace_kernels.cu).
 #include <algorithm>
 
+// SFU-only square roots / normalisations / sincos in the sampling helpers (materials.cuh) are a gain for
+// the one large shading kernel of the bidirectional tracer and a loss here: measured on C3, sample stage
+// of a 1024^2 x 64 spp frame, 11.2-11.8 ms with the IEEE forms against 13.5-15.4 ms with the SFU forms
+// (same rays per sample; profiles/r2c_mc_math.log), C4 6.6 against 7.3 ms.
+#ifndef M3D_FAST_SQRT
+#define M3D_FAST_SQRT 0
+#endif
+#ifndef M3D_FAST_NORMALIZE
+#define M3D_FAST_NORMALIZE 0
+#endif
+#ifndef M3D_FAST_SINCOS
+#define M3D_FAST_SINCOS 0
+#endif
 #include "materials.cuh"
 #include "path.h"
 #include "scene_hit.cuh"
@@ -22,6 +35,26 @@ namespace {
 
 constexpr int kShadeBlock = 128;
 
+// Per-thread asynchronous copies global -> shared (LDGSTS): the streamed inputs of the bounce kernels
+// are fetched two tiles ahead without holding registers.  Every thread reads back only what it copied
+// itself, so cp.async.wait_group orders the data and no block barrier is needed.
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+#ifndef M3D_RESOLVE_STAGES
+#define M3D_RESOLVE_STAGES 3  // tiles of streamed inputs in flight per block (1: plain loads)
+#endif
+
 __device__ __forceinline__ bool focus_applies(const DeviceFocus &f, int material) {
   return material < 64 ? ((f.mask >> material) & 1ull) != 0ull : false;
 }
@@ -29,12 +62,11 @@ __device__ __forceinline__ bool focus_applies(const DeviceFocus &f, int material
 // focus_point.go:155-163
 __device__ __forceinline__ V3f sample_around_uniform(Rng &g, float min_cos, V3f direction) {
   const float cos_lat = 1.f - g.f32() * (1.f - min_cos);
-  const float sin_lat = sqrtf(fmaxf(0.f, 1.f - cos_lat * cos_lat));
+  const float sin_lat = sqrt_fast(fmaxf(0.f, 1.f - cos_lat * cos_lat));
   float sl, cl;
   sincos_2pi(g.f32(), &sl, &cl);
-  V3f xa, za;
-  ortho_basis(direction, xa, za);
-  return direction * cos_lat + (xa * cl + za * sl) * sin_lat;
+  const Basis b = ortho_basis(direction);
+  return direction * cos_lat + (b.x * cl + b.z * sl) * sin_lat;
 }
 
 // Whether focus point f overrides the material's sampler at `point`, and its direction info.
@@ -44,17 +76,17 @@ __device__ __forceinline__ bool focus_active(const DeviceFocus &f, int material,
                                              float &min_cos) {
   if (!focus_applies(f, material)) return false;
   const V3f diff = point - v3f(f.target);
-  const float d = norm(diff);
+  const float d2 = dot(diff, diff);
+  if (d2 == 0.f) return false;  // Target == point (inside any sphere as well)
+  const float inv_d = rsqrtf(d2);  // SFU reciprocal square root: Monte-Carlo sampling, see sqrt_fast
+  dir = diff * inv_d;
   if (f.kind == M3D_FOCUS_PHONG) {
-    if (d == 0.f) return false;
-    dir = diff * (1.f / d);
     min_cos = 0.f;
     return true;
   }
-  if (d < f.radius) return false;
-  const float ratio = f.radius / d;
-  min_cos = sqrtf(fmaxf(0.f, 1.f - ratio * ratio));
-  dir = diff * (1.f / d);
+  if (d2 < f.radius * f.radius) return false;
+  const float ratio = f.radius * inv_d;
+  min_cos = sqrt_fast(fmaxf(0.f, 1.f - ratio * ratio));
   return true;
 }
 
@@ -141,15 +173,57 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
   __shared__ int s_kbase[2][4];
   const int wib = (int)(threadIdx.x >> 5);
   int parity = 0;
-  for (int bbase = (int)blockIdx.x * kShadeBlock; bbase < n; bbase += (int)gridDim.x * kShadeBlock, parity ^= 1) {
+  constexpr int kStages = M3D_RESOLVE_STAGES;
+  __shared__ float4 s_in[kStages > 1 ? kStages : 1][3][kShadeBlock];  // origin, direction, raw hit
+  __shared__ int32_t s_ids[kStages > 1 ? kStages : 1][2][kShadeBlock];  // slot, skip id
+  const int stride = (int)gridDim.x * kShadeBlock;
+  auto prefetch_tile = [&](int tile_base, int st) {
+    const int qq = tile_base + (int)threadIdx.x;
+    if (qq < n) {
+      cp_async_16(&s_in[st][0][threadIdx.x], org_in + qq);
+      cp_async_16(&s_in[st][1][threadIdx.x], dir_in + qq);
+      cp_async_16(&s_in[st][2][threadIdx.x], buf.raw + qq);
+      cp_async_4(&s_ids[st][0][threadIdx.x], queue_in + qq);
+      cp_async_4(&s_ids[st][1][threadIdx.x], skip_in + qq);
+    }
+    cp_async_commit();  // (possibly empty: the group count per trip stays fixed)
+  };
+  int st_use = 0, st_fill = kStages - 1;
+  if (kStages > 1) {
+#pragma unroll
+    for (int k = 0; k < kStages - 1; k++) {
+      // (int64: the look-ahead may pass INT_MAX for the largest batches)
+      const int64_t tb = (int64_t)blockIdx.x * kShadeBlock + (int64_t)k * stride;
+      prefetch_tile(tb < n ? (int)tb : n, k);
+    }
+  }
+  for (int bbase = (int)blockIdx.x * kShadeBlock; bbase < n; bbase += stride, parity ^= 1) {
     const int q = bbase + (int)threadIdx.x;
     int kind = -1;  // material kind whose sampler continues this path, -1: the path ends
+    if (kStages > 1) {
+      const int64_t tb = (int64_t)bbase + (int64_t)(kStages - 1) * stride;
+      prefetch_tile(tb < n ? (int)tb : n, st_fill);
+      cp_async_wait<kStages - 1>();  // this trip's tile has landed
+    }
     if (q < n) {
-      const int slot = queue_in[q];
-      const float4 o = __ldcs(org_in + q), d = __ldcs(dir_in + q), raw = __ldcs(buf.raw + q);
+      int slot, skip_id;
+      float4 o, d, raw;
+      if (kStages > 1) {
+        slot = s_ids[st_use][0][threadIdx.x];
+        skip_id = s_ids[st_use][1][threadIdx.x];
+        o = s_in[st_use][0][threadIdx.x];
+        d = s_in[st_use][1][threadIdx.x];
+        raw = s_in[st_use][2][threadIdx.x];
+      } else {
+        slot = queue_in[q];
+        skip_id = skip_in[q];
+        o = __ldcs(org_in + q);
+        d = __ldcs(dir_in + q);
+        raw = __ldcs(buf.raw + q);
+      }
       // float32 hit evaluation: Monte-Carlo parity is statistical, the float64 refinement of the
       // first-hit API (1e-5 on t and normals) is not needed here; shapes stay float64
-      const SceneHit h = resolve_scene_hit<SB>(sc, o, d, raw, skip_in[q], false);
+      const SceneHit h = resolve_scene_hit<SB>(sc, o, d, raw, skip_id, false);
       if (LIGHTS && pp.num_lights > 0 && h.obj < 0) {
         // no shadow rays for a miss: give the slots an empty parameter interval
         for (int l = 0; l < pp.num_lights; l++) {
@@ -164,7 +238,7 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
         const V3f org = v3f(o.x, o.y, o.z), dir = v3f(d.x, d.y, d.z), nrm = v3f(h.nx, h.ny, h.nz);
         const V3f point = org + dir * h.t;
         const MatAt m = material_at(sc, h.obj, point);
-        const V3f dest = normalize(dir) * -1.f;
+        const V3f dest = dir * -rsqrtf(dot(dir, dir));  // (one SFU op; measured faster here than the IEEE form)
         // raytrace.go:150-155
         V3f color = mat_emission(sc, m);
         if (depth == 0) color = color + mat_ambient(sc, m);
@@ -244,6 +318,8 @@ path_resolve_kernel(DeviceScene sc, DevicePathParams pp, const DevicePointLight 
         }
       }
     }
+    st_use = st_use + 1 == kStages ? 0 : st_use + 1;
+    st_fill = st_fill + 1 == kStages ? 0 : st_fill + 1;
   }
 }
 
