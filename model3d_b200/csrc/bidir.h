@@ -53,7 +53,16 @@ struct DeviceLightTri {
 
 // SoA path-vertex storage: field f of vertex `depth` of slot s lives at
 // verts[(f * D + depth) * cap + s]; 7 float4 fields per vertex (see bidir_kernels.cu).
-constexpr int kBidirVertexFields = 7;
+// Sub-path vertices: seven float4 fields per vertex, field-major (consecutive slots of one field and depth
+// are adjacent).  M3D_BIDIR_VERT_AOS = 1 (build option) keeps the fields of one vertex together in a
+// 128-byte record instead: measured SLOWER on C5 (1024^2 x 128 spp: eye 127 -> 140 ms, light 106 -> 126,
+// prefix 61 -> 73, connect 228 -> 248): most paths are alive at the shallow depths where the time goes, so
+// the queue-ordered lanes of the shading kernels hold nearly consecutive slots and the field-major stores
+// are coalesced, while the record layout strides every lane by 128 bytes.
+#ifndef M3D_BIDIR_VERT_AOS
+#define M3D_BIDIR_VERT_AOS 0
+#endif
+constexpr int kBidirVertexFields = M3D_BIDIR_VERT_AOS ? 8 : 7;
 
 struct BidirBuffers {
   int64_t cap;

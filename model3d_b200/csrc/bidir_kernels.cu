@@ -53,7 +53,11 @@ struct BVert {
 };
 
 __device__ __forceinline__ size_t vidx(int field, int D, int64_t cap, int depth, int slot) {
+#if M3D_BIDIR_VERT_AOS
+  return ((size_t)slot * D + depth) * kBidirVertexFields + field;
+#else
   return ((size_t)field * D + depth) * (size_t)cap + slot;
+#endif
 }
 
 __device__ __forceinline__ void store_vertex(float4 *__restrict__ verts, int D, int64_t cap, int depth, int slot,
