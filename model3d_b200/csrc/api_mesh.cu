@@ -302,6 +302,10 @@ int32_t m3d_mesh_first_ray_collisions_device(m3d_mesh *mesh, const void *d_org_t
   p.counters = nullptr;
   p.ray_counter = next_work_counter(ctx);
   if (!p.ray_counter) return fail(M3D_ERR_OOM, "work counter allocation failed");
+  if (trace_cull_wanted(n, mesh->bvh.num_nodes)) {  // survivor list of the bounds cull
+    M3D_CUDA(ctx->scratch[13].reserve((size_t)(n + 1) * sizeof(int)));
+    p.cull_scratch = ctx->scratch[13].as<int>();
+  }
   if (flags & M3D_TRACE_COUNTERS) {
     p.counters = stats_counters(ctx, s);
     if (!p.counters) return fail(M3D_ERR_CUDA, "counter allocation failed");
@@ -465,6 +469,13 @@ static int32_t first_ray_collisions_one_device(m3d_mesh *mesh, const float *org,
     if (!p.ray_counter) {
       rc = fail(M3D_ERR_OOM, "work counter allocation failed");
       break;
+    }
+    if (trace_cull_wanted(m, mesh->bvh.num_nodes)) {  // (the chunks' kernels run one after the other on ctx->stream)
+      if (ctx->scratch[13].reserve((size_t)(chunk + 1) * sizeof(int)) != cudaSuccess) {
+        rc = fail(M3D_ERR_OOM, "cull scratch allocation failed");
+        break;
+      }
+      p.cull_scratch = ctx->scratch[13].as<int>();
     }
     launch_trace_first_hit(mesh->bvh, p, ctx->stream);
     launch_unpack_hits(d_hit0, d_hit1, m, t ? d_t : nullptr, prim ? d_prim : nullptr, nullptr,

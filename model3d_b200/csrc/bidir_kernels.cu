@@ -487,6 +487,9 @@ template <int PHK>
 __global__ void __launch_bounds__(256, M3D_BPREFIX_MINB)
 bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
   __shared__ int s_cnt[kBidirMaxDepth * (kBidirMaxDepth + 1)], s_base[kBidirMaxDepth * (kBidirMaxDepth + 1)];
+  // the thread's current row of the K table, then of the H table: indexed by a loop counter, so as a
+  // local array it lived in local memory (14 M local loads per launch of a 128-spp C5 frame)
+  __shared__ double s_row[kBidirMaxDepth][256];
   const int n_slots = b.nP * b.S;
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = bp.max_light_depth + 1;
@@ -502,7 +505,7 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
     double eye_density = 1.0;
     D3c eye_bsdf = {1.0, 1.0, 1.0};
     double ep_prev = 1.0;             // EP[i-2] while vertex E_{i-1} is handled
-    double krow[kBidirMaxDepth];      // K[i+1][.], carried from row to row
+    // s_row[m][thread] = K[i+1][m], carried from row to row
     BVert pv;
     for (int i = 1; i <= ne; i++) {
       const BVert v = load_vertex(buf.ev, buf.De, buf.cap, i - 1, slot);
@@ -524,8 +527,8 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
         // K[i+1][m] = g(RS[i-2]) K[i][m] + g(GE[i-1] EP[i-2]),  m = 0 .. i-2
         const double grs = mis_pow<PHK>(full_dd(v) * rsp, ph), gnew = mis_pow<PHK>(ge * ep_prev, ph);
         for (int m = 0; m <= i - 2; m++) {
-          const double kv = (m <= i - 3 ? grs * krow[m] : 0.0) + gnew;
-          krow[m] = kv;
+          const double kv = (m <= i - 3 ? grs * s_row[m][threadIdx.x] : 0.0) + gnew;
+          s_row[m][threadIdx.x] = kv;
           tab(mt.k(i + 1, m)) = kv;
         }
       }
@@ -540,7 +543,7 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
     double density = 0.0;
     D3c light_bsdf = {0.0, 0.0, 0.0};
     double lt_prev = 0.0, slp = 1.0;  // LT[j-2], SLP[j] while vertex L_{j-1} is handled
-    double hrow[kBidirMaxDepth];      // H[j][.]
+    // s_row[t-1][thread] = H[j][t] from here on (the K rows are complete)
     BVert prev;
     for (int j = 1; j <= nl; j++) {
       const BVert lj = load_vertex(buf.lv, buf.Dl, buf.cap, j - 1, slot);
@@ -559,8 +562,8 @@ bidir_prefix_kernel(DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
           // H[j][t_lo] = g(sd(L_{j-2})) H[j-1][t_lo] + g(LT[j-2]),  t_lo = 1 .. j-2
           const double gs = mis_pow<PHK>(sdp, ph), gl = mis_pow<PHK>(lt_prev, ph);
           for (int t = 1; t <= j - 2; t++) {
-            const double hv = (t <= j - 3 ? gs * hrow[t - 1] : 0.0) + gl;
-            hrow[t - 1] = hv;
+            const double hv = (t <= j - 3 ? gs * s_row[t - 1][threadIdx.x] : 0.0) + gl;
+            s_row[t - 1][threadIdx.x] = hv;
             tab(mt.h(j, t)) = hv;
           }
         }

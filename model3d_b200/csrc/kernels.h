@@ -27,7 +27,14 @@ struct TraceLaunch {
   const int *n_ptr = nullptr;          // optional device count (<= n): wavefront queues whose
                                        // length is only known on the device
   uint32_t one_bits = 0x3f800000u;     // bits of 1.0f, kept opaque to ptxas (see unit_plus_byte)
+  // Optional scratch of the bounds cull (trace_cull_wanted): n + 1 ints of device memory.  When given
+  // (plain mesh batches only: no skip ids, no device-side count), rays that miss the bounds of all
+  // vertices are retired by a streaming pre-pass and the traversal walks the list of survivors.
+  int *cull_scratch = nullptr;
+  const int *ray_list = nullptr;       // set by launch_trace_bvh_only itself
 };
+// Whether a plain mesh batch of n rays should be given cull_scratch
+bool trace_cull_wanted(int64_t n, int64_t num_nodes);
 
 // BVH traversal only: hit0 = (t_f32, 0, 0, bits(leaf-order triangle index | -1))
 void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream);

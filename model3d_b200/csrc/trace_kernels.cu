@@ -42,6 +42,9 @@ constexpr int kWarpsPerBlock = kTraceBlock / 32;
 // 5 16.1, 6 16.4, 8 17.1
 #define M3D_TINY_TRI_ROUNDS 4
 #endif
+#ifndef M3D_CULL_DEFAULT
+#define M3D_CULL_DEFAULT 0  // bounds cull in front of large plain mesh batches (see cull_rays_kernel)
+#endif
 #ifndef M3D_MASK_LUT
 #define M3D_MASK_LUT 1  // child hit bits from a shared-memory table (ALU-pipe relief): C2 2.405 -> 2.347 ms
 #endif
@@ -70,11 +73,13 @@ constexpr bool kPrefetchQueuedTri = M3D_PREFETCH_QUEUED_TRI != 0;
 // finish_hits_kernel re-evaluates hits in float64 in a separate, fully coherent pass.
 // HAS_SKIP = false (plain mesh batches: no per-ray surface to ignore) drops the skip-id load and
 // compare and frees a register of the 80.
-template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS, bool HAS_SKIP>
+// HAS_LIST: the rays to trace are p.ray_list[0 .. n) (survivors of the bounds cull) instead of 0 .. n.
+template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS, bool HAS_SKIP, bool HAS_LIST = false>
 __global__ void __launch_bounds__(kTraceBlock, (MIN_BLOCKS * 128) / kTraceBlock)
 trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ ray_counter) {
   __shared__ uint2 s_stack[kSmemStack][kTraceBlock];
   __shared__ float4 s_stage[3][kTraceBlock];  // per warp: 32 prepared rays (origin|tmin, dir|tmax, 1/dir|err)
+  __shared__ int s_stage_idx[HAS_LIST ? kTraceBlock : 1];  // ... and their ray indices (HAS_LIST)
 #if M3D_MASK_LUT
   __shared__ uint32_t s_lut[256 * 3];  // hit bits by child meta byte, one entry per 12 bytes (see intersect_node)
   for (int m = (int)threadIdx.x; m < 256; m += kTraceBlock) s_lut[3 * m] = (((uint32_t)m >> 5) & 7u) << (m & 31);
@@ -129,9 +134,17 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
             batch_next = (int)base;
             batch_end = (int)base + ray_batch < n ? (int)base + ray_batch : n;
             // pull the batch's rays towards the SM now; they are staged 32 at a time later
-            for (int r = batch_next + 4 * (int)lane; r < batch_end; r += 128) {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.org_tmin + r));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dir_tmax + r));
+            if (HAS_LIST) {
+              for (int r = batch_next + (int)lane; r < batch_end; r += 32) {
+                const int i = __ldg(p.ray_list + r);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.org_tmin + i));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dir_tmax + i));
+              }
+            } else {
+              for (int r = batch_next + 4 * (int)lane; r < batch_end; r += 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.org_tmin + r));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dir_tmax + r));
+              }
             }
           }
         }
@@ -139,7 +152,8 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
           const int cnt = batch_end - batch_next < 32 ? batch_end - batch_next : 32;
           __syncwarp();  // every lane has consumed its entry of the previous stage
           if ((int)lane < cnt) {
-            const int idx = batch_next + (int)lane;
+            const int idx = HAS_LIST ? __ldg(p.ray_list + batch_next + (int)lane) : batch_next + (int)lane;
+            if (HAS_LIST) s_stage_idx[threadIdx.x] = idx;
             const float4 o = __ldcs(p.org_tmin + idx);  // streaming: keep the BVH in L2
             const float4 d = __ldcs(p.dir_tmax + idx);
             RayF ray;
@@ -163,7 +177,7 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
         if (rank < avail) {
           const int e = (int)(threadIdx.x & ~31u) + stage_pos + rank;
           const float4 o = s_stage[0][e], d = s_stage[1][e], c = s_stage[2][e];
-          const int idx = stage_base + stage_pos + rank;
+          const int idx = HAS_LIST ? s_stage_idx[e] : stage_base + stage_pos + rank;
           rp.ox = o.x; rp.oy = o.y; rp.oz = o.z; rp.tmin = o.w;
           rp.d = mk3(d.x, d.y, d.z);
           rp.idx = c.x; rp.idy = c.y; rp.idz = c.z; rp.err = c.w;
@@ -280,6 +294,68 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
       atomicAdd(p.counters + 1, tt);
     }
   }
+}
+
+// Bounds cull in front of large plain mesh batches: one streaming pass retires the rays that miss the
+// bounds of all vertices (C2's ray mix: 54 %) with their raw miss record and appends the others to the
+// list the traversal walks.  In the traversal such a ray costs a staged entry, a lane for one trip of
+// the lock-step loop (the root's eight child boxes) and a scattered 16-byte store; here it costs 32
+// coalesced bytes in and 16 out.  Conservative: the box is widened by 4e-6 of the origin's distance to
+// it (> 30 x the float32 error of the slab arithmetic), the accept rule is the traversal's
+// (bvh.go:322-351: near <= far within [tmin, tmax]; zero direction components as +-2^-64), and a
+// comparison with a NaN keeps the ray.
+__global__ void __launch_bounds__(256)
+cull_rays_kernel(DeviceBVH bvh, const float4 *__restrict__ org_tmin, const float4 *__restrict__ dir_tmax, int n,
+                 float4 *__restrict__ hit0, int *__restrict__ list, int *__restrict__ count) {
+  constexpr int kPer = 4;
+  __shared__ int s_cnt[kPer * 8];
+  __shared__ int s_base;
+  const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+  const int base = (int)blockIdx.x * (256 * kPer) + (int)threadIdx.x;
+  unsigned balls[kPer];
+  bool keep[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; k++) {
+    const int i = base + 256 * k;
+    keep[k] = false;
+    if (i < n) {
+      const float4 o = __ldg(org_tmin + i), d = __ldg(dir_tmax + i);
+      const float ooeps = 5.421010862e-20f;
+      const float dx = fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x);
+      const float dy = fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y);
+      const float dz = fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z);
+      const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+      const float dmax = fmaxf(fmaxf(fmaxf(fabsf(o.x - bvh.bmin[0]), fabsf(o.x - bvh.bmax[0])),
+                                     fmaxf(fabsf(o.y - bvh.bmin[1]), fabsf(o.y - bvh.bmax[1]))),
+                               fmaxf(fabsf(o.z - bvh.bmin[2]), fabsf(o.z - bvh.bmax[2])));
+      const float m = 4e-6f * dmax + 1e-30f;
+      const float ax = (bvh.bmin[0] - m - o.x) * ix, bx = (bvh.bmax[0] + m - o.x) * ix;
+      const float ay = (bvh.bmin[1] - m - o.y) * iy, by = (bvh.bmax[1] + m - o.y) * iy;
+      const float az = (bvh.bmin[2] - m - o.z) * iz, bz = (bvh.bmax[2] + m - o.z) * iz;
+      const float t_near = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), o.w));
+      const float t_far = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), d.w));
+      keep[k] = !(t_near > t_far);
+      if (!keep[k]) __stcs(hit0 + i, make_float4(d.w, 0.f, 0.f, __int_as_float(-1)));
+    }
+    balls[k] = __ballot_sync(0xffffffffu, keep[k]);
+    if (lane == 0) s_cnt[k * 8 + warp] = __popc(balls[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int v = threadIdx.x < kPer * 8 ? s_cnt[threadIdx.x] : 0;
+    int incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += u;
+    }
+    if (threadIdx.x < kPer * 8) s_cnt[threadIdx.x] = incl - v;
+    if (threadIdx.x == 31) s_base = incl ? atomicAdd(count, incl) : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kPer; k++)
+    if (keep[k]) list[s_base + s_cnt[k * 8 + warp] + __popc(balls[k] & ((1u << lane) - 1u))] = base + 256 * k;
 }
 
 __global__ void pack_rays_kernel(const float *__restrict__ org3, const float *__restrict__ dir3,
@@ -444,21 +520,30 @@ void launch_count_hits(const DeviceBVH &bvh, const float *org3, const float *dir
 namespace {
 }  // namespace
 
-template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS, bool HAS_SKIP>
+template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS, bool HAS_SKIP, bool HAS_LIST = false>
 static void launch_trace_instance(const DeviceBVH &bvh, const TraceLaunch &p, cudaStream_t stream) {
   // persistent grid: as many blocks as stay resident
   static const int blocks_per_sm = [] {
     int b = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &b, trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS, HAS_SKIP>, kTraceBlock, 0);
+        &b, trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS, HAS_SKIP, HAS_LIST>, kTraceBlock, 0);
     return b > 0 ? b : 1;
   }();
   long long want = (p.n + kTraceBlock - 1) / kTraceBlock;
   long long grid = (long long)device_sm_count() * blocks_per_sm;
   if (grid > want) grid = want;
   unsigned int *rc32 = reinterpret_cast<unsigned int *>(p.ray_counter);
-  trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS, HAS_SKIP>
+  trace_first_hit_kernel<COUNT, MIN_BLOCKS, TRI_ROUNDS, HAS_SKIP, HAS_LIST>
       <<<(unsigned)grid, kTraceBlock, 0, stream>>>(bvh, p, rc32);
+}
+
+// M3D_CULL=0|1 overrides the default (tuning / A-B runs)
+bool trace_cull_wanted(int64_t n, int64_t num_nodes) {
+  static const int mode = [] {
+    const char *e = getenv("M3D_CULL");
+    return e ? atoi(e) : M3D_CULL_DEFAULT;
+  }();
+  return mode != 0 && n >= ((int64_t)1 << 20) && n < ((int64_t)1 << 31) - 4096 && num_nodes > kTinySceneNodes;
 }
 
 template <bool COUNT, int MIN_BLOCKS, int TRI_ROUNDS = 1>
@@ -482,7 +567,21 @@ void launch_trace_bvh_only(const DeviceBVH &bvh, const TraceLaunch &p_in, cudaSt
     const char *e = getenv("M3D_TRACE_TRI_ROUNDS");
     return e ? atoi(e) : 0;
   }();
-  const TraceLaunch &p = p_in;
+  TraceLaunch p = p_in;
+  if (p.cull_scratch && !p.skip_tris && !p.n_ptr && bvh.num_nodes > kTinySceneNodes) {
+    int *count = p.cull_scratch, *list = p.cull_scratch + 1;
+    cudaMemsetAsync(count, 0, sizeof(int), stream);
+    cull_rays_kernel<<<(unsigned)((p.n + 1023) / 1024), 256, 0, stream>>>(bvh, p.org_tmin, p.dir_tmax, (int)p.n, p.hit0,
+                                                                         list, count);
+    p.ray_list = list;
+    p.n_ptr = count;
+    cudaMemsetAsync(p.ray_counter, 0, sizeof(unsigned long long), stream);
+    if (p.counters)
+      launch_trace_instance<true, 6, 1, false, true>(bvh, p, stream);
+    else
+      launch_trace_instance<false, 6, 1, false, true>(bvh, p, stream);
+    return;
+  }
   // tiny hierarchies (cornell_box: 72 triangles in 4 nodes) spend their time in the triangle phase
   const int tri_rounds = tri_rounds_env > 0 ? tri_rounds_env : (bvh.num_nodes <= kTinySceneNodes ? M3D_TINY_TRI_ROUNDS : 1);
   cudaMemsetAsync(p.ray_counter, 0, sizeof(unsigned long long), stream);

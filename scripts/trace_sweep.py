@@ -46,6 +46,8 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 same = bool(torch.equal(ref_prim.view(torch.int32), h0[:, 3].contiguous().view(torch.int32)))
 env = {k: v for k, v in os.environ.items() if k.startswith("M3D_")}
-print("env %s mix %s: %.3f ms/step %.2f Grays/s nodes/ray %.3f tris/ray %.3f prim_checksum %d stable %s" % (
+# checksum over every bit of both hit records (final outputs must not depend on tuning knobs)
+bits = int(h0.view(torch.int32).to(torch.int64).sum().item()) ^ (int(h1.view(torch.int32).to(torch.int64).sum().item()) << 1)
+print("env %s mix %s: %.3f ms/step %.2f Grays/s nodes/ray %.3f tris/ray %.3f prim_checksum %d all_bits %d stable %s" % (
     env, mix, ms, n / ms / 1e6, st["nodes_visited"] / n, st["tris_tested"] / n,
-    int(h0[:, 3].contiguous().view(torch.int32).to(torch.int64).sum().item()), same), flush=True)
+    int(h0[:, 3].contiguous().view(torch.int32).to(torch.int64).sum().item()), bits, same), flush=True)
