@@ -599,6 +599,7 @@ def secondary_path_metrics(rank, world, local_rank, reduce_mode="fused", steps=5
                    "Mrays_per_s": m["total_rays"] / (ms * 1e-3) / 1e6,
                    "ms_per_frame": ms, "render_ms_per_rank": m["render_ms_per_rank"],
                    "reduce_wait_ms_per_rank": m["reduce_wait_ms_per_rank"],
+                   "kernel_ms_per_rank": m["kernel_ms_per_rank"], "clocks": m["clocks"],
                    "scaling": "strong (sample shards); " + m["reduce"]}
         del m
     return out

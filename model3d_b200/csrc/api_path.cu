@@ -28,6 +28,16 @@ namespace {
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Bytes carve_path_buffers reserves for `cap` slots (every array padded to 256 bytes)
+size_t path_buffer_bytes(int64_t cap, int num_lights) {
+  const size_t c = (size_t)cap, nl = (size_t)num_lights;
+  size_t total = 0;
+  for (int i = 0; i < 2; i++) total += 2 * align256(c * 16) + 2 * align256(c * 4);  // org, dir, skip, queue
+  total += 6 * align256(c * 16) + 4 * align256(c * 4);  // raw, thr, accum, hit records; work lists
+  total += 4 * align256(c * nl * 16) + align256(c * nl * 4) + align256(64);  // shadow rays; counters
+  return total;
+}
+
 // Carves the path-state arrays out of one scratch allocation.
 int32_t carve_path_buffers(m3d_ctx *ctx, int64_t cap, int num_lights, PathBuffers &b) {
   const size_t c = (size_t)cap, nl = (size_t)num_lights;
@@ -51,6 +61,7 @@ int32_t carve_path_buffers(m3d_ctx *ctx, int64_t cap, int num_lights, PathBuffer
   const size_t o_sorg = take(c * nl * 16), o_sdir = take(c * nl * 16), o_sraw = take(c * nl * 16),
                o_spay = take(c * nl * 16), o_sskip = take(c * nl * 4);
   const size_t o_counts = take(64);
+  if (total != path_buffer_bytes(cap, num_lights)) return fail(M3D_ERR_CUDA, "path buffer size bookkeeping is out of step");
   M3D_CUDA(ctx->scratch[4].reserve(total));
   char *p = ctx->scratch[4].as<char>();
   b.cap = cap;
@@ -233,8 +244,10 @@ static int32_t render_path_one_device(m3d_scene *scene, const m3d_camera *cam, c
   const int64_t want_slots = std::min<int64_t>(
       total, std::min<int64_t>((int64_t)1 << batch_log2, ((int64_t)1 << 30) / std::max<int64_t>(1, num_lights)));
   int64_t budget = (int64_t)48 << 30;
-  // carve_path_buffers pads every array to 256 bytes: 32 arrays
-  if ((int64_t)ctx->scratch[4].bytes < want_slots * per_slot + 32 * 256) {
+  // (the bound has to be the carve's own byte count: an estimate above it asked on every call, and
+  // with CUDA IPC / peer mappings in the process the query costs 4-70 ms -- measured at 2 GPUs under
+  // torchrun: 78 ms of kernels per C3 frame, 79-161 ms between the events around the call)
+  if (ctx->scratch[4].bytes < path_buffer_bytes(want_slots, num_lights)) {
     size_t free_b = 0, total_b = 0;
     M3D_CUDA(cudaMemGetInfo(&free_b, &total_b));
     budget = std::min<int64_t>(budget, (int64_t)((free_b + ctx->scratch[4].bytes) / 2));

@@ -117,9 +117,45 @@ __device__ __forceinline__ void eval_vertex(const DeviceScene &sc, BVert &v, int
 // One out-of-line copy for callers that evaluate several vertices (the connection kernel's two junction
 // vertices): the material code is ~2,000 instructions per inlined copy.
 #ifndef M3D_CONNECT_EVAL_NOINLINE
-#define M3D_CONNECT_EVAL_NOINLINE 0
+// 0: inlined twice (4,488 instructions), 1: out of line by reference (round 2: 202 -> 162 Msamples/s),
+// 2: out of line by value (3,304 instructions; connection stage 227.6 -> 223.8 ms per 128-spp C5 frame)
+#define M3D_CONNECT_EVAL_NOINLINE 2
 #endif
-#if M3D_CONNECT_EVAL_NOINLINE
+#if M3D_CONNECT_EVAL_NOINLINE == 2
+// values in, values out (a BVert & would put the whole vertex into local memory: measured 202 -> 162
+// Msamples/s in round 2); the scene is reached through the address of the __grid_constant__ parameter
+struct VertexEval {
+  float sd_fin, sd_del, dd_fin, dd_del;
+  V3f bsdf_fin, bsdf_del;
+};
+static __device__ __noinline__ VertexEval eval_vertex_values(const DeviceScene *scp, int obj, V3f point, V3f normal,
+                                                          V3f source, V3f dest) {
+  BVert v;
+  v.obj = obj;
+  v.point = point;
+  v.normal = normal;
+  v.source = source;
+  v.dest = dest;
+  eval_vertex(*scp, v, 0);
+  VertexEval r;
+  r.sd_fin = v.sd_fin;
+  r.sd_del = v.sd_del;
+  r.dd_fin = v.dd_fin;
+  r.dd_del = v.dd_del;
+  r.bsdf_fin = v.bsdf_fin;
+  r.bsdf_del = v.bsdf_del;
+  return r;
+}
+__device__ __forceinline__ void eval_vertex_call(const DeviceScene &sc, BVert &v) {
+  const VertexEval r = eval_vertex_values(&sc, v.obj, v.point, v.normal, v.source, v.dest);
+  v.sd_fin = r.sd_fin;
+  v.sd_del = r.sd_del;
+  v.dd_fin = r.dd_fin;
+  v.dd_del = r.dd_del;
+  v.bsdf_fin = r.bsdf_fin;
+  v.bsdf_del = r.bsdf_del;
+}
+#elif M3D_CONNECT_EVAL_NOINLINE
 static __device__ __noinline__ void eval_vertex_call(const DeviceScene &sc, BVert &v) { eval_vertex(sc, v, 0); }
 #else
 __device__ __forceinline__ void eval_vertex_call(const DeviceScene &sc, BVert &v) { eval_vertex(sc, v, 0); }
@@ -839,7 +875,7 @@ __device__ __forceinline__ void connect_item(const DeviceScene &sc, const Device
 // One thread per work item; threads of a warp share (i, j) except where two classes meet.
 template <int PHK>
 __global__ void __launch_bounds__(kBlock, M3D_BCONNECT_MINB)
-bidir_connect_kernel(DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
+bidir_connect_kernel(const __grid_constant__ DeviceScene sc, DeviceBidirParams bp, PathBatch b, BidirBuffers buf) {
 #if M3D_CONNECT_CHUNKED
   // M3D_CONNECT_PARTS consecutive blocks share a chunk and stride over its items
   const int chunk = (int)(blockIdx.x / M3D_CONNECT_PARTS), part = (int)(blockIdx.x % M3D_CONNECT_PARTS);
