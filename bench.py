@@ -608,7 +608,8 @@ def secondary_path_metrics(rank, world, local_rank, reduce_mode="fused", steps=5
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps (default: 100 first-hit batches / RayCaster frames, 10 C3 / C4 frames, 5 C5 frames)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--rays", type=int, default=N_RAYS)
@@ -629,6 +630,8 @@ def main():
     args = ap.parse_args()
     if not args.spp:
         args.spp = 1024 if args.workload == "c5" else 256
+    if args.steps is None:  # a C5 frame at 1024 spp takes seconds: keep the default run within minutes
+        args.steps = {"c3": 10, "c4": 10, "c5": 5}.get(args.workload, 100)
     if args.impl == "reference":
         if args.workload in ("c3", "c4", "c5"):
             run_reference_path(args)
