@@ -470,3 +470,43 @@ def test_shared_origin_and_dropped_outputs(built):
     assert full.Collides.sum() > 1000
     assert lean.Stats["h2d_bytes"] == d.shape[0] * 12 and full.Stats["h2d_bytes"] == d.shape[0] * 24
     assert lean.Stats["d2h_bytes"] == d.shape[0] * 8 and full.Stats["d2h_bytes"] == d.shape[0] * 32
+
+
+_CULL_WORKER = r"""
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from model3d_b200 import MeshCollider, meshes
+tris = meshes.NewMeshIcosphere((0, 0, 0), 1.0, 24).astype(np.float32).reshape(-1, 9)
+rng = np.random.default_rng(5)
+n = (1 << 20) + 777                       # at least 2^20 rays: the size from which the cull applies
+o = (rng.normal(size=(n, 3)) * 2.0).astype(np.float32)
+d = rng.normal(size=(n, 3)).astype(np.float32)
+d[::97, 0] = 0.0                          # axis-parallel components, some of them -0.0
+d[::193, 1] = -0.0
+o[::389] = 0.0                            # origins inside the mesh
+r = MeshCollider(tris).FirstRayCollisions(o, d, counters=True)
+h = hashlib.sha256()
+for a in (r.Triangle, r.Scale, r.Normal, r.Barycentric):
+    h.update(np.ascontiguousarray(a).tobytes())
+print("RESULT", h.hexdigest(), int(r.Collides.sum()), r.Stats["nodes_visited"])
+"""
+
+
+def test_bounds_cull_option_gives_identical_results(built, tmp_path):
+    """M3D_CULL=1 (a streaming bounds cull in front of large plain mesh batches, off by
+    default) must not change a single output bit; it only lowers the number of nodes visited."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "cull_worker.py"
+    script.write_text(_CULL_WORKER)
+    out = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ, M3D_CULL=mode)
+        p = subprocess.run([sys.executable, str(script), root], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        line = [l for l in p.stdout.splitlines() if l.startswith("RESULT")][-1].split()
+        out[mode] = (line[1], int(line[2]), int(line[3]))
+    assert out["0"][0] == out["1"][0], "outputs differ with the bounds cull"
+    assert out["0"][1] == out["1"][1] and out["0"][1] > 10000
+    assert out["1"][2] < out["0"][2], "the cull did not retire any ray (%d vs %d nodes)" % (out["1"][2], out["0"][2])
