@@ -319,6 +319,29 @@ M3D_HD RayPre precompute_ray(const RayF &ray, const float *scene_min, const floa
   return rp;
 }
 
+// Whether a ray certainly misses the bounds [bmin, bmax] of all vertices (the optional bounds cull in
+// front of large mesh batches, cull_rays_kernel).  Conservative: the box is widened by 4e-6 of the origin's
+// largest distance to it (> 30 x the float32 error of the slab arithmetic below), the accept rule is the
+// traversal's (bvh.go:322-351: near <= far within [tmin, tmax]; zero direction components as +-2^-64 like
+// precompute_ray), and a comparison with a NaN keeps the ray.
+M3D_HD bool ray_misses_bounds(float ox, float oy, float oz, float tmin, float dx, float dy, float dz, float tmax,
+                              const float *bmin, const float *bmax) {
+  const float ooeps = 5.421010862e-20f;
+  const float ex = fabsf(dx) > ooeps ? dx : copysignf(ooeps, dx);
+  const float ey = fabsf(dy) > ooeps ? dy : copysignf(ooeps, dy);
+  const float ez = fabsf(dz) > ooeps ? dz : copysignf(ooeps, dz);
+  const float ix = 1.0f / ex, iy = 1.0f / ey, iz = 1.0f / ez;
+  const float dmax = max3f(fmaxf(fabsf(ox - bmin[0]), fabsf(ox - bmax[0])), fmaxf(fabsf(oy - bmin[1]), fabsf(oy - bmax[1])),
+                           fmaxf(fabsf(oz - bmin[2]), fabsf(oz - bmax[2])));
+  const float m = 4e-6f * dmax + 1e-30f;
+  const float ax = (bmin[0] - m - ox) * ix, bx = (bmax[0] + m - ox) * ix;
+  const float ay = (bmin[1] - m - oy) * iy, by = (bmax[1] + m - oy) * iy;
+  const float az = (bmin[2] - m - oz) * iz, bz = (bmax[2] + m - oz) * iz;
+  const float t_near = fmaxf(max3f(fminf(ax, bx), fminf(ay, by), fminf(az, bz)), tmin);
+  const float t_far = fminf(min3f(fmaxf(ax, bx), fmaxf(ay, by), fmaxf(az, bz)), tmax);
+  return t_near > t_far;
+}
+
 // Ray/triangle test of the traversal: the reference's Moeller-Trumbore (primitives.go:
 // 207-249) in float32.  Its barycentrics carry an absolute error of a few ulp of
 // |o - v0| * |d| * |edge| / det, far larger than 1 ulp for small, distant triangles, so a

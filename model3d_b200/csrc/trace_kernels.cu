@@ -300,10 +300,8 @@ trace_first_hit_kernel(DeviceBVH bvh, TraceLaunch p, unsigned int *__restrict__ 
 // bounds of all vertices (C2's ray mix: 54 %) with their raw miss record and appends the others to the
 // list the traversal walks.  In the traversal such a ray costs a staged entry, a lane for one trip of
 // the lock-step loop (the root's eight child boxes) and a scattered 16-byte store; here it costs 32
-// coalesced bytes in and 16 out.  Conservative: the box is widened by 4e-6 of the origin's distance to
-// it (> 30 x the float32 error of the slab arithmetic), the accept rule is the traversal's
-// (bvh.go:322-351: near <= far within [tmin, tmax]; zero direction components as +-2^-64), and a
-// comparison with a NaN keeps the ray.
+// coalesced bytes in and 16 out.  The test is ray_misses_bounds (trace_core.cuh; conservative, covered on
+// the CPU by tests/test_emul_traversal.py).
 __global__ void __launch_bounds__(256)
 cull_rays_kernel(DeviceBVH bvh, const float4 *__restrict__ org_tmin, const float4 *__restrict__ dir_tmax, int n,
                  float4 *__restrict__ hit0, int *__restrict__ list, int *__restrict__ count) {
@@ -320,21 +318,7 @@ cull_rays_kernel(DeviceBVH bvh, const float4 *__restrict__ org_tmin, const float
     keep[k] = false;
     if (i < n) {
       const float4 o = __ldg(org_tmin + i), d = __ldg(dir_tmax + i);
-      const float ooeps = 5.421010862e-20f;
-      const float dx = fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x);
-      const float dy = fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y);
-      const float dz = fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z);
-      const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
-      const float dmax = fmaxf(fmaxf(fmaxf(fabsf(o.x - bvh.bmin[0]), fabsf(o.x - bvh.bmax[0])),
-                                     fmaxf(fabsf(o.y - bvh.bmin[1]), fabsf(o.y - bvh.bmax[1]))),
-                               fmaxf(fabsf(o.z - bvh.bmin[2]), fabsf(o.z - bvh.bmax[2])));
-      const float m = 4e-6f * dmax + 1e-30f;
-      const float ax = (bvh.bmin[0] - m - o.x) * ix, bx = (bvh.bmax[0] + m - o.x) * ix;
-      const float ay = (bvh.bmin[1] - m - o.y) * iy, by = (bvh.bmax[1] + m - o.y) * iy;
-      const float az = (bvh.bmin[2] - m - o.z) * iz, bz = (bvh.bmax[2] + m - o.z) * iz;
-      const float t_near = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), o.w));
-      const float t_far = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), d.w));
-      keep[k] = !(t_near > t_far);
+      keep[k] = !ray_misses_bounds(o.x, o.y, o.z, o.w, d.x, d.y, d.z, d.w, bvh.bmin, bvh.bmax);
       if (!keep[k]) __stcs(hit0 + i, make_float4(d.w, 0.f, 0.f, __int_as_float(-1)));
     }
     balls[k] = __ballot_sync(0xffffffffu, keep[k]);

@@ -25,6 +25,15 @@ void *emul_build(const float *tris, int64_t n) {
   return e;
 }
 void emul_destroy(void *h) { delete (Emul *)h; }
+// the bounds-cull predicate of cull_rays_kernel (trace_core.cuh: ray_misses_bounds) per ray
+void emul_ray_misses_bounds(const float *org3, const float *dir3, int64_t n, float tmin, float tmax, const float *bmin,
+                            const float *bmax, uint8_t *out) {
+  for (int64_t i = 0; i < n; i++)
+    out[i] = m3d::ray_misses_bounds(org3[3 * i], org3[3 * i + 1], org3[3 * i + 2], tmin, dir3[3 * i], dir3[3 * i + 1],
+                                    dir3[3 * i + 2], tmax, bmin, bmax)
+                 ? 1
+                 : 0;
+}
 void emul_info(void *h, int64_t *out /*nodes, tris, depth*/, double *sah) {
   auto *e = (Emul *)h;
   out[0] = (int64_t)e->bvh.nodes.size();

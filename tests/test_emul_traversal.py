@@ -126,3 +126,47 @@ def test_emulated_collect_hits_matches_oracle(emul, oracle):
         rt = ref["t"][a0:a0 + rc[i]][ro]
         # raw float32 t of the traversal (the kernel re-evaluates every hit in float64 afterwards)
         assert np.all(np.abs(t[i, :counts[i]][go] - rt) <= 1e-4 * np.maximum(np.abs(rt), 1.0))  # glancing hits are ill-conditioned in float32
+
+
+def test_bounds_cull_predicate_is_conservative(emul, oracle):
+    """ray_misses_bounds (trace_core.cuh), the test of the optional bounds cull in front of large mesh
+    batches: whenever it retires a ray, the float64 oracle reports a miss -- for origins near and far,
+    axis-parallel and signed-zero direction components, rays grazing the bounds, origins inside."""
+    tris = oracle.mesh_icosphere((0.3, -0.2, 0.1), 1.0, 12).astype(np.float32)
+    v = tris.reshape(-1, 3)
+    bmin, bmax = v.min(0).astype(np.float32), v.max(0).astype(np.float32)
+    rng = np.random.default_rng(11)
+    sets = []
+    for scale in (0.5, 2.0, 50.0, 1e4):
+        o = (rng.normal(size=(20000, 3)) * scale).astype(np.float32)
+        d = rng.normal(size=(20000, 3)).astype(np.float32)
+        sets.append((o, d))
+    # axis-parallel rays along the faces of the bounds (grazing) and signed zeros
+    o = (rng.uniform(-3, 3, size=(20000, 3))).astype(np.float32)
+    d = np.zeros((20000, 3), np.float32)
+    ax = rng.integers(0, 3, size=20000)
+    d[np.arange(20000), ax] = rng.choice([-1.0, 1.0], size=20000)
+    d[::3] = np.where(d[::3] == 0, -0.0, d[::3])
+    k = rng.integers(0, 3, size=20000)
+    face = np.where(rng.random(20000) < 0.5, bmin[k], bmax[k])
+    sel = k != ax
+    o[sel, k[sel]] = face[sel]
+    sets.append((o, d))
+    # rays aimed at points on the bounds' surface from outside
+    o = (rng.normal(size=(20000, 3)) * 4).astype(np.float32)
+    tgt = rng.uniform(bmin, bmax, size=(20000, 3)).astype(np.float32)
+    kk = rng.integers(0, 3, size=20000)
+    tgt[np.arange(20000), kk] = np.where(rng.random(20000) < 0.5, bmin[kk], bmax[kk])
+    sets.append((o, (tgt - o).astype(np.float32)))
+    col = oracle.Collider(tris)
+    culled_total = 0
+    for o, d in sets:
+        o, d = np.ascontiguousarray(o), np.ascontiguousarray(d)
+        out = np.zeros(o.shape[0], np.uint8)
+        emul.emul_ray_misses_bounds(P(o, C.c_float), P(d, C.c_float), C.c_int64(o.shape[0]), C.c_float(0.0),
+                                    C.c_float(np.inf), P(bmin, C.c_float), P(bmax, C.c_float), P(out, C.c_uint8))
+        ref = col.first_hits(o, d, threads=8)
+        bad = (out == 1) & (ref["prim"] >= 0)
+        assert not bad.any(), "the cull retired %d rays the oracle hits" % int(bad.sum())
+        culled_total += int(out.sum())
+    assert culled_total > 20000  # and it does retire rays
